@@ -1,0 +1,463 @@
+// ORACLE / TEST INFRASTRUCTURE ONLY — never linked into the product library.
+//
+// C-ABI driver around the reference's own, unmodified sources (compiled where they lie under
+// /root/reference by oracle/Makefile).  It adds no algorithm: every entry point calls the
+// reference function it names (file:line relative to /root/reference/code/) and copies plain
+// arrays in and out so that tests/ and bench.py's cpu_baseline / --impl reference arm can drive
+// it through ctypes.  Intermediate results are published as named blobs (ref_blob).
+//
+//   * time() is interposed (link flag -Bsymbolic-functions) so that the time-seeded RANSAC
+//     (3rd_party/ransac/RansacShapeDetector.cpp:463-464) is reproducible: ref_set_seed(s>=0).
+//   * P/plade.cpp is compiled a second time with MatchingLines/registration/extract renamed on
+//     the command line; the renamed MatchingLines call lands in the hook below, which records
+//     what registration() (PLADE/plade.cpp:31-536) built and forwards to the real function.
+//   * cv::fitLine (imgproc) is referenced by PLADE/util.cpp:684 (Fit3DLine) but that path is
+//     dead — boundary lines are never produced (PLADE/plade.cpp:175-178,383-384) — so it is
+//     stubbed here instead of compiling OpenCV imgproc.
+#include "util.h"
+#include "plade.h"
+#include "plane_extraction.h"
+#include <opencv2/imgproc/imgproc.hpp>
+
+#include <map>
+#include <string>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
+#include <chrono>
+
+// ---- reference symbols without a header declaration --------------------------------------------
+std::vector<PLANE> extract(pcl::PointCloud<pcl::PointNormal>::Ptr cloud, int init_min_support);  // PLADE/plade.cpp:602
+bool plade_oracle_registration_hooked(Eigen::Matrix<float, 4, 4> &transformation,
+                                      pcl::PointCloud<pcl::PointNormal>::Ptr target_cloud,
+                                      pcl::PointCloud<pcl::PointNormal>::Ptr source_cloud,
+                                      const std::vector<PLANE> &target_planes,
+                                      const std::vector<PLANE> &source_planes);
+
+namespace cv {
+void fitLine(InputArray, OutputArray, int, double, double, double) {
+  fprintf(stderr, "oracle: cv::fitLine stub reached (dead path in the reference)\n");
+  abort();
+}
+}  // namespace cv
+
+// ---- deterministic time() ----------------------------------------------------------------------
+static long g_seed = -1;
+extern "C" time_t time(time_t *t) {
+  time_t v;
+  if (g_seed >= 0) v = (time_t) g_seed;
+  else v = (time_t) std::chrono::duration_cast<std::chrono::seconds>(
+               std::chrono::system_clock::now().time_since_epoch()).count();
+  if (t) *t = v;
+  return v;
+}
+
+// ---- blob store --------------------------------------------------------------------------------
+static std::map<std::string, std::vector<char> > g_blobs;
+template <typename T> static void put(const std::string &name, const std::vector<T> &v) {
+  std::vector<char> &b = g_blobs[name];
+  b.resize(v.size() * sizeof(T));
+  if (!v.empty()) memcpy(b.data(), v.data(), b.size());
+}
+template <typename T> static void put1(const std::string &name, T v) { put(name, std::vector<T>(1, v)); }
+
+typedef pcl::PointCloud<pcl::PointNormal> CloudPN;
+typedef pcl::PointCloud<pcl::PointXYZ> CloudXYZ;
+
+static CloudPN::Ptr make_cloud(const float *xyzn, size_t n) {
+  CloudPN::Ptr c(new CloudPN);
+  c->resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    const float *p = xyzn + 6 * i;
+    c->at(i) = pcl::PointNormal(p[0], p[1], p[2], p[3], p[4], p[5]);
+  }
+  return c;
+}
+static CloudXYZ::Ptr make_xyz(const float *xyz, size_t n) {
+  CloudXYZ::Ptr c(new CloudXYZ);
+  c->resize(n);
+  for (size_t i = 0; i < n; ++i) c->at(i) = pcl::PointXYZ(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  return c;
+}
+static void put_xyz(const std::string &name, const CloudXYZ &c) {
+  std::vector<float> v(c.size() * 3);
+  for (size_t i = 0; i < c.size(); ++i) { v[3 * i] = c[i].x; v[3 * i + 1] = c[i].y; v[3 * i + 2] = c[i].z; }
+  put(name, v);
+}
+static void to_rowmajor(const Eigen::Matrix4f &T, float *out16) {
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out16[4 * r + c] = T(r, c);
+}
+static std::vector<PLANE> make_planes(const int *offsets, const int *indices, const float *params, int np) {
+  std::vector<PLANE> planes;
+  for (int i = 0; i < np; ++i) {
+    PLANE pl(indices + offsets[i], indices + offsets[i + 1]);
+    pl.normal = Eigen::Vector3f(params[4 * i], params[4 * i + 1], params[4 * i + 2]);
+    pl.d = params[4 * i + 3];
+    planes.push_back(pl);
+  }
+  return planes;
+}
+static void put_planes(const std::string &prefix, const std::vector<PLANE> &planes) {
+  std::vector<int> off(1, 0), idx;
+  std::vector<float> par;
+  for (size_t i = 0; i < planes.size(); ++i) {
+    idx.insert(idx.end(), planes[i].begin(), planes[i].end());
+    off.push_back((int) idx.size());
+    par.push_back(planes[i].normal.x()); par.push_back(planes[i].normal.y());
+    par.push_back(planes[i].normal.z()); par.push_back(planes[i].d);
+  }
+  put(prefix + "plane_offsets", off);
+  put(prefix + "plane_indices", idx);
+  put(prefix + "plane_params", par);
+}
+
+// ---- the MatchingLines hook (called from the renamed copy of PLADE/plade.cpp:536) -----------------
+static bool g_dump = false;
+static void dump_side(const std::string &p, MatchInformation &m) {
+  put_xyz(p + "ds", *m.points);
+  std::vector<float> c(m.boundingCenter.data(), m.boundingCenter.data() + 3);
+  put(p + "center", c);
+  const std::vector<INTERSECTION_LINE> &lines = *m.pIntersectionLine;
+  std::vector<float> lv; std::vector<int> lp;
+  for (size_t i = 0; i < lines.size(); ++i) {
+    for (int k = 0; k < 3; ++k) lv.push_back(lines[i].lineVec[k]);
+    for (int k = 0; k < 3; ++k) lv.push_back(lines[i].linePoint[k]);
+    lp.push_back(lines[i].supportPlanes.size() > 0 ? lines[i].supportPlanes[0] : -1);
+    lp.push_back(lines[i].supportPlanes.size() > 1 ? lines[i].supportPlanes[1] : -1);
+  }
+  put(p + "lines", lv); put(p + "line_planes", lp);
+  const std::vector<std::vector<NearstPointsTwoLine> > &tab = *m.pNearstPointsTwoLines;
+  size_t L = tab.size();
+  std::vector<double> len(L * L, 0.0); std::vector<float> p1(L * L * 3, 0.f), p2(L * L * 3, 0.f);
+  for (size_t i = 0; i < L; ++i) for (size_t j = 0; j < L; ++j) {
+    if (i == j) continue;
+    len[i * L + j] = tab[i][j].length;
+    for (int k = 0; k < 3; ++k) { p1[(i * L + j) * 3 + k] = tab[i][j].points1[k]; p2[(i * L + j) * 3 + k] = tab[i][j].points2[k]; }
+  }
+  put(p + "pair_len", len); put(p + "pair_p1", p1); put(p + "pair_p2", p2);
+  std::vector<float> planes;
+  for (size_t i = 0; i < m.pPlanes->size(); ++i) for (int k = 0; k < 4; ++k) planes.push_back((*m.pPlanes)[i][k]);
+  put(p + "planes", planes);
+  std::vector<int> off(1, 0); std::vector<float> pds, corners, centers, radii;
+  for (size_t i = 0; i < m.pDownSamplePlanePoints->size(); ++i) {
+    const CloudXYZ &c2 = *(*m.pDownSamplePlanePoints)[i];
+    for (size_t j = 0; j < c2.size(); ++j) { pds.push_back(c2[j].x); pds.push_back(c2[j].y); pds.push_back(c2[j].z); }
+    off.push_back((int) (pds.size() / 3));
+    const std::vector<Eigen::Vector3f> &fc = (*m.pBoundingBoxFourCornerPoints)[i];
+    for (size_t j = 0; j < 4; ++j) for (int k = 0; k < 3; ++k) corners.push_back(j < fc.size() ? fc[j][k] : 0.f);
+    for (int k = 0; k < 3; ++k) centers.push_back((*m.pBoundingBoxCenterForEachPlane)[i][k]);
+    radii.push_back((*m.pBoundingBoxRadiusForEachPlane)[i]);
+  }
+  put(p + "plane_ds_offsets", off); put(p + "plane_ds", pds); put(p + "plane_corners4", corners);
+  put(p + "plane_center", centers); put(p + "plane_radius", radii);
+}
+
+static std::vector<MatchedResult> g_last_results;
+static MatchInformation g_last_current, g_last_main;
+
+void plade_oracle_MatchingLines_hook(MatchInformation current, MatchInformation main,
+                                     std::vector<std::pair<int, int> > linesTobeMatched,
+                                     std::vector<std::vector<int> > coarseMatches,
+                                     std::vector<MatchedResult> &pMatchedResult, Parameter parameter) {
+  if (g_dump) {
+    dump_side("src_", current);
+    dump_side("tgt_", main);
+    std::vector<int> q;
+    for (size_t i = 0; i < linesTobeMatched.size(); ++i) { q.push_back(linesTobeMatched[i].first); q.push_back(linesTobeMatched[i].second); }
+    put("lines_to_match", q);
+    const std::vector<PAIRLINE> &lf22 = (*parameter.mainLinesInformation)[0];
+    std::vector<float> desc, v1, v2, p1, p2; std::vector<int> pr;
+    for (size_t i = 0; i < lf22.size(); ++i) {
+      for (int k = 0; k < 8; ++k) desc.push_back(lf22[i].descriptor[k]);
+      for (int k = 0; k < 3; ++k) { v1.push_back(lf22[i].lineVec1[k]); v2.push_back(lf22[i].lineVec2[k]); p1.push_back(lf22[i].linePoints1[k]); p2.push_back(lf22[i].linePoints2[k]); }
+      pr.push_back(lf22[i].originalIndex1); pr.push_back(lf22[i].originalIndex2);
+    }
+    put("tgt_db_desc", desc); put("tgt_db_vec1", v1); put("tgt_db_vec2", v2); put("tgt_db_p1", p1); put("tgt_db_p2", p2);
+    put("tgt_db_pair", pr);
+    std::vector<double> par;
+    par.push_back(parameter.lengthThreshold); par.push_back(parameter.angleThreshold);
+    par.push_back(parameter.cosAngleThreshold); par.push_back(parameter.maxCandidateResultNum);
+    par.push_back(parameter.maxNeighbor); par.push_back(parameter.maxRadius);
+    put("match_params", par);
+  }
+  MatchingLines(current, main, linesTobeMatched, coarseMatches, pMatchedResult, parameter);  // PLADE/util.cpp:31
+  g_last_results = pMatchedResult;
+  g_last_current = current;  // holds shared_ptrs to the ds clouds (kept alive)
+  g_last_main = main;
+  if (g_dump) {
+    std::vector<float> R, T; std::vector<int> np, pl, off(1, 0);
+    for (size_t i = 0; i < pMatchedResult.size(); ++i) {
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R.push_back(pMatchedResult[i].R(r, c));
+      for (int r = 0; r < 3; ++r) T.push_back(pMatchedResult[i].T(r));
+      np.push_back((int) pMatchedResult[i].matchedPlanes.size());
+      for (size_t k = 0; k < pMatchedResult[i].matchedPlanes.size(); ++k) { pl.push_back(pMatchedResult[i].matchedPlanes[k].first); pl.push_back(pMatchedResult[i].matchedPlanes[k].second); }
+      off.push_back((int) pl.size() / 2);
+    }
+    put("mr_R", R); put("mr_T", T); put("mr_nplanes", np); put("mr_planes", pl); put("mr_plane_offsets", off);
+  }
+}
+
+// Verification of the recorded hypotheses with the reference's own ComputeOverlap
+// (PLADE/util.h:612-647), driven exactly like PLADE/plade.cpp:545-564.
+static void dump_verification(CloudPN::Ptr source_cloud, int n_src_planes) {
+  const float average_space = average_spacing(source_cloud, 6);              // PLADE/plade.cpp:41
+  float downSampleDistance = average_space * 4;                              // :46
+  double w, h, d; Eigen::Vector3f center;
+  CloudXYZ::Ptr src_ds = g_last_current.points, tgt_ds = g_last_main.points;
+  ComputeBoundingBox<pcl::PointXYZ>(src_ds, center, w, h, d);               // :295
+  double currentRadius = MAX(MAX(w, h), d) / 2;                              // :299
+  put1<float>("average_space", average_space);
+  put1<float>("downsample_distance", downSampleDistance);
+  put1<double>("src_radius", currentRadius);
+  pcl::search::KdTree<pcl::PointXYZ>::Ptr tgt_tree(new pcl::search::KdTree<pcl::PointXYZ>);
+  tgt_tree->setInputCloud(tgt_ds);
+  std::vector<float> overlap, score, centers;
+  for (size_t i = 0; i < g_last_results.size(); ++i) {
+    Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
+    T.block(0, 0, 3, 3) = g_last_results[i].R;
+    T.block(0, 3, 3, 1) = g_last_results[i].T;
+    CloudXYZ::Ptr trans(new CloudXYZ);
+    pcl::transformPointCloud(*src_ds, *trans, T);
+    Eigen::Vector3f cc = g_last_results[i].R * g_last_current.boundingCenter + g_last_results[i].T;
+    pcl::search::KdTree<pcl::PointXYZ>::Ptr kd(new pcl::search::KdTree<pcl::PointXYZ>);
+    kd->setInputCloud(trans);
+    float ov;
+    ComputeOverlap<pcl::PointXYZ>(kd, tgt_tree, cc, currentRadius, downSampleDistance, ov);
+    overlap.push_back(ov);
+    float sc = 0.2 * (g_last_results[i].matchedPlanes.size() / double(n_src_planes)) + 0.8 * ov;
+    score.push_back(sc);
+    for (int k = 0; k < 3; ++k) centers.push_back(cc[k]);
+  }
+  put("ver_overlap", overlap); put("ver_score", score); put("ver_center", centers);
+}
+
+extern "C" {
+
+void ref_set_seed(long seed) { g_seed = seed; }
+void ref_clear_blobs() { g_blobs.clear(); }
+const void *ref_blob(const char *name, size_t *nbytes) {
+  std::map<std::string, std::vector<char> >::iterator it = g_blobs.find(name);
+  if (it == g_blobs.end()) { *nbytes = 0; return 0; }
+  *nbytes = it->second.size();
+  return it->second.data();
+}
+int ref_blob_names(char *buf, size_t cap) {
+  std::string s;
+  for (std::map<std::string, std::vector<char> >::iterator it = g_blobs.begin(); it != g_blobs.end(); ++it) { s += it->first; s += "\n"; }
+  if (s.size() + 1 > cap) return -1;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return (int) s.size();
+}
+
+// bool registration(T, target_file, source_file)  PLADE/plade.cpp:665 (swap rule included)
+int ref_registration_files(const char *tgt, const char *src, float *out16) {
+  Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
+  bool ok = registration(T, std::string(tgt), std::string(src));
+  to_rowmajor(T, out16);
+  return ok ? 1 : 0;
+}
+
+// bool registration(T, target_cloud, source_cloud)  PLADE/plade.cpp:638 (no swap at this level)
+int ref_registration_clouds(const float *tgt, size_t nt, const float *src, size_t ns, float *out16) {
+  Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
+  bool ok = registration(T, make_cloud(tgt, nt), make_cloud(src, ns));
+  to_rowmajor(T, out16);
+  return ok ? 1 : 0;
+}
+
+// bool registration(T, target_cloud, source_cloud, target_planes, source_planes)  PLADE/plade.cpp:31
+// dump != 0: run the hooked copy and publish stage blobs (+ verification scores).
+int ref_registration_planes(const float *tgt, size_t nt, const float *src, size_t ns,
+                            const int *t_off, const int *t_idx, const float *t_par, int t_np,
+                            const int *s_off, const int *s_idx, const float *s_par, int s_np,
+                            float *out16, int dump) {
+  Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
+  CloudPN::Ptr tc = make_cloud(tgt, nt), sc = make_cloud(src, ns);
+  std::vector<PLANE> tp = make_planes(t_off, t_idx, t_par, t_np), sp = make_planes(s_off, s_idx, s_par, s_np);
+  bool ok;
+  if (dump) {
+    g_dump = true;
+    g_last_results.clear();
+    ok = plade_oracle_registration_hooked(T, tc, sc, tp, sp);
+    g_dump = false;
+    if (!g_last_results.empty()) dump_verification(sc, s_np);
+    std::vector<float> t16(16); to_rowmajor(T, t16.data()); put("final_T", t16);
+    g_last_current = MatchInformation(); g_last_main = MatchInformation();
+  } else {
+    ok = registration(T, tc, sc, tp, sp);
+  }
+  to_rowmajor(T, out16);
+  return ok ? 1 : 0;
+}
+
+// std::vector<PLANE> extract(cloud, init_min_support)  PLADE/plade.cpp:602  -> blobs <prefix>plane_*
+int ref_extract(const float *xyzn, size_t n, int init_min_support, const char *prefix) {
+  std::vector<PLANE> planes = extract(make_cloud(xyzn, n), init_min_support);
+  put_planes(prefix, planes);
+  return (int) planes.size();
+}
+
+// PlaneExtraction::detect(cloud, min_support, .005, .02, .8, .001)  PLADE/plane_extraction.cpp:173
+int ref_detect(const float *xyzn, size_t n, int min_support, float dist_thresh, float bitmap_reso,
+               float normal_thresh, float overlook_prob, const char *prefix) {
+  CloudPN::Ptr c = make_cloud(xyzn, n);
+  std::vector<PLANE> planes = PlaneExtraction::detect(*c, min_support, dist_thresh, bitmap_reso, normal_thresh, overlook_prob);
+  put_planes(prefix, planes);
+  return (int) planes.size();
+}
+
+// float average_spacing(cloud, 6)  PLADE/util.cpp:1619
+float ref_average_spacing(const float *xyzn, size_t n) { return average_spacing(make_cloud(xyzn, n), 6); }
+
+// DownSamplePointCloud<PointXYZ|PointNormal>  PLADE/util.h:162-184 -> blob `name` (float xyz)
+int ref_voxel_downsample(const float *pts, size_t n, int stride, float leaf, const char *name) {
+  CloudXYZ::Ptr out(new CloudXYZ);
+  int rc;
+  if (stride == 6) { CloudPN::Ptr c = make_cloud(pts, n); rc = DownSamplePointCloud<pcl::PointNormal>(c, out, leaf, leaf, leaf); }
+  else { CloudXYZ::Ptr c = make_xyz(pts, n); rc = DownSamplePointCloud<pcl::PointXYZ>(c, out, leaf, leaf, leaf); }
+  if (rc != 0) return -1;
+  put_xyz(name, *out);
+  return (int) out->size();
+}
+
+// ComputeBoundingBox<PointXYZ>  PLADE/util.h:187-248 ; out: center[3], whd[3] (width,height,depth), corners[24]
+int ref_bounding_box(const float *xyz, size_t n, float *center, double *whd, float *corners) {
+  CloudXYZ::Ptr c = make_xyz(xyz, n);
+  Eigen::Vector3f ctr; CloudXYZ cp;
+  int rc = ComputeBoundingBox<pcl::PointXYZ>(c, ctr, whd[0], whd[1], whd[2], &cp);
+  if (rc != 0) return rc;
+  for (int k = 0; k < 3; ++k) center[k] = ctr[k];
+  for (size_t i = 0; i < cp.size() && i < 8; ++i) { corners[3 * i] = cp[i].x; corners[3 * i + 1] = cp[i].y; corners[3 * i + 2] = cp[i].z; }
+  return 0;
+}
+
+// ComputeIntersectionLineOfTwoPlanes  PLADE/util.cpp:626-676
+int ref_plane_intersection(const float *p1, const float *p2, float *vec, float *pt) {
+  Eigen::Vector4f a(p1[0], p1[1], p1[2], p1[3]), b(p2[0], p2[1], p2[2], p2[3]);
+  Eigen::Vector3f v, p;
+  int rc = ComputeIntersectionLineOfTwoPlanes(a, b, v, p);
+  for (int k = 0; k < 3; ++k) { vec[k] = v[k]; pt[k] = p[k]; }
+  return rc;
+}
+
+// ComputeNearstTwoPointsOfTwo3DLine  PLADE/util.cpp:1167-1229 (9x9 float cv::solve, DECOMP_SVD)
+int ref_nearest_points_two_lines(const float *v1, const float *p1, const float *v2, const float *p2,
+                                 float *q1, float *q2, double *len) {
+  Eigen::Vector3f a(v1[0], v1[1], v1[2]), b(p1[0], p1[1], p1[2]), c(v2[0], v2[1], v2[2]), d(p2[0], p2[1], p2[2]), o1, o2;
+  int rc = ComputeNearstTwoPointsOfTwo3DLine(a, b, c, d, o1, o2, *len);
+  for (int k = 0; k < 3; ++k) { q1[k] = o1[k]; q2[k] = o2[k]; }
+  return rc;
+}
+
+// ComputeIntersectionPointOf23DLine  PLADE/util.cpp:1461-1500 (6x5 float cv::solve)
+int ref_line_line_intersection(const float *v1, const float *p1, const float *v2, const float *p2, float *out) {
+  Eigen::Vector3f a(v1[0], v1[1], v1[2]), b(p1[0], p1[1], p1[2]), c(v2[0], v2[1], v2[2]), d(p2[0], p2[1], p2[2]), o;
+  int rc = ComputeIntersectionPointOf23DLine(a, b, c, d, o);
+  for (int k = 0; k < 3; ++k) out[k] = o[k];
+  return rc;
+}
+
+// KdTreeSearchNDim<VectorXf,8>::find_neighbors(q, 0, 0.04, ...)  3rd_party/ann_1.1.2/include/ANN/ANN.h:979-1029
+// exactly as PLADE/util.cpp:163 uses it.  Output CSR: offsets[nq+1] in blob "<name>_offsets",
+// db indices "<name>_idx", ANN squared distances (double->float as the wrapper does) "<name>_dist".
+int ref_match_descriptors(const float *db, int ndb, const float *q, int nq, double radius, const char *name) {
+  std::vector<Eigen::VectorXf> pts(ndb, Eigen::VectorXf(8));
+  KdTreeSearchNDim<Eigen::VectorXf, 8> tree;
+  tree.begin();
+  for (int i = 0; i < ndb; ++i) { for (int k = 0; k < 8; ++k) pts[i][k] = db[8 * i + k]; tree.add_point(&pts[i]); }
+  tree.end();
+  std::vector<int> off(1, 0), idx; std::vector<float> dist;
+  std::vector<int> nb; std::vector<float> nd;
+  for (int i = 0; i < nq; ++i) {
+    Eigen::VectorXf v(8);
+    for (int k = 0; k < 8; ++k) v[k] = q[8 * i + k];
+    tree.find_neighbors(v, 0, radius, nb, nd);
+    idx.insert(idx.end(), nb.begin(), nb.end());
+    dist.insert(dist.end(), nd.begin(), nd.end());
+    off.push_back((int) idx.size());
+  }
+  std::string n(name);
+  put(n + "_offsets", off); put(n + "_idx", idx); put(n + "_dist", dist);
+  return (int) idx.size();
+}
+
+// ComputeDescriptorVectorForPairLines(method22)  PLADE/util.cpp:533-602 ; desc[1..7], newLine1/2
+void ref_pair_descriptor(const float *l1vec, const float *l2vec, const float *l1sp1, const float *l1sp2,
+                         const float *l2sp1, const float *l2sp2, float *desc8, float *nl1, float *nl2) {
+  INTERSECTION_LINE a, b;
+  a.lineVec = Eigen::Vector3f(l1vec[0], l1vec[1], l1vec[2]);
+  b.lineVec = Eigen::Vector3f(l2vec[0], l2vec[1], l2vec[2]);
+  Eigen::Vector3f s11(l1sp1[0], l1sp1[1], l1sp1[2]), s12(l1sp2[0], l1sp2[1], l1sp2[2]);
+  Eigen::Vector3f s21(l2sp1[0], l2sp1[1], l2sp1[2]), s22(l2sp2[0], l2sp2[1], l2sp2[2]);
+  Eigen::VectorXf d(8); d.setZero();
+  Eigen::Vector3f n1, n2;
+  ComputeDescriptorVectorForPairLines(a, b, s11, s12, s21, s22, d, n1, n2, method22);
+  for (int k = 0; k < 8; ++k) desc8[k] = d[k];
+  for (int k = 0; k < 3; ++k) { nl1[k] = n1[k]; nl2[k] = n2[k]; }
+}
+
+// ComputeTransformationUsingTwoVecAndOnePoint  PLADE/util.cpp:604-624 (Eigen::umeyama, 3 points), batched.
+// in: per item sv1,sv2,dv1,dv2,sp,tp (18 floats) ; out: R row-major 9 + T 3
+void ref_transform_from_two_vecs(const float *in, int n, float *R9, float *T3) {
+  for (int i = 0; i < n; ++i) {
+    const float *p = in + 18 * i;
+    Eigen::Vector3f a(p[0], p[1], p[2]), b(p[3], p[4], p[5]), c(p[6], p[7], p[8]), d(p[9], p[10], p[11]);
+    Eigen::Vector3f sp(p[12], p[13], p[14]), tp(p[15], p[16], p[17]);
+    Eigen::Matrix3f R; Eigen::Vector3f T;
+    ComputeTransformationUsingTwoVecAndOnePoint(a, b, c, d, sp, tp, R, T);
+    for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) R9[9 * i + 3 * r + cc] = R(r, cc);
+    for (int r = 0; r < 3; ++r) T3[3 * i + r] = T(r);
+  }
+}
+
+// ClusterTransformation  PLADE/util.cpp:1245-1277 ; labels[n] = cluster id in CEC emission order
+int ref_cluster_transformations(const float *R9, const float *T3, int n, float dist_thresh, float ang_thresh, int *labels) {
+  std::vector<Eigen::Matrix3f> Rs(n); std::vector<Eigen::Vector3f> Ts(n);
+  for (int i = 0; i < n; ++i) {
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Rs[i](r, c) = R9[9 * i + 3 * r + c];
+    for (int r = 0; r < 3; ++r) Ts[i](r) = T3[3 * i + r];
+  }
+  pcl::IndicesClusters clusters;
+  ClusterTransformation(Rs, Ts, dist_thresh, ang_thresh, clusters);
+  for (size_t c = 0; c < clusters.size(); ++c)
+    for (size_t k = 0; k < clusters[c].indices.size(); ++k) labels[clusters[c].indices[k]] = (int) c;
+  return (int) clusters.size();
+}
+
+// Verification body PLADE/plade.cpp:547-560 + ComputeOverlap PLADE/util.h:612-647 for H hypotheses.
+// centers[3H] are the ball centres (R*c+T) as the caller computed them; out: overlap ratio (float) and
+// the integer inlier count recovered from it is NOT exposed by the reference, so counts[] is the
+// numerator re-counted with the same two radiusSearch calls.
+void ref_compute_overlap(const float *src_ds, size_t ns, const float *tgt_ds, size_t nt,
+                         const float *R9, const float *T3, const float *centers, int H,
+                         float query_radius, float inlier_distance, float *overlap, int *counts) {
+  CloudXYZ::Ptr s = make_xyz(src_ds, ns), t = make_xyz(tgt_ds, nt);
+  pcl::search::KdTree<pcl::PointXYZ>::Ptr tgt_tree(new pcl::search::KdTree<pcl::PointXYZ>);
+  tgt_tree->setInputCloud(t);
+  for (int i = 0; i < H; ++i) {
+    Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T(r, c) = R9[9 * i + 3 * r + c]; T(r, 3) = T3[3 * i + r]; }
+    CloudXYZ::Ptr trans(new CloudXYZ);
+    pcl::transformPointCloud(*s, *trans, T);
+    Eigen::Vector3f cc(centers[3 * i], centers[3 * i + 1], centers[3 * i + 2]);
+    pcl::search::KdTree<pcl::PointXYZ>::Ptr kd(new pcl::search::KdTree<pcl::PointXYZ>);
+    kd->setInputCloud(trans);
+    ComputeOverlap<pcl::PointXYZ>(kd, tgt_tree, cc, query_radius, inlier_distance, overlap[i]);
+    if (counts) {
+      std::vector<int> nb; std::vector<float> nd;
+      int cnt = 0;
+      if (tgt_tree->radiusSearch(pcl::PointXYZ(cc(0), cc(1), cc(2)), query_radius, nb, nd) > 0) {
+        CloudXYZ::Ptr ball(new CloudXYZ);
+        ball->resize(nb.size());
+        for (size_t k = 0; k < nb.size(); ++k) (*ball)[k] = (*t)[nb[k]];
+        pcl::search::KdTree<pcl::PointXYZ> bt;
+        bt.setInputCloud(ball);
+        for (size_t k = 0; k < trans->size(); ++k)
+          if (bt.radiusSearch(trans->at(k), inlier_distance, nb, nd, 1) > 0) cnt++;
+      }
+      counts[i] = cnt;
+    }
+  }
+}
+
+}  // extern "C"
