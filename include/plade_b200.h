@@ -1,0 +1,129 @@
+/*
+ * plade_b200 — C ABI of the B200-native PLADE registration hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The C++ overloads of
+ * the reference (`bool registration(Eigen::Matrix4f&, ...)`, /root/reference/code/PLADE/plade.h:44-96)
+ * are thin inline wrappers over these entry points (include/plade.h).
+ *
+ * Conventions
+ *   - clouds: interleaved float records  x y z nx ny nz  (exactly the vertex record of the PLY files
+ *     the reference reads, PLADE/ply_reader.cpp:46-148 -> PLADE/util.cpp:1505-1546).
+ *   - TARGET always comes first, as in the reference (PLADE/plade.h:44-47).
+ *   - out16: row-major 4x4 that maps SOURCE onto TARGET; set to identity first, overwritten only on
+ *     success (PLADE/plade.cpp:696, :569-575).
+ *   - return value: 1 = success, 0 = failure (the reference's bool); the message that the reference
+ *     prints on std::cerr is also available through plade_last_error().  Nothing aborts or throws
+ *     across the boundary.  The library needs a CUDA device: there is no CPU fallback.
+ *   - a context is single-threaded and owns its CUDA stream and scratch memory (the reference is not
+ *     re-entrant at all); use one context per host thread / per GPU.
+ *   - planes: CSR offsets[np+1] + point indices + params[4*np] = (nx, ny, nz, d), n.x + d = 0
+ *     (PLANE, PLADE/plane_extraction.h:44-50).
+ */
+#ifndef PLADE_B200_H
+#define PLADE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct plade_ctx plade_ctx;
+typedef struct plade_cloud plade_cloud;   /* a cloud resident in HBM */
+typedef void (*plade_allreduce_max_u64)(unsigned long long *value, void *user);
+
+/* ---- context ---------------------------------------------------------------------------------- */
+plade_ctx *plade_ctx_create(int device);          /* device < 0: current device; NULL on failure */
+void plade_ctx_destroy(plade_ctx *ctx);
+const char *plade_last_error(plade_ctx *ctx);
+const char *plade_create_error(void);             /* why the last plade_ctx_create returned NULL */
+/* tunables; names = fields of plade::Params (defaults are the reference's literals). 1 if known. */
+int plade_set_param(plade_ctx *ctx, const char *name, double value);
+/* hypothesis sharding for multi-GPU verification (PLADE/plade.cpp:547-564 iterations are independent):
+ * this context verifies hypotheses h with h % world == rank and `reduce` (may be NULL when world == 1)
+ * must all-reduce(MAX) one u64 across the ranks (NCCL in bench.py). */
+void plade_set_shard(plade_ctx *ctx, int rank, int world, plade_allreduce_max_u64 reduce, void *user);
+long long plade_launch_count(plade_ctx *ctx);     /* kernels launched by this context so far */
+/* seconds of the last registration: upload, planes, spacing, downsample, lines, descriptors, match,
+ * hypotheses, penetration, verify, total (11 values) */
+int plade_stage_times(plade_ctx *ctx, double *out, int n);
+
+/* ---- registration() — the four reference overloads -------------------------------------------- */
+/* registration(T, target_file, source_file)                         PLADE/plade.cpp:665-707 */
+int plade_register_files(plade_ctx *ctx, const char *target_ply, const char *source_ply, float out16[16]);
+/* registration(T, target_cloud, source_cloud)                       PLADE/plade.cpp:638-662 */
+int plade_register_clouds(plade_ctx *ctx, const float *tgt_xyzn, size_t nt, const float *src_xyzn, size_t ns,
+                          float out16[16]);
+/* registration(T, target_cloud, source_cloud, planes, planes)       PLADE/plade.cpp:31-580 */
+int plade_register_with_planes(plade_ctx *ctx, const float *tgt_xyzn, size_t nt, const float *src_xyzn, size_t ns,
+                               const int *t_off, const int *t_idx, const float *t_par, int t_np,
+                               const int *s_off, const int *s_idx, const float *s_par, int s_np, float out16[16]);
+/* registration(T, target_cloud, source_cloud, min_support, min_support)   PLADE/plade.cpp:583-599 */
+int plade_register_min_support(plade_ctx *ctx, const float *tgt_xyzn, size_t nt, const float *src_xyzn, size_t ns,
+                               int min_support_target, int min_support_source, float out16[16]);
+
+/* HBM-resident variants (inputs uploaded once; used for the device-resident throughput figure) */
+plade_cloud *plade_cloud_upload(plade_ctx *ctx, const float *xyzn, size_t n);
+void plade_cloud_free(plade_ctx *ctx, plade_cloud *cloud);
+size_t plade_cloud_size(const plade_cloud *cloud);
+int plade_register_resident(plade_ctx *ctx, const plade_cloud *tgt, const plade_cloud *src, float out16[16]);
+int plade_register_resident_with_planes(plade_ctx *ctx, const plade_cloud *tgt, const plade_cloud *src,
+                                        const int *t_off, const int *t_idx, const float *t_par, int t_np,
+                                        const int *s_off, const int *s_idx, const float *s_par, int s_np,
+                                        float out16[16]);
+
+/* ---- stage entry points (what the parity tests call) ------------------------------------------ */
+/* extract(cloud, init_min_support) PLADE/plade.cpp:602-635 / PlaneExtraction::detect
+ * PLADE/plane_extraction.cpp:173-200.  Returns the number of planes (>= 0) or -1; fetch them with
+ * plade_planes_size / plade_planes_get. */
+int plade_extract_planes(plade_ctx *ctx, const float *xyzn, size_t n, int init_min_support);
+int plade_detect_planes(plade_ctx *ctx, const float *xyzn, size_t n, int min_support);
+int plade_planes_size(plade_ctx *ctx, int *n_planes, long long *n_indices);
+int plade_planes_get(plade_ctx *ctx, int *offsets, int *indices, float *params);
+/* Plane consensus score (the RANSAC predicate, 3rd_party/ransac/FlatNormalThreshPointCompatibilityFunc.h
+ * :15-22 with Plane::Distance 3rd_party/ransac/Plane.h:31): for each of n_planes (nx,ny,nz,dist with
+ * n.x = dist) counts[p] = #{ i : assigned[i] == -1 && |dist - n.p_i| < eps && |n.n_i| >= normal_thresh };
+ * if inlier_mask != NULL (n bytes) it receives the mask of plane 0. */
+int plade_score_planes(plade_ctx *ctx, const float *xyzn, size_t n, const int *assigned, const float *planes4,
+                       int n_planes, float eps, float normal_thresh, unsigned int *counts, unsigned char *inlier_mask);
+/* average_spacing(cloud, 6) PLADE/util.cpp:1619-1648 */
+float plade_average_spacing(plade_ctx *ctx, const float *xyzn, size_t n);
+/* DownSamplePointCloud / pcl::VoxelGrid  PLADE/util.h:162-184; xyz has `stride` floats per point
+ * (3 or 6); out_xyz needs room for n*3 floats; returns the number of voxels or -1. */
+long long plade_voxel_downsample(plade_ctx *ctx, const float *pts, size_t n, int stride, float leaf, float *out_xyz);
+/* ComputeBoundingBox PLADE/util.h:187-248: center[3], whd[3] = width, height, depth, corners[24] */
+int plade_bounding_box(plade_ctx *ctx, const float *xyz, size_t n, float *center, double *whd, float *corners);
+/* descriptor radius search, KdTreeSearchNDim<.,8>::find_neighbors(q, 0, radius) ANN.h:979-1029.
+ * offsets[nq+1]; returns the total number of matches M (or -1); plade_match_results copies the M
+ * (db index, squared distance) pairs, per query ascending in (distance, index). */
+long long plade_match_descriptors(plade_ctx *ctx, const float *db8, int ndb, const float *q8, int nq, float radius,
+                                  int *offsets);
+int plade_match_results(plade_ctx *ctx, int *idx, double *dist2);
+/* ComputeTransformationUsingTwoVecAndOnePoint PLADE/util.cpp:604-624, batched: in = n x 18 floats
+ * (sv1 sv2 dv1 dv2 sourcePoint targetPoint); out R9 row-major, T3. */
+int plade_transforms_from_matches(plade_ctx *ctx, const float *in18, int n, float *R9, float *T3);
+/* ClusterTransformation PLADE/util.cpp:1245-1277: labels[i] = smallest index of i's cluster. */
+int plade_cluster_transforms(plade_ctx *ctx, const float *R9, const float *T3, int n, float dist_thresh,
+                             float ang_thresh, int *labels);
+/* Verification, PLADE/plade.cpp:547-560 + ComputeOverlap PLADE/util.h:612-647: counts[h] = number of
+ * source ds points with a target ds point (inside ball(centers[h], ball_radius)) closer than
+ * inlier_dist after applying (R[h], T[h]).  xyz arrays are packed 3 floats per point. */
+int plade_verify_hypotheses(plade_ctx *ctx, const float *src_ds_xyz, size_t ns, const float *tgt_ds_xyz, size_t nt,
+                            const float *R9, const float *T3, const float *centers3, int H, float ball_radius,
+                            float inlier_dist, unsigned int *counts);
+/* Same with both ds clouds already resident (uploaded once by plade_verify_upload); times only the
+ * kernel path.  Used by bench.py for the roofline of the dominant kernel. */
+int plade_verify_upload(plade_ctx *ctx, const float *src_ds_xyz, size_t ns, const float *tgt_ds_xyz, size_t nt,
+                        float inlier_dist);
+int plade_verify_resident(plade_ctx *ctx, const float *R9, const float *T3, const float *centers3, int H,
+                          float ball_radius, float inlier_dist, unsigned int *counts, float *kernel_ms);
+
+/* ---- debugging / parity dumps ------------------------------------------------------------------- */
+void plade_set_debug(plade_ctx *ctx, int on);     /* record named stage blobs during registration */
+const void *plade_debug_blob(plade_ctx *ctx, const char *name, size_t *nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLADE_B200_H */

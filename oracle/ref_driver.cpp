@@ -18,6 +18,7 @@
 #include "plade.h"
 #include "plane_extraction.h"
 #include <opencv2/imgproc/imgproc.hpp>
+#include <MiscLib/Random.h>
 
 #include <map>
 #include <string>
@@ -233,7 +234,11 @@ static void dump_verification(CloudPN::Ptr source_cloud, int n_src_planes) {
 
 extern "C" {
 
-void ref_set_seed(long seed) { g_seed = seed; }
+// Fixed-seed mode also rewinds the RANSAC library's lagged-Fibonacci cursor: rn_setseed()
+// (3rd_party/ransac/MiscLib/Random.cpp:25-58) refills the buffer but leaves MiscLib::rn_point where the
+// previous Detect() stopped, so without this a call's result depends on the calls made before it.
+static void rewind_rng() { if (g_seed >= 0) MiscLib::rn_point = MiscLib_RN_BUFSIZE; }
+void ref_set_seed(long seed) { g_seed = seed; rewind_rng(); }
 void ref_clear_blobs() { g_blobs.clear(); }
 const void *ref_blob(const char *name, size_t *nbytes) {
   std::map<std::string, std::vector<char> >::iterator it = g_blobs.find(name);
@@ -251,6 +256,7 @@ int ref_blob_names(char *buf, size_t cap) {
 
 // bool registration(T, target_file, source_file)  PLADE/plade.cpp:665 (swap rule included)
 int ref_registration_files(const char *tgt, const char *src, float *out16) {
+  rewind_rng();
   Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
   bool ok = registration(T, std::string(tgt), std::string(src));
   to_rowmajor(T, out16);
@@ -259,6 +265,7 @@ int ref_registration_files(const char *tgt, const char *src, float *out16) {
 
 // bool registration(T, target_cloud, source_cloud)  PLADE/plade.cpp:638 (no swap at this level)
 int ref_registration_clouds(const float *tgt, size_t nt, const float *src, size_t ns, float *out16) {
+  rewind_rng();
   Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
   bool ok = registration(T, make_cloud(tgt, nt), make_cloud(src, ns));
   to_rowmajor(T, out16);
@@ -292,6 +299,7 @@ int ref_registration_planes(const float *tgt, size_t nt, const float *src, size_
 
 // std::vector<PLANE> extract(cloud, init_min_support)  PLADE/plade.cpp:602  -> blobs <prefix>plane_*
 int ref_extract(const float *xyzn, size_t n, int init_min_support, const char *prefix) {
+  rewind_rng();
   std::vector<PLANE> planes = extract(make_cloud(xyzn, n), init_min_support);
   put_planes(prefix, planes);
   return (int) planes.size();
@@ -300,6 +308,7 @@ int ref_extract(const float *xyzn, size_t n, int init_min_support, const char *p
 // PlaneExtraction::detect(cloud, min_support, .005, .02, .8, .001)  PLADE/plane_extraction.cpp:173
 int ref_detect(const float *xyzn, size_t n, int min_support, float dist_thresh, float bitmap_reso,
                float normal_thresh, float overlook_prob, const char *prefix) {
+  rewind_rng();
   CloudPN::Ptr c = make_cloud(xyzn, n);
   std::vector<PLANE> planes = PlaneExtraction::detect(*c, min_support, dist_thresh, bitmap_reso, normal_thresh, overlook_prob);
   put_planes(prefix, planes);

@@ -1,0 +1,452 @@
+// extern "C" boundary of libplade_b200.so (declared in include/plade_b200.h).  Every entry point
+// catches C++ exceptions (CUDA errors included), records the message and returns the failure value:
+// nothing throws or aborts across the ABI.
+#include "../../include/plade_b200.h"
+#include "pipeline.h"
+#include "ply.h"
+#include <cstring>
+#include <iostream>
+#include <memory>
+
+using namespace plade;
+
+namespace plade {
+void score_planes_full(Device &dev, const float4 *pos, const float4 *nrm, const int *assigned, size_t n, const float4 *d_planes,
+                       int n_planes, float eps, float nthresh, unsigned int *d_counts, unsigned char *d_mask0);
+}
+
+struct plade_cloud {
+  CloudDev c;
+};
+
+struct plade_ctx {
+  std::unique_ptr<Registrar> reg;
+  std::vector<PlaneRec> planes;          // result of the last extract/detect stage call
+  std::vector<int> match_idx;
+  std::vector<double> match_d2;
+  CloudDev tmp_t, tmp_s;
+  // resident buffers for plade_verify_upload / plade_verify_resident
+  DevBuf<float4> v_src, v_tgt;
+  size_t v_ns = 0, v_nt = 0;
+  TargetGrid v_grid;
+  DevBuf<HypParams> v_hyp;
+  DevBuf<unsigned int> v_counts;
+  DevBuf<float4> stage_a, stage_b;
+  DevBuf<int> stage_i;
+  DevBuf<unsigned int> stage_u;
+  DevBuf<unsigned char> stage_m;
+  std::string err;
+};
+
+static std::string g_create_error;
+
+#define PLADE_TRY(ctx, fail, ...)                                                      \
+  if (!(ctx)) return fail;                                                             \
+  try { __VA_ARGS__ } catch (const std::exception &e) {                                     \
+    (ctx)->err = e.what();                                                             \
+    (ctx)->reg->last_error = e.what();                                                 \
+    std::cerr << "plade_b200: " << e.what() << std::endl;                              \
+    return fail;                                                                       \
+  }
+
+static std::vector<PlaneRec> planes_from_csr(const int *off, const int *idx, const float *par, int np) {
+  std::vector<PlaneRec> v(np > 0 ? np : 0);
+  for (int i = 0; i < np; ++i) {
+    v[i].idx.assign(idx + off[i], idx + off[i + 1]);
+    v[i].n[0] = par[4 * i]; v[i].n[1] = par[4 * i + 1]; v[i].n[2] = par[4 * i + 2];
+    v[i].d = par[4 * i + 3];
+  }
+  return v;
+}
+
+static void identity16(float *o) { for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? 1.f : 0.f; }
+
+// host xyz (stride floats per point) -> device float4
+static void upload_xyz(Registrar &r, const float *pts, size_t n, int stride, DevBuf<float4> &out) {
+  std::vector<float4> h(n);
+  for (size_t i = 0; i < n; ++i) h[i] = make_float4(pts[i * stride], pts[i * stride + 1], pts[i * stride + 2], 0.f);
+  float4 *d = out.ensure(std::max<size_t>(n, 1));
+  if (n) PLADE_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, r.dev.stream));
+  PLADE_CUDA(cudaStreamSynchronize(r.dev.stream));
+}
+
+extern "C" {
+
+plade_ctx *plade_ctx_create(int device) {
+  try {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (plade_b200 has no CPU fallback)";
+      std::cerr << "plade_b200: " << g_create_error << std::endl;
+      return nullptr;
+    }
+    plade_ctx *c = new plade_ctx;
+    c->reg.reset(new Registrar(device));
+    return c;
+  } catch (const std::exception &e) {
+    g_create_error = e.what();
+    std::cerr << "plade_b200: " << e.what() << std::endl;
+    return nullptr;
+  }
+}
+void plade_ctx_destroy(plade_ctx *ctx) { delete ctx; }
+const char *plade_last_error(plade_ctx *ctx) { return ctx ? (ctx->err.empty() ? ctx->reg->last_error.c_str() : ctx->err.c_str()) : ""; }
+const char *plade_create_error(void) { return g_create_error.c_str(); }
+
+int plade_set_param(plade_ctx *ctx, const char *name, double v) {
+  if (!ctx) return 0;
+  Params &p = ctx->reg->params;
+  std::string n(name);
+  if (n == "ransac_dist_thresh") p.ransac_dist_thresh = (float) v;
+  else if (n == "ransac_bitmap_reso") p.ransac_bitmap_reso = (float) v;
+  else if (n == "ransac_normal_thresh") p.ransac_normal_thresh = (float) v;
+  else if (n == "ransac_prob") p.ransac_prob = (float) v;
+  else if (n == "init_min_support") p.init_min_support = (int) v;
+  else if (n == "min_planes") p.min_planes = (int) v;
+  else if (n == "max_planes") p.max_planes = (int) v;
+  else if (n == "min_allowed_support") p.min_allowed_support = (int) v;
+  else if (n == "max_trials") p.max_trials = (int) v;
+  else if (n == "max_candidates") p.max_candidates = (int) v;
+  else if (n == "descriptor_radius") p.descriptor_radius = v;
+  else if (n == "seed") p.seed = (unsigned long long) v;
+  else return 0;
+  return 1;
+}
+
+void plade_set_shard(plade_ctx *ctx, int rank, int world, plade_allreduce_max_u64 reduce, void *user) {
+  if (!ctx) return;
+  ctx->reg->shard_rank = rank;
+  ctx->reg->shard_world = world < 1 ? 1 : world;
+  ctx->reg->allreduce = reduce;
+  ctx->reg->allreduce_user = user;
+}
+long long plade_launch_count(plade_ctx *ctx) { return ctx ? ctx->reg->dev.launches.n : 0; }
+int plade_stage_times(plade_ctx *ctx, double *out, int n) {
+  if (!ctx) return 0;
+  const StageTimes &t = ctx->reg->times;
+  double v[11] = {t.upload, t.planes, t.spacing, t.downsample, t.lines, t.descriptors, t.match, t.hypotheses, t.penetration, t.verify, t.total};
+  for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
+  return 11;
+}
+void plade_set_debug(plade_ctx *ctx, int on) { if (ctx) { ctx->reg->debug = on != 0; if (on) ctx->reg->blobs.clear(); } }
+const void *plade_debug_blob(plade_ctx *ctx, const char *name, size_t *nbytes) {
+  *nbytes = 0;
+  if (!ctx) return nullptr;
+  auto it = ctx->reg->blobs.find(name);
+  if (it == ctx->reg->blobs.end()) return nullptr;
+  *nbytes = it->second.size();
+  return it->second.data();
+}
+
+// ---- registration ---------------------------------------------------------------------------------------
+int plade_register_clouds(plade_ctx *ctx, const float *tgt, size_t nt, const float *src, size_t ns, float out16[16]) {
+  identity16(out16);
+  PLADE_TRY(ctx, 0, {
+    ctx->err.clear();
+    Registrar &r = *ctx->reg;
+    r.upload(tgt, nt, ctx->tmp_t);
+    r.upload(src, ns, ctx->tmp_s);
+    return r.register_clouds(ctx->tmp_t, ctx->tmp_s, out16) ? 1 : 0;
+  })
+}
+
+int plade_register_files(plade_ctx *ctx, const char *target_ply, const char *source_ply, float out16[16]) {
+  identity16(out16);
+  PLADE_TRY(ctx, 0, {
+    ctx->err.clear();
+    std::cout << "target file: " << target_ply << std::endl;
+    std::cout << "source file: " << source_ply << std::endl;
+    if (file_extension(target_ply) != "ply" || file_extension(source_ply) != "ply") {
+      std::cerr << "only PLY format is accepted" << std::endl;
+      ctx->err = "only PLY format is accepted";
+      return 0;
+    }
+    std::vector<float> t, s;
+    if (!load_ply_xyzn(target_ply, t)) { std::cerr << "loading target point cloud failed" << std::endl; ctx->err = "loading target point cloud failed"; return 0; }
+    if (!load_ply_xyzn(source_ply, s)) { std::cerr << "loading source point cloud failed" << std::endl; ctx->err = "loading source point cloud failed"; return 0; }
+    // swap rule, PLADE/plade.cpp:689-704
+    bool switched = false;
+    if (s.size() / 6 >= (t.size() / 6) * 1.2f) {
+      std::swap(t, s);
+      switched = true;
+      std::cout << "---->>> ATTENTION: target and source have been switched for efficiency <<<----" << std::endl;
+    }
+    Registrar &r = *ctx->reg;
+    r.upload(t.data(), t.size() / 6, ctx->tmp_t);
+    r.upload(s.data(), s.size() / 6, ctx->tmp_s);
+    if (!r.register_clouds(ctx->tmp_t, ctx->tmp_s, out16)) { std::cerr << "registration failed" << std::endl; return 0; }
+    if (switched) {
+      // rigid inverse of [R | T]; the reference calls Matrix4f::inverse() (general 4x4 inverse), equal up to rounding
+      double R[9], T[3];
+      for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[3 * i + j] = out16[4 * i + j]; T[i] = out16[4 * i + 3]; }
+      // general inverse of the 3x3 block via adjugate (R need not be exactly orthonormal in float)
+      double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+      double inv[9] = {(R[4] * R[8] - R[5] * R[7]) / det, (R[2] * R[7] - R[1] * R[8]) / det, (R[1] * R[5] - R[2] * R[4]) / det,
+                       (R[5] * R[6] - R[3] * R[8]) / det, (R[0] * R[8] - R[2] * R[6]) / det, (R[2] * R[3] - R[0] * R[5]) / det,
+                       (R[3] * R[7] - R[4] * R[6]) / det, (R[1] * R[6] - R[0] * R[7]) / det, (R[0] * R[4] - R[1] * R[3]) / det};
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) out16[4 * i + j] = (float) inv[3 * i + j];
+        out16[4 * i + 3] = (float) -(inv[3 * i] * T[0] + inv[3 * i + 1] * T[1] + inv[3 * i + 2] * T[2]);
+      }
+    }
+    return 1;
+  })
+}
+
+int plade_register_with_planes(plade_ctx *ctx, const float *tgt, size_t nt, const float *src, size_t ns, const int *t_off,
+                               const int *t_idx, const float *t_par, int t_np, const int *s_off, const int *s_idx,
+                               const float *s_par, int s_np, float out16[16]) {
+  identity16(out16);
+  PLADE_TRY(ctx, 0, {
+    ctx->err.clear();
+    Registrar &r = *ctx->reg;
+    r.upload(tgt, nt, ctx->tmp_t);
+    r.upload(src, ns, ctx->tmp_s);
+    return r.register_with_planes(ctx->tmp_t, ctx->tmp_s, planes_from_csr(t_off, t_idx, t_par, t_np),
+                                  planes_from_csr(s_off, s_idx, s_par, s_np), out16) ? 1 : 0;
+  })
+}
+
+int plade_register_min_support(plade_ctx *ctx, const float *tgt, size_t nt, const float *src, size_t ns, int ms_t, int ms_s,
+                               float out16[16]) {
+  identity16(out16);
+  PLADE_TRY(ctx, 0, {
+    ctx->err.clear();
+    Registrar &r = *ctx->reg;
+    r.upload(tgt, nt, ctx->tmp_t);
+    r.upload(src, ns, ctx->tmp_s);
+    return r.register_min_support(ctx->tmp_t, ctx->tmp_s, ms_t, ms_s, out16) ? 1 : 0;
+  })
+}
+
+plade_cloud *plade_cloud_upload(plade_ctx *ctx, const float *xyzn, size_t n) {
+  PLADE_TRY(ctx, nullptr, {
+    plade_cloud *c = new plade_cloud;
+    ctx->reg->upload(xyzn, n, c->c);
+    return c;
+  })
+}
+void plade_cloud_free(plade_ctx *, plade_cloud *cloud) { delete cloud; }
+size_t plade_cloud_size(const plade_cloud *cloud) { return cloud ? cloud->c.n : 0; }
+
+int plade_register_resident(plade_ctx *ctx, const plade_cloud *tgt, const plade_cloud *src, float out16[16]) {
+  identity16(out16);
+  PLADE_TRY(ctx, 0, {
+    ctx->err.clear();
+    if (!tgt || !src) return 0;
+    return ctx->reg->register_clouds(tgt->c, src->c, out16) ? 1 : 0;
+  })
+}
+
+int plade_register_resident_with_planes(plade_ctx *ctx, const plade_cloud *tgt, const plade_cloud *src, const int *t_off,
+                                        const int *t_idx, const float *t_par, int t_np, const int *s_off, const int *s_idx,
+                                        const float *s_par, int s_np, float out16[16]) {
+  identity16(out16);
+  PLADE_TRY(ctx, 0, {
+    ctx->err.clear();
+    if (!tgt || !src) return 0;
+    return ctx->reg->register_with_planes(tgt->c, src->c, planes_from_csr(t_off, t_idx, t_par, t_np),
+                                          planes_from_csr(s_off, s_idx, s_par, s_np), out16) ? 1 : 0;
+  })
+}
+
+// ---- stages -------------------------------------------------------------------------------------------------
+int plade_extract_planes(plade_ctx *ctx, const float *xyzn, size_t n, int init_min_support) {
+  PLADE_TRY(ctx, -1, {
+    ctx->reg->upload(xyzn, n, ctx->tmp_t);
+    ctx->planes = ctx->reg->extract_planes(ctx->tmp_t, init_min_support);
+    return (int) ctx->planes.size();
+  })
+}
+int plade_detect_planes(plade_ctx *ctx, const float *xyzn, size_t n, int min_support) {
+  PLADE_TRY(ctx, -1, {
+    ctx->reg->upload(xyzn, n, ctx->tmp_t);
+    ctx->planes = ctx->reg->detect_planes(ctx->tmp_t, min_support);
+    return (int) ctx->planes.size();
+  })
+}
+int plade_planes_size(plade_ctx *ctx, int *n_planes, long long *n_indices) {
+  if (!ctx) return 0;
+  *n_planes = (int) ctx->planes.size();
+  long long t = 0;
+  for (auto &p : ctx->planes) t += (long long) p.idx.size();
+  *n_indices = t;
+  return 1;
+}
+int plade_planes_get(plade_ctx *ctx, int *offsets, int *indices, float *params) {
+  if (!ctx) return 0;
+  int o = 0;
+  offsets[0] = 0;
+  for (size_t i = 0; i < ctx->planes.size(); ++i) {
+    const PlaneRec &p = ctx->planes[i];
+    memcpy(indices + o, p.idx.data(), sizeof(int) * p.idx.size());
+    o += (int) p.idx.size();
+    offsets[i + 1] = o;
+    params[4 * i] = p.n[0]; params[4 * i + 1] = p.n[1]; params[4 * i + 2] = p.n[2]; params[4 * i + 3] = p.d;
+  }
+  return 1;
+}
+
+int plade_score_planes(plade_ctx *ctx, const float *xyzn, size_t n, const int *assigned, const float *planes4, int n_planes,
+                       float eps, float normal_thresh, unsigned int *counts, unsigned char *inlier_mask) {
+  PLADE_TRY(ctx, 0, {
+    Registrar &r = *ctx->reg;
+    cudaStream_t s = r.dev.stream;
+    r.upload(xyzn, n, ctx->tmp_t);
+    int *d_as = nullptr;
+    if (assigned) {
+      d_as = ctx->stage_i.ensure(std::max<size_t>(n, 1));
+      PLADE_CUDA(cudaMemcpyAsync(d_as, assigned, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    }
+    float4 *d_pl = ctx->stage_a.ensure(std::max(n_planes, 1));
+    PLADE_CUDA(cudaMemcpyAsync(d_pl, planes4, sizeof(float4) * n_planes, cudaMemcpyHostToDevice, s));
+    unsigned int *d_c = ctx->stage_u.ensure(std::max(n_planes, 1));
+    unsigned char *d_m = inlier_mask ? ctx->stage_m.ensure(std::max<size_t>(n, 1)) : nullptr;
+    score_planes_full(r.dev, ctx->tmp_t.pos.p, ctx->tmp_t.nrm.p, d_as, n, d_pl, n_planes, eps, normal_thresh, d_c, d_m);
+    PLADE_CUDA(cudaMemcpyAsync(counts, d_c, sizeof(unsigned int) * n_planes, cudaMemcpyDeviceToHost, s));
+    if (inlier_mask && n) PLADE_CUDA(cudaMemcpyAsync(inlier_mask, d_m, n, cudaMemcpyDeviceToHost, s));
+    PLADE_CUDA(cudaStreamSynchronize(s));
+    return 1;
+  })
+}
+
+float plade_average_spacing(plade_ctx *ctx, const float *xyzn, size_t n) {
+  PLADE_TRY(ctx, -1.f, {
+    ctx->reg->upload(xyzn, n, ctx->tmp_t);
+    return ctx->reg->average_spacing(ctx->tmp_t);
+  })
+}
+
+long long plade_voxel_downsample(plade_ctx *ctx, const float *pts, size_t n, int stride, float leaf, float *out_xyz) {
+  PLADE_TRY(ctx, -1, {
+    Registrar &r = *ctx->reg;
+    if (n == 0 || !(leaf > 0)) return -1;     // DownSamplePointCloud returns -1 (PLADE/util.h:165-167)
+    upload_xyz(r, pts, n, stride, ctx->stage_a);
+    size_t nv = voxel_downsample(r.dev, r.vox, ctx->stage_a.p, n, leaf, ctx->stage_b);
+    std::vector<float4> h(nv);
+    if (nv) PLADE_CUDA(cudaMemcpyAsync(h.data(), ctx->stage_b.p, sizeof(float4) * nv, cudaMemcpyDeviceToHost, r.dev.stream));
+    PLADE_CUDA(cudaStreamSynchronize(r.dev.stream));
+    for (size_t i = 0; i < nv; ++i) { out_xyz[3 * i] = h[i].x; out_xyz[3 * i + 1] = h[i].y; out_xyz[3 * i + 2] = h[i].z; }
+    return (long long) nv;
+  })
+}
+
+int plade_bounding_box(plade_ctx *ctx, const float *xyz, size_t n, float *center, double *whd, float *corners) {
+  PLADE_TRY(ctx, -1, {
+    std::vector<float4> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
+    V3 c, c8[8];
+    int rc = compute_bounding_box(h.data(), n, c, whd[0], whd[1], whd[2], c8);
+    if (rc != 0) return rc;
+    center[0] = c.x; center[1] = c.y; center[2] = c.z;
+    for (int k = 0; k < 8; ++k) { corners[3 * k] = c8[k].x; corners[3 * k + 1] = c8[k].y; corners[3 * k + 2] = c8[k].z; }
+    return 0;
+  })
+}
+
+long long plade_match_descriptors(plade_ctx *ctx, const float *db8, int ndb, const float *q8, int nq, float radius, int *offsets) {
+  PLADE_TRY(ctx, -1, {
+    Registrar &r = *ctx->reg;
+    std::vector<int> off;
+    size_t m = match_descriptors(r.dev, r.match_sc, db8, ndb, q8, nq, radius, off, ctx->match_idx, ctx->match_d2);
+    memcpy(offsets, off.data(), sizeof(int) * off.size());
+    return (long long) m;
+  })
+}
+int plade_match_results(plade_ctx *ctx, int *idx, double *dist2) {
+  if (!ctx) return 0;
+  if (!ctx->match_idx.empty()) {
+    memcpy(idx, ctx->match_idx.data(), sizeof(int) * ctx->match_idx.size());
+    memcpy(dist2, ctx->match_d2.data(), sizeof(double) * ctx->match_d2.size());
+  }
+  return 1;
+}
+
+int plade_transforms_from_matches(plade_ctx *ctx, const float *in18, int n, float *R9, float *T3) {
+  PLADE_TRY(ctx, 0, {
+    Registrar &r = *ctx->reg;
+    static_assert(sizeof(MatchPairIn) == 18 * sizeof(float), "MatchPairIn layout");
+    std::vector<RigidOut> out;
+    transforms_from_matches(r.dev, r.hyp_sc, reinterpret_cast<const MatchPairIn *>(in18), (size_t) n, out);
+    for (int i = 0; i < n; ++i) { memcpy(R9 + 9 * i, out[i].R, sizeof(float) * 9); memcpy(T3 + 3 * i, out[i].T, sizeof(float) * 3); }
+    return 1;
+  })
+}
+
+int plade_cluster_transforms(plade_ctx *ctx, const float *R9, const float *T3, int n, float dist_thresh, float ang_thresh, int *labels) {
+  PLADE_TRY(ctx, 0, {
+    Registrar &r = *ctx->reg;
+    std::vector<RigidOut> rt(n);
+    for (int i = 0; i < n; ++i) {
+      memcpy(rt[i].R, R9 + 9 * i, sizeof(float) * 9);
+      memcpy(rt[i].T, T3 + 3 * i, sizeof(float) * 3);
+      // pcl::getEulerAngles on the float rotation (same expression as the K4a kernel)
+      rt[i].euler[0] = (float) std::atan2((double) rt[i].R[7], (double) rt[i].R[8]);
+      rt[i].euler[1] = (float) std::asin(-(double) rt[i].R[6]);
+      rt[i].euler[2] = (float) std::atan2((double) rt[i].R[3], (double) rt[i].R[0]);
+      rt[i].pad = 0;
+    }
+    std::vector<int> label;
+    cluster_transforms(r.dev, r.hyp_sc, rt, dist_thresh, ang_thresh, label);
+    if (n) memcpy(labels, label.data(), sizeof(int) * n);
+    return 1;
+  })
+}
+
+static void fill_hyp(std::vector<HypParams> &hp, const float *R9, const float *T3, const float *c3, int H) {
+  hp.resize(H);
+  for (int i = 0; i < H; ++i) {
+    memcpy(hp[i].R, R9 + 9 * i, sizeof(float) * 9);
+    memcpy(hp[i].T, T3 + 3 * i, sizeof(float) * 3);
+    memcpy(hp[i].c, c3 + 3 * i, sizeof(float) * 3);
+    hp[i].pad = 0;
+  }
+}
+
+int plade_verify_upload(plade_ctx *ctx, const float *src_ds_xyz, size_t ns, const float *tgt_ds_xyz, size_t nt, float inlier_dist) {
+  PLADE_TRY(ctx, 0, {
+    Registrar &r = *ctx->reg;
+    upload_xyz(r, src_ds_xyz, ns, 3, ctx->v_src);
+    upload_xyz(r, tgt_ds_xyz, nt, 3, ctx->v_tgt);
+    ctx->v_ns = ns; ctx->v_nt = nt;
+    build_target_grid(r.dev, ctx->v_tgt.p, nt, inlier_dist, ctx->v_grid);
+    PLADE_CUDA(cudaStreamSynchronize(r.dev.stream));
+    return 1;
+  })
+}
+
+int plade_verify_resident(plade_ctx *ctx, const float *R9, const float *T3, const float *centers3, int H, float ball_radius,
+                          float inlier_dist, unsigned int *counts, float *kernel_ms) {
+  PLADE_TRY(ctx, 0, {
+    Registrar &r = *ctx->reg;
+    cudaStream_t s = r.dev.stream;
+    std::vector<HypParams> hp;
+    fill_hyp(hp, R9, T3, centers3, H);
+    HypParams *d_h = ctx->v_hyp.ensure(std::max(H, 1));
+    unsigned int *d_c = ctx->v_counts.ensure(std::max(H, 1));
+    if (H) PLADE_CUDA(cudaMemcpyAsync(d_h, hp.data(), sizeof(HypParams) * H, cudaMemcpyHostToDevice, s));
+    cudaEvent_t e0, e1;
+    PLADE_CUDA(cudaEventCreate(&e0));
+    PLADE_CUDA(cudaEventCreate(&e1));
+    PLADE_CUDA(cudaEventRecord(e0, s));
+    verify_hypotheses(r.dev, ctx->v_src.p, ctx->v_ns, ctx->v_grid, d_h, H, ball_radius, inlier_dist, d_c);
+    PLADE_CUDA(cudaEventRecord(e1, s));
+    if (H) PLADE_CUDA(cudaMemcpyAsync(counts, d_c, sizeof(unsigned int) * H, cudaMemcpyDeviceToHost, s));
+    PLADE_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    PLADE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (kernel_ms) *kernel_ms = ms;
+    return 1;
+  })
+}
+
+int plade_verify_hypotheses(plade_ctx *ctx, const float *src_ds_xyz, size_t ns, const float *tgt_ds_xyz, size_t nt, const float *R9,
+                            const float *T3, const float *centers3, int H, float ball_radius, float inlier_dist, unsigned int *counts) {
+  if (!plade_verify_upload(ctx, src_ds_xyz, ns, tgt_ds_xyz, nt, inlier_dist)) return 0;
+  return plade_verify_resident(ctx, R9, T3, centers3, H, ball_radius, inlier_dist, counts, nullptr);
+}
+
+}  // extern "C"

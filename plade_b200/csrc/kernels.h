@@ -1,0 +1,117 @@
+// Internal C++ interface between the host pipeline and the sm_100a kernels.
+// Every stage cites the reference loop it replaces (paths relative to /root/reference/code/).
+#pragma once
+#include "common.h"
+
+namespace plade {
+
+struct Device {
+  int id = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  LaunchCounter launches;
+};
+
+// ------------------------------------------------------------------------------------------------
+// K5 — hypothesis verification (PLADE/plade.cpp:547-564 + ComputeOverlap PLADE/util.h:612-647)
+// ------------------------------------------------------------------------------------------------
+struct HypParams {       // 64 B, one per hypothesis
+  float R[9];            // row-major
+  float T[3];
+  float c[3];            // ball centre = R * source_bbox_centre + T, computed by the caller
+  float pad;
+};
+
+struct TargetGrid {
+  DevBuf<float4> pts;        // target ds points sorted by cell
+  DevBuf<int> cell_start;    // ncells + 1
+  DevBuf<unsigned int> keys, keys_alt;
+  DevBuf<int> order, order_alt;
+  DevBuf<unsigned char> cub_tmp;
+  DevBuf<float> mm;          // 6 ordered-int encoded bbox values
+  float minx = 0, miny = 0, minz = 0, inv_cell = 0, cell = 0;
+  int nx = 0, ny = 0, nz = 0;
+  size_t n = 0;
+};
+
+// Build the uniform grid (cell edge >= inlier_dist) over n target points (device float4, w ignored).
+void build_target_grid(Device &dev, const float4 *d_tgt, size_t n, float inlier_dist, TargetGrid &grid);
+
+// counts[h] = #{ s : exists t in ball(c_h, ball_radius) with dist2(transform_h(s), t) < inlier_dist^2 }
+// radii follow kdtree_flann.hpp:193: r2 = float(double(r) * double(r)), strict '<'.
+void verify_hypotheses(Device &dev, const float4 *d_src, size_t ns, const TargetGrid &grid,
+                       const HypParams *d_hyp, int H, float ball_radius, float inlier_dist,
+                       unsigned int *d_counts);
+
+// ------------------------------------------------------------------------------------------------
+// K2b — voxel-grid down-sampling (pcl VoxelGrid::applyFilter, filters/impl/voxel_grid.hpp:214-437)
+// K2a — average spacing (PLADE/util.cpp:1619-1648)
+// ------------------------------------------------------------------------------------------------
+struct VoxelScratch {
+  DevBuf<unsigned long long> keys, keys_alt;
+  DevBuf<int> idx, idx_alt;
+  DevBuf<int> seg_start;
+  DevBuf<int> flags;
+  DevBuf<unsigned char> cub_tmp;
+  DevBuf<float> minmax;   // 6 floats
+  DevBuf<int> counter;
+};
+
+// Down-sample `n` points (device float4 xyz_, optional gather list `d_sel` of m indices, or nullptr
+// for all n) with leaf size `leaf`.  Output centroids (float4, w = 0) in PCL's output order
+// (voxel index ascending, i.e. z-major / y / x-minor).  Returns the number of voxels.
+// If group != nullptr, group[i] (>= 0) partitions the selected points into independent clouds that
+// are voxelised separately in one pass; out_group_start receives ngroups+1 offsets (host).
+size_t voxel_downsample(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n, float leaf,
+                        DevBuf<float4> &out);
+size_t voxel_downsample_groups(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n,
+                               const int *d_group, int ngroups, float leaf, DevBuf<float4> &out,
+                               std::vector<int> &out_group_start);
+
+// k nearest squared distances (ascending, float, FLANN L2_Simple arithmetic) of nq query points
+// (indices into d_pts) against all n points.  d_out: nq * k floats.
+void knn_sqdist(Device &dev, const float4 *d_pts, size_t n, const int *d_query_idx, int nq, int k,
+                float *d_out);
+
+// ------------------------------------------------------------------------------------------------
+// K3c — descriptor radius matching (KdTreeSearchNDim<.,8>::find_neighbors, ANN.h:979-1029)
+// ------------------------------------------------------------------------------------------------
+struct MatchScratch {
+  DevBuf<float> db, q;
+  DevBuf<int> counts, offsets;
+  DevBuf<int> out_idx, out_idx_alt;
+  DevBuf<unsigned long long> out_key, out_key_alt;
+  DevBuf<int> out_q, out_q_alt;
+  DevBuf<unsigned char> cub_tmp;
+};
+// Host in / host out.  offsets[nq+1]; idx/dist2 sorted per query by (dist2 asc, idx asc).
+size_t match_descriptors(Device &dev, MatchScratch &sc, const float *h_db, int ndb, const float *h_q,
+                         int nq, float radius, std::vector<int> &offsets, std::vector<int> &idx,
+                         std::vector<double> &dist2);
+
+// ------------------------------------------------------------------------------------------------
+// K4a/b/c — hypothesis generation
+// ------------------------------------------------------------------------------------------------
+struct MatchPairIn {    // one (query pair, db pair) match, PLADE/util.cpp:316-322
+  float sv1[3], sv2[3], dv1[3], dv2[3], sp[3], tp[3];
+};
+struct RigidOut { float R[9]; float T[3]; float euler[3]; float pad; };
+
+struct HypScratch {
+  DevBuf<MatchPairIn> in;
+  DevBuf<RigidOut> rt;
+  DevBuf<int> label, cell_key, cell_order, cell_start;
+  DevBuf<unsigned int> keys, keys_alt;
+  DevBuf<int> order_alt;
+  DevBuf<unsigned char> cub_tmp;
+  DevBuf<int> misc;
+};
+// K4a: R from umeyama({v1,v2,v1xv2} -> {w1,w2,w1xw2}), T = tp - R*sp, euler as pcl::getEulerAngles.
+void transforms_from_matches(Device &dev, HypScratch &sc, const MatchPairIn *h_in, size_t m,
+                             std::vector<RigidOut> &out);
+// K4b: connected components of {(a,b): |Ta-Tb|^2 < dist_thresh^2 (float), |euler_a-euler_b|^2 < ang_thresh}.
+// label[i] = smallest member index of i's component.
+void cluster_transforms(Device &dev, HypScratch &sc, const std::vector<RigidOut> &rt, float dist_thresh,
+                        float ang_thresh, std::vector<int> &label);
+
+}  // namespace plade

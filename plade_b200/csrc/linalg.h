@@ -1,0 +1,96 @@
+// Small host-side linear algebra for the registration pipeline (no Eigen/OpenCV dependency).
+// Float expressions that feed decisions restate the reference's evaluation order (no FMA: the host
+// objects are built with -ffp-contract=off).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+namespace plade {
+
+struct V3 {
+  float x, y, z;
+  V3() : x(0), y(0), z(0) {}
+  V3(float a, float b, float c) : x(a), y(b), z(c) {}
+  float &operator[](int i) { return (&x)[i]; }
+  float operator[](int i) const { return (&x)[i]; }
+};
+inline V3 operator+(const V3 &a, const V3 &b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(const V3 &a, const V3 &b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator*(const V3 &a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+inline V3 operator*(float s, const V3 &a) { return V3(s * a.x, s * a.y, s * a.z); }
+inline V3 operator/(const V3 &a, float s) { return V3(a.x / s, a.y / s, a.z / s); }
+inline V3 operator-(const V3 &a) { return V3(-a.x, -a.y, -a.z); }
+// Eigen fixed-size dot / squaredNorm: ((a0*b0 + a1*b1) + a2*b2)
+inline float dot(const V3 &a, const V3 &b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline float sqnorm(const V3 &a) { return dot(a, a); }
+inline float norm(const V3 &a) { return std::sqrt(sqnorm(a)); }
+inline V3 cross(const V3 &a, const V3 &b) {
+  return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// Eigen::MatrixBase::normalize(): z = squaredNorm(); if (z > 0) v /= sqrt(z)
+inline void normalize(V3 &a) {
+  float z = sqnorm(a);
+  if (z > 0) { float s = std::sqrt(z); a.x /= s; a.y /= s; a.z /= s; }
+}
+
+struct M3 {           // row-major
+  float m[9];
+  float operator()(int r, int c) const { return m[3 * r + c]; }
+  float &operator()(int r, int c) { return m[3 * r + c]; }
+};
+// Eigen lazy 3x3 * 3x1 coefficient product: row dot, left to right
+inline V3 mul(const M3 &R, const V3 &v) {
+  return V3((R.m[0] * v.x + R.m[1] * v.y) + R.m[2] * v.z, (R.m[3] * v.x + R.m[4] * v.y) + R.m[5] * v.z,
+            (R.m[6] * v.x + R.m[7] * v.y) + R.m[8] * v.z);
+}
+
+// Symmetric 3x3 eigen-decomposition (cyclic Jacobi in double), eigenvalues ascending, eigenvectors
+// in the columns of V (unit length).  Stands in for Eigen::SelfAdjointEigenSolver<Matrix3f>
+// (PLADE/util.h:199); eigenvector signs are arbitrary there as well.
+inline void sym_eig3(const double Ain[3][3], double w[3], double V[3][3]) {
+  double A[3][3];
+  memcpy(A, Ain, sizeof(A));
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = (i == j);
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = std::fabs(A[0][1]) + std::fabs(A[0][2]) + std::fabs(A[1][2]);
+    double diag = std::fabs(A[0][0]) + std::fabs(A[1][1]) + std::fabs(A[2][2]);
+    if (off == 0.0 || off <= 1e-18 * diag) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double apq = A[p][q];
+        if (apq == 0.0) continue;
+        double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) { double a = A[k][p], b = A[k][q]; A[k][p] = c * a - s * b; A[k][q] = s * a + c * b; }
+        for (int k = 0; k < 3; ++k) { double a = A[p][k], b = A[q][k]; A[p][k] = c * a - s * b; A[q][k] = s * a + c * b; }
+        for (int k = 0; k < 3; ++k) { double a = V[k][p], b = V[k][q]; V[k][p] = c * a - s * b; V[k][q] = s * a + c * b; }
+      }
+  }
+  int ord[3] = {0, 1, 2};
+  double ev[3] = {A[0][0], A[1][1], A[2][2]};
+  std::sort(ord, ord + 3, [&](int a, int b) { return ev[a] < ev[b]; });
+  double Vs[3][3];
+  for (int k = 0; k < 3; ++k) { w[k] = ev[ord[k]]; for (int r = 0; r < 3; ++r) Vs[r][k] = V[r][ord[k]]; }
+  memcpy(V, Vs, sizeof(Vs));
+}
+
+// Closest points of two 3-D lines, closed form in double; stands in for the 9x9 float
+// cv::solve(DECOMP_SVD) of ComputeNearstTwoPointsOfTwo3DLine (PLADE/util.cpp:1167-1229).
+// d1, d2 must be unit vectors.  Returns false for (numerically) parallel lines.
+inline bool closest_points_two_lines(const V3 &d1, const V3 &p1, const V3 &d2, const V3 &p2, V3 &q1, V3 &q2) {
+  double a = (double) d1.x * d2.x + (double) d1.y * d2.y + (double) d1.z * d2.z;
+  double b = (double) d1.x * d1.x + (double) d1.y * d1.y + (double) d1.z * d1.z;
+  double c = (double) d2.x * d2.x + (double) d2.y * d2.y + (double) d2.z * d2.z;
+  double den = b * c - a * a;
+  if (!(den > 1e-14 * b * c)) return false;
+  double wx = (double) p2.x - p1.x, wy = (double) p2.y - p1.y, wz = (double) p2.z - p1.z;
+  double w1 = wx * d1.x + wy * d1.y + wz * d1.z, w2 = wx * d2.x + wy * d2.y + wz * d2.z;
+  double t1 = (c * w1 - a * w2) / den, t2 = (a * w1 - b * w2) / den;
+  q1 = V3((float) (p1.x + t1 * d1.x), (float) (p1.y + t1 * d1.y), (float) (p1.z + t1 * d1.z));
+  q2 = V3((float) (p2.x + t2 * d2.x), (float) (p2.y + t2 * d2.y), (float) (p2.z + t2 * d2.z));
+  return true;
+}
+
+}  // namespace plade

@@ -1,0 +1,802 @@
+// Host orchestrator: restates the control flow of registration() (PLADE/plade.cpp:31-580) and
+// MatchingLines() (PLADE/util.cpp:31-520) on flat arrays, with the data-parallel stages on the GPU.
+// Order-defining host logic (match order, cluster seed order, the two std::sort calls with their
+// comparators, the candidate budget) follows the reference statement by statement because it
+// decides WHICH hypothesis wins; file:line citations are relative to /root/reference/code/.
+#include "pipeline.h"
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <numeric>
+
+namespace plade {
+
+namespace {
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct Line {            // INTERSECTION_LINE, PLADE/util.h:70-78
+  V3 vec, pt;
+  int p0, p1;
+};
+struct NearPts {         // NearstPointsTwoLine, PLADE/util.h:61-68
+  V3 a, b;
+  double length;
+};
+struct LenIdx {          // LENGTHINDEX, PLADE/util.h:347-350
+  float length;
+  int index;
+};
+inline bool cmp_less(const LenIdx &a, const LenIdx &b) { return a.length < b.length; }       // util.h:352
+inline bool cmp_greater(const LenIdx &a, const LenIdx &b) { return a.length > b.length; }    // util.h:360
+
+struct Side {            // MatchInformation, PLADE/util.h:80-102
+  size_t n_ds = 0;
+  std::vector<float4> ds;
+  V3 center;
+  double radius = 0;
+  std::vector<std::array<float, 4>> planes;
+  std::vector<int> plane_ds_start;          // P+1
+  std::vector<float4> plane_ds;
+  std::vector<std::array<V3, 4>> corners4;
+  std::vector<V3> plane_center;
+  std::vector<float> plane_radius;
+  std::vector<Line> lines;
+};
+
+// transformPointCloud formula (common/impl/transforms.hpp:69-71)
+inline V3 xform(const M3 &R, const V3 &T, const V3 &p) {
+  return V3(((R.m[0] * p.x + R.m[1] * p.y) + R.m[2] * p.z) + T.x, ((R.m[3] * p.x + R.m[4] * p.y) + R.m[5] * p.z) + T.y,
+            ((R.m[6] * p.x + R.m[7] * p.y) + R.m[8] * p.z) + T.z);
+}
+inline float l2simple(const V3 &a, const V3 &b) {     // FLANN L2_Simple (dist.h:84-90)
+  float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+  float r = dx * dx;
+  r += dy * dy;
+  r += dz * dz;
+  return r;
+}
+
+// ComputeNearstTwoPointsOfTwo3DLine (PLADE/util.cpp:1167-1229): normalises both directions IN PLACE,
+// fails on identical directions, closest points (closed form here), length = |p1 - p2| (float norm).
+int nearest_two_lines(V3 &v1, const V3 &p1, V3 &v2, const V3 &p2, V3 &q1, V3 &q2, double &len) {
+  normalize(v1);
+  normalize(v2);
+  if (v1.x == v2.x && v1.y == v2.y && v1.z == v2.z) return -1;
+  if (!closest_points_two_lines(v1, p1, v2, p2, q1, q2)) { q1 = p1; q2 = p2; }
+  len = norm(q1 - q2);
+  return 0;
+}
+
+// ComputeDescriptorVectorForPairLines, method22 (PLADE/util.cpp:533-602)
+void pair_descriptor(const V3 &l1, const V3 &l2, const V3 &l1sp1, const V3 &l1sp2, const V3 &l2sp1, const V3 &l2sp2,
+                     float *d, V3 &newLine1, V3 &newLine2) {
+  float angle1 = std::fabs(dot(l1, l2sp1)), angle2 = std::fabs(dot(l1, l2sp2));
+  V3 n2a, n2b;
+  if (angle1 <= angle2) { n2a = l2sp1; n2b = l2sp2; } else { n2a = l2sp2; n2b = l2sp1; }
+  newLine2 = cross(n2a, n2b);
+  V3 n1a, n1b;
+  angle1 = std::fabs(dot(l2, l1sp1));
+  angle2 = std::fabs(dot(l2, l1sp2));
+  if (angle1 <= angle2) { n1a = l1sp1; n1b = l1sp2; } else { n1a = l1sp2; n1b = l1sp1; }
+  newLine1 = cross(n1a, n1b);
+  d[1] = dot(newLine1, newLine2);
+  d[2] = dot(n1a, n1b);
+  d[3] = dot(n2a, n2b);
+  d[4] = dot(newLine1, n2a);
+  d[5] = dot(newLine1, n2b);
+  d[6] = dot(newLine2, n1a);
+  d[7] = dot(newLine2, n1b);
+}
+
+// ComputeIntersectionPointOf23DLine (PLADE/util.cpp:1461-1500): least-squares "intersection" of two
+// lines (6x5 float SVD solve in the reference) = midpoint of their closest points, closed form.
+int line_line_point(const V3 &v1, const V3 &p1, const V3 &v2, const V3 &p2, V3 &out) {
+  if (std::fabs(dot(v1, v2)) > 0.9999) return -1;
+  V3 q1, q2;
+  if (!closest_points_two_lines(v1, p1, v2, p2, q1, q2)) return -1;
+  out = V3((float) (0.5 * ((double) q1.x + q2.x)), (float) (0.5 * ((double) q1.y + q2.y)), (float) (0.5 * ((double) q1.z + q2.z)));
+  return 0;
+}
+
+struct PlaneCloudView {
+  const V3 *pts;
+  size_t n;
+  V3 lo, hi;   // axis-aligned bounds, used only to skip searches that cannot hit
+};
+// pcl radiusSearch on a plane's ds cloud: #points with L2_Simple(query, p) < float(r*r); optional index list
+int radius_count(const PlaneCloudView &c, const V3 &q, float radius, int cap, std::vector<int> *out) {
+  float r2 = (float) ((double) radius * (double) radius);
+  if (out) out->clear();
+  float m = radius * 1.001f;
+  if (q.x < c.lo.x - m || q.x > c.hi.x + m || q.y < c.lo.y - m || q.y > c.hi.y + m || q.z < c.lo.z - m || q.z > c.hi.z + m) return 0;
+  int cnt = 0;
+  for (size_t i = 0; i < c.n; ++i) {
+    if (l2simple(q, c.pts[i]) < r2) {
+      ++cnt;
+      if (out) out->push_back((int) i);
+      if (cap > 0 && cnt >= cap) break;
+    }
+  }
+  return cnt;
+}
+
+// AreTwoPlanesPenetrable (PLADE/util.cpp:1279-1458)
+int planes_penetrable(const float plane1[4], const float plane2[4], const V3 c1[4], const V3 c2[4], const PlaneCloudView &k1,
+                      const PlaneCloudView &k2, bool &pen, float searchRadius, int minPointsNum, float minDistance) {
+  pen = false;
+  V3 lineVec, linePoint;
+  if (0 != plane_intersection_line(plane1, plane2, lineVec, linePoint)) return -1;
+  std::vector<V3> ip1, ip2;
+  for (int i = 1; i <= 4; ++i) {
+    V3 tl = c1[i % 4] - c1[(i - 1) % 4];
+    normalize(tl);
+    V3 ip;
+    if (0 != line_line_point(lineVec, linePoint, tl, c1[i - 1], ip)) continue;
+    if (dot(c1[(i - 1) % 4] - ip, c1[i % 4] - ip) > 0) continue;
+    ip1.push_back(ip);
+  }
+  for (int i = 1; i <= 4; ++i) {
+    V3 tl = c2[i % 4] - c2[(i - 1) % 4];
+    normalize(tl);
+    V3 ip;
+    if (0 != line_line_point(lineVec, linePoint, tl, c2[i - 1], ip)) continue;
+    if (dot(c2[(i - 1) % 4] - ip, c2[i % 4] - ip) > 0) continue;
+    ip2.push_back(ip);
+  }
+  if (ip1.empty()) return 0; else if (ip1.size() != 2) return -1;
+  if (ip2.empty()) return 0; else if (ip2.size() != 2) return -1;
+  V3 direc = ip1[1] - ip1[0];
+  normalize(direc);
+  V3 inter[4] = {ip1[0], ip1[1], ip2[0], ip2[1]};
+  std::vector<LenIdx> lv(4);
+  for (int i = 0; i < 4; ++i) { lv[i].length = dot(inter[i] - inter[0], direc); lv[i].index = i; }
+  std::sort(lv.begin(), lv.end(), cmp_less);
+  if (0 == (lv[0].index / 2 - lv[1].index / 2)) return 0;
+  const V3 startPoint = inter[lv[1].index], endPoint = inter[lv[2].index];
+  float length = norm(endPoint - startPoint);
+  std::vector<int> nb;
+  for (int pass = 0; pass < 2; ++pass) {
+    const PlaneCloudView &gate = pass == 0 ? k2 : k1;     // needs >= 2 points within r/2
+    const PlaneCloudView &probe = pass == 0 ? k1 : k2;    // classified against the other plane
+    const float *pl = pass == 0 ? plane2 : plane1;
+    int pos = 0, neg = 0;
+    std::vector<char> fresh(probe.n, 1);
+    for (float dist = 0; dist < length; dist += searchRadius) {
+      V3 sp = startPoint + dist * direc;
+      if (radius_count(gate, sp, searchRadius / 2, 2, nullptr) < 2) continue;
+      radius_count(probe, sp, searchRadius, 0, &nb);
+      for (int id : nb) {
+        if (!fresh[id]) continue;
+        fresh[id] = 0;
+        const V3 &p = probe.pts[id];
+        float td = pl[0] * p.x + pl[1] * p.y + pl[2] * p.z + pl[3];
+        if (std::fabs(td) > minDistance) { if (td >= 0) ++pos; else ++neg; }
+      }
+    }
+    if (pass == 0) { if (pos < minPointsNum || neg < minPointsNum) return 0; }
+    else { if (pos < minPointsNum && neg < minPointsNum) return 0; }
+    if (double(std::max(pos, neg)) / std::min(pos, neg + 1) > 5) return 0;
+  }
+  pen = true;
+  return 0;
+}
+
+}  // namespace
+
+int plane_intersection_line(const float pl1[4], const float pl2[4], V3 &lineVec, V3 &linePoint) {
+  V3 p1(pl1[0], pl1[1], pl1[2]), p2(pl2[0], pl2[1], pl2[2]);
+  normalize(p1);
+  normalize(p2);
+  if (std::fabs(dot(p1, p2)) > 0.95) return -1;
+  lineVec = cross(p1, p2);
+  normalize(lineVec);
+  double b0 = -(double) pl1[3], b1 = -(double) pl2[3];
+  auto solve2 = [&](float a00, float a01, float a10, float a11, double &x0, double &x1) {
+    // cv::Mat::inv() 2x2 CV_64F closed form (opencv core lapack.cpp, n == 2 branch) then A^-1 * B
+    double A00 = a00, A01 = a01, A10 = a10, A11 = a11;
+    double det = A00 * A11 - A01 * A10;
+    double i00 = 0, i01 = 0, i10 = 0, i11 = 0;
+    if (det != 0.) { double d = 1. / det; i11 = A00 * d; i00 = A11 * d; i01 = -A01 * d; i10 = -A10 * d; }
+    x0 = i00 * b0 + i01 * b1;
+    x1 = i10 * b0 + i11 * b1;
+  };
+  double x0, x1;
+  if (std::fabs(pl1[0] * pl2[1] - pl2[0] * pl1[1]) > 1e-6) {
+    solve2(pl1[0], pl1[1], pl2[0], pl2[1], x0, x1);
+    linePoint = V3((float) x0, (float) x1, 0.f);
+  } else if (std::fabs(pl1[0] * pl2[2] - pl2[0] * pl1[2]) > 1e-6) {
+    solve2(pl1[0], pl1[2], pl2[0], pl2[2], x0, x1);
+    linePoint = V3((float) x0, 0.f, (float) x1);
+  } else if (std::fabs(pl1[1] * pl2[2] - pl2[1] * pl1[2]) > 1e-6) {
+    solve2(pl1[1], pl1[2], pl2[1], pl2[2], x0, x1);
+    linePoint = V3(0.f, (float) x0, (float) x1);
+  } else {
+    return -1;
+  }
+  return 0;
+}
+
+int compute_bounding_box(const float4 *pts, size_t n, V3 &centerPoint, double &width, double &height, double &depth,
+                         V3 corners[8]) {
+  if (n == 0) return -1;
+  // compute3DCentroid (centroid.hpp:79-122): sequential float sums
+  float cx = 0, cy = 0, cz = 0;
+  for (size_t i = 0; i < n; ++i) { cx += pts[i].x; cy += pts[i].y; cz += pts[i].z; }
+  const float fn = (float) n;
+  cx /= fn; cy /= fn; cz /= fn;
+  // computeCovarianceMatrixNormalized (centroid.hpp:180-259)
+  float c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+  for (size_t i = 0; i < n; ++i) {
+    float px = pts[i].x - cx, py = pts[i].y - cy, pz = pts[i].z - cz;
+    c11 += py * py; c12 += py * pz; c22 += pz * pz;
+    c00 += px * px; c01 += py * px; c02 += pz * px;
+  }
+  c00 /= fn; c01 /= fn; c02 /= fn; c11 /= fn; c12 /= fn; c22 /= fn;
+  double A[3][3] = {{c00, c01, c02}, {c01, c11, c12}, {c02, c12, c22}}, w[3], V[3][3];
+  sym_eig3(A, w, V);
+  M3 E;   // eigDx, columns = eigenvectors (ascending eigenvalue); col2 := col0 x col1
+  V3 e0((float) V[0][0], (float) V[1][0], (float) V[2][0]), e1((float) V[0][1], (float) V[1][1], (float) V[2][1]);
+  V3 e2 = cross(e0, e1);
+  for (int r = 0; r < 3; ++r) { E(r, 0) = e0[r]; E(r, 1) = e1[r]; E(r, 2) = e2[r]; }
+  M3 Rt;  // eigDx^T
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Rt(r, c) = E(c, r);
+  V3 ctr(cx, cy, cz);
+  V3 t = -1.f * mul(Rt, ctr);
+  V3 mn(3.402823466e38f, 3.402823466e38f, 3.402823466e38f), mx(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f);
+  for (size_t i = 0; i < n; ++i) {
+    V3 q = xform(Rt, t, V3(pts[i].x, pts[i].y, pts[i].z));
+    mn.x = std::min(mn.x, q.x); mn.y = std::min(mn.y, q.y); mn.z = std::min(mn.z, q.z);
+    mx.x = std::max(mx.x, q.x); mx.y = std::max(mx.y, q.y); mx.z = std::max(mx.z, q.z);
+  }
+  V3 mean_diag = 0.5f * (mx + mn);
+  centerPoint = mul(E, mean_diag) + ctr;
+  width = mx.x - mn.x;
+  depth = mx.y - mn.y;
+  height = mx.z - mn.z;
+  if (corners) {
+    float x = mn.x, y = mn.y, z = mn.z;
+    V3 loc[8] = {mn,
+                 V3(x, (float) (y + depth), z),
+                 V3(x, (float) (y + depth), (float) (z + height)),
+                 V3(x, y, (float) (z + height)),
+                 V3((float) (x + width), y, (float) (z + height)),
+                 V3((float) (x + width), (float) (y + depth), z),
+                 V3((float) (x + width), y, z),
+                 V3((float) (x + width), (float) (y + depth), (float) (z + height))};
+    for (int k = 0; k < 8; ++k) corners[k] = xform(E, ctr, loc[k]);
+  }
+  return 0;
+}
+
+Registrar::Registrar(int device) {
+  if (device >= 0) PLADE_CUDA(cudaSetDevice(device));
+  PLADE_CUDA(cudaGetDevice(&dev.id));
+  cudaDeviceProp prop;
+  PLADE_CUDA(cudaGetDeviceProperties(&prop, dev.id));
+  dev.num_sms = prop.multiProcessorCount;
+  PLADE_CUDA(cudaStreamCreateWithFlags(&dev.stream, cudaStreamNonBlocking));
+}
+
+Registrar::~Registrar() {
+  if (dev.stream) cudaStreamDestroy(dev.stream);
+}
+
+// defined in split.cu
+void split_cloud(Device &dev, const float *d_xyzn, size_t n, float4 *pos, float4 *nrm);
+
+void Registrar::upload(const float *xyzn, size_t n, CloudDev &out) {
+  out.n = n;
+  if (n == 0) return;
+  static thread_local DevBuf<float> staging;
+  float *d_in = staging.ensure(n * 6);
+  PLADE_CUDA(cudaMemcpyAsync(d_in, xyzn, sizeof(float) * n * 6, cudaMemcpyHostToDevice, dev.stream));
+  split_cloud(dev, d_in, n, out.pos.ensure(n), out.nrm.ensure(n));
+  PLADE_CUDA(cudaStreamSynchronize(dev.stream));
+}
+
+// average_spacing (PLADE/util.cpp:1619-1648): k = 6, ~10000 strided samples
+float Registrar::average_spacing(const CloudDev &c) {
+  const int k = 6, samples = 10000;
+  size_t num = c.n;
+  if (num == 0) return 0.f;
+  size_t step = 1;
+  if (num > (size_t) samples) step = num / samples;
+  std::vector<int> q;
+  for (size_t i = 0; i < num; i += step) q.push_back((int) i);
+  int kk = (int) std::min<size_t>(k, num);
+  int *d_q = qidx.ensure(q.size());
+  float *d_o = knn_out.ensure(q.size() * kk);
+  PLADE_CUDA(cudaMemcpyAsync(d_q, q.data(), sizeof(int) * q.size(), cudaMemcpyHostToDevice, dev.stream));
+  knn_sqdist(dev, c.pos.p, num, d_q, (int) q.size(), kk, d_o);
+  std::vector<float> h(q.size() * kk);
+  PLADE_CUDA(cudaMemcpyAsync(h.data(), d_o, sizeof(float) * h.size(), cudaMemcpyDeviceToHost, dev.stream));
+  PLADE_CUDA(cudaStreamSynchronize(dev.stream));
+  double total = 0.0;
+  size_t total_count = 0;
+  for (size_t s = 0; s < q.size(); ++s) {
+    int nbs = kk;
+    if (nbs <= 1) continue;
+    double avg = 0.0;
+    for (int i = 1; i < nbs; ++i) avg += std::sqrt(h[s * kk + i]);   // float sqrt, double accumulate
+    total += (avg / nbs);
+    ++total_count;
+  }
+  return static_cast<float>(total / total_count);
+}
+
+bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float out16[16]) {
+  double t0 = now_s();
+  std::cout << "extracting planes for both point clouds...\n";
+  std::vector<PlaneRec> tp = extract_planes(tgt, params.init_min_support);
+  if ((int) tp.size() < params.min_planes) {
+    std::cerr << "too few (only " << tp.size() << ") planes extracted from the target point cloud" << std::endl;
+    last_error = "too few planes in target";
+    return false;
+  }
+  std::vector<PlaneRec> sp = extract_planes(src, params.init_min_support);
+  if ((int) sp.size() < params.min_planes) {
+    std::cerr << "two few (only " << sp.size() << ") planes extracted from the source point cloud" << std::endl;
+    last_error = "too few planes in source";
+    return false;
+  }
+  times.planes = now_s() - t0;
+  return register_with_planes(tgt, src, tp, sp, out16);
+}
+
+bool Registrar::register_min_support(const CloudDev &tgt, const CloudDev &src, int ms_t, int ms_s, float out16[16]) {
+  double t0 = now_s();
+  std::vector<PlaneRec> tp = detect_planes(tgt, ms_t);
+  std::vector<PlaneRec> sp = detect_planes(src, ms_s);
+  times.planes = now_s() - t0;
+  return register_with_planes(tgt, src, tp, sp, out16);
+}
+
+bool Registrar::register_with_planes(const CloudDev &tgt, const CloudDev &src, const std::vector<PlaneRec> &tplanes,
+                                     const std::vector<PlaneRec> &splanes, float out16[16]) {
+  const double t_begin = now_s();
+  for (int i = 0; i < 16; ++i) out16[i] = (i % 5 == 0) ? 1.f : 0.f;
+  cudaStream_t s = dev.stream;
+  if (tgt.n == 0 || src.n == 0) { last_error = "empty cloud"; return false; }
+
+  // ---- constants, PLADE/plade.cpp:41-56 -----------------------------------------------------------
+  double t0 = now_s();
+  const float average_space = average_spacing(src);
+  times.spacing = now_s() - t0;
+  float downSampleDistance = average_space * 4;
+  float lengthThreshold = average_space * 5;
+  float angleThreshold = (float) (5.0 / 180 * M_PI);
+  float cosAngleThreshold = std::cos(angleThreshold);
+  const int maxCandidateResultNum = params.max_candidates;
+  float scale = (float) (lengthThreshold / std::cos(M_PI_2 - angleThreshold));
+  if (debug) {
+    put("average_space", std::vector<float>(1, average_space));
+    put("downsample_distance", std::vector<float>(1, downSampleDistance));
+  }
+  if (!(downSampleDistance > 0)) { last_error = "degenerate spacing"; return false; }
+
+  // ---- per-side set-up, PLADE/plade.cpp:74-122 / :287-335 -----------------------------------------
+  t0 = now_s();
+  Side S[2];   // 0 = target ("main"), 1 = source ("current")
+  const CloudDev *clouds[2] = {&tgt, &src};
+  const std::vector<PlaneRec> *planes_in[2] = {&tplanes, &splanes};
+  DevBuf<float4> *ds_dev[2] = {&ds_tgt, &ds_src};
+  for (int side = 0; side < 2; ++side) {
+    Side &A = S[side];
+    const CloudDev &C = *clouds[side];
+    const std::vector<PlaneRec> &P = *planes_in[side];
+    A.n_ds = voxel_downsample(dev, vox, C.pos.p, C.n, downSampleDistance, *ds_dev[side]);
+    A.ds.resize(A.n_ds);
+    PLADE_CUDA(cudaMemcpyAsync(A.ds.data(), ds_dev[side]->p, sizeof(float4) * A.n_ds, cudaMemcpyDeviceToHost, s));
+    // plane membership -> group id per point
+    std::vector<int> grp(C.n, -1);
+    for (size_t i = 0; i < P.size(); ++i)
+      for (int id : P[i].idx) if (id >= 0 && (size_t) id < C.n) grp[id] = (int) i;
+    int *d_grp = group.ensure(C.n);
+    PLADE_CUDA(cudaMemcpyAsync(d_grp, grp.data(), sizeof(int) * C.n, cudaMemcpyHostToDevice, s));
+    size_t nv = voxel_downsample_groups(dev, vox, C.pos.p, C.n, d_grp, (int) P.size(), downSampleDistance, ds_planes, A.plane_ds_start);
+    A.plane_ds.resize(nv);
+    if (nv) PLADE_CUDA(cudaMemcpyAsync(A.plane_ds.data(), ds_planes.p, sizeof(float4) * nv, cudaMemcpyDeviceToHost, s));
+    PLADE_CUDA(cudaStreamSynchronize(s));
+    double w, h, d;
+    if (0 != compute_bounding_box(A.ds.data(), A.n_ds, A.center, w, h, d, nullptr)) { last_error = "empty down-sampled cloud"; return false; }
+    A.radius = std::max(std::max(w, h), d) / 2;
+    A.planes.resize(P.size());
+    A.corners4.resize(P.size());
+    A.plane_center.resize(P.size());
+    A.plane_radius.resize(P.size());
+    for (size_t i = 0; i < P.size(); ++i) {
+      A.planes[i] = {P[i].n[0], P[i].n[1], P[i].n[2], P[i].d};
+      V3 c8[8], ctr;
+      double pw, ph, pd;
+      size_t b = A.plane_ds_start[i], e = A.plane_ds_start[i + 1];
+      for (int k = 0; k < 4; ++k) A.corners4[i][k] = V3();
+      A.plane_center[i] = V3();
+      A.plane_radius[i] = 0;
+      if (e <= b || 0 != compute_bounding_box(A.plane_ds.data() + b, e - b, ctr, pw, ph, pd, c8)) continue;
+      // ProjectPoints2Plane on corners [0,4) (PLADE/util.h:293-329)
+      float Aa = P[i].n[0], B = P[i].n[1], Cc = P[i].n[2], D = P[i].d;
+      for (int k = 0; k < 4; ++k) {
+        const V3 &q = c8[k];
+        float kk = -(Aa * q.x + B * q.y + Cc * q.z + D) / (Aa * Aa + B * B + Cc * Cc);
+        A.corners4[i][k] = V3(q.x + kk * Aa, q.y + kk * B, q.z + kk * Cc);
+      }
+      A.plane_center[i] = (A.corners4[i][0] + A.corners4[i][2]) / 2.f;
+      A.plane_radius[i] = norm(A.corners4[i][0] - A.corners4[i][2]) / 2;
+    }
+  }
+  times.downsample = now_s() - t0;
+
+  // ---- intersection lines, PLADE/plade.cpp:124-172 / :337-381 ---------------------------------------
+  t0 = now_s();
+  for (int side = 0; side < 2; ++side) {
+    Side &A = S[side];
+    size_t np = A.planes.size();
+    for (size_t i = 0; i < np; ++i)
+      for (size_t j = i + 1; j < np; ++j) {
+        Line L;
+        if (0 != plane_intersection_line(A.planes[i].data(), A.planes[j].data(), L.vec, L.pt)) continue;
+        V3 tv = L.pt - A.center;
+        double distance = std::sqrt((double) sqnorm(tv) - std::pow((double) dot(tv, L.vec), 2));
+        if (distance > A.radius) continue;
+        // ComputeMeanDistanceOfLine2Plane (util.h:390-426) only re-normalises lineVec (its result is unused);
+        // it fails iff the plane has no bounding-box corners, i.e. an empty down-sampled plane
+        if (A.plane_ds_start[i + 1] == A.plane_ds_start[i]) continue;
+        normalize(L.vec);
+        if (A.plane_ds_start[j + 1] == A.plane_ds_start[j]) continue;
+        normalize(L.vec);
+        L.p0 = (int) i;
+        L.p1 = (int) j;
+        A.lines.push_back(L);
+      }
+  }
+  Side &M = S[0], &Cu = S[1];
+  const size_t mainLinesNum = M.lines.size(), currentLinesNum = Cu.lines.size();
+  times.lines = now_s() - t0;
+  if (debug) {
+    for (int side = 0; side < 2; ++side) {
+      std::string p = side == 0 ? "tgt_" : "src_";
+      std::vector<float> lv, ds, pc, pr, c4;
+      std::vector<int> lp;
+      for (const Line &L : S[side].lines) {
+        lv.insert(lv.end(), {L.vec.x, L.vec.y, L.vec.z, L.pt.x, L.pt.y, L.pt.z});
+        lp.push_back(L.p0); lp.push_back(L.p1);
+      }
+      for (const float4 &q : S[side].ds) ds.insert(ds.end(), {q.x, q.y, q.z});
+      put(p + "lines", lv); put(p + "line_planes", lp); put(p + "ds", ds);
+      put(p + "center", std::vector<float>{S[side].center.x, S[side].center.y, S[side].center.z});
+      put(p + "radius", std::vector<double>(1, S[side].radius));
+      std::vector<float> pds;
+      for (const float4 &q : S[side].plane_ds) pds.insert(pds.end(), {q.x, q.y, q.z});
+      put(p + "plane_ds", pds); put(p + "plane_ds_offsets", S[side].plane_ds_start);
+      for (size_t i = 0; i < S[side].planes.size(); ++i) {
+        for (int k = 0; k < 4; ++k) c4.insert(c4.end(), {S[side].corners4[i][k].x, S[side].corners4[i][k].y, S[side].corners4[i][k].z});
+        pc.insert(pc.end(), {S[side].plane_center[i].x, S[side].plane_center[i].y, S[side].plane_center[i].z});
+        pr.push_back(S[side].plane_radius[i]);
+      }
+      put(p + "plane_corners4", c4); put(p + "plane_center", pc); put(p + "plane_radius", pr);
+    }
+  }
+  if (mainLinesNum == 0 || currentLinesNum == 0) {
+    std::cerr << "registration failed: no matched result found" << std::endl;
+    last_error = "no intersection lines";
+    return false;
+  }
+
+  // ---- target descriptor table "22", ConstructPairLinesKdTree (PLADE/util.cpp:706-1165) -------------
+  t0 = now_s();
+  const float angleThresh10 = (float) std::cos(10.0 / 180 * M_PI);
+  std::vector<float> db_desc;                 // 8 per entry
+  struct DbRec { V3 v1, v2, p1; };
+  std::vector<DbRec> db;
+  std::vector<int> db_pair;
+  {
+    std::vector<V3> sp(M.planes.size());
+    for (size_t i = 0; i < sp.size(); ++i) sp[i] = V3(M.planes[i][0], M.planes[i][1], M.planes[i][2]);
+    std::vector<NearPts> tab(mainLinesNum * mainLinesNum);
+    for (size_t i = 0; i < mainLinesNum; ++i) {
+      Line &l1 = M.lines[i];
+      for (size_t j = 0; j < mainLinesNum; ++j) {
+        if (i == j) continue;
+        Line &l2 = M.lines[j];
+        NearPts &e = tab[i * mainLinesNum + j];
+        if (i > j) {
+          const NearPts &o = tab[j * mainLinesNum + i];
+          e.a = o.b; e.b = o.a; e.length = o.length;
+        } else {
+          if (0 != nearest_two_lines(l1.vec, l1.pt, l2.vec, l2.pt, e.a, e.b, e.length)) e.length = -1;
+          e.length = e.length / scale;
+        }
+        if (std::fabs(dot(l1.vec, l2.vec)) > angleThresh10) continue;
+        float d[8];
+        V3 nl1, nl2;
+        pair_descriptor(l1.vec, l2.vec, sp[l1.p0], sp[l1.p1], sp[l2.p0], sp[l2.p1], d, nl1, nl2);
+        d[0] = (float) e.length;
+        db_desc.insert(db_desc.end(), d, d + 8);
+        db.push_back({nl1, nl2, e.a});
+        db_pair.push_back((int) i); db_pair.push_back((int) j);
+      }
+    }
+  }
+  // ---- source pair table + query descriptors, PLADE/plade.cpp:453-521, PLADE/util.cpp:133-168 ---------
+  std::vector<float> q_desc;
+  struct QRec { V3 v1, v2, p1; int i, j; };
+  std::vector<QRec> qrec;
+  {
+    std::vector<V3> sp(Cu.planes.size());
+    for (size_t i = 0; i < sp.size(); ++i) sp[i] = V3(Cu.planes[i][0], Cu.planes[i][1], Cu.planes[i][2]);
+    std::vector<NearPts> tab(currentLinesNum * currentLinesNum);
+    for (size_t i = 0; i < currentLinesNum; ++i)
+      for (size_t j = i + 1; j < currentLinesNum; ++j) {
+        NearPts &e = tab[i * currentLinesNum + j];
+        if (0 != nearest_two_lines(Cu.lines[i].vec, Cu.lines[i].pt, Cu.lines[j].vec, Cu.lines[j].pt, e.a, e.b, e.length)) e.length = -1;
+        e.length = e.length / scale;
+      }
+    for (size_t i = 0; i < currentLinesNum; ++i)
+      for (size_t j = i + 1; j < currentLinesNum; ++j) {
+        const Line &l1 = Cu.lines[i], &l2 = Cu.lines[j];
+        if (std::fabs(dot(l1.vec, l2.vec)) > angleThresh10) continue;
+        const NearPts &e = tab[i * currentLinesNum + j];
+        float d[8];
+        QRec r;
+        pair_descriptor(l1.vec, l2.vec, sp[l1.p0], sp[l1.p1], sp[l2.p0], sp[l2.p1], d, r.v1, r.v2);
+        d[0] = (float) e.length;
+        r.p1 = e.a; r.i = (int) i; r.j = (int) j;
+        q_desc.insert(q_desc.end(), d, d + 8);
+        qrec.push_back(r);
+      }
+  }
+  times.descriptors = now_s() - t0;
+  if (debug) {
+    put("tgt_db_desc", db_desc); put("tgt_db_pair", db_pair); put("src_q_desc", q_desc);
+    std::vector<int> qp;
+    for (const QRec &r : qrec) { qp.push_back(r.i); qp.push_back(r.j); }
+    put("lines_to_match", qp);
+  }
+
+  // ---- K3c: radius matching, PLADE/util.cpp:163 -----------------------------------------------------
+  t0 = now_s();
+  std::vector<int> m_off, m_idx;
+  std::vector<double> m_d2;
+  size_t n_match = match_descriptors(dev, match_sc, db_desc.data(), (int) (db_desc.size() / 8), q_desc.data(),
+                                     (int) (q_desc.size() / 8), (float) params.descriptor_radius, m_off, m_idx, m_d2);
+  times.match = now_s() - t0;
+  if (debug) { put("match_offsets", m_off); put("match_idx", m_idx); put("match_dist2", m_d2); }
+
+  // ---- K4a: one rigid transform per match, PLADE/util.cpp:303-327 -------------------------------------
+  t0 = now_s();
+  std::vector<MatchPairIn> mp(n_match);
+  {
+    size_t k = 0;
+    for (size_t qi = 0; qi < qrec.size(); ++qi)
+      for (int e = m_off[qi]; e < m_off[qi + 1]; ++e, ++k) {
+        const QRec &q = qrec[qi];
+        const DbRec &d = db[m_idx[e]];
+        MatchPairIn &o = mp[k];
+        for (int c = 0; c < 3; ++c) { o.sv1[c] = q.v1[c]; o.sv2[c] = q.v2[c]; o.dv1[c] = d.v1[c]; o.dv2[c] = d.v2[c]; o.sp[c] = q.p1[c]; o.tp[c] = d.p1[c]; }
+      }
+  }
+  std::vector<RigidOut> rt;
+  transforms_from_matches(dev, hyp_sc, mp.data(), n_match, rt);
+  if (n_match == 0) {
+    std::cerr << "registration failed: no matched result found" << std::endl;
+    last_error = "no descriptor matches";
+    return false;
+  }
+  // ---- K4b: ClusterTransformation(len/2, ang/2), PLADE/util.cpp:331 ------------------------------------
+  std::vector<int> label;
+  cluster_transforms(dev, hyp_sc, rt, (float) ((double) lengthThreshold / 2), (float) ((double) angleThreshold / 2), label);
+  // clusters in CEC emission order = ascending smallest member; size per cluster
+  std::vector<int> rep;                         // representative (= label value) per cluster, ascending
+  std::vector<int> csize;
+  {
+    std::vector<int> cid(n_match, -1);
+    for (size_t i = 0; i < n_match; ++i)
+      if (label[i] == (int) i) { cid[i] = (int) rep.size(); rep.push_back((int) i); csize.push_back(0); }
+    for (size_t i = 0; i < n_match; ++i) csize[cid[label[i]]]++;
+  }
+  if (debug) {
+    std::vector<float> R, T;
+    for (const RigidOut &r : rt) { R.insert(R.end(), r.R, r.R + 9); T.insert(T.end(), r.T, r.T + 3); }
+    put("init_R", R); put("init_T", T); put("cluster_label", label);
+  }
+  // sort by cluster size, same struct / comparator / algorithm as PLADE/util.cpp:335-347
+  std::vector<LenIdx> sortVec(rep.size());
+  for (size_t i = 0; i < sortVec.size(); ++i) { sortVec[i].index = (int) i; sortVec[i].length = (float) csize[i]; }
+  std::sort(sortVec.begin(), sortVec.end(), cmp_greater);
+
+  // ---- K4c: centre gate + plane consistency, PLADE/util.cpp:352-401 -----------------------------------
+  const size_t currentPlanesNum = Cu.planes.size(), mainPlanesNum = M.planes.size();
+  const float maxRadius = (float) M.radius;
+  std::vector<std::vector<std::pair<int, int>>> matches;
+  std::vector<int> cand_rt;     // index into rt
+  for (size_t ii = 0; ii < sortVec.size(); ++ii) {
+    int k = rep[sortVec[ii].index];
+    M3 R; memcpy(R.m, rt[k].R, sizeof(R.m));
+    V3 T(rt[k].T[0], rt[k].T[1], rt[k].T[2]);
+    V3 tc = mul(R, Cu.center) + T;
+    if (norm(tc - M.center) > maxRadius) continue;
+    std::vector<std::pair<int, int>> cur;
+    for (size_t i1 = 0; i1 < currentPlanesNum; ++i1) {
+      V3 plane1 = mul(R, V3(Cu.planes[i1][0], Cu.planes[i1][1], Cu.planes[i1][2]));
+      float d = -(-Cu.planes[i1][3] + dot(plane1, T));
+      V3 srcCenter2Dest = mul(R, Cu.plane_center[i1]) + T;
+      for (size_t j1 = 0; j1 < mainPlanesNum; ++j1) {
+        V3 plane_A(M.planes[j1][0], M.planes[j1][1], M.planes[j1][2]);
+        if (dot(plane1, plane_A) < cosAngleThreshold) continue;
+        double center2PlaneDistance = (std::fabs(dot(plane_A, srcCenter2Dest) + M.planes[j1][3]) + std::fabs(dot(plane1, M.plane_center[j1]) + d)) / 2;
+        if (center2PlaneDistance > lengthThreshold) continue;
+        double distance = norm(srcCenter2Dest - M.plane_center[j1]);
+        if (distance / (Cu.plane_radius[i1] + M.plane_radius[j1]) > 1) continue;
+        cur.push_back(std::make_pair((int) i1, (int) j1));
+        break;
+      }
+    }
+    matches.push_back(cur);
+    cand_rt.push_back(k);
+  }
+  // ---- candidate budget, PLADE/util.cpp:403-445 ----------------------------------------------------------
+  size_t maxMatchNum = 0;
+  for (auto &m : matches) maxMatchNum = std::max(maxMatchNum, m.size());
+  std::vector<std::vector<int>> matchedPlanes;
+  if (maxMatchNum > 0) {
+    int matchedCount = 0;
+    for (size_t i = maxMatchNum; i >= 2; i--) {
+      std::vector<int> tmp;
+      for (size_t j = 0; j < matches.size(); ++j)
+        if (i == matches[j].size()) { tmp.push_back((int) j); matchedCount++; }
+      matchedPlanes.push_back(tmp);
+      if (matchedCount >= maxCandidateResultNum) break;
+    }
+  }
+  times.hypotheses = now_s() - t0;
+
+  // ---- K4d: penetration filter, PLADE/util.cpp:447-519 ------------------------------------------------------
+  t0 = now_s();
+  std::vector<MatchedHyp> results;
+  {
+    // static target plane clouds
+    std::vector<std::vector<V3>> tp(mainPlanesNum);
+    std::vector<PlaneCloudView> tview(mainPlanesNum);
+    auto make_view = [](const std::vector<V3> &v) {
+      PlaneCloudView w{v.data(), v.size(), V3(3e38f, 3e38f, 3e38f), V3(-3e38f, -3e38f, -3e38f)};
+      for (const V3 &p : v) {
+        w.lo.x = std::min(w.lo.x, p.x); w.lo.y = std::min(w.lo.y, p.y); w.lo.z = std::min(w.lo.z, p.z);
+        w.hi.x = std::max(w.hi.x, p.x); w.hi.y = std::max(w.hi.y, p.y); w.hi.z = std::max(w.hi.z, p.z);
+      }
+      return w;
+    };
+    for (size_t j = 0; j < mainPlanesNum; ++j) {
+      for (int e = M.plane_ds_start[j]; e < M.plane_ds_start[j + 1]; ++e) tp[j].push_back(V3(M.plane_ds[e].x, M.plane_ds[e].y, M.plane_ds[e].z));
+      tview[j] = make_view(tp[j]);
+    }
+    int count = 0;
+    bool stop = false;
+    for (size_t m = 0; m < matchedPlanes.size() && !stop; ++m)
+      for (size_t i = 0; i < matchedPlanes[m].size(); ++i) {
+        if (count++ > maxCandidateResultNum) { stop = true; break; }
+        int index = matchedPlanes[m][i];
+        int k = cand_rt[index];
+        M3 R; memcpy(R.m, rt[k].R, sizeof(R.m));
+        V3 T(rt[k].T[0], rt[k].T[1], rt[k].T[2]);
+        bool pen = false;
+        for (size_t i1 = 0; i1 < currentPlanesNum; ++i1) {
+          pen = false;
+          V3 pn = mul(R, V3(Cu.planes[i1][0], Cu.planes[i1][1], Cu.planes[i1][2]));
+          float plane1[4] = {pn.x, pn.y, pn.z, -(-Cu.planes[i1][3] + dot(pn, T))};
+          std::vector<V3> sp_pts;
+          for (int e = Cu.plane_ds_start[i1]; e < Cu.plane_ds_start[i1 + 1]; ++e)
+            sp_pts.push_back(xform(R, T, V3(Cu.plane_ds[e].x, Cu.plane_ds[e].y, Cu.plane_ds[e].z)));
+          PlaneCloudView sview = make_view(sp_pts);
+          V3 c1[4];
+          for (int c = 0; c < 4; ++c) c1[c] = xform(R, T, Cu.corners4[i1][c]);
+          V3 currentCenter2Main = mul(R, Cu.plane_center[i1]) + T;
+          for (size_t j1 = 0; j1 < mainPlanesNum; ++j1) {
+            V3 plane_A(M.planes[j1][0], M.planes[j1][1], M.planes[j1][2]);
+            double c2p = (std::fabs(dot(plane_A, currentCenter2Main) + M.planes[j1][3]) + std::fabs(dot(pn, M.plane_center[j1]) + plane1[3])) / 2;
+            if (c2p < lengthThreshold && dot(pn, plane_A) > angleThreshold) continue;
+            if (sp_pts.empty() || tp[j1].empty()) continue;   // empty corner sets => AreTwoPlanesPenetrable returns -1
+            if (0 != planes_penetrable(plane1, M.planes[j1].data(), c1, M.corners4[j1].data(), sview, tview[j1], pen,
+                                       lengthThreshold, 10, (float) ((double) lengthThreshold / 2)))
+              continue;
+            if (pen) break;
+          }
+          if (pen) break;
+        }
+        if (pen) continue;
+        MatchedHyp r;
+        r.R = R; r.T = T; r.planes = matches[index];
+        results.push_back(r);
+      }
+  }
+  times.penetration = now_s() - t0;
+  if (debug) {
+    std::vector<float> R, T;
+    std::vector<int> np;
+    for (const MatchedHyp &r : results) {
+      R.insert(R.end(), r.R.m, r.R.m + 9);
+      T.insert(T.end(), {r.T.x, r.T.y, r.T.z});
+      np.push_back((int) r.planes.size());
+    }
+    put("mr_R", R); put("mr_T", T); put("mr_nplanes", np);
+  }
+  if (results.empty()) {
+    std::cerr << "registration failed: no matched result found" << std::endl;
+    last_error = "no matched result";
+    return false;
+  }
+
+  // ---- K5: verification, PLADE/plade.cpp:545-575 ------------------------------------------------------------
+  t0 = now_s();
+  const int H = (int) results.size();
+  std::vector<HypParams> hp(H);
+  for (int i = 0; i < H; ++i) {
+    memcpy(hp[i].R, results[i].R.m, sizeof(float) * 9);
+    hp[i].T[0] = results[i].T.x; hp[i].T[1] = results[i].T.y; hp[i].T[2] = results[i].T.z;
+    V3 cc = mul(results[i].R, Cu.center) + results[i].T;
+    hp[i].c[0] = cc.x; hp[i].c[1] = cc.y; hp[i].c[2] = cc.z;
+    hp[i].pad = 0;
+  }
+  // hypothesis shard of this rank (all ranks hold replicas of the clouds)
+  std::vector<int> mine;
+  for (int i = 0; i < H; ++i) if (i % shard_world == shard_rank) mine.push_back(i);
+  std::vector<HypParams> hp_mine(mine.size());
+  for (size_t i = 0; i < mine.size(); ++i) hp_mine[i] = hp[mine[i]];
+  build_target_grid(dev, ds_tgt.p, M.n_ds, downSampleDistance, grid);
+  HypParams *d_h = d_hyp.ensure(std::max<size_t>(1, hp_mine.size()));
+  unsigned int *d_c = d_counts.ensure(std::max<size_t>(1, hp_mine.size()));
+  if (!hp_mine.empty()) PLADE_CUDA(cudaMemcpyAsync(d_h, hp_mine.data(), sizeof(HypParams) * hp_mine.size(), cudaMemcpyHostToDevice, s));
+  verify_hypotheses(dev, ds_src.p, Cu.n_ds, grid, d_h, (int) hp_mine.size(), (float) Cu.radius, downSampleDistance, d_c);
+  std::vector<unsigned int> counts_mine(hp_mine.size());
+  if (!hp_mine.empty()) PLADE_CUDA(cudaMemcpyAsync(counts_mine.data(), d_c, sizeof(unsigned int) * hp_mine.size(), cudaMemcpyDeviceToHost, s));
+  PLADE_CUDA(cudaStreamSynchronize(s));
+  const size_t denom = std::min(Cu.n_ds, M.n_ds);
+  auto score_of = [&](int i, unsigned int cnt) {
+    float overlap = (float) (double(cnt) / denom);                                   // util.h:644
+    return (float) (0.2 * (results[i].planes.size() / double(currentPlanesNum)) + 0.8 * overlap);   // plade.cpp:561-562
+  };
+  int best = -1;
+  if (shard_world == 1) {
+    std::vector<LenIdx> ov(H);
+    for (int i = 0; i < H; ++i) { ov[i].index = i; ov[i].length = score_of(i, counts_mine[i]); }
+    if (debug) {
+      std::vector<float> sc; std::vector<int> cn;
+      for (int i = 0; i < H; ++i) { sc.push_back(ov[i].length); cn.push_back((int) counts_mine[i]); }
+      put("ver_score", sc); put("ver_count", cn);
+      std::vector<float> cc;
+      for (int i = 0; i < H; ++i) cc.insert(cc.end(), hp[i].c, hp[i].c + 3);
+      put("ver_center", cc);
+    }
+    std::sort(ov.begin(), ov.end(), cmp_greater);        // plade.cpp:565 (same struct, comparator, algorithm)
+    best = ov[0].index;
+  } else {
+    // packed key {score bits, ~index}: max picks the highest score, ties -> lowest index
+    unsigned long long key = 0;
+    for (size_t i = 0; i < mine.size(); ++i) {
+      float sc = score_of(mine[i], counts_mine[i]);
+      unsigned int bits;
+      memcpy(&bits, &sc, 4);
+      unsigned long long k = ((unsigned long long) bits << 32) | (0xFFFFFFFFu - (unsigned int) mine[i]);
+      key = std::max(key, k);
+    }
+    if (allreduce) allreduce(&key, allreduce_user);
+    best = (int) (0xFFFFFFFFu - (unsigned int) (key & 0xFFFFFFFFu));
+    if (best < 0 || best >= H) { last_error = "sharded verification failed"; return false; }
+  }
+  times.verify = now_s() - t0;
+
+  const MatchedHyp &W = results[best];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) out16[4 * r + c] = W.R(r, c);
+    out16[4 * r + 3] = W.T[r];
+  }
+  out16[12] = out16[13] = out16[14] = 0.f;
+  out16[15] = 1.f;
+  times.total = now_s() - t_begin;
+  return true;
+}
+
+}  // namespace plade

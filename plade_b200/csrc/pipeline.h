@@ -1,0 +1,109 @@
+// Host orchestrator of the registration hot path (the role of PLADE/plade.cpp:31-580 and
+// PLADE/util.cpp:31-520 in the reference), driving the sm_100a kernels of kernels.h.
+#pragma once
+#include "kernels.h"
+#include "linalg.h"
+#include <array>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace plade {
+
+// One extracted plane: point indices + (n, d) with n.x + d = 0  (PLANE, PLADE/plane_extraction.h:44-50)
+struct PlaneRec {
+  std::vector<int> idx;
+  float n[3];
+  float d;
+};
+
+// Device-resident input cloud: positions and normals as two float4 streams.
+struct CloudDev {
+  DevBuf<float4> pos, nrm;
+  size_t n = 0;
+};
+
+// Tunables: every default is the literal the reference hard-codes.
+struct Params {
+  // RANSAC (PLADE/plade.cpp:591-595,607,627; PLADE/plane_extraction.cpp:93-98)
+  float ransac_dist_thresh = 0.005f, ransac_bitmap_reso = 0.02f, ransac_normal_thresh = 0.8f, ransac_prob = 0.001f;
+  int init_min_support = 10000, min_planes = 10, max_planes = 40, min_allowed_support = 200, max_trials = 10;
+  // matching (PLADE/plade.cpp:46-56)
+  int max_candidates = 200;
+  float face_matches_weight = 0.2f;
+  double descriptor_radius = 0.04;      // PLADE/util.cpp:115
+  unsigned long long seed = 20240611ull;  // GPU RANSAC candidate sampling (the reference seeds from time())
+};
+
+struct StageTimes {
+  double upload = 0, planes = 0, spacing = 0, downsample = 0, lines = 0, descriptors = 0, match = 0, hypotheses = 0,
+         penetration = 0, verify = 0, total = 0;
+};
+
+struct MatchedHyp {     // MatchedResult, PLADE/util.h:128-134
+  M3 R;
+  V3 T;
+  std::vector<std::pair<int, int>> planes;
+};
+
+// Cross-rank reduction hook for the sharded verification (rank r verifies hypotheses h with
+// h % world == r); nullptr => single process.
+typedef void (*AllreduceMaxU64)(unsigned long long *value, void *user);
+
+class Registrar {
+ public:
+  explicit Registrar(int device);
+  ~Registrar();
+
+  void upload(const float *xyzn, size_t n, CloudDev &out);   // interleaved x y z nx ny nz (host)
+
+  // registration(T, target, source) — PLADE/plade.cpp:638 (plane extraction + the body below)
+  bool register_clouds(const CloudDev &tgt, const CloudDev &src, float out16[16]);
+  // registration(T, target, source, min_support_tgt, min_support_src) — PLADE/plade.cpp:583
+  bool register_min_support(const CloudDev &tgt, const CloudDev &src, int ms_t, int ms_s, float out16[16]);
+  // registration(T, target, source, target_planes, source_planes) — PLADE/plade.cpp:31
+  bool register_with_planes(const CloudDev &tgt, const CloudDev &src, const std::vector<PlaneRec> &tp,
+                            const std::vector<PlaneRec> &sp, float out16[16]);
+
+  // stage entry points (host buffers)
+  float average_spacing(const CloudDev &c);
+  std::vector<PlaneRec> extract_planes(const CloudDev &c, int init_min_support);             // extract(), plade.cpp:602
+  std::vector<PlaneRec> detect_planes(const CloudDev &c, int min_support);                   // PlaneExtraction::detect
+
+  Device dev;
+  Params params;
+  StageTimes times;
+  bool debug = false;
+  std::map<std::string, std::vector<char>> blobs;
+  std::string last_error;
+  int shard_rank = 0, shard_world = 1;
+  AllreduceMaxU64 allreduce = nullptr;
+  void *allreduce_user = nullptr;
+
+  // scratch (grow-only, reused across calls)
+  VoxelScratch vox;
+  TargetGrid grid;
+  MatchScratch match_sc;
+  HypScratch hyp_sc;
+  DevBuf<float4> ds_tgt, ds_src, ds_planes;
+  DevBuf<int> group, qidx;
+  DevBuf<float> knn_out;
+  DevBuf<HypParams> d_hyp;
+  DevBuf<unsigned int> d_counts;
+  PinBuf<float> pin_in;
+
+  template <typename T> void put(const std::string &name, const std::vector<T> &v) {
+    if (!debug) return;
+    std::vector<char> &b = blobs[name];
+    b.resize(v.size() * sizeof(T));
+    if (!v.empty()) memcpy(b.data(), v.data(), b.size());
+  }
+};
+
+// Oriented bounding box exactly as ComputeBoundingBox (PLADE/util.h:187-248).
+int compute_bounding_box(const float4 *pts, size_t n, V3 &center, double &width, double &height, double &depth,
+                         V3 corners[8]);
+// ComputeIntersectionLineOfTwoPlanes (PLADE/util.cpp:626-676); planes are (n, d).
+int plane_intersection_line(const float p1[4], const float p2[4], V3 &vec, V3 &pt);
+
+}  // namespace plade

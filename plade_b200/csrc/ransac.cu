@@ -1,0 +1,797 @@
+// K1 — efficient-RANSAC plane extraction on sm_100a.
+//
+// Replaces PlaneExtraction::detect (PLADE/plane_extraction.cpp:61-200) -> RansacShapeDetector::Detect
+// (3rd_party/ransac/RansacShapeDetector.cpp:455-907) for the only primitive PLADE registers (planes).
+// What is kept from the reference, statement for statement:
+//   * thresholds: eps = dist_thresh * scale, bitmapEps = bitmap_reso * scale, scale = max(dx, dy) of the
+//     bounding box (the z extent is lost by the bug at plane_extraction.cpp:71-80, R/PointCloud.h:94-98);
+//   * 3-point plane construction and rejection |(p2-p1)x(p3-p2)|^2 < 1e-6 (R/Plane.cpp:29-38), sample
+//     verification against the normal threshold (RansacShapeDetector.cpp:143-153);
+//   * the per-point compatibility predicate (R/FlatNormalThreshPointCompatibilityFunc.h:15-22 with
+//     Plane::Distance R/Plane.h:31), bit-exact: |dist - n.p| < eps && |n.n_i| >= normalThresh, float,
+//     dot products left to right, no FMA;
+//   * acceptance of a candidate: global score at 3*eps over all unassigned points (R/Candidate.h:284-292),
+//     largest 8-connected component of the inlier bitmap at bitmapEps after a cross closing
+//     (R/BitmapPrimitiveShape.cpp:97-205, R/Bitmap.cpp:154,459,633), then up to three least-squares
+//     refits accepted while the gaussian-weighted score improves (RansacShapeDetector.cpp:619-655,
+//     R/ScoreComputer.h:10-13, R/GfxTL/Plane.h:58-95 with the Jacobi eigen-solver of R/GfxTL/Jacobi.h);
+//   * the stopping rule P(overlooking a min_support plane) <= overlook_prob with
+//     P = (1 - size / (n * levels * 4))^drawn (R/RansacShapeDetector.h:61-67) and the drawn-candidate
+//     rescaling after each accepted shape (RansacShapeDetector.cpp:673-674).
+// What is B200-native instead of translated: the octree, the nested random subsets and the lazy
+// per-candidate bound refinement (R/Candidate.h:155-213) exist to save CPU work one candidate at a time.
+// Here thousands of candidates are drawn per round from windows of a Morton-ordered list of the
+// unassigned points (the analogue of "three points from one octree cell of a random level") and ALL of
+// them are scored at once against a stratified subsample whose tiles are staged through shared memory
+// by 1-D TMA bulk copies; the best one is then verified on the full cloud.  Candidate draws come from a
+// counter-based generator with a fixed seed (the reference seeds rand() from time()), so detection is
+// reproducible; parity with the reference is at plane level (normal, offset, support), not bit level.
+#include "pipeline.h"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+
+namespace plade {
+
+namespace {
+
+constexpr int kCandPerRound = 4096;
+constexpr int kSubsample = 65536;
+constexpr int kScoreTile = 512;       // points per TMA tile (pos + nrm = 16 KB)
+constexpr int kScoreThreads = 256;    // one candidate per thread
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(phase)
+                 : "memory");
+  } while (!ok);
+}
+
+// counter-based RNG (splitmix64 finaliser)
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// The reference predicate.  plane = (nx, ny, nz, dist) with n.x = dist.
+__device__ __forceinline__ bool compatible(const float4 &pl, const float4 &p, const float4 &nr, float eps, float nthresh) {
+  float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p.x), __fmul_rn(pl.y, p.y)), __fmul_rn(pl.z, p.z));
+  float dist = fabsf(__fsub_rn(pl.w, dp));
+  if (!(dist < eps)) return false;
+  float dn = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, nr.x), __fmul_rn(pl.y, nr.y)), __fmul_rn(pl.z, nr.z));
+  return fabsf(dn) >= nthresh;
+}
+
+// ---- Morton order -------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int expand10(unsigned int v) {
+  v &= 0x3ff;
+  v = (v | (v << 16)) & 0x030000FF;
+  v = (v | (v << 8)) & 0x0300F00F;
+  v = (v | (v << 4)) & 0x030C30C3;
+  v = (v | (v << 2)) & 0x09249249;
+  return v;
+}
+__global__ void morton_kernel(const float4 *__restrict__ pos, int n, float3 mn, float inv_ext, unsigned int *__restrict__ keys,
+                              int *__restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pos[i];
+  unsigned int x = (unsigned int) fminf(fmaxf((p.x - mn.x) * inv_ext * 1024.f, 0.f), 1023.f);
+  unsigned int y = (unsigned int) fminf(fmaxf((p.y - mn.y) * inv_ext * 1024.f, 0.f), 1023.f);
+  unsigned int z = (unsigned int) fminf(fmaxf((p.z - mn.z) * inv_ext * 1024.f, 0.f), 1023.f);
+  keys[i] = (expand10(x) << 2) | (expand10(y) << 1) | expand10(z);
+  idx[i] = i;
+}
+
+__global__ void bbox_kernel(const float4 *__restrict__ p, int n, int *__restrict__ out6) {
+  float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 v = p[i];
+    mn[0] = fminf(mn[0], v.x); mn[1] = fminf(mn[1], v.y); mn[2] = fminf(mn[2], v.z);
+    mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z);
+  }
+  typedef cub::BlockReduce<float, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  for (int k = 0; k < 3; ++k) {
+    float a = BR(tmp).Reduce(mn[k], cub::Min());
+    __syncthreads();
+    float b = BR(tmp).Reduce(mx[k], cub::Max());
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int ai = __float_as_int(a), bi = __float_as_int(b);
+      atomicMin(out6 + k, ai >= 0 ? ai : ai ^ 0x7fffffff);
+      atomicMax(out6 + 3 + k, bi >= 0 ? bi : bi ^ 0x7fffffff);
+    }
+  }
+}
+
+// ---- candidate generation --------------------------------------------------------------------------------
+__global__ void gen_candidates_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm,
+                                      const int *__restrict__ order, int m, int nlevels, float nthresh,
+                                      unsigned long long seed, float4 *__restrict__ cand, int *__restrict__ n_valid) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  float4 out = make_float4(0.f, 0.f, 0.f, 3.0e38f);
+  if (c < kCandPerRound && m >= 3) {
+    unsigned long long s = mix64(seed * 0x100000001B3ull + (unsigned long long) c);
+    int r0 = (int) (s % (unsigned long long) m);
+    s = mix64(s);
+    int level = (int) (s % (unsigned long long) nlevels);
+    long long w = 4ll << level;                       // half window in Morton order
+    s = mix64(s);
+    long long span = 2 * w + 1;
+    long long r1 = r0 - w + (long long) (s % (unsigned long long) span);
+    s = mix64(s);
+    long long r2 = r0 - w + (long long) (s % (unsigned long long) span);
+    r1 = min(max(r1, 0ll), (long long) m - 1);
+    r2 = min(max(r2, 0ll), (long long) m - 1);
+    if (r1 != r0 && r2 != r0 && r1 != r2) {
+      int i0 = order[r0], i1 = order[(int) r1], i2 = order[(int) r2];
+      float4 p1 = pos[i0], p2 = pos[i1], p3 = pos[i2];
+      // Plane::Init(p1, p2, p3): normal = (p2 - p1) x (p3 - p2)
+      float ax = __fsub_rn(p2.x, p1.x), ay = __fsub_rn(p2.y, p1.y), az = __fsub_rn(p2.z, p1.z);
+      float bx = __fsub_rn(p3.x, p2.x), by = __fsub_rn(p3.y, p2.y), bz = __fsub_rn(p3.z, p2.z);
+      float nx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+      float ny = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+      float nz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+      float sq = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz));
+      if (sq >= 1e-6f) {
+        float l = sqrtf(sq);
+        nx = __fdiv_rn(nx, l); ny = __fdiv_rn(ny, l); nz = __fdiv_rn(nz, l);
+        float dist = __fadd_rn(__fadd_rn(__fmul_rn(p1.x, nx), __fmul_rn(p1.y, ny)), __fmul_rn(p1.z, nz));
+        float4 pl = make_float4(nx, ny, nz, dist);
+        // sample verification: normals of all three samples must agree with the plane
+        float4 n1 = nrm[i0], n2 = nrm[i1], n3 = nrm[i2];
+        float d1 = fabsf(__fadd_rn(__fadd_rn(__fmul_rn(nx, n1.x), __fmul_rn(ny, n1.y)), __fmul_rn(nz, n1.z)));
+        float d2 = fabsf(__fadd_rn(__fadd_rn(__fmul_rn(nx, n2.x), __fmul_rn(ny, n2.y)), __fmul_rn(nz, n2.z)));
+        float d3 = fabsf(__fadd_rn(__fadd_rn(__fmul_rn(nx, n3.x), __fmul_rn(ny, n3.y)), __fmul_rn(nz, n3.z)));
+        if (d1 >= nthresh && d2 >= nthresh && d3 >= nthresh) { out = pl; ok = true; }
+      }
+    }
+  }
+  if (c < kCandPerRound) cand[c] = out;
+  unsigned int mk = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && mk) atomicAdd(n_valid, __popc(mk));
+}
+
+__global__ void gather_sub_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const int *__restrict__ order,
+                                  int m, int S, unsigned long long seed, float4 *__restrict__ sub /* [2*S]: pos | nrm interleaved per tile */) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= S) return;
+  // stratified: one point from each of S equal strata of the Morton-ordered list
+  long long b = (long long) k * m / S, e = (long long) (k + 1) * m / S;
+  if (e <= b) e = b + 1;
+  unsigned long long s = mix64(seed ^ (0xABCDEFull + (unsigned long long) k));
+  int r = (int) (b + (long long) (s % (unsigned long long) (e - b)));
+  int i = order[min(r, m - 1)];
+  int tile = k / kScoreTile, j = k - tile * kScoreTile;
+  sub[(size_t) tile * 2 * kScoreTile + j] = pos[i];
+  sub[(size_t) tile * 2 * kScoreTile + kScoreTile + j] = nrm[i];
+}
+
+// K1a: every candidate of the round against the subsample.  grid = (tile groups, candidate groups).
+__global__ void __launch_bounds__(kScoreThreads)
+score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__restrict__ cand, int n_cand, float eps,
+                        float nthresh, int tiles_per_block, unsigned int *__restrict__ counts) {
+  __shared__ __align__(128) float4 buf[2][2 * kScoreTile];
+  __shared__ __align__(8) uint64_t bar[2];
+  const int tid = threadIdx.x;
+  const int c = blockIdx.y * kScoreThreads + tid;
+  const float4 pl = (c < n_cand) ? cand[c] : make_float4(0.f, 0.f, 0.f, 3.0e38f);
+  const int n_tiles = (S + kScoreTile - 1) / kScoreTile;
+  const int t0 = blockIdx.x * tiles_per_block, t1 = min(n_tiles, t0 + tiles_per_block);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int t, int b) {
+    int np = min(kScoreTile, S - t * kScoreTile);
+    // a partial last tile still carries pos at [0, np) and nrm at [kScoreTile, kScoreTile + np)
+    uint32_t bytes = (np == kScoreTile) ? 2u * kScoreTile * 16u : (uint32_t) (kScoreTile + np) * 16u;
+    mbar_expect_tx(&bar[b], bytes);
+    tma_load_1d(buf[b], sub + (size_t) t * 2 * kScoreTile, bytes, &bar[b]);
+  };
+  uint32_t phase[2] = {0, 0};
+  if (tid == 0 && t0 < t1) issue(t0, 0);
+  unsigned int cnt = 0;
+  for (int t = t0; t < t1; ++t) {
+    const int b = (t - t0) & 1;
+    if (tid == 0 && t + 1 < t1) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(t + 1, b ^ 1);
+    }
+    mbar_wait(&bar[b], phase[b]);
+    phase[b] ^= 1;
+    const int np = min(kScoreTile, S - t * kScoreTile);
+    const float4 *P = buf[b], *N = buf[b] + kScoreTile;
+#pragma unroll 4
+    for (int j = 0; j < np; ++j) cnt += compatible(pl, P[j], N[j], eps, nthresh) ? 1u : 0u;
+    __syncthreads();   // everyone done with buf[b] before it is refilled two iterations later
+  }
+  if (c < n_cand && cnt) atomicAdd(&counts[c], cnt);
+}
+
+// K1a/K1b stage API: n_planes planes against the whole cloud (assigned[i] == -1 only).
+__global__ void score_planes_full_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm,
+                                         const int *__restrict__ assigned, int n, const float4 *__restrict__ planes,
+                                         int n_planes, float eps, float nthresh, unsigned int *__restrict__ counts,
+                                         unsigned char *__restrict__ mask0) {
+  extern __shared__ float4 spl[];
+  for (int i = threadIdx.x; i < n_planes; i += blockDim.x) spl[i] = planes[i];
+  __syncthreads();
+  for (int p = 0; p < n_planes; ++p) {
+    unsigned int c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      bool in = (assigned == nullptr || assigned[i] == -1) && compatible(spl[p], pos[i], nrm[i], eps, nthresh);
+      if (p == 0 && mask0) mask0[i] = in ? 1 : 0;
+      c += in ? 1u : 0u;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counts[p], c);
+  }
+}
+
+// ---- refinement kernels --------------------------------------------------------------------------------
+struct PlaneFrame {      // plane + in-plane frame (PlanePrimitiveShape: m_plane, m_hcs)
+  float4 pl;             // n, dist
+  float3 pos, u, v;
+};
+
+__device__ __forceinline__ int f2o(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+
+// pass A: inlier flags at eps3 + (u, v) bounding box
+__global__ void flag_uv_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const int *__restrict__ assigned,
+                               int n, PlaneFrame f, float eps3, float nthresh, unsigned char *__restrict__ flag,
+                               int *__restrict__ uvbox /* 4 ordered ints: umin vmin umax vmax */) {
+  float umin = 3.4e38f, vmin = 3.4e38f, umax = -3.4e38f, vmax = -3.4e38f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pos[i];
+    bool in = assigned[i] == -1 && compatible(f.pl, p, nrm[i], eps3, nthresh);
+    flag[i] = in ? 1 : 0;
+    if (in) {
+      // PlanePrimitiveShape::ParametersImpl (R/PlanePrimitiveShape.h:97-109)
+      float px = __fsub_rn(p.x, f.pos.x), py = __fsub_rn(p.y, f.pos.y), pz = __fsub_rn(p.z, f.pos.z);
+      float u = __fadd_rn(__fadd_rn(__fmul_rn(px, f.u.x), __fmul_rn(py, f.u.y)), __fmul_rn(pz, f.u.z));
+      float v = __fadd_rn(__fadd_rn(__fmul_rn(px, f.v.x), __fmul_rn(py, f.v.y)), __fmul_rn(pz, f.v.z));
+      umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+    }
+  }
+  typedef cub::BlockReduce<float, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  float a = BR(tmp).Reduce(umin, cub::Min()); __syncthreads();
+  float b = BR(tmp).Reduce(vmin, cub::Min()); __syncthreads();
+  float c = BR(tmp).Reduce(umax, cub::Max()); __syncthreads();
+  float d = BR(tmp).Reduce(vmax, cub::Max());
+  if (threadIdx.x == 0) {
+    atomicMin(uvbox + 0, f2o(a)); atomicMin(uvbox + 1, f2o(b));
+    atomicMax(uvbox + 2, f2o(c)); atomicMax(uvbox + 3, f2o(d));
+  }
+}
+
+// pass C: rasterise (BuildBitmap / InBitmap, R/BitmapPrimitiveShape.h:101-150, R/PlanePrimitiveShape.cpp:200-207)
+__global__ void raster_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ flag, int n, PlaneFrame f,
+                              float umin, float vmin, float bmp_eps, int uext, int vext, int *__restrict__ pix,
+                              unsigned char *__restrict__ bitmap) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!flag[i]) return;
+  float4 p = pos[i];
+  float px = __fsub_rn(p.x, f.pos.x), py = __fsub_rn(p.y, f.pos.y), pz = __fsub_rn(p.z, f.pos.z);
+  float u = __fadd_rn(__fadd_rn(__fmul_rn(px, f.u.x), __fmul_rn(py, f.u.y)), __fmul_rn(pz, f.u.z));
+  float v = __fadd_rn(__fadd_rn(__fmul_rn(px, f.v.x), __fmul_rn(py, f.v.y)), __fmul_rn(pz, f.v.z));
+  int bu = (int) floorf(__fdiv_rn(__fsub_rn(u, umin), bmp_eps));
+  int bv = (int) floorf(__fdiv_rn(__fsub_rn(v, vmin), bmp_eps));
+  bu = min(max(bu, 0), uext - 1);
+  bv = min(max(bv, 0), vext - 1);
+  int id = bu + bv * uext;
+  pix[i] = id;
+  bitmap[id] = 1;
+}
+
+// pass E: members of the largest component; count, sum of positions, gaussian-weighted score
+__global__ void select_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ flag, const int *__restrict__ pix,
+                              const unsigned char *__restrict__ comp_mask, int n, float4 pl, float eps3,
+                              unsigned char *__restrict__ member, double *__restrict__ acc /* cnt, sx, sy, sz, score */) {
+  double cnt = 0, sx = 0, sy = 0, sz = 0, sc = 0;
+  const float denom = 2.f / 9.f * eps3 * eps3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    bool mem = flag[i] && comp_mask[pix[i]];
+    member[i] = mem ? 1 : 0;
+    if (mem) {
+      float4 p = pos[i];
+      float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p.x), __fmul_rn(pl.y, p.y)), __fmul_rn(pl.z, p.z));
+      float d = fabsf(__fsub_rn(pl.w, dp));
+      cnt += 1; sx += p.x; sy += p.y; sz += p.z;
+      sc += (double) expf(-d * d / denom);
+    }
+  }
+  typedef cub::BlockReduce<double, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  double r0 = BR(tmp).Sum(cnt); __syncthreads();
+  double r1 = BR(tmp).Sum(sx); __syncthreads();
+  double r2 = BR(tmp).Sum(sy); __syncthreads();
+  double r3 = BR(tmp).Sum(sz); __syncthreads();
+  double r4 = BR(tmp).Sum(sc);
+  if (threadIdx.x == 0 && r0 > 0) {
+    atomicAdd(acc + 0, r0); atomicAdd(acc + 1, r1); atomicAdd(acc + 2, r2); atomicAdd(acc + 3, r3); atomicAdd(acc + 4, r4);
+  }
+}
+
+// pass G: covariance about `mean` over the members (K1d)
+__global__ void cov_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ member, int n, float3 mean,
+                           double *__restrict__ acc6) {
+  double c[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (!member[i]) continue;
+    float4 p = pos[i];
+    double dx = (double) (p.x - mean.x), dy = (double) (p.y - mean.y), dz = (double) (p.z - mean.z);
+    c[0] += dx * dx; c[1] += dx * dy; c[2] += dx * dz; c[3] += dy * dy; c[4] += dy * dz; c[5] += dz * dz;
+  }
+  typedef cub::BlockReduce<double, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  for (int k = 0; k < 6; ++k) {
+    double r = BR(tmp).Sum(c[k]);
+    __syncthreads();
+    if (threadIdx.x == 0 && r != 0) atomicAdd(acc6 + k, r);
+  }
+}
+
+__global__ void mark_kernel(const unsigned char *__restrict__ member, int n, int shape_id, int *__restrict__ assigned) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && member[i]) assigned[i] = shape_id;
+}
+
+struct IsUnassigned {
+  const int *assigned;
+  __device__ bool operator()(const int &i) const { return assigned[i] == -1; }
+};
+
+// ---- host pieces ----------------------------------------------------------------------------------------
+// HyperplaneCoordinateSystem::FromNormal (R/GfxTL/HyperplaneCoordinateSystem.h:81-93), AutoCAD arbitrary axis
+void frame_from_normal(const float n[3], float u[3], float v[3]) {
+  V3 N(n[0], n[1], n[2]), a0;
+  if (std::fabs(n[0]) < 0.015625f && std::fabs(n[1]) < 0.015625f) a0 = cross(V3(0, 1, 0), N);
+  else a0 = cross(V3(0, 0, 1), N);
+  normalize(a0);
+  V3 a1 = cross(N, a0);
+  normalize(a1);
+  u[0] = a0.x; u[1] = a0.y; u[2] = a0.z;
+  v[0] = a1.x; v[1] = a1.y; v[2] = a1.z;
+}
+
+// cross closing (DilateCross then ErodeCross, no wrapping) + 8-connected labelling; returns the
+// per-pixel mask of the component with the most pixels (first one on ties), R/Bitmap.cpp:154,459,633.
+void largest_component(std::vector<unsigned char> &bmp, int ue, int ve, std::vector<unsigned char> &mask) {
+  std::vector<unsigned char> dil((size_t) ue * ve), ero((size_t) ue * ve);
+  auto at = [&](const std::vector<unsigned char> &b, int x, int y, unsigned char oob) -> unsigned char {
+    if (x < 0 || y < 0 || x >= ue || y >= ve) return oob;
+    return b[(size_t) y * ue + x];
+  };
+  for (int y = 0; y < ve; ++y)
+    for (int x = 0; x < ue; ++x)
+      dil[(size_t) y * ue + x] = at(bmp, x, y, 0) | at(bmp, x - 1, y, 0) | at(bmp, x + 1, y, 0) | at(bmp, x, y - 1, 0) | at(bmp, x, y + 1, 0);
+  for (int y = 0; y < ve; ++y)
+    for (int x = 0; x < ue; ++x)
+      ero[(size_t) y * ue + x] = at(dil, x, y, 1) & at(dil, x - 1, y, 1) & at(dil, x + 1, y, 1) & at(dil, x, y - 1, 1) & at(dil, x, y + 1, 1);
+  bmp = ero;
+  // 8-connected components by flood fill in raster order (component ids in order of first pixel)
+  std::vector<int> lab((size_t) ue * ve, 0);
+  std::vector<size_t> sizes(1, 0);
+  std::vector<int> stack;
+  int cur = 0;
+  for (int y0 = 0; y0 < ve; ++y0)
+    for (int x0 = 0; x0 < ue; ++x0) {
+      size_t id0 = (size_t) y0 * ue + x0;
+      if (!bmp[id0] || lab[id0]) continue;
+      ++cur;
+      sizes.push_back(0);
+      stack.push_back((int) id0);
+      lab[id0] = cur;
+      while (!stack.empty()) {
+        int id = stack.back();
+        stack.pop_back();
+        sizes[cur]++;
+        int x = id % ue, y = id / ue;
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            int xx = x + dx, yy = y + dy;
+            if (xx < 0 || yy < 0 || xx >= ue || yy >= ve) continue;
+            size_t j = (size_t) yy * ue + xx;
+            if (bmp[j] && !lab[j]) { lab[j] = cur; stack.push_back((int) j); }
+          }
+      }
+    }
+  mask.assign((size_t) ue * ve, 0);
+  if (cur == 0) return;
+  int best = 1;
+  for (int c = 2; c <= cur; ++c) if (sizes[best] < sizes[c]) best = c;
+  for (size_t i = 0; i < lab.size(); ++i) mask[i] = lab[i] == best;
+}
+
+// Jacobi eigen-solver for symmetric 3x3 (float), the textbook cyclic algorithm started from V = I that
+// R/GfxTL/Jacobi.h implements; the eigenvector of smallest |eigenvalue| is the plane normal and its
+// sign is whatever the rotation sequence produces (it is never flipped afterwards).
+bool jacobi3f(float a[3][3], float d[3], float v[3][3]) {
+  float b[3], z[3];
+  for (int ip = 0; ip < 3; ++ip) { for (int iq = 0; iq < 3; ++iq) v[ip][iq] = 0.f; v[ip][ip] = 1.f; }
+  for (int ip = 0; ip < 3; ++ip) { b[ip] = d[ip] = a[ip][ip]; z[ip] = 0.f; }
+  for (int i = 1; i <= 200; ++i) {
+    float sm = 0.f;
+    for (int ip = 0; ip < 2; ++ip) for (int iq = ip + 1; iq < 3; ++iq) sm += std::fabs(a[ip][iq]);
+    if (sm == 0.f) return true;
+    float tresh = i < 4 ? 0.2f * sm / 9.f : 0.f;
+    for (int ip = 0; ip < 2; ++ip)
+      for (int iq = ip + 1; iq < 3; ++iq) {
+        float g = 100.f * std::fabs(a[ip][iq]);
+        volatile float t1 = std::fabs(d[ip]) + g, t2 = std::fabs(d[iq]) + g;
+        if (i > 4 && t1 == std::fabs(d[ip]) && t2 == std::fabs(d[iq])) a[ip][iq] = 0.f;
+        else if (std::fabs(a[ip][iq]) > tresh) {
+          float h = d[iq] - d[ip], t;
+          volatile float t3 = std::fabs(h) + g;
+          if (t3 == std::fabs(h)) t = a[ip][iq] / h;
+          else {
+            float theta = 0.5f * h / a[ip][iq];
+            t = 1.f / (std::fabs(theta) + std::sqrt(1.f + theta * theta));
+            if (theta < 0.f) t = -t;
+          }
+          float c = 1.f / std::sqrt(1.f + t * t), s = t * c, tau = s / (1.f + c);
+          h = t * a[ip][iq];
+          z[ip] -= h; z[iq] += h; d[ip] -= h; d[iq] += h;
+          a[ip][iq] = 0.f;
+          auto rot = [&](float m[3][3], int i1, int j1, int i2, int j2) {
+            float gg = m[i1][j1], hh = m[i2][j2];
+            m[i1][j1] = gg - s * (hh + gg * tau);
+            m[i2][j2] = hh + s * (gg - hh * tau);
+          };
+          for (int j = 0; j <= ip - 1; ++j) rot(a, j, ip, j, iq);
+          for (int j = ip + 1; j <= iq - 1; ++j) rot(a, ip, j, j, iq);
+          for (int j = iq + 1; j < 3; ++j) rot(a, ip, j, iq, j);
+          for (int j = 0; j < 3; ++j) rot(v, j, ip, j, iq);
+        }
+      }
+    for (int ip = 0; ip < 3; ++ip) { b[ip] += z[ip]; d[ip] = b[ip]; z[ip] = 0.f; }
+  }
+  return false;
+}
+
+double failure_probability(double size, double n, double drawn, double levels) {
+  // CandidateFailureProbability, R/RansacShapeDetector.h:61-67 (reqSamples = 3)
+  return std::min(std::pow(1.0 - size / (n * levels * 4.0), drawn), 1.0);
+}
+
+struct RansacScratch {
+  DevBuf<unsigned int> keys, keys_alt, counts;
+  DevBuf<int> order, order_alt, assigned, pix, misc;
+  DevBuf<float4> cand, sub;
+  DevBuf<unsigned char> flag, member, member2, bitmap, mask, cub_tmp;
+  DevBuf<double> acc;
+};
+
+struct FoundPlane { float n[3]; float pos[3]; long long size; };
+
+}  // namespace
+
+static thread_local RansacScratch g_rs;
+
+std::vector<PlaneRec> Registrar::detect_planes(const CloudDev &c, int min_support) {
+  std::vector<PlaneRec> result;
+  const int n = (int) c.n;
+  if (n < 3) { std::cerr << "point set has less than 3 points" << std::endl; return result; }
+  cudaStream_t s = dev.stream;
+  RansacScratch &rs = g_rs;
+  const int blocks_n = std::min(div_up(n, 256), dev.num_sms * 8);
+
+  // bounding box -> scale (bug-compatible: z ignored)
+  int *d_misc = rs.misc.ensure(64);
+  {
+    int init[6];
+    float big = 3.4e38f, nbig = -3.4e38f;
+    int bi, nbi;
+    memcpy(&bi, &big, 4); memcpy(&nbi, &nbig, 4);
+    nbi ^= 0x7fffffff;
+    init[0] = init[1] = init[2] = bi; init[3] = init[4] = init[5] = nbi;
+    PLADE_CUDA(cudaMemcpyAsync(d_misc, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  }
+  bbox_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, n, d_misc);
+  PLADE_LAUNCH_CHECK();
+  int h6[6];
+  PLADE_CUDA(cudaMemcpyAsync(h6, d_misc, sizeof(h6), cudaMemcpyDeviceToHost, s));
+  PLADE_CUDA(cudaStreamSynchronize(s));
+  float mn[3], mx[3];
+  for (int k = 0; k < 3; ++k) {
+    int a = h6[k], b = h6[3 + k];
+    a = a >= 0 ? a : a ^ 0x7fffffff; b = b >= 0 ? b : b ^ 0x7fffffff;
+    memcpy(&mn[k], &a, 4); memcpy(&mx[k], &b, 4);
+  }
+  const float scale = std::max(mx[0] - mn[0], mx[1] - mn[1]);
+  const float eps = params.ransac_dist_thresh * scale;
+  const float bmp_eps = params.ransac_bitmap_reso * scale;
+  const float nthresh = params.ransac_normal_thresh;
+  const float eps3 = 3 * eps;
+  const double prob = params.ransac_prob;
+
+  // Morton order of all points
+  unsigned int *keys = rs.keys.ensure(n), *keys2 = rs.keys_alt.ensure(n);
+  int *order = rs.order.ensure(n), *order2 = rs.order_alt.ensure(n);
+  float ext = std::max(std::max(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
+  morton_kernel<<<div_up(n, 256), 256, 0, s>>>(c.pos.p, n, make_float3(mn[0], mn[1], mn[2]), ext > 0 ? 1.f / ext : 0.f, keys, order);
+  PLADE_LAUNCH_CHECK();
+  size_t tb = 0, tb2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, order, order2, n, 0, 30, s);
+  IsUnassigned pred{nullptr};
+  cub::DeviceSelect::If(nullptr, tb2, order, order2, d_misc, n, pred, s);
+  unsigned char *tmp = rs.cub_tmp.ensure(std::max(tb, tb2));
+  cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, order, order2, n, 0, 30, s);
+  dev.launches.add(8);
+  int *cur_order = order2, *alt_order = order;
+
+  int *assigned = rs.assigned.ensure(n);
+  PLADE_CUDA(cudaMemsetAsync(assigned, 0xff, sizeof(int) * n, s));
+  unsigned char *flag = rs.flag.ensure(n), *member_a = rs.member.ensure(n), *member_b = rs.member2.ensure(n);
+  int *pix = rs.pix.ensure(n);
+  float4 *cand = rs.cand.ensure(kCandPerRound);
+  unsigned int *counts = rs.counts.ensure(kCandPerRound);
+  double *acc = rs.acc.ensure(16);
+  int *d_nvalid = d_misc + 8, *d_uvbox = d_misc + 16, *d_nsel = d_misc + 24;
+
+  std::vector<FoundPlane> found;
+  int m = n;                       // unassigned points
+  double drawn = 0;
+  unsigned long long round_seed = params.seed;
+  std::vector<unsigned int> h_counts(kCandPerRound);
+  std::vector<float4> h_cand(kCandPerRound);
+  float4 best_pl = make_float4(0, 0, 0, 0);
+  double best_est = 0;
+  const int max_rounds = 4000;
+  int rejects = 0;
+  for (int round = 0; round < max_rounds && m >= min_support && m >= 3; ++round) {
+    int nlevels = 1;
+    while ((8ll << nlevels) < m) ++nlevels;
+    // --- candidates + subsample + scores
+    const int S = std::min(m, kSubsample);
+    float4 *sub = rs.sub.ensure((size_t) div_up(S, kScoreTile) * 2 * kScoreTile);
+    PLADE_CUDA(cudaMemsetAsync(d_nvalid, 0, sizeof(int), s));
+    PLADE_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * kCandPerRound, s));
+    round_seed = mix64(round_seed + 1);
+    gen_candidates_kernel<<<div_up(kCandPerRound, 128), 128, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, nlevels, nthresh, round_seed, cand, d_nvalid);
+    gather_sub_kernel<<<div_up(S, 256), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S, round_seed, sub);
+    const int n_tiles = div_up(S, kScoreTile);
+    const int tiles_per_block = std::max(1, n_tiles / 32);
+    dim3 grid(div_up(n_tiles, tiles_per_block), kCandPerRound / kScoreThreads);
+    score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub, S, cand, kCandPerRound, eps, nthresh, tiles_per_block, counts);
+    PLADE_LAUNCH_CHECK();
+    dev.launches.add(3);
+    int n_valid = 0;
+    PLADE_CUDA(cudaMemcpyAsync(h_counts.data(), counts, sizeof(unsigned int) * kCandPerRound, cudaMemcpyDeviceToHost, s));
+    PLADE_CUDA(cudaMemcpyAsync(h_cand.data(), cand, sizeof(float4) * kCandPerRound, cudaMemcpyDeviceToHost, s));
+    PLADE_CUDA(cudaMemcpyAsync(&n_valid, d_nvalid, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PLADE_CUDA(cudaStreamSynchronize(s));
+    drawn += n_valid;
+    for (int k = 0; k < kCandPerRound; ++k) {
+      double est = (double) h_counts[k] * m / S;
+      if (est > best_est) { best_est = est; best_pl = h_cand[k]; }
+    }
+    const bool enough_for_min = failure_probability(min_support, m, drawn, nlevels) <= prob;
+    const bool best_ok = best_est >= min_support && failure_probability(best_est, m, drawn, nlevels) <= prob;
+    if (!best_ok) {
+      if (enough_for_min && best_est < min_support) break;     // nothing of min_support size left (w.h.p.)
+      continue;
+    }
+    // --- refine the best candidate on the full cloud -------------------------------------------------------
+    PlaneFrame fr;
+    auto make_frame = [&](const float nrm3[3], const float pos3[3]) {
+      PlaneFrame f;
+      float u[3], v[3];
+      frame_from_normal(nrm3, u, v);
+      float dist = (pos3[0] * nrm3[0] + pos3[1] * nrm3[1]) + pos3[2] * nrm3[2];   // m_pos.dot(m_normal)
+      f.pl = make_float4(nrm3[0], nrm3[1], nrm3[2], dist);
+      f.pos = make_float3(pos3[0], pos3[1], pos3[2]);
+      f.u = make_float3(u[0], u[1], u[2]);
+      f.v = make_float3(v[0], v[1], v[2]);
+      return f;
+    };
+    struct Eval { long long size; double score; double sum[3]; bool ok; };
+    auto evaluate = [&](const PlaneFrame &f, unsigned char *member) -> Eval {
+      Eval e{0, 0, {0, 0, 0}, false};
+      int init[4];
+      { float big = 3.4e38f, nb = -3.4e38f; int a, b; memcpy(&a, &big, 4); memcpy(&b, &nb, 4); b ^= 0x7fffffff; init[0] = init[1] = a; init[2] = init[3] = b; }
+      PLADE_CUDA(cudaMemcpyAsync(d_uvbox, init, sizeof(init), cudaMemcpyHostToDevice, s));
+      flag_uv_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, f, eps3, nthresh, flag, d_uvbox);
+      PLADE_LAUNCH_CHECK();
+      dev.launches.add();
+      int hb[4];
+      PLADE_CUDA(cudaMemcpyAsync(hb, d_uvbox, sizeof(hb), cudaMemcpyDeviceToHost, s));
+      PLADE_CUDA(cudaStreamSynchronize(s));
+      float uv[4];
+      for (int k = 0; k < 4; ++k) { int a = hb[k]; a = a >= 0 ? a : a ^ 0x7fffffff; memcpy(&uv[k], &a, 4); }
+      if (uv[0] > uv[2]) return e;     // no inliers
+      // BitmapExtent (R/PlanePrimitiveShape.cpp:192-198)
+      size_t ue = (size_t) std::ceil((uv[2] - uv[0]) / bmp_eps) + 1, ve = (size_t) std::ceil((uv[3] - uv[1]) / bmp_eps) + 1;
+      if (ue < 2) ue = 2;
+      if (ve < 2) ve = 2;
+      if (ue * ve > (size_t) 1 << 26) return e;
+      unsigned char *bitmap = rs.bitmap.ensure(ue * ve), *mask = rs.mask.ensure(ue * ve);
+      PLADE_CUDA(cudaMemsetAsync(bitmap, 0, ue * ve, s));
+      raster_kernel<<<div_up(n, 256), 256, 0, s>>>(c.pos.p, flag, n, f, uv[0], uv[1], bmp_eps, (int) ue, (int) ve, pix, bitmap);
+      PLADE_LAUNCH_CHECK();
+      std::vector<unsigned char> hbmp(ue * ve), hmask;
+      PLADE_CUDA(cudaMemcpyAsync(hbmp.data(), bitmap, ue * ve, cudaMemcpyDeviceToHost, s));
+      PLADE_CUDA(cudaStreamSynchronize(s));
+      largest_component(hbmp, (int) ue, (int) ve, hmask);
+      PLADE_CUDA(cudaMemcpyAsync(mask, hmask.data(), ue * ve, cudaMemcpyHostToDevice, s));
+      PLADE_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 16, s));
+      select_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, flag, pix, mask, n, f.pl, eps3, member, acc);
+      PLADE_LAUNCH_CHECK();
+      dev.launches.add(2);
+      double h[5];
+      PLADE_CUDA(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, s));
+      PLADE_CUDA(cudaStreamSynchronize(s));
+      e.size = (long long) h[0]; e.sum[0] = h[1]; e.sum[1] = h[2]; e.sum[2] = h[3]; e.score = h[4]; e.ok = e.size > 0;
+      return e;
+    };
+    auto ls_fit = [&](const Eval &e, const unsigned char *member, float nrm3[3], float pos3[3]) -> bool {
+      // Plane::LeastSquaresFit (R/Plane.h:66-74): mean, covariance, eigenvector of smallest |lambda|
+      float3 mean = make_float3((float) (e.sum[0] / e.size), (float) (e.sum[1] / e.size), (float) (e.sum[2] / e.size));
+      PLADE_CUDA(cudaMemsetAsync(acc + 8, 0, sizeof(double) * 6, s));
+      cov_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, member, n, mean, acc + 8);
+      PLADE_LAUNCH_CHECK();
+      dev.launches.add();
+      double h[6];
+      PLADE_CUDA(cudaMemcpyAsync(h, acc + 8, sizeof(h), cudaMemcpyDeviceToHost, s));
+      PLADE_CUDA(cudaStreamSynchronize(s));
+      float a[3][3], d[3], v[3][3];
+      a[0][0] = (float) (h[0] / e.size); a[0][1] = a[1][0] = (float) (h[1] / e.size); a[0][2] = a[2][0] = (float) (h[2] / e.size);
+      a[1][1] = (float) (h[3] / e.size); a[1][2] = a[2][1] = (float) (h[4] / e.size); a[2][2] = (float) (h[5] / e.size);
+      if (!jacobi3f(a, d, v)) return false;
+      int k = 0;
+      for (int j = 1; j < 3; ++j) if (std::fabs(d[j]) < std::fabs(d[k])) k = j;
+      nrm3[0] = v[0][k]; nrm3[1] = v[1][k]; nrm3[2] = v[2][k];
+      pos3[0] = mean.x; pos3[1] = mean.y; pos3[2] = mean.z;
+      return true;
+    };
+
+    float cn[3] = {best_pl.x, best_pl.y, best_pl.z};
+    // position of the 3-point plane: any point on it (the reference keeps the first sample); n * dist lies on the plane
+    float cp[3] = {best_pl.x * best_pl.w, best_pl.y * best_pl.w, best_pl.z * best_pl.w};
+    fr = make_frame(cn, cp);
+    fr.pl.w = best_pl.w;
+    unsigned char *acc_member = member_a, *work_member = member_b;
+    Eval cur = evaluate(fr, acc_member);   // GlobalScore + ConnectedComponent (+ weighted score of the clone)
+    float acc_n[3] = {cn[0], cn[1], cn[2]}, acc_p[3] = {cp[0], cp[1], cp[2]};
+    long long acc_size = cur.ok ? cur.size : 0;
+    if (cur.ok) {
+      Eval clone = cur;
+      const unsigned char *clone_member = acc_member;
+      double newScore = clone.score, oldScore;
+      int iter = 0;
+      do {
+        ++iter;
+        oldScore = newScore;
+        float fn[3], fp[3];
+        if (!ls_fit(clone, clone_member, fn, fp)) break;
+        PlaneFrame f2 = make_frame(fn, fp);
+        Eval e2 = evaluate(f2, work_member);
+        newScore = e2.score;
+        if (!e2.ok) break;
+        clone = e2;
+        clone_member = work_member;
+        if (newScore > oldScore && e2.size > min_support) {
+          memcpy(acc_n, fn, sizeof(fn)); memcpy(acc_p, fp, sizeof(fp));
+          acc_size = e2.size;
+          std::swap(acc_member, work_member);      // the clone becomes the candidate
+          clone_member = acc_member;
+        }
+      } while (newScore > oldScore && iter < 3);
+    }
+    best_est = 0;    // the pool is invalid once points are removed (or the candidate failed)
+    // the reference only accepts a candidate whose fully evaluated (connected-component) support
+    // reaches min_support (FindBestCandidate, RansacShapeDetector.cpp:297,423-430)
+    if (acc_size < min_support) {
+      if (++rejects >= 32 && enough_for_min) break;
+      continue;
+    }
+    rejects = 0;
+    unsigned char *member = acc_member;
+    // --- accept: remove the points (RansacShapeDetector.cpp:659-675) ---------------------------------------------
+    mark_kernel<<<div_up(n, 256), 256, 0, s>>>(member, n, (int) found.size(), assigned);
+    PLADE_LAUNCH_CHECK();
+    FoundPlane fp;
+    memcpy(fp.n, acc_n, sizeof(acc_n)); memcpy(fp.pos, acc_p, sizeof(acc_p));
+    fp.size = acc_size;
+    found.push_back(fp);
+    drawn = std::pow(1.f - (acc_size / float(m)), 3.f) * drawn;
+    // compact the Morton list to the still-unassigned points
+    IsUnassigned pr{assigned};
+    size_t tb3 = 0;
+    cub::DeviceSelect::If(nullptr, tb3, cur_order, alt_order, d_nsel, m, pr, s);
+    tmp = rs.cub_tmp.ensure(tb3);
+    cub::DeviceSelect::If(tmp, tb3, cur_order, alt_order, d_nsel, m, pr, s);
+    dev.launches.add(3);
+    int new_m = 0;
+    PLADE_CUDA(cudaMemcpyAsync(&new_m, d_nsel, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PLADE_CUDA(cudaStreamSynchronize(s));
+    std::swap(cur_order, alt_order);
+    m = new_m;
+  }
+
+  // ---- output (PLADE/plane_extraction.cpp:115-160): drop shapes below min_support, unit normal, d = -n.p --------
+  std::vector<int> h_assigned(n);
+  PLADE_CUDA(cudaMemcpyAsync(h_assigned.data(), assigned, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  PLADE_CUDA(cudaStreamSynchronize(s));
+  std::vector<std::vector<int>> lists(found.size());
+  for (size_t k = 0; k < found.size(); ++k) lists[k].reserve((size_t) found[k].size);
+  for (int i = 0; i < n; ++i) if (h_assigned[i] >= 0) lists[h_assigned[i]].push_back(i);
+  for (size_t k = 0; k < found.size(); ++k) {
+    if ((long long) lists[k].size() < (long long) min_support) continue;
+    PlaneRec pr;
+    pr.idx.swap(lists[k]);
+    V3 nn(found[k].n[0], found[k].n[1], found[k].n[2]);
+    float l = std::sqrt(nn.x * nn.x + nn.y * nn.y + nn.z * nn.z);     // Vec3f::normalize
+    if (l > 0) { nn.x /= l; nn.y /= l; nn.z /= l; }
+    pr.n[0] = nn.x; pr.n[1] = nn.y; pr.n[2] = nn.z;
+    pr.d = -(nn.x * found[k].pos[0] + nn.y * found[k].pos[1] + nn.z * found[k].pos[2]);
+    result.push_back(std::move(pr));
+  }
+  return result;
+}
+
+// extract(), PLADE/plade.cpp:602-635
+std::vector<PlaneRec> Registrar::extract_planes(const CloudDev &c, int init_min_support) {
+  const int min_num = params.min_planes, max_num = params.max_planes, min_allowed_support = params.min_allowed_support;
+  std::vector<PlaneRec> planes = detect_planes(c, init_min_support);
+  if ((int) planes.size() >= min_num && (int) planes.size() <= max_num) return planes;
+  if ((int) planes.size() > max_num) {
+    // the reference sorts with a (non-strict) `>=` comparator; a stable descending sort is the defined equivalent
+    std::stable_sort(planes.begin(), planes.end(), [](const PlaneRec &a, const PlaneRec &b) { return a.idx.size() > b.idx.size(); });
+    size_t total = planes.size();
+    planes.resize(max_num);
+    std::cout << planes.size() << " of the " << total << " extracted planes will be used for registration" << std::endl;
+    return planes;
+  }
+  const int max_trials = params.max_trials;
+  int min_support = init_min_support / 2;
+  int trials = 1;
+  while ((int) planes.size() < min_num && trials < max_trials && min_support >= min_allowed_support) {
+    planes = detect_planes(c, min_support);
+    min_support /= 2;
+    ++trials;
+  }
+  if (trials > 1)
+    std::cout << "min_support = " << min_support << " used for extracting the " << planes.size() << " planes from point cloud" << std::endl;
+  return planes;
+}
+
+// stage API: plane consensus counts over the whole cloud (K1a/K1b predicate)
+void score_planes_full(Device &dev, const float4 *pos, const float4 *nrm, const int *assigned, size_t n, const float4 *d_planes,
+                       int n_planes, float eps, float nthresh, unsigned int *d_counts, unsigned char *d_mask0) {
+  PLADE_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned int) * n_planes, dev.stream));
+  if (n == 0 || n_planes == 0) return;
+  int blocks = std::min(div_up((long long) n, 256), dev.num_sms * 8);
+  score_planes_full_kernel<<<blocks, 256, sizeof(float4) * n_planes, dev.stream>>>(pos, nrm, assigned, (int) n, d_planes, n_planes, eps,
+                                                                                 nthresh, d_counts, d_mask0);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add();
+}
+
+}  // namespace plade

@@ -1,0 +1,302 @@
+// K5 — hypothesis verification on sm_100a.
+//
+// Replaces the reference loop PLADE/plade.cpp:547-564: per hypothesis, transform the down-sampled
+// source cloud (pcl::transformPointCloud, common/impl/transforms.hpp:64-72), restrict the target to
+// the ball around the transformed source centre and count source points that have a target point
+// within the inlier distance (ComputeOverlap, PLADE/util.h:612-647; FLANN L2_Simple, dist.h:84-90;
+// strict '<' against float(r*r), kdtree_flann.hpp:193 / result_set.h:479,582).
+//
+// Design: the reference builds two kd-trees per hypothesis; here the target ds cloud is binned ONCE
+// into a uniform grid (cell edge just above the inlier distance) and one persistent kernel walks
+// (source tile x hypothesis chunk) work items.  A tile of source points is staged into shared
+// memory with one 1-D TMA bulk copy (cp.async.bulk + mbarrier) and reused for every hypothesis of
+// the chunk, so the source cloud streams from HBM/L2 once per chunk instead of once per hypothesis.
+// All float arithmetic uses explicit round-to-nearest mul/add (the library is also built with
+// -fmad=false) so the inlier decision is bit-identical to the scalar reference.
+#include "kernels.h"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+
+namespace plade {
+
+namespace {
+
+constexpr int kTile = 2048;          // source points per shared-memory tile (32 KB)
+constexpr int kThreads = 256;
+constexpr int kHypChunk = 32;        // hypotheses per work item
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!ok);
+}
+
+struct GridView {
+  const float4 *pts;
+  const int *cell_start;
+  float minx, miny, minz, inv_cell;
+  int nx, ny, nz;
+};
+
+// FLANN L2_Simple: result = 0; result += d*d for x, y, z in order (no FMA contraction).
+__device__ __forceinline__ float dist2_l2simple(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  float r = __fmul_rn(dx, dx);
+  r = __fadd_rn(r, __fmul_rn(dy, dy));
+  r = __fadd_rn(r, __fmul_rn(dz, dz));
+  return r;
+}
+
+__device__ __forceinline__ bool point_has_inlier(const GridView &g, const HypParams &hp, float rball2, float rin2,
+                                                 float sx, float sy, float sz) {
+  // pcl::transformPointCloud: x' = ((m00*x + m01*y) + m02*z) + m03, plain float, left to right.
+  float x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.R[0], sx), __fmul_rn(hp.R[1], sy)), __fmul_rn(hp.R[2], sz)), hp.T[0]);
+  float y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.R[3], sx), __fmul_rn(hp.R[4], sy)), __fmul_rn(hp.R[5], sz)), hp.T[1]);
+  float z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.R[6], sx), __fmul_rn(hp.R[7], sy)), __fmul_rn(hp.R[8], sz)), hp.T[2]);
+  float fx = (x - g.minx) * g.inv_cell, fy = (y - g.miny) * g.inv_cell, fz = (z - g.minz) * g.inv_cell;
+  // outside the grid by more than one cell (or NaN) => no target point can be within the inlier radius
+  if (!(fx >= -1.0f && fy >= -1.0f && fz >= -1.0f && fx < (float) (g.nx + 1) && fy < (float) (g.ny + 1) &&
+        fz < (float) (g.nz + 1)))
+    return false;
+  int cx = (int) floorf(fx), cy = (int) floorf(fy), cz = (int) floorf(fz);
+  int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+  int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
+  int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
+  if (x0 > x1) return false;
+  for (int zz = z0; zz <= z1; ++zz) {
+    for (int yy = y0; yy <= y1; ++yy) {
+      int row = (zz * g.ny + yy) * g.nx;
+      int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
+      for (int i = b; i < e; ++i) {
+        float4 t = __ldg(g.pts + i);
+        if (dist2_l2simple(x, y, z, t.x, t.y, t.z) < rin2) {
+          // coarse-overlap ball: target point must be inside ball(c, ball_radius)
+          if (dist2_l2simple(hp.c[0], hp.c[1], hp.c[2], t.x, t.y, t.z) < rball2) return true;
+        }
+      }
+    }
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(kThreads)
+verify_kernel(const float4 *__restrict__ src, int ns, GridView g, const HypParams *__restrict__ hyps, int H,
+              float rball2, float rin2, unsigned int *__restrict__ counts, int n_tiles, int n_chunks) {
+  __shared__ __align__(128) float4 tile[kTile];
+  __shared__ __align__(16) HypParams hp_s[kHypChunk];
+  __shared__ unsigned int cnt_s[kHypChunk];
+  __shared__ __align__(8) uint64_t bar;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  const int n_work = n_tiles * n_chunks;
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int chunk = w / n_tiles, t = w - chunk * n_tiles;
+    const int p0 = t * kTile;
+    const int np = min(kTile, ns - p0);
+    const int h0 = chunk * kHypChunk;
+    const int nh = min(kHypChunk, H - h0);
+    if (tid == 0) {
+      // order prior generic-proxy reads of `tile` before the async-proxy overwrite
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bar, (uint32_t) np * 16u);
+      tma_load_1d(tile, src + p0, (uint32_t) np * 16u, &bar);
+    }
+    for (int i = tid; i < nh * 16; i += kThreads)
+      reinterpret_cast<float *>(hp_s)[i] = __ldg(reinterpret_cast<const float *>(hyps + h0) + i);
+    if (tid < kHypChunk) cnt_s[tid] = 0;
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    __syncthreads();
+    for (int h = 0; h < nh; ++h) {
+      const HypParams hp = hp_s[h];
+      int c = 0;
+      for (int i = tid; i < np; i += kThreads) {
+        float4 s = tile[i];
+        c += point_has_inlier(g, hp, rball2, rin2, s.x, s.y, s.z) ? 1 : 0;
+      }
+      c = __reduce_add_sync(0xffffffffu, c);
+      if ((tid & 31) == 0 && c) atomicAdd(&cnt_s[h], (unsigned int) c);
+    }
+    __syncthreads();
+    if (tid < nh && cnt_s[tid]) atomicAdd(&counts[h0 + tid], cnt_s[tid]);
+    __syncthreads();
+  }
+}
+
+// ---- grid build ----------------------------------------------------------------------------------
+__global__ void minmax_kernel(const float4 *__restrict__ p, int n, float *__restrict__ out6) {
+  float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 v = p[i];
+    mn[0] = fminf(mn[0], v.x); mn[1] = fminf(mn[1], v.y); mn[2] = fminf(mn[2], v.z);
+    mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z);
+  }
+  typedef cub::BlockReduce<float, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  for (int k = 0; k < 3; ++k) {
+    float a = BR(tmp).Reduce(mn[k], cub::Min());
+    __syncthreads();
+    float b = BR(tmp).Reduce(mx[k], cub::Max());
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // float atomics via int ordering tricks are avoided: two-stage through ordered-int encoding
+      int ai = __float_as_int(a), bi = __float_as_int(b);
+      ai = ai >= 0 ? ai : ai ^ 0x7fffffff;
+      bi = bi >= 0 ? bi : bi ^ 0x7fffffff;
+      atomicMin(reinterpret_cast<int *>(out6) + k, ai);
+      atomicMax(reinterpret_cast<int *>(out6) + 3 + k, bi);
+    }
+  }
+}
+
+__global__ void cell_key_kernel(const float4 *__restrict__ p, int n, float minx, float miny, float minz,
+                                float inv_cell, int nx, int ny, int nz, unsigned int *__restrict__ keys,
+                                int *__restrict__ order) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 v = p[i];
+  int cx = min(max((int) floorf((v.x - minx) * inv_cell), 0), nx - 1);
+  int cy = min(max((int) floorf((v.y - miny) * inv_cell), 0), ny - 1);
+  int cz = min(max((int) floorf((v.z - minz) * inv_cell), 0), nz - 1);
+  keys[i] = (unsigned int) ((cz * ny + cy) * nx + cx);
+  order[i] = i;
+}
+
+__global__ void gather_cells_kernel(const float4 *__restrict__ p, const int *__restrict__ order,
+                                    const unsigned int *__restrict__ keys, int n, float4 *__restrict__ out,
+                                    int *__restrict__ cell_start, int ncells) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 v = p[order[i]];
+  v.w = 0.f;
+  out[i] = v;
+  unsigned int k = keys[i];
+  unsigned int prev = (i == 0) ? 0u : keys[i - 1] + 1u;   // first cell that starts at i
+  if (i == 0 || keys[i - 1] != k)
+    for (unsigned int c = prev; c <= k; ++c) cell_start[c] = i;
+  if (i == n - 1)
+    for (unsigned int c = k + 1; c <= (unsigned int) ncells; ++c) cell_start[c] = n;
+}
+
+inline float ordered_int_to_float(int v) {
+  v = v >= 0 ? v : v ^ 0x7fffffff;
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+}
+
+}  // namespace
+
+void build_target_grid(Device &dev, const float4 *d_tgt, size_t n, float inlier_dist, TargetGrid &grid) {
+  grid.n = n;
+  if (n == 0) { grid.nx = grid.ny = grid.nz = 0; return; }
+  cudaStream_t s = dev.stream;
+  // bounding box
+  float *d6 = grid.mm.ensure(6);
+  int init[6];
+  {
+    float big = 3.4e38f, nbig = -3.4e38f;
+    int bi, nbi;
+    memcpy(&bi, &big, 4); memcpy(&nbi, &nbig, 4);
+    nbi = nbi ^ 0x7fffffff;
+    init[0] = init[1] = init[2] = bi;
+    init[3] = init[4] = init[5] = nbi;
+  }
+  PLADE_CUDA(cudaMemcpyAsync(d6, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  int blocks = std::min(div_up((long long) n, 256), dev.num_sms * 8);
+  minmax_kernel<<<blocks, 256, 0, s>>>(d_tgt, (int) n, d6);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add();
+  int h6[6];
+  PLADE_CUDA(cudaMemcpyAsync(h6, d6, sizeof(h6), cudaMemcpyDeviceToHost, s));
+  PLADE_CUDA(cudaStreamSynchronize(s));
+  float mn[3], mx[3];
+  for (int k = 0; k < 3; ++k) { mn[k] = ordered_int_to_float(h6[k]); mx[k] = ordered_int_to_float(h6[3 + k]); }
+
+  // Cell edge slightly above the inlier distance so that |dx| < r always lands within +-1 cell even
+  // after float rounding of the cell coordinate; grown further if the grid would exceed 2^26 cells.
+  double cell = (double) inlier_dist * (1.0 + 1.0 / 1024.0);
+  if (!(cell > 0)) cell = 1e-6;
+  double ex = (double) mx[0] - mn[0], ey = (double) mx[1] - mn[1], ez = (double) mx[2] - mn[2];
+  for (;;) {
+    double cells = (std::floor(ex / cell) + 1) * (std::floor(ey / cell) + 1) * (std::floor(ez / cell) + 1);
+    if (cells <= 67108864.0) break;
+    cell *= 1.26;
+  }
+  grid.cell = (float) cell;
+  grid.inv_cell = (float) (1.0 / cell);
+  grid.minx = mn[0]; grid.miny = mn[1]; grid.minz = mn[2];
+  grid.nx = (int) std::floor(ex / cell) + 1;
+  grid.ny = (int) std::floor(ey / cell) + 1;
+  grid.nz = (int) std::floor(ez / cell) + 1;
+  int ncells = grid.nx * grid.ny * grid.nz;
+
+  unsigned int *keys = grid.keys.ensure(n), *keys2 = grid.keys_alt.ensure(n);
+  int *ord = grid.order.ensure(n), *ord2 = grid.order_alt.ensure(n);
+  cell_key_kernel<<<div_up((long long) n, 256), 256, 0, s>>>(d_tgt, (int) n, grid.minx, grid.miny, grid.minz,
+                                                            grid.inv_cell, grid.nx, grid.ny, grid.nz, keys, ord);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add();
+  size_t tmp_bytes = 0;
+  int end_bit = 1;
+  while ((1ll << end_bit) < ncells) ++end_bit;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, ord, ord2, (int) n, 0, end_bit, s);
+  unsigned char *tmp = grid.cub_tmp.ensure(tmp_bytes);
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, ord, ord2, (int) n, 0, end_bit, s);
+  dev.launches.add(3);
+  float4 *pts = grid.pts.ensure(n);
+  int *cs = grid.cell_start.ensure((size_t) ncells + 1);
+  gather_cells_kernel<<<div_up((long long) n, 256), 256, 0, s>>>(d_tgt, ord2, keys2, (int) n, pts, cs, ncells);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add();
+}
+
+void verify_hypotheses(Device &dev, const float4 *d_src, size_t ns, const TargetGrid &grid,
+                       const HypParams *d_hyp, int H, float ball_radius, float inlier_dist,
+                       unsigned int *d_counts) {
+  cudaStream_t s = dev.stream;
+  PLADE_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned int) * (size_t) H, s));
+  if (H == 0 || ns == 0 || grid.n == 0) return;
+  // static_cast<float>(radius * radius) with radius a double (kdtree_flann.hpp:193)
+  float rball2 = (float) ((double) ball_radius * (double) ball_radius);
+  float rin2 = (float) ((double) inlier_dist * (double) inlier_dist);
+  GridView g{grid.pts.p, grid.cell_start.p, grid.minx, grid.miny, grid.minz, grid.inv_cell, grid.nx, grid.ny, grid.nz};
+  int n_tiles = div_up((long long) ns, kTile);
+  int n_chunks = div_up(H, kHypChunk);
+  long long n_work = (long long) n_tiles * n_chunks;
+  int blocks = (int) std::min<long long>(n_work, (long long) dev.num_sms * 4);
+  verify_kernel<<<blocks, kThreads, 0, s>>>(d_src, (int) ns, g, d_hyp, H, rball2, rin2, d_counts, n_tiles, n_chunks);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add();
+}
+
+}  // namespace plade

@@ -1,0 +1,421 @@
+"""GPU parity tests: every CUDA stage, called through the C ABI, against the oracle on the same inputs.
+
+Bars: bit-exact for integer / index work (inlier counts, match sets, voxel membership, plane-consensus
+masks, cluster labels); floating-point stages carry their tolerance in the test.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from plade_b200 import Planes
+from plade_b200.synth import make_pair, perturbed_hypotheses, transform_error
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_rigid(rng, n, rot_deg=20.0, trans=0.3):
+    Rs, Ts = [], []
+    for _ in range(n):
+        a = rng.normal(size=3)
+        a /= np.linalg.norm(a)
+        ang = np.deg2rad(rng.uniform(0, rot_deg))
+        K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+        Rs.append(np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K)
+        Ts.append(rng.uniform(-trans, trans, size=3))
+    return np.array(Rs, np.float32), np.array(Ts, np.float32)
+
+
+# ---------------------------------------------------------------------------------------------- K5
+def test_verify_counts_bit_exact_random(ctx, restate):
+    rng = np.random.default_rng(0)
+    tgt = rng.uniform(0, 1, size=(6000, 3)).astype(np.float32)
+    src = (tgt[rng.permutation(6000)[:4000]] + rng.normal(0, 0.004, size=(4000, 3))).astype(np.float32)
+    R, T = _rand_rigid(rng, 37, rot_deg=6, trans=0.05)
+    R[0], T[0] = np.eye(3), 0
+    centers = (np.einsum("hij,j->hi", R, src.mean(0)) + T).astype(np.float32)
+    for ball, inl in ((0.6, 0.01), (0.25, 0.02), (5.0, 0.003)):
+        got = ctx.verify_hypotheses(src, tgt, R, T, centers, ball, inl)
+        want = restate.verify_counts(src, tgt, R, T, centers, ball, inl)
+        assert np.array_equal(got, want)
+    assert got[0] > 0
+
+
+def test_verify_edge_cases(ctx, restate):
+    rng = np.random.default_rng(1)
+    tgt = rng.uniform(0, 1, size=(500, 3)).astype(np.float32)
+    src = rng.uniform(0, 1, size=(300, 3)).astype(np.float32)
+    R, T = _rand_rigid(rng, 3)
+    c = np.zeros((3, 3), np.float32)
+    # no hypotheses, empty clouds, ball that contains nothing, single points, duplicates
+    assert len(ctx.verify_hypotheses(src, tgt, R[:0], T[:0], c[:0], 1.0, 0.05)) == 0
+    assert np.array_equal(ctx.verify_hypotheses(src[:0], tgt, R, T, c, 1.0, 0.05), np.zeros(3, np.uint32))
+    assert np.array_equal(ctx.verify_hypotheses(src, tgt[:0], R, T, c, 1.0, 0.05), np.zeros(3, np.uint32))
+    far = np.full((3, 3), 100.0, np.float32)
+    assert np.array_equal(ctx.verify_hypotheses(src, tgt, R, T, far, 0.5, 0.05), np.zeros(3, np.uint32))
+    one = np.array([[0.5, 0.5, 0.5]], np.float32)
+    I = np.eye(3, dtype=np.float32)[None]
+    z = np.zeros((1, 3), np.float32)
+    assert ctx.verify_hypotheses(one, one, I, z, one, 1.0, 0.01)[0] == 1
+    dup = np.repeat(one, 64, axis=0)
+    got = ctx.verify_hypotheses(dup, dup, I, z, one, 1.0, 0.01)
+    assert got[0] == 64 and np.array_equal(got, restate.verify_counts(dup, dup, I, z, one, 1.0, 0.01))
+    # ragged tile sizes around the 2048-point tile and the 32-hypothesis chunk
+    for ns, H in ((2047, 31), (2048, 32), (2049, 33), (4097, 65)):
+        s = rng.uniform(0, 1, size=(ns, 3)).astype(np.float32)
+        Rr, Tr = _rand_rigid(rng, H, rot_deg=3, trans=0.02)
+        cc = (np.einsum("hij,j->hi", Rr, s.mean(0)) + Tr).astype(np.float32)
+        assert np.array_equal(ctx.verify_hypotheses(s, tgt, Rr, Tr, cc, 0.7, 0.06), restate.verify_counts(s, tgt, Rr, Tr, cc, 0.7, 0.06))
+
+
+def test_verify_golden_polyhedron(ctx, restate, poly_stages):
+    """The reference's own ComputeOverlap (FLANN kd-trees) on its own hypotheses -> overlap ratios."""
+    g = poly_stages
+    src, tgt = g["src_ds"].reshape(-1, 3), g["tgt_ds"].reshape(-1, 3)
+    R, T, c = g["mr_R"].reshape(-1, 9), g["mr_T"].reshape(-1, 3), g["ver_center"].reshape(-1, 3)
+    ball, inl = float(g["src_radius"][0]), float(g["downsample_distance"][0])
+    got = ctx.verify_hypotheses(src, tgt, R, T, c, ball, inl)
+    assert np.array_equal(got, restate.verify_counts(src, tgt, R, T, c, ball, inl))
+    overlap = (got.astype(np.float64) / min(len(src), len(tgt))).astype(np.float32)
+    assert np.array_equal(overlap, g["ver_overlap"])          # bit-exact against the reference's floats
+    score = (0.2 * (g["mr_nplanes"] / float(len(g["s_par"]))) + 0.8 * overlap.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(score, g["ver_score"])
+
+
+def test_verify_golden_synth(ctx, synth_stages):
+    g = synth_stages
+    src, tgt = g["src_ds"].reshape(-1, 3), g["tgt_ds"].reshape(-1, 3)
+    got = ctx.verify_hypotheses(src, tgt, g["mr_R"].reshape(-1, 9), g["mr_T"].reshape(-1, 3), g["ver_center"].reshape(-1, 3),
+                                float(g["src_radius"][0]), float(g["downsample_distance"][0]))
+    overlap = (got.astype(np.float64) / min(len(src), len(tgt))).astype(np.float32)
+    assert np.array_equal(overlap, g["ver_overlap"])
+
+
+def test_verify_full_size_properties(ctx):
+    """BASELINE-size property checks (no oracle at this size): identity on itself counts every point,
+    a far translation counts none, the count is invariant to hypothesis order and chunking."""
+    rng = np.random.default_rng(3)
+    tgt, src, gt = make_pair(n_points=400000, n_planes=20, seed=5)
+    leaf = 0.012
+    ds_t = ctx.voxel_downsample(tgt[:, :3], leaf)
+    ds_s = ctx.voxel_downsample(src[:, :3], leaf)
+    I = np.eye(3, dtype=np.float32)[None]
+    z = np.zeros((1, 3), np.float32)
+    c = ds_t.mean(0, keepdims=True).astype(np.float32)
+    assert ctx.verify_hypotheses(ds_t, ds_t, I, z, c, 10.0, leaf)[0] == len(ds_t)
+    assert ctx.verify_hypotheses(ds_t, ds_t, I, z + 50.0, c + 50.0, 10.0, leaf)[0] == 0
+    R, T, true_idx = perturbed_hypotheses(gt, 257, seed=7)
+    cen = (np.einsum("hij,j->hi", R, ds_s.mean(0)) + T).astype(np.float32)
+    a = ctx.verify_hypotheses(ds_s, ds_t, R, T, cen, 2.0, leaf)
+    perm = rng.permutation(257)
+    b = ctx.verify_hypotheses(ds_s, ds_t, R[perm], T[perm], cen[perm], 2.0, leaf)
+    assert np.array_equal(a[perm], b)
+    assert int(np.argmax(a)) == true_idx
+    one = ctx.verify_hypotheses(ds_s, ds_t, R[true_idx:true_idx + 1], T[true_idx:true_idx + 1], cen[true_idx:true_idx + 1], 2.0, leaf)
+    assert one[0] == a[true_idx]
+
+
+# ---------------------------------------------------------------------------------------------- K2
+def test_voxel_downsample_bit_exact(ctx, restate):
+    rng = np.random.default_rng(4)
+    for n, leaf in ((1, 0.1), (17, 0.5), (5000, 0.05), (60000, 0.013)):
+        pts = rng.uniform(-1, 1, size=(n, 3)).astype(np.float32)
+        got, want = ctx.voxel_downsample(pts, leaf), restate.voxel_downsample(pts, leaf)
+        assert got.shape == want.shape and np.array_equal(got, want)
+    pn = rng.uniform(-1, 1, size=(3000, 6)).astype(np.float32)        # stride-6 input (PointNormal)
+    assert np.array_equal(ctx.voxel_downsample(pn, 0.07), restate.voxel_downsample(pn, 0.07))
+    with pytest.raises(RuntimeError):
+        ctx.voxel_downsample(pn[:0], 0.07)                             # DownSamplePointCloud returns -1
+    with pytest.raises(RuntimeError):
+        ctx.voxel_downsample(pn, 0.0)
+
+
+def test_voxel_golden_reference_clouds(ctx, restate, poly_pair, poly_stages):
+    """Same voxels as the reference's pcl::VoxelGrid; centroids equal up to the order of the float
+    additions inside a voxel (the reference's std::sort is unstable): <= 2 ulp of the coordinate."""
+    g = poly_stages
+    leaf = float(g["downsample_distance"][0])
+    for name, cloud in (("tgt_ds", poly_pair["tgt"]), ("src_ds", poly_pair["src"])):
+        got = ctx.voxel_downsample(cloud, leaf)
+        want = g[name].reshape(-1, 3)
+        assert got.shape == want.shape
+        assert np.array_equal(np.floor(got / leaf), np.floor(want / leaf))
+        assert np.max(np.abs(got - want)) <= 4 * np.finfo(np.float32).eps * 2.0
+        assert np.array_equal(got, restate.voxel_downsample(cloud, leaf))
+
+
+def test_average_spacing(ctx, restate, poly_pair, poly_stages):
+    got = ctx.average_spacing(poly_pair["src"])
+    assert got == float(poly_stages["average_space"][0])               # bit-exact vs the reference (FLANN kNN)
+    rng = np.random.default_rng(5)
+    for n in (5, 6, 100, 25000):
+        pts = rng.uniform(0, 1, size=(n, 6)).astype(np.float32)
+        assert ctx.average_spacing(pts) == restate.average_spacing(pts)
+
+
+def test_bounding_box_vs_reference(ctx, poly_stages, ref):
+    pts = poly_stages["src_ds"].reshape(-1, 3)
+    rc, c, whd, corners = ctx.bounding_box(pts)
+    rc2, c2, whd2, corners2 = ref.bounding_box(pts)
+    assert rc == rc2 == 0
+    assert np.allclose(c, c2, atol=2e-5) and np.allclose(np.sort(whd), np.sort(whd2), atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------- K1
+def test_score_planes_bit_exact(ctx, restate):
+    tgt, _, _ = make_pair(n_points=50000, n_planes=12, seed=3)
+    rng = np.random.default_rng(6)
+    planes = []
+    for _ in range(24):
+        i = rng.integers(0, len(tgt), size=3)
+        p = tgt[i, :3].astype(np.float64)
+        n = np.cross(p[1] - p[0], p[2] - p[1])
+        if np.linalg.norm(n) < 1e-9:
+            continue
+        n /= np.linalg.norm(n)
+        planes.append([*n, float(n @ p[0])])
+    planes.append([0, 0, 1, float(tgt[:, 2].min())])
+    planes = np.array(planes, np.float32)
+    assigned = np.where(rng.random(len(tgt)) < 0.3, 0, -1).astype(np.int32)
+    for eps in (0.004, 0.02):
+        got, gmask = ctx.score_planes(tgt, planes, eps, 0.8, assigned, want_mask=True)
+        want, wmask = restate.score_planes(tgt, planes, eps, 0.8, assigned, want_mask=True)
+        assert np.array_equal(got, want) and np.array_equal(gmask, wmask)
+    assert np.array_equal(ctx.score_planes(tgt, planes, 0.01, 0.8), restate.score_planes(tgt, planes, 0.01, 0.8))
+
+
+def _match_planes(ours, theirs_par, theirs_sizes, eps):
+    """For each reference plane (largest first) find our plane with the same normal (up to sign) and offset."""
+    res = []
+    for k in np.argsort(-theirs_sizes):
+        n, d = theirs_par[k, :3], theirs_par[k, 3]
+        best = None
+        for j in range(len(ours)):
+            m, e = ours.params[j, :3], ours.params[j, 3]
+            s = np.sign(n @ m)
+            ang = np.degrees(np.arccos(np.clip(abs(n @ m), 0, 1)))
+            if ang < 1.0 and abs(d - s * e) < eps:
+                best = (j, ang, abs(d - s * e))
+                break
+        res.append((k, best))
+    return res
+
+
+def test_ransac_planes_vs_reference_golden(ctx, poly_pair, poly_stages):
+    """Statistical parity: the big planes the reference finds are found with the same
+    parameters (normal < 0.5 deg, |d| < eps) and support within 5 %."""
+    g = poly_stages
+    cloud = poly_pair["tgt"]
+    scale = max(np.ptp(cloud[:, 0]), np.ptp(cloud[:, 1]))
+    eps = 0.005 * scale
+    ours = ctx.detect_planes(cloud, 1000)
+    sizes = np.diff(g["t_off"])
+    big = [k for k in range(len(sizes)) if sizes[k] >= 2000]
+    matched = _match_planes(ours, g["t_par"], sizes, eps)
+    ours_sizes = ours.sizes()
+    for k, best in matched:
+        if k not in big:
+            continue
+        assert best is not None, "reference plane %d (support %d) not found" % (k, sizes[k])
+        j, ang, dd = best
+        assert ang < 0.5 and dd < eps
+        assert abs(int(ours_sizes[j]) - int(sizes[k])) <= 0.05 * sizes[k] + 50
+    # every returned plane respects min_support, indices are unique and in range
+    assert ours_sizes.min() >= 1000
+    assert len(np.unique(ours.indices)) == len(ours.indices) and ours.indices.max() < len(cloud)
+
+
+def test_ransac_synthetic_ground_truth(ctx):
+    tgt, src, gt, It, Is = make_pair(n_points=300000, n_planes=20, seed=9, return_ids=True)
+    planes = ctx.extract_planes(tgt, 10000)
+    assert 10 <= len(planes) <= 40
+    # each extracted plane is (almost) pure: > 97 % of its points come from one generated rectangle
+    for k in range(len(planes)):
+        ids = It[planes.indices[planes.offsets[k]:planes.offsets[k + 1]]]
+        assert np.bincount(ids).max() >= 0.97 * len(ids)
+    # deterministic for a fixed seed
+    again = ctx.extract_planes(tgt, 10000)
+    assert np.array_equal(planes.offsets, again.offsets) and np.array_equal(planes.params, again.params)
+
+
+# ---------------------------------------------------------------------------------------------- K3c
+def test_match_descriptors_bit_exact(ctx, restate, poly_stages):
+    g = poly_stages
+    db = g["tgt_db_desc"].reshape(-1, 8)
+    rng = np.random.default_rng(7)
+    q = db[rng.permutation(len(db))[:700]] + rng.normal(0, 0.012, size=(700, 8)).astype(np.float32)
+    q = np.concatenate([q, db[:50]])                                     # exact duplicates: distance 0
+    off, idx, d2 = ctx.match_descriptors(db, q, 0.04)
+    woff, widx, wd2 = restate.match_descriptors(db, q, 0.04)
+    assert np.array_equal(off, woff) and np.array_equal(idx, widx) and np.array_equal(d2, wd2)
+    assert len(idx) > 700
+    # empty / no-match cases
+    off, idx, d2 = ctx.match_descriptors(db, q[:0], 0.04)
+    assert len(idx) == 0 and np.array_equal(off, [0])
+    off, idx, d2 = ctx.match_descriptors(db, q + 10.0, 0.04)
+    assert len(idx) == 0 and np.all(off == 0)
+
+
+def test_match_descriptors_vs_ann(ctx, ref, poly_stages):
+    """Against the reference's own ANN kd-tree: same neighbour sets, same ascending distances."""
+    db = poly_stages["tgt_db_desc"].reshape(-1, 8)
+    rng = np.random.default_rng(8)
+    q = db[rng.permutation(len(db))[:300]] + rng.normal(0, 0.01, size=(300, 8)).astype(np.float32)
+    off, idx, d2 = ctx.match_descriptors(db, q, 0.04)
+    roff, ridx, rd = ref.match_descriptors(db, q, 0.04)
+    assert np.array_equal(off, roff)
+    for a in range(len(q)):
+        s = slice(off[a], off[a + 1])
+        assert set(idx[s]) == set(ridx[s])
+        assert np.array_equal(d2[s].astype(np.float32), rd[s])           # ANN returns float(double dist)
+
+
+# ---------------------------------------------------------------------------------------------- K4
+def test_transforms_from_matches_vs_eigen_umeyama(ctx, ref):
+    """Tolerance: |dR|_max <= 5e-6, |dT| <= 5e-6 * (1 + |p|) against the reference (Eigen float JacobiSVD)."""
+    rng = np.random.default_rng(9)
+    n = 500
+    v1 = rng.normal(size=(n, 3)); v2 = rng.normal(size=(n, 3))
+    v1 /= np.linalg.norm(v1, axis=1, keepdims=True); v2 /= np.linalg.norm(v2, axis=1, keepdims=True)
+    v1 *= rng.uniform(0.3, 1, size=(n, 1)); v2 *= rng.uniform(0.3, 1, size=(n, 1))
+    R, _ = _rand_rigid(rng, n, rot_deg=170)
+    w1 = np.einsum("nij,nj->ni", R, v1) + rng.normal(0, 1e-3, size=(n, 3))
+    w2 = np.einsum("nij,nj->ni", R, v2) + rng.normal(0, 1e-3, size=(n, 3))
+    sp, tp = rng.uniform(-1, 1, size=(n, 3)), rng.uniform(-1, 1, size=(n, 3))
+    inp = np.concatenate([v1, v2, w1, w2, sp, tp], axis=1).astype(np.float32)
+    Rg, Tg = ctx.transforms_from_matches(inp)
+    Rr, Tr = ref.transform_from_two_vecs(inp)
+    assert np.max(np.abs(Rg - Rr)) <= 5e-6
+    assert np.max(np.abs(Tg - Tr)) <= 1e-5
+    assert np.allclose(np.einsum("nij,nkj->nik", Rg, Rg), np.eye(3), atol=1e-5) and np.all(np.linalg.det(Rg) > 0.999)
+
+
+def test_cluster_transforms(ctx, restate, ref):
+    rng = np.random.default_rng(10)
+    centres_R, centres_T = _rand_rigid(rng, 12, rot_deg=120, trans=1.0)
+    Rs, Ts = [], []
+    for k in range(12):
+        m = int(rng.integers(1, 60))
+        dR, dT = _rand_rigid(rng, m, rot_deg=0.6, trans=0.004)
+        Rs.append(np.einsum("mij,jk->mik", dR, centres_R[k])); Ts.append(centres_T[k] + dT)
+    R = np.concatenate(Rs).astype(np.float32); T = np.concatenate(Ts).astype(np.float32)
+    perm = rng.permutation(len(R)); R, T = R[perm], T[perm]
+    for tol, ang in ((0.01, 0.0436), (0.004, 0.0005)):
+        got = ctx.cluster_transforms(R, T, tol, ang)
+        assert np.array_equal(got, restate.cluster_transforms(R, T, tol, ang))
+        nc, rlab = ref.cluster_transformations(R, T, tol, ang)              # the reference's CEC
+        # same partition; our label = smallest member index = first element the reference emits
+        assert len(np.unique(got)) == nc
+        for c in range(nc):
+            members = np.where(rlab == c)[0]
+            assert len(np.unique(got[members])) == 1 and got[members[0]] == members.min()
+    assert len(ctx.cluster_transforms(R[:0], T[:0], 0.01, 0.04)) == 0
+
+
+# ------------------------------------------------------------------------------------- whole back-end
+def _planes(g, p):
+    return Planes(g[p + "_off"], g[p + "_idx"], g[p + "_par"])
+
+
+@pytest.mark.parametrize("which", ["poly", "synth"])
+def test_registration_with_reference_planes(ctx, poly_pair, poly_stages, synth_stages, which):
+    """registration(T, tgt, src, planes, planes) on the REFERENCE's planes: same hypothesis list, same
+    winner.  Tolerance (north_star): rotation <= 0.1 deg, translation <= 1e-3 of the scene diagonal."""
+    if which == "poly":
+        g, tgt, src = poly_stages, poly_pair["tgt"], poly_pair["src"]
+    else:
+        g = synth_stages
+        tgt, src, _ = make_pair(n_points=200000, n_planes=20, seed=11)
+    ctx.set_debug(True)
+    ok, T = ctx.register_with_planes(tgt, src, _planes(g, "t"), _planes(g, "s"))
+    ctx.set_debug(False)
+    assert ok == bool(g["ok"][0])
+    diag = float(np.linalg.norm(np.ptp(tgt[:, :3], axis=0)))
+    rot, tr = transform_error(T, g["T"], diag)
+    assert rot <= 0.1 and tr <= 1e-3
+    # stage-level agreement with the reference's dumps
+    assert ctx.blob("average_space", np.float32)[0] == g["average_space"][0]
+    for side in ("src", "tgt"):
+        assert len(ctx.blob(side + "_ds", np.float32)) == len(g[side + "_ds"])
+        assert np.allclose(ctx.blob(side + "_center", np.float32), g[side + "_center"], atol=1e-5)
+        assert np.array_equal(ctx.blob(side + "_line_planes", np.int32), g[side + "_line_planes"])
+        assert np.allclose(ctx.blob(side + "_lines", np.float32), g[side + "_lines"], atol=2e-5)
+    assert np.array_equal(ctx.blob("tgt_db_pair", np.int32), g["tgt_db_pair"])
+    assert np.allclose(ctx.blob("tgt_db_desc", np.float32), g["tgt_db_desc"], atol=5e-5)
+    assert np.array_equal(ctx.blob("lines_to_match", np.int32), g["lines_to_match"])
+    R, Tt = ctx.blob("mr_R", np.float32).reshape(-1, 9), ctx.blob("mr_T", np.float32).reshape(-1, 3)
+    assert len(R) == len(g["mr_nplanes"])
+    assert np.array_equal(ctx.blob("mr_nplanes", np.int32), g["mr_nplanes"])
+    assert np.allclose(R, g["mr_R"].reshape(-1, 9), atol=2e-5) and np.allclose(Tt, g["mr_T"].reshape(-1, 3), atol=5e-5)
+    assert np.allclose(ctx.blob("ver_score", np.float32), g["ver_score"], atol=2e-3)
+    assert int(np.argmax(ctx.blob("ver_score", np.float32))) == int(np.argmax(g["ver_score"]))
+
+
+def test_registration_end_to_end_polyhedron(ctx, poly_pair):
+    """Config 1 (correctness gate): full pipeline incl. GPU RANSAC.  The reference itself only reaches
+    the ground truth for some RANSAC seeds; ours must reach it with its fixed seed."""
+    ok, T = ctx.register_clouds(poly_pair["tgt"], poly_pair["src"])
+    assert ok
+    diag = float(np.linalg.norm(np.ptp(poly_pair["tgt"][:, :3], axis=0)))
+    rot, tr = transform_error(T, poly_pair["gt"], diag)
+    assert rot <= 0.5 and tr <= 5e-3
+    rot_p, tr_p = transform_error(T, poly_pair["published"], diag)
+    assert rot_p <= 0.5 and tr_p <= 5e-3
+
+
+def test_registration_end_to_end_synthetic(ctx):
+    tgt, src, gt = make_pair(n_points=300000, n_planes=20, seed=11)
+    ok, T = ctx.register_clouds(tgt, src)
+    assert ok
+    diag = float(np.linalg.norm(np.ptp(tgt[:, :3], axis=0)))
+    rot, tr = transform_error(T, gt, diag)
+    assert rot <= 0.5 and tr <= 5e-3
+
+
+def test_sharded_verification_matches_single(ctx, poly_pair, poly_stages):
+    """world_size-2 hypothesis sharding inside one process: both shards + max-reduce pick the same winner."""
+    import plade_b200
+    g = poly_stages
+    tp, sp = _planes(g, "t"), _planes(g, "s")
+    ok, T1 = ctx.register_with_planes(poly_pair["tgt"], poly_pair["src"], tp, sp)
+    keys = []
+    ctxs = [plade_b200.Context() for _ in range(2)]
+    try:
+        # pass 1: collect each rank's local key; pass 2: feed the global max back
+        for r, c in enumerate(ctxs):
+            c.set_shard(r, 2, lambda k: (keys.append(k), k)[1])
+            c.register_with_planes(poly_pair["tgt"], poly_pair["src"], tp, sp)
+        gmax = max(keys)
+        for r, c in enumerate(ctxs):
+            c.set_shard(r, 2, lambda k: gmax)
+            ok2, T2 = c.register_with_planes(poly_pair["tgt"], poly_pair["src"], tp, sp)
+            assert ok2 and np.array_equal(T1, T2)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_file_overload_and_errors(ctx, poly_pair, tmp_path):
+    from tests.plyio import write_ply
+    t, s = str(tmp_path / "t.ply"), str(tmp_path / "s.ply")
+    write_ply(t, poly_pair["tgt"]); write_ply(s, poly_pair["src"])
+    ok, T = ctx.register_files(t, s)
+    ok2, T2 = ctx.register_clouds(poly_pair["tgt"], poly_pair["src"])
+    assert ok and ok2 and np.array_equal(T, T2)
+    ok, T = ctx.register_files(str(tmp_path / "t.xyz"), s)              # only PLY format is accepted
+    assert not ok and np.array_equal(T, np.eye(4))
+    ok, T = ctx.register_files(str(tmp_path / "missing.ply"), s)
+    assert not ok and np.array_equal(T, np.eye(4))
+    # too few planes -> false + identity (PLADE/plade.cpp:646-657)
+    rng = np.random.default_rng(11)
+    blob = rng.normal(size=(20000, 6)).astype(np.float32)
+    ok, T = ctx.register_clouds(blob, blob)
+    assert not ok and np.array_equal(T, np.eye(4))
+    # swap rule: source >= 1.2 x target -> swapped internally, inverse returned (PLADE/plade.cpp:689-704)
+    big = np.concatenate([poly_pair["src"], poly_pair["src"][:30000] + np.float32(1e-4)])
+    write_ply(s, big)
+    ok, T3 = ctx.register_files(t, s)
+    assert ok
+    diag = float(np.linalg.norm(np.ptp(poly_pair["tgt"][:, :3], axis=0)))
+    rot, tr = transform_error(T3, poly_pair["gt"], diag)
+    assert rot <= 0.5 and tr <= 5e-3
