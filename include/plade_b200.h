@@ -46,8 +46,14 @@ int plade_set_param(plade_ctx *ctx, const char *name, double value);
 void plade_set_shard(plade_ctx *ctx, int rank, int world, plade_allreduce_max_u64 reduce, void *user);
 long long plade_launch_count(plade_ctx *ctx);     /* kernels launched by this context so far */
 /* seconds of the last registration: upload, planes, spacing, downsample, lines, descriptors, match,
- * hypotheses, penetration, verify, total (11 values) */
+ * hypotheses, penetration, verify, total, then the verification kernel of that call as timed with
+ * CUDA events on the context stream: kernel_ms, hypotheses, source ds points, target ds points (15 values) */
 int plade_stage_times(plade_ctx *ctx, double *out, int n);
+/* CUDA-event stopwatch on the context's own stream (the stream every kernel of this context is
+ * launched on): start records an event, stop records a second one, waits for it and returns the
+ * elapsed device time in milliseconds. */
+int plade_timer_start(plade_ctx *ctx);
+float plade_timer_stop_ms(plade_ctx *ctx);
 
 /* ---- registration() — the four reference overloads -------------------------------------------- */
 /* registration(T, target_file, source_file)                         PLADE/plade.cpp:665-707 */

@@ -30,6 +30,8 @@ SIGNATURES = {
     "plade_set_shard": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ALLREDUCE_FN, ctypes.c_void_p]),
     "plade_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
     "plade_stage_times": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int]),
+    "plade_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
+    "plade_timer_stop_ms": (ctypes.c_float, [ctypes.c_void_p]),
     "plade_register_files": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, _c_float_p]),
     "plade_register_clouds": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, _c_float_p, ctypes.c_size_t, _c_float_p]),
     "plade_register_with_planes": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, _c_float_p, ctypes.c_size_t,
@@ -98,7 +100,7 @@ def _p(a, t):
 
 
 STAGE_NAMES = ["upload", "planes", "spacing", "downsample", "lines", "descriptors", "match", "hypotheses",
-               "penetration", "verify", "total"]
+               "penetration", "verify", "total", "verify_kernel_ms", "verify_h", "verify_ns", "verify_nt"]
 
 
 class Planes:
@@ -162,9 +164,15 @@ class Context:
         return int(self.lib.plade_launch_count(self.h))
 
     def stage_times(self):
-        out = np.zeros(11, dtype=np.float64)
-        self.lib.plade_stage_times(self.h, _p(out, _c_double_p), 11)
+        out = np.zeros(15, dtype=np.float64)
+        self.lib.plade_stage_times(self.h, _p(out, _c_double_p), 15)
         return dict(zip(STAGE_NAMES, out.tolist()))
+
+    def timer_start(self):
+        self.lib.plade_timer_start(self.h)
+
+    def timer_stop_ms(self):
+        return float(self.lib.plade_timer_stop_ms(self.h))
 
     def blob(self, name, dtype):
         n = ctypes.c_size_t(0)

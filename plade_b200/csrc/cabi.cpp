@@ -125,9 +125,23 @@ long long plade_launch_count(plade_ctx *ctx) { return ctx ? ctx->reg->dev.launch
 int plade_stage_times(plade_ctx *ctx, double *out, int n) {
   if (!ctx) return 0;
   const StageTimes &t = ctx->reg->times;
-  double v[11] = {t.upload, t.planes, t.spacing, t.downsample, t.lines, t.descriptors, t.match, t.hypotheses, t.penetration, t.verify, t.total};
-  for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
-  return 11;
+  double v[15] = {t.upload, t.planes, t.spacing, t.downsample, t.lines, t.descriptors, t.match, t.hypotheses, t.penetration, t.verify, t.total,
+                  t.verify_kernel_ms, t.verify_h, t.verify_ns, t.verify_nt};
+  for (int i = 0; i < n && i < 15; ++i) out[i] = v[i];
+  return 15;
+}
+int plade_timer_start(plade_ctx *ctx) {
+  PLADE_TRY(ctx, 0, { PLADE_CUDA(cudaEventRecord(ctx->reg->ev_user0, ctx->reg->dev.stream)); return 1; })
+}
+float plade_timer_stop_ms(plade_ctx *ctx) {
+  PLADE_TRY(ctx, -1.f, {
+    Registrar &r = *ctx->reg;
+    PLADE_CUDA(cudaEventRecord(r.ev_user1, r.dev.stream));
+    PLADE_CUDA(cudaEventSynchronize(r.ev_user1));
+    float ms = 0;
+    PLADE_CUDA(cudaEventElapsedTime(&ms, r.ev_user0, r.ev_user1));
+    return ms;
+  })
 }
 void plade_set_debug(plade_ctx *ctx, int on) { if (ctx) { ctx->reg->debug = on != 0; if (on) ctx->reg->blobs.clear(); } }
 const void *plade_debug_blob(plade_ctx *ctx, const char *name, size_t *nbytes) {

@@ -279,9 +279,14 @@ Registrar::Registrar(int device) {
   PLADE_CUDA(cudaGetDeviceProperties(&prop, dev.id));
   dev.num_sms = prop.multiProcessorCount;
   PLADE_CUDA(cudaStreamCreateWithFlags(&dev.stream, cudaStreamNonBlocking));
+  PLADE_CUDA(cudaEventCreate(&ev0));
+  PLADE_CUDA(cudaEventCreate(&ev1));
+  PLADE_CUDA(cudaEventCreate(&ev_user0));
+  PLADE_CUDA(cudaEventCreate(&ev_user1));
 }
 
 Registrar::~Registrar() {
+  for (cudaEvent_t e : {ev0, ev1, ev_user0, ev_user1}) if (e) cudaEventDestroy(e);
   if (dev.stream) cudaStreamDestroy(dev.stream);
 }
 
@@ -749,10 +754,18 @@ bool Registrar::register_with_planes(const CloudDev &tgt, const CloudDev &src, c
   HypParams *d_h = d_hyp.ensure(std::max<size_t>(1, hp_mine.size()));
   unsigned int *d_c = d_counts.ensure(std::max<size_t>(1, hp_mine.size()));
   if (!hp_mine.empty()) PLADE_CUDA(cudaMemcpyAsync(d_h, hp_mine.data(), sizeof(HypParams) * hp_mine.size(), cudaMemcpyHostToDevice, s));
+  PLADE_CUDA(cudaEventRecord(ev0, s));
   verify_hypotheses(dev, ds_src.p, Cu.n_ds, grid, d_h, (int) hp_mine.size(), (float) Cu.radius, downSampleDistance, d_c);
+  PLADE_CUDA(cudaEventRecord(ev1, s));
   std::vector<unsigned int> counts_mine(hp_mine.size());
   if (!hp_mine.empty()) PLADE_CUDA(cudaMemcpyAsync(counts_mine.data(), d_c, sizeof(unsigned int) * hp_mine.size(), cudaMemcpyDeviceToHost, s));
   PLADE_CUDA(cudaStreamSynchronize(s));
+  {
+    float ms = 0;
+    PLADE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    times.verify_kernel_ms = ms;
+    times.verify_h = (double) hp_mine.size(); times.verify_ns = (double) Cu.n_ds; times.verify_nt = (double) M.n_ds;
+  }
   const size_t denom = std::min(Cu.n_ds, M.n_ds);
   auto score_of = [&](int i, unsigned int cnt) {
     float overlap = (float) (double(cnt) / denom);                                   // util.h:644

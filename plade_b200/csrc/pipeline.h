@@ -38,6 +38,8 @@ struct Params {
 struct StageTimes {
   double upload = 0, planes = 0, spacing = 0, downsample = 0, lines = 0, descriptors = 0, match = 0, hypotheses = 0,
          penetration = 0, verify = 0, total = 0;
+  // the dominant kernel (K5) timed with CUDA events on the context stream, and its launch shape
+  double verify_kernel_ms = 0, verify_h = 0, verify_ns = 0, verify_nt = 0;
 };
 
 struct MatchedHyp {     // MatchedResult, PLADE/util.h:128-134
@@ -91,6 +93,7 @@ class Registrar {
   DevBuf<HypParams> d_hyp;
   DevBuf<unsigned int> d_counts;
   PinBuf<float> pin_in;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_user0 = nullptr, ev_user1 = nullptr;
 
   template <typename T> void put(const std::string &name, const std::vector<T> &v) {
     if (!debug) return;

@@ -564,7 +564,11 @@ std::vector<PlaneRec> Registrar::detect_planes(const CloudDev &c, int min_suppor
   float4 best_pl = make_float4(0, 0, 0, 0);
   double best_est = 0;
   const int max_rounds = 4000;
-  int rejects = 0;
+  int rejects = 0, dry_rounds = 0;
+  struct PoolEntry { double est; float4 pl; };
+  constexpr int kPoolSize = 64;
+  std::vector<PoolEntry> pool;
+  std::vector<float4> h_pool(kPoolSize), banned;
   for (int round = 0; round < max_rounds && m >= min_support && m >= 3; ++round) {
     int nlevels = 1;
     while ((8ll << nlevels) < m) ++nlevels;
@@ -575,6 +579,10 @@ std::vector<PlaneRec> Registrar::detect_planes(const CloudDev &c, int min_suppor
     PLADE_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * kCandPerRound, s));
     round_seed = mix64(round_seed + 1);
     gen_candidates_kernel<<<div_up(kCandPerRound, 128), 128, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, nlevels, nthresh, round_seed, cand, d_nvalid);
+    if (!pool.empty()) {   // carried candidates occupy the first slots
+      for (size_t q = 0; q < pool.size(); ++q) h_pool[q] = pool[q].pl;
+      PLADE_CUDA(cudaMemcpyAsync(cand, h_pool.data(), sizeof(float4) * pool.size(), cudaMemcpyHostToDevice, s));
+    }
     gather_sub_kernel<<<div_up(S, 256), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S, round_seed, sub);
     const int n_tiles = div_up(S, kScoreTile);
     const int tiles_per_block = std::max(1, n_tiles / 32);
@@ -588,16 +596,44 @@ std::vector<PlaneRec> Registrar::detect_planes(const CloudDev &c, int min_suppor
     PLADE_CUDA(cudaMemcpyAsync(&n_valid, d_nvalid, sizeof(int), cudaMemcpyDeviceToHost, s));
     PLADE_CUDA(cudaStreamSynchronize(s));
     drawn += n_valid;
-    for (int k = 0; k < kCandPerRound; ++k) {
-      double est = (double) h_counts[k] * m / S;
-      if (est > best_est) { best_est = est; best_pl = h_cand[k]; }
+    // Candidate pool (the reference keeps its candidate list across iterations, RansacShapeDetector.cpp:
+    // 548-855): the best distinct planes of this round are re-scored next round in the first slots, so a
+    // plane that lost against a bigger one is still there after the bigger one has been removed.
+    {
+      std::vector<int> ord(kCandPerRound);
+      for (int k = 0; k < kCandPerRound; ++k) ord[k] = k;
+      std::partial_sort(ord.begin(), ord.begin() + std::min(kCandPerRound, 1024), ord.end(),
+                        [&](int a, int b) { return h_counts[a] != h_counts[b] ? h_counts[a] > h_counts[b] : a < b; });
+      pool.clear();
+      for (int q = 0; q < std::min(kCandPerRound, 1024) && (int) pool.size() < kPoolSize; ++q) {
+        const int k = ord[q];
+        if (h_counts[k] == 0) break;
+        const float4 &a = h_cand[k];
+        bool dup = false;
+        for (const PoolEntry &e : pool) {
+          float dn = a.x * e.pl.x + a.y * e.pl.y + a.z * e.pl.z;
+          float dd = dn >= 0 ? std::fabs(a.w - e.pl.w) : std::fabs(a.w + e.pl.w);
+          if (std::fabs(dn) > 0.995f && dd < 2 * eps) { dup = true; break; }
+        }
+        for (const float4 &e : banned) {
+          if (dup) break;
+          float dn = a.x * e.x + a.y * e.y + a.z * e.z;
+          float dd = dn >= 0 ? std::fabs(a.w - e.w) : std::fabs(a.w + e.w);
+          if (std::fabs(dn) > 0.995f && dd < 2 * eps) dup = true;
+        }
+        if (!dup) pool.push_back({(double) h_counts[k] * m / S, a});
+      }
     }
+    best_est = pool.empty() ? 0.0 : pool[0].est;
+    if (!pool.empty()) best_pl = pool[0].pl;
     const bool enough_for_min = failure_probability(min_support, m, drawn, nlevels) <= prob;
     const bool best_ok = best_est >= min_support && failure_probability(best_est, m, drawn, nlevels) <= prob;
     if (!best_ok) {
-      if (enough_for_min && best_est < min_support) break;     // nothing of min_support size left (w.h.p.)
+      // nothing of min_support size left (w.h.p.): require the evidence in three consecutive rounds
+      if (enough_for_min && best_est < min_support) { if (++dry_rounds >= 3) break; } else dry_rounds = 0;
       continue;
     }
+    dry_rounds = 0;
     // --- refine the best candidate on the full cloud -------------------------------------------------------
     PlaneFrame fr;
     auto make_frame = [&](const float nrm3[3], const float pos3[3]) {
@@ -708,10 +744,12 @@ std::vector<PlaneRec> Registrar::detect_planes(const CloudDev &c, int min_suppor
     // the reference only accepts a candidate whose fully evaluated (connected-component) support
     // reaches min_support (FindBestCandidate, RansacShapeDetector.cpp:297,423-430)
     if (acc_size < min_support) {
-      if (++rejects >= 32 && enough_for_min) break;
+      // its score can only shrink from here on: never look at this plane (or a duplicate of it) again
+      banned.push_back(best_pl);
+      if (!pool.empty()) pool.erase(pool.begin());
+      if (++rejects >= 256) break;
       continue;
     }
-    rejects = 0;
     unsigned char *member = acc_member;
     // --- accept: remove the points (RansacShapeDetector.cpp:659-675) ---------------------------------------------
     mark_kernel<<<div_up(n, 256), 256, 0, s>>>(member, n, (int) found.size(), assigned);
