@@ -2,6 +2,8 @@
 // Every stage cites the reference loop it replaces (paths relative to /root/reference/code/).
 #pragma once
 #include "common.h"
+#include "linalg.h"
+#include <array>
 
 namespace plade {
 
@@ -113,5 +115,25 @@ void transforms_from_matches(Device &dev, HypScratch &sc, const MatchPairIn *h_i
 // label[i] = smallest member index of i's component.
 void cluster_transforms(Device &dev, HypScratch &sc, const std::vector<RigidOut> &rt, float dist_thresh,
                         float ang_thresh, std::vector<int> &label);
+
+// ------------------------------------------------------------------------------------------------
+// K4d — penetration filter (PLADE/util.cpp:450-519, AreTwoPlanesPenetrable PLADE/util.cpp:1279-1458)
+// ------------------------------------------------------------------------------------------------
+struct PenSide {                                   // per-plane data of one cloud
+  std::vector<std::array<float, 4>> planes;        // (n, d)
+  std::vector<std::array<V3, 4>> corners4;         // bounding rectangle projected on the plane
+  std::vector<V3> center;
+  std::vector<int> ds_start;                       // P + 1 offsets into d_pts
+  const float4 *d_pts = nullptr;                   // device: per-plane down-sampled points
+};
+struct PenScratch {
+  DevBuf<float> tables;
+  DevBuf<unsigned char> triples;
+  DevBuf<int> flags;
+};
+// pen_out[h] = 1 iff hypothesis h (12 floats: R row-major, T) makes some source plane penetrate a
+// non-coincident target plane.
+void penetration_filter(Device &dev, PenScratch &sc, const PenSide &src, const PenSide &tgt, const float *h_hyp12, int H,
+                        float lengthThreshold, float angleThreshold, std::vector<unsigned char> &pen_out);
 
 }  // namespace plade

@@ -47,19 +47,6 @@ struct Side {            // MatchInformation, PLADE/util.h:80-102
   std::vector<Line> lines;
 };
 
-// transformPointCloud formula (common/impl/transforms.hpp:69-71)
-inline V3 xform(const M3 &R, const V3 &T, const V3 &p) {
-  return V3(((R.m[0] * p.x + R.m[1] * p.y) + R.m[2] * p.z) + T.x, ((R.m[3] * p.x + R.m[4] * p.y) + R.m[5] * p.z) + T.y,
-            ((R.m[6] * p.x + R.m[7] * p.y) + R.m[8] * p.z) + T.z);
-}
-inline float l2simple(const V3 &a, const V3 &b) {     // FLANN L2_Simple (dist.h:84-90)
-  float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
-  float r = dx * dx;
-  r += dy * dy;
-  r += dz * dz;
-  return r;
-}
-
 // ComputeNearstTwoPointsOfTwo3DLine (PLADE/util.cpp:1167-1229): normalises both directions IN PLACE,
 // fails on identical directions, closest points (closed form here), length = |p1 - p2| (float norm).
 int nearest_two_lines(V3 &v1, const V3 &p1, V3 &v2, const V3 &p2, V3 &q1, V3 &q2, double &len) {
@@ -92,133 +79,7 @@ void pair_descriptor(const V3 &l1, const V3 &l2, const V3 &l1sp1, const V3 &l1sp
   d[7] = dot(newLine2, n1b);
 }
 
-// ComputeIntersectionPointOf23DLine (PLADE/util.cpp:1461-1500): least-squares "intersection" of two
-// lines (6x5 float SVD solve in the reference) = midpoint of their closest points, closed form.
-int line_line_point(const V3 &v1, const V3 &p1, const V3 &v2, const V3 &p2, V3 &out) {
-  if (std::fabs(dot(v1, v2)) > 0.9999) return -1;
-  V3 q1, q2;
-  if (!closest_points_two_lines(v1, p1, v2, p2, q1, q2)) return -1;
-  out = V3((float) (0.5 * ((double) q1.x + q2.x)), (float) (0.5 * ((double) q1.y + q2.y)), (float) (0.5 * ((double) q1.z + q2.z)));
-  return 0;
-}
-
-struct PlaneCloudView {
-  const V3 *pts;
-  size_t n;
-  V3 lo, hi;   // axis-aligned bounds, used only to skip searches that cannot hit
-};
-// pcl radiusSearch on a plane's ds cloud: #points with L2_Simple(query, p) < float(r*r); optional index list
-int radius_count(const PlaneCloudView &c, const V3 &q, float radius, int cap, std::vector<int> *out) {
-  float r2 = (float) ((double) radius * (double) radius);
-  if (out) out->clear();
-  float m = radius * 1.001f;
-  if (q.x < c.lo.x - m || q.x > c.hi.x + m || q.y < c.lo.y - m || q.y > c.hi.y + m || q.z < c.lo.z - m || q.z > c.hi.z + m) return 0;
-  int cnt = 0;
-  for (size_t i = 0; i < c.n; ++i) {
-    if (l2simple(q, c.pts[i]) < r2) {
-      ++cnt;
-      if (out) out->push_back((int) i);
-      if (cap > 0 && cnt >= cap) break;
-    }
-  }
-  return cnt;
-}
-
-// AreTwoPlanesPenetrable (PLADE/util.cpp:1279-1458)
-int planes_penetrable(const float plane1[4], const float plane2[4], const V3 c1[4], const V3 c2[4], const PlaneCloudView &k1,
-                      const PlaneCloudView &k2, bool &pen, float searchRadius, int minPointsNum, float minDistance) {
-  pen = false;
-  V3 lineVec, linePoint;
-  if (0 != plane_intersection_line(plane1, plane2, lineVec, linePoint)) return -1;
-  std::vector<V3> ip1, ip2;
-  for (int i = 1; i <= 4; ++i) {
-    V3 tl = c1[i % 4] - c1[(i - 1) % 4];
-    normalize(tl);
-    V3 ip;
-    if (0 != line_line_point(lineVec, linePoint, tl, c1[i - 1], ip)) continue;
-    if (dot(c1[(i - 1) % 4] - ip, c1[i % 4] - ip) > 0) continue;
-    ip1.push_back(ip);
-  }
-  for (int i = 1; i <= 4; ++i) {
-    V3 tl = c2[i % 4] - c2[(i - 1) % 4];
-    normalize(tl);
-    V3 ip;
-    if (0 != line_line_point(lineVec, linePoint, tl, c2[i - 1], ip)) continue;
-    if (dot(c2[(i - 1) % 4] - ip, c2[i % 4] - ip) > 0) continue;
-    ip2.push_back(ip);
-  }
-  if (ip1.empty()) return 0; else if (ip1.size() != 2) return -1;
-  if (ip2.empty()) return 0; else if (ip2.size() != 2) return -1;
-  V3 direc = ip1[1] - ip1[0];
-  normalize(direc);
-  V3 inter[4] = {ip1[0], ip1[1], ip2[0], ip2[1]};
-  std::vector<LenIdx> lv(4);
-  for (int i = 0; i < 4; ++i) { lv[i].length = dot(inter[i] - inter[0], direc); lv[i].index = i; }
-  std::sort(lv.begin(), lv.end(), cmp_less);
-  if (0 == (lv[0].index / 2 - lv[1].index / 2)) return 0;
-  const V3 startPoint = inter[lv[1].index], endPoint = inter[lv[2].index];
-  float length = norm(endPoint - startPoint);
-  std::vector<int> nb;
-  for (int pass = 0; pass < 2; ++pass) {
-    const PlaneCloudView &gate = pass == 0 ? k2 : k1;     // needs >= 2 points within r/2
-    const PlaneCloudView &probe = pass == 0 ? k1 : k2;    // classified against the other plane
-    const float *pl = pass == 0 ? plane2 : plane1;
-    int pos = 0, neg = 0;
-    std::vector<char> fresh(probe.n, 1);
-    for (float dist = 0; dist < length; dist += searchRadius) {
-      V3 sp = startPoint + dist * direc;
-      if (radius_count(gate, sp, searchRadius / 2, 2, nullptr) < 2) continue;
-      radius_count(probe, sp, searchRadius, 0, &nb);
-      for (int id : nb) {
-        if (!fresh[id]) continue;
-        fresh[id] = 0;
-        const V3 &p = probe.pts[id];
-        float td = pl[0] * p.x + pl[1] * p.y + pl[2] * p.z + pl[3];
-        if (std::fabs(td) > minDistance) { if (td >= 0) ++pos; else ++neg; }
-      }
-    }
-    if (pass == 0) { if (pos < minPointsNum || neg < minPointsNum) return 0; }
-    else { if (pos < minPointsNum && neg < minPointsNum) return 0; }
-    if (double(std::max(pos, neg)) / std::min(pos, neg + 1) > 5) return 0;
-  }
-  pen = true;
-  return 0;
-}
-
 }  // namespace
-
-int plane_intersection_line(const float pl1[4], const float pl2[4], V3 &lineVec, V3 &linePoint) {
-  V3 p1(pl1[0], pl1[1], pl1[2]), p2(pl2[0], pl2[1], pl2[2]);
-  normalize(p1);
-  normalize(p2);
-  if (std::fabs(dot(p1, p2)) > 0.95) return -1;
-  lineVec = cross(p1, p2);
-  normalize(lineVec);
-  double b0 = -(double) pl1[3], b1 = -(double) pl2[3];
-  auto solve2 = [&](float a00, float a01, float a10, float a11, double &x0, double &x1) {
-    // cv::Mat::inv() 2x2 CV_64F closed form (opencv core lapack.cpp, n == 2 branch) then A^-1 * B
-    double A00 = a00, A01 = a01, A10 = a10, A11 = a11;
-    double det = A00 * A11 - A01 * A10;
-    double i00 = 0, i01 = 0, i10 = 0, i11 = 0;
-    if (det != 0.) { double d = 1. / det; i11 = A00 * d; i00 = A11 * d; i01 = -A01 * d; i10 = -A10 * d; }
-    x0 = i00 * b0 + i01 * b1;
-    x1 = i10 * b0 + i11 * b1;
-  };
-  double x0, x1;
-  if (std::fabs(pl1[0] * pl2[1] - pl2[0] * pl1[1]) > 1e-6) {
-    solve2(pl1[0], pl1[1], pl2[0], pl2[1], x0, x1);
-    linePoint = V3((float) x0, (float) x1, 0.f);
-  } else if (std::fabs(pl1[0] * pl2[2] - pl2[0] * pl1[2]) > 1e-6) {
-    solve2(pl1[0], pl1[2], pl2[0], pl2[2], x0, x1);
-    linePoint = V3((float) x0, 0.f, (float) x1);
-  } else if (std::fabs(pl1[1] * pl2[2] - pl2[1] * pl1[2]) > 1e-6) {
-    solve2(pl1[1], pl1[2], pl2[1], pl2[2], x0, x1);
-    linePoint = V3(0.f, (float) x0, (float) x1);
-  } else {
-    return -1;
-  }
-  return 0;
-}
 
 int compute_bounding_box(const float4 *pts, size_t n, V3 &centerPoint, double &width, double &height, double &depth,
                          V3 corners[8]) {
@@ -389,6 +250,7 @@ bool Registrar::register_with_planes(const CloudDev &tgt, const CloudDev &src, c
   const CloudDev *clouds[2] = {&tgt, &src};
   const std::vector<PlaneRec> *planes_in[2] = {&tplanes, &splanes};
   DevBuf<float4> *ds_dev[2] = {&ds_tgt, &ds_src};
+  DevBuf<float4> *ds_pl[2] = {&ds_planes_t, &ds_planes_s};
   for (int side = 0; side < 2; ++side) {
     Side &A = S[side];
     const CloudDev &C = *clouds[side];
@@ -402,9 +264,9 @@ bool Registrar::register_with_planes(const CloudDev &tgt, const CloudDev &src, c
       for (int id : P[i].idx) if (id >= 0 && (size_t) id < C.n) grp[id] = (int) i;
     int *d_grp = group.ensure(C.n);
     PLADE_CUDA(cudaMemcpyAsync(d_grp, grp.data(), sizeof(int) * C.n, cudaMemcpyHostToDevice, s));
-    size_t nv = voxel_downsample_groups(dev, vox, C.pos.p, C.n, d_grp, (int) P.size(), downSampleDistance, ds_planes, A.plane_ds_start);
+    size_t nv = voxel_downsample_groups(dev, vox, C.pos.p, C.n, d_grp, (int) P.size(), downSampleDistance, *ds_pl[side], A.plane_ds_start);
     A.plane_ds.resize(nv);
-    if (nv) PLADE_CUDA(cudaMemcpyAsync(A.plane_ds.data(), ds_planes.p, sizeof(float4) * nv, cudaMemcpyDeviceToHost, s));
+    if (nv) PLADE_CUDA(cudaMemcpyAsync(A.plane_ds.data(), ds_pl[side]->p, sizeof(float4) * nv, cudaMemcpyDeviceToHost, s));
     PLADE_CUDA(cudaStreamSynchronize(s));
     double w, h, d;
     if (0 != compute_bounding_box(A.ds.data(), A.n_ds, A.center, w, h, d, nullptr)) { last_error = "empty down-sampled cloud"; return false; }
@@ -663,59 +525,35 @@ bool Registrar::register_with_planes(const CloudDev &tgt, const CloudDev &src, c
   t0 = now_s();
   std::vector<MatchedHyp> results;
   {
-    // static target plane clouds
-    std::vector<std::vector<V3>> tp(mainPlanesNum);
-    std::vector<PlaneCloudView> tview(mainPlanesNum);
-    auto make_view = [](const std::vector<V3> &v) {
-      PlaneCloudView w{v.data(), v.size(), V3(3e38f, 3e38f, 3e38f), V3(-3e38f, -3e38f, -3e38f)};
-      for (const V3 &p : v) {
-        w.lo.x = std::min(w.lo.x, p.x); w.lo.y = std::min(w.lo.y, p.y); w.lo.z = std::min(w.lo.z, p.z);
-        w.hi.x = std::max(w.hi.x, p.x); w.hi.y = std::max(w.hi.y, p.y); w.hi.z = std::max(w.hi.z, p.z);
-      }
-      return w;
-    };
-    for (size_t j = 0; j < mainPlanesNum; ++j) {
-      for (int e = M.plane_ds_start[j]; e < M.plane_ds_start[j + 1]; ++e) tp[j].push_back(V3(M.plane_ds[e].x, M.plane_ds[e].y, M.plane_ds[e].z));
-      tview[j] = make_view(tp[j]);
-    }
+    // the candidates the reference would look at, in its order (count++ > maxCandidateResultNum stops the walk)
+    std::vector<int> cand;
     int count = 0;
     bool stop = false;
     for (size_t m = 0; m < matchedPlanes.size() && !stop; ++m)
       for (size_t i = 0; i < matchedPlanes[m].size(); ++i) {
         if (count++ > maxCandidateResultNum) { stop = true; break; }
-        int index = matchedPlanes[m][i];
-        int k = cand_rt[index];
-        M3 R; memcpy(R.m, rt[k].R, sizeof(R.m));
-        V3 T(rt[k].T[0], rt[k].T[1], rt[k].T[2]);
-        bool pen = false;
-        for (size_t i1 = 0; i1 < currentPlanesNum; ++i1) {
-          pen = false;
-          V3 pn = mul(R, V3(Cu.planes[i1][0], Cu.planes[i1][1], Cu.planes[i1][2]));
-          float plane1[4] = {pn.x, pn.y, pn.z, -(-Cu.planes[i1][3] + dot(pn, T))};
-          std::vector<V3> sp_pts;
-          for (int e = Cu.plane_ds_start[i1]; e < Cu.plane_ds_start[i1 + 1]; ++e)
-            sp_pts.push_back(xform(R, T, V3(Cu.plane_ds[e].x, Cu.plane_ds[e].y, Cu.plane_ds[e].z)));
-          PlaneCloudView sview = make_view(sp_pts);
-          V3 c1[4];
-          for (int c = 0; c < 4; ++c) c1[c] = xform(R, T, Cu.corners4[i1][c]);
-          V3 currentCenter2Main = mul(R, Cu.plane_center[i1]) + T;
-          for (size_t j1 = 0; j1 < mainPlanesNum; ++j1) {
-            V3 plane_A(M.planes[j1][0], M.planes[j1][1], M.planes[j1][2]);
-            double c2p = (std::fabs(dot(plane_A, currentCenter2Main) + M.planes[j1][3]) + std::fabs(dot(pn, M.plane_center[j1]) + plane1[3])) / 2;
-            if (c2p < lengthThreshold && dot(pn, plane_A) > angleThreshold) continue;
-            if (sp_pts.empty() || tp[j1].empty()) continue;   // empty corner sets => AreTwoPlanesPenetrable returns -1
-            if (0 != planes_penetrable(plane1, M.planes[j1].data(), c1, M.corners4[j1].data(), sview, tview[j1], pen,
-                                       lengthThreshold, 10, (float) ((double) lengthThreshold / 2)))
-              continue;
-            if (pen) break;
-          }
-          if (pen) break;
-        }
-        if (pen) continue;
-        MatchedHyp r;
-        r.R = R; r.T = T; r.planes = matches[index];
-        results.push_back(r);
+        cand.push_back(matchedPlanes[m][i]);
       }
+    std::vector<float> hyp12(cand.size() * 12);
+    for (size_t c = 0; c < cand.size(); ++c) {
+      const RigidOut &r = rt[cand_rt[cand[c]]];
+      memcpy(&hyp12[12 * c], r.R, sizeof(float) * 9);
+      memcpy(&hyp12[12 * c + 9], r.T, sizeof(float) * 3);
+    }
+    PenSide ps, pt;
+    ps.planes = Cu.planes; ps.corners4 = Cu.corners4; ps.center = Cu.plane_center; ps.ds_start = Cu.plane_ds_start; ps.d_pts = ds_planes_s.p;
+    pt.planes = M.planes; pt.corners4 = M.corners4; pt.center = M.plane_center; pt.ds_start = M.plane_ds_start; pt.d_pts = ds_planes_t.p;
+    std::vector<unsigned char> pen;
+    penetration_filter(dev, pen_sc, ps, pt, hyp12.data(), (int) cand.size(), lengthThreshold, angleThreshold, pen);
+    for (size_t c = 0; c < cand.size(); ++c) {
+      if (pen[c]) continue;
+      const int index = cand[c], k = cand_rt[index];
+      MatchedHyp r;
+      memcpy(r.R.m, rt[k].R, sizeof(r.R.m));
+      r.T = V3(rt[k].T[0], rt[k].T[1], rt[k].T[2]);
+      r.planes = matches[index];
+      results.push_back(r);
+    }
   }
   times.penetration = now_s() - t0;
   if (debug) {

@@ -87,7 +87,8 @@ class Registrar {
   TargetGrid grid;
   MatchScratch match_sc;
   HypScratch hyp_sc;
-  DevBuf<float4> ds_tgt, ds_src, ds_planes;
+  DevBuf<float4> ds_tgt, ds_src, ds_planes_t, ds_planes_s;
+  PenScratch pen_sc;
   DevBuf<int> group, qidx;
   DevBuf<float> knn_out;
   DevBuf<HypParams> d_hyp;
@@ -106,7 +107,5 @@ class Registrar {
 // Oriented bounding box exactly as ComputeBoundingBox (PLADE/util.h:187-248).
 int compute_bounding_box(const float4 *pts, size_t n, V3 &center, double &width, double &height, double &depth,
                          V3 corners[8]);
-// ComputeIntersectionLineOfTwoPlanes (PLADE/util.cpp:626-676); planes are (n, d).
-int plane_intersection_line(const float p1[4], const float p2[4], V3 &vec, V3 &pt);
 
 }  // namespace plade
