@@ -197,32 +197,55 @@ float Registrar::average_spacing(const CloudDev &c) {
 bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float out16[16]) {
   double t0 = now_s();
   std::cout << "extracting planes for both point clouds...\n";
-  std::vector<PlaneRec> tp = extract_planes(tgt, params.init_min_support);
+  std::vector<PlaneParam> tp = extract_planes_dev(tgt, params.init_min_support, group_t);
   if ((int) tp.size() < params.min_planes) {
     std::cerr << "too few (only " << tp.size() << ") planes extracted from the target point cloud" << std::endl;
     last_error = "too few planes in target";
     return false;
   }
-  std::vector<PlaneRec> sp = extract_planes(src, params.init_min_support);
+  std::vector<PlaneParam> sp = extract_planes_dev(src, params.init_min_support, group_s);
   if ((int) sp.size() < params.min_planes) {
     std::cerr << "two few (only " << sp.size() << ") planes extracted from the source point cloud" << std::endl;
     last_error = "too few planes in source";
     return false;
   }
   times.planes = now_s() - t0;
-  return register_with_planes(tgt, src, tp, sp, out16);
+  return register_core(tgt, src, tp, sp, group_t.p, group_s.p, out16);
 }
 
 bool Registrar::register_min_support(const CloudDev &tgt, const CloudDev &src, int ms_t, int ms_s, float out16[16]) {
   double t0 = now_s();
-  std::vector<PlaneRec> tp = detect_planes(tgt, ms_t);
-  std::vector<PlaneRec> sp = detect_planes(src, ms_s);
+  std::vector<PlaneParam> tp = detect_planes_dev(tgt, ms_t, group_t);
+  std::vector<PlaneParam> sp = detect_planes_dev(src, ms_s, group_s);
   times.planes = now_s() - t0;
-  return register_with_planes(tgt, src, tp, sp, out16);
+  return register_core(tgt, src, tp, sp, group_t.p, group_s.p, out16);
 }
 
 bool Registrar::register_with_planes(const CloudDev &tgt, const CloudDev &src, const std::vector<PlaneRec> &tplanes,
                                      const std::vector<PlaneRec> &splanes, float out16[16]) {
+  // caller-supplied planes: host index lists -> plane index per point, uploaded once
+  const CloudDev *clouds[2] = {&tgt, &src};
+  const std::vector<PlaneRec> *pin[2] = {&tplanes, &splanes};
+  DevBuf<int> *gbuf[2] = {&group_t, &group_s};
+  std::vector<PlaneParam> pp[2];
+  for (int side = 0; side < 2; ++side) {
+    const size_t n = clouds[side]->n;
+    std::vector<int> grp(n, -1);
+    for (size_t i = 0; i < pin[side]->size(); ++i) {
+      const PlaneRec &p = (*pin[side])[i];
+      for (int id : p.idx) if (id >= 0 && (size_t) id < n) grp[id] = (int) i;
+      pp[side].push_back({{p.n[0], p.n[1], p.n[2]}, p.d, (long long) p.idx.size()});
+    }
+    int *d = gbuf[side]->ensure(std::max<size_t>(n, 1));
+    if (n) PLADE_CUDA(cudaMemcpyAsync(d, grp.data(), sizeof(int) * n, cudaMemcpyHostToDevice, dev.stream));
+    PLADE_CUDA(cudaStreamSynchronize(dev.stream));
+  }
+  times.planes = 0;
+  return register_core(tgt, src, pp[0], pp[1], group_t.p, group_s.p, out16);
+}
+
+bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const std::vector<PlaneParam> &tplanes,
+                              const std::vector<PlaneParam> &splanes, const int *d_group_t, const int *d_group_s, float out16[16]) {
   const double t_begin = now_s();
   for (int i = 0; i < 16; ++i) out16[i] = (i % 5 == 0) ? 1.f : 0.f;
   cudaStream_t s = dev.stream;
@@ -248,23 +271,18 @@ bool Registrar::register_with_planes(const CloudDev &tgt, const CloudDev &src, c
   t0 = now_s();
   Side S[2];   // 0 = target ("main"), 1 = source ("current")
   const CloudDev *clouds[2] = {&tgt, &src};
-  const std::vector<PlaneRec> *planes_in[2] = {&tplanes, &splanes};
+  const std::vector<PlaneParam> *planes_in[2] = {&tplanes, &splanes};
+  const int *d_groups[2] = {d_group_t, d_group_s};
   DevBuf<float4> *ds_dev[2] = {&ds_tgt, &ds_src};
   DevBuf<float4> *ds_pl[2] = {&ds_planes_t, &ds_planes_s};
   for (int side = 0; side < 2; ++side) {
     Side &A = S[side];
     const CloudDev &C = *clouds[side];
-    const std::vector<PlaneRec> &P = *planes_in[side];
+    const std::vector<PlaneParam> &P = *planes_in[side];
     A.n_ds = voxel_downsample(dev, vox, C.pos.p, C.n, downSampleDistance, *ds_dev[side]);
     A.ds.resize(A.n_ds);
     PLADE_CUDA(cudaMemcpyAsync(A.ds.data(), ds_dev[side]->p, sizeof(float4) * A.n_ds, cudaMemcpyDeviceToHost, s));
-    // plane membership -> group id per point
-    std::vector<int> grp(C.n, -1);
-    for (size_t i = 0; i < P.size(); ++i)
-      for (int id : P[i].idx) if (id >= 0 && (size_t) id < C.n) grp[id] = (int) i;
-    int *d_grp = group.ensure(C.n);
-    PLADE_CUDA(cudaMemcpyAsync(d_grp, grp.data(), sizeof(int) * C.n, cudaMemcpyHostToDevice, s));
-    size_t nv = voxel_downsample_groups(dev, vox, C.pos.p, C.n, d_grp, (int) P.size(), downSampleDistance, *ds_pl[side], A.plane_ds_start);
+    size_t nv = voxel_downsample_groups(dev, vox, C.pos.p, C.n, d_groups[side], (int) P.size(), downSampleDistance, *ds_pl[side], A.plane_ds_start);
     A.plane_ds.resize(nv);
     if (nv) PLADE_CUDA(cudaMemcpyAsync(A.plane_ds.data(), ds_pl[side]->p, sizeof(float4) * nv, cudaMemcpyDeviceToHost, s));
     PLADE_CUDA(cudaStreamSynchronize(s));

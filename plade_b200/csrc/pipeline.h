@@ -17,6 +17,13 @@ struct PlaneRec {
   float d;
 };
 
+// Plane parameters + support; the membership lives in a device "group" array (plane index per point, -1 = none)
+struct PlaneParam {
+  float n[3];
+  float d;
+  long long size;
+};
+
 // Device-resident input cloud: positions and normals as two float4 streams.
 struct CloudDev {
   DevBuf<float4> pos, nrm;
@@ -71,6 +78,12 @@ class Registrar {
   float average_spacing(const CloudDev &c);
   std::vector<PlaneRec> extract_planes(const CloudDev &c, int init_min_support);             // extract(), plade.cpp:602
   std::vector<PlaneRec> detect_planes(const CloudDev &c, int min_support);                   // PlaneExtraction::detect
+  // device-resident variants used by the registration path: membership stays in HBM (group_out[n])
+  std::vector<PlaneParam> detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out);
+  std::vector<PlaneParam> extract_planes_dev(const CloudDev &c, int init_min_support, DevBuf<int> &group_out);
+  std::vector<PlaneRec> planes_to_host(const CloudDev &c, const std::vector<PlaneParam> &pp, const DevBuf<int> &group);
+  bool register_core(const CloudDev &tgt, const CloudDev &src, const std::vector<PlaneParam> &tp, const std::vector<PlaneParam> &sp,
+                     const int *d_group_t, const int *d_group_s, float out16[16]);
 
   Device dev;
   Params params;
@@ -89,7 +102,7 @@ class Registrar {
   HypScratch hyp_sc;
   DevBuf<float4> ds_tgt, ds_src, ds_planes_t, ds_planes_s;
   PenScratch pen_sc;
-  DevBuf<int> group, qidx;
+  DevBuf<int> group_t, group_s, qidx;
   DevBuf<float> knn_out;
   DevBuf<HypParams> d_hyp;
   DevBuf<unsigned int> d_counts;

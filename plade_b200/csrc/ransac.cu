@@ -494,8 +494,16 @@ struct FoundPlane { float n[3]; float pos[3]; long long size; };
 
 static thread_local RansacScratch g_rs;
 
-std::vector<PlaneRec> Registrar::detect_planes(const CloudDev &c, int min_support) {
-  std::vector<PlaneRec> result;
+__global__ void remap_group_kernel(const int *__restrict__ assigned, int n, const int *__restrict__ remap, int n_remap,
+                                   int *__restrict__ group) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int a = assigned[i];
+  group[i] = (a >= 0 && a < n_remap) ? remap[a] : -1;
+}
+
+std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out) {
+  std::vector<PlaneParam> result;
   const int n = (int) c.n;
   if (n < 3) { std::cerr << "point set has less than 3 points" << std::endl; return result; }
   cudaStream_t s = dev.stream;
@@ -774,50 +782,90 @@ std::vector<PlaneRec> Registrar::detect_planes(const CloudDev &c, int min_suppor
   }
 
   // ---- output (PLADE/plane_extraction.cpp:115-160): drop shapes below min_support, unit normal, d = -n.p --------
-  std::vector<int> h_assigned(n);
-  PLADE_CUDA(cudaMemcpyAsync(h_assigned.data(), assigned, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
-  std::vector<std::vector<int>> lists(found.size());
-  for (size_t k = 0; k < found.size(); ++k) lists[k].reserve((size_t) found[k].size);
-  for (int i = 0; i < n; ++i) if (h_assigned[i] >= 0) lists[h_assigned[i]].push_back(i);
+  // membership stays on the device: group_out[i] = index of the returned plane of point i, or -1
+  std::vector<int> remap(std::max<size_t>(found.size(), 1), -1);
   for (size_t k = 0; k < found.size(); ++k) {
-    if ((long long) lists[k].size() < (long long) min_support) continue;
-    PlaneRec pr;
-    pr.idx.swap(lists[k]);
+    if (found[k].size < (long long) min_support) continue;
+    remap[k] = (int) result.size();
+    PlaneParam pr;
     V3 nn(found[k].n[0], found[k].n[1], found[k].n[2]);
     float l = std::sqrt(nn.x * nn.x + nn.y * nn.y + nn.z * nn.z);     // Vec3f::normalize
     if (l > 0) { nn.x /= l; nn.y /= l; nn.z /= l; }
     pr.n[0] = nn.x; pr.n[1] = nn.y; pr.n[2] = nn.z;
     pr.d = -(nn.x * found[k].pos[0] + nn.y * found[k].pos[1] + nn.z * found[k].pos[2]);
-    result.push_back(std::move(pr));
+    pr.size = found[k].size;
+    result.push_back(pr);
   }
+  int *d_remap = rs.order_alt.p == cur_order ? rs.order.p : rs.order_alt.p;   // the inactive order buffer is free now
+  PLADE_CUDA(cudaMemcpyAsync(d_remap, remap.data(), sizeof(int) * remap.size(), cudaMemcpyHostToDevice, s));
+  int *g = group_out.ensure(n);
+  remap_group_kernel<<<div_up(n, 256), 256, 0, s>>>(assigned, n, d_remap, (int) found.size(), g);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add();
+  PLADE_CUDA(cudaStreamSynchronize(s));
   return result;
 }
 
 // extract(), PLADE/plade.cpp:602-635
-std::vector<PlaneRec> Registrar::extract_planes(const CloudDev &c, int init_min_support) {
+std::vector<PlaneParam> Registrar::extract_planes_dev(const CloudDev &c, int init_min_support, DevBuf<int> &group_out) {
   const int min_num = params.min_planes, max_num = params.max_planes, min_allowed_support = params.min_allowed_support;
-  std::vector<PlaneRec> planes = detect_planes(c, init_min_support);
+  std::vector<PlaneParam> planes = detect_planes_dev(c, init_min_support, group_out);
   if ((int) planes.size() >= min_num && (int) planes.size() <= max_num) return planes;
   if ((int) planes.size() > max_num) {
     // the reference sorts with a (non-strict) `>=` comparator; a stable descending sort is the defined equivalent
-    std::stable_sort(planes.begin(), planes.end(), [](const PlaneRec &a, const PlaneRec &b) { return a.idx.size() > b.idx.size(); });
-    size_t total = planes.size();
-    planes.resize(max_num);
-    std::cout << planes.size() << " of the " << total << " extracted planes will be used for registration" << std::endl;
-    return planes;
+    std::vector<int> ord(planes.size());
+    for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int) i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return planes[a].size > planes[b].size; });
+    std::vector<int> remap(planes.size(), -1);
+    std::vector<PlaneParam> kept;
+    for (int r = 0; r < max_num; ++r) { remap[ord[r]] = r; kept.push_back(planes[ord[r]]); }
+    static thread_local DevBuf<int> d_remap;
+    int *dr = d_remap.ensure(remap.size());
+    PLADE_CUDA(cudaMemcpyAsync(dr, remap.data(), sizeof(int) * remap.size(), cudaMemcpyHostToDevice, dev.stream));
+    remap_group_kernel<<<div_up((long long) c.n, 256), 256, 0, dev.stream>>>(group_out.p, (int) c.n, dr, (int) remap.size(), group_out.p);
+    PLADE_LAUNCH_CHECK();
+    PLADE_CUDA(cudaStreamSynchronize(dev.stream));
+    std::cout << kept.size() << " of the " << planes.size() << " extracted planes will be used for registration" << std::endl;
+    return kept;
   }
   const int max_trials = params.max_trials;
   int min_support = init_min_support / 2;
   int trials = 1;
   while ((int) planes.size() < min_num && trials < max_trials && min_support >= min_allowed_support) {
-    planes = detect_planes(c, min_support);
+    planes = detect_planes_dev(c, min_support, group_out);
     min_support /= 2;
     ++trials;
   }
   if (trials > 1)
     std::cout << "min_support = " << min_support << " used for extracting the " << planes.size() << " planes from point cloud" << std::endl;
   return planes;
+}
+
+// host view of a device-resident plane set (stage API): index lists in ascending point order
+std::vector<PlaneRec> Registrar::planes_to_host(const CloudDev &c, const std::vector<PlaneParam> &pp, const DevBuf<int> &group) {
+  std::vector<int> h(c.n);
+  if (c.n) PLADE_CUDA(cudaMemcpyAsync(h.data(), group.p, sizeof(int) * c.n, cudaMemcpyDeviceToHost, dev.stream));
+  PLADE_CUDA(cudaStreamSynchronize(dev.stream));
+  std::vector<PlaneRec> out(pp.size());
+  for (size_t k = 0; k < pp.size(); ++k) {
+    out[k].idx.reserve((size_t) pp[k].size);
+    for (int a = 0; a < 3; ++a) out[k].n[a] = pp[k].n[a];
+    out[k].d = pp[k].d;
+  }
+  for (size_t i = 0; i < c.n; ++i) if (h[i] >= 0 && (size_t) h[i] < out.size()) out[h[i]].idx.push_back((int) i);
+  return out;
+}
+
+std::vector<PlaneRec> Registrar::detect_planes(const CloudDev &c, int min_support) {
+  static thread_local DevBuf<int> g;
+  std::vector<PlaneParam> pp = detect_planes_dev(c, min_support, g);
+  return planes_to_host(c, pp, g);
+}
+
+std::vector<PlaneRec> Registrar::extract_planes(const CloudDev &c, int init_min_support) {
+  static thread_local DevBuf<int> g;
+  std::vector<PlaneParam> pp = extract_planes_dev(c, init_min_support, g);
+  return planes_to_host(c, pp, g);
 }
 
 // stage API: plane consensus counts over the whole cloud (K1a/K1b predicate)

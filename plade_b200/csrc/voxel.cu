@@ -37,13 +37,28 @@ inline float o2f(int v) { v = v >= 0 ? v : v ^ 0x7fffffff; float f; memcpy(&f, &
 
 __global__ void group_bbox_kernel(const float4 *__restrict__ p, int n, const int *__restrict__ group,
                                   int *__restrict__ bbox /* ngroups*6 ordered ints */) {
+  // per-block boxes in shared memory first (global atomics on <= 64 x 6 addresses from every thread
+  // serialise in L2: 11.7 ms for 2 x 2M points in the first profile), one flush per block at the end
+  __shared__ int sb[kMaxGroups * 6];
+  for (int k = threadIdx.x; k < kMaxGroups * 6; k += blockDim.x) sb[k] = (k % 6 < 3) ? 0x7f7fffff : (int) (0xff7fffff ^ 0x7fffffff);
+  __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int g = group ? group[i] : 0;
-    if (g < 0) continue;
+    if (g < 0 || g >= kMaxGroups) continue;
     float4 v = p[i];
-    int *b = bbox + 6 * g;
-    atomicMin(b + 0, f2o(v.x)); atomicMin(b + 1, f2o(v.y)); atomicMin(b + 2, f2o(v.z));
-    atomicMax(b + 3, f2o(v.x)); atomicMax(b + 4, f2o(v.y)); atomicMax(b + 5, f2o(v.z));
+    int *b = sb + 6 * g;
+    int ox = f2o(v.x), oy = f2o(v.y), oz = f2o(v.z);
+    if (ox < b[0]) atomicMin(b + 0, ox);
+    if (oy < b[1]) atomicMin(b + 1, oy);
+    if (oz < b[2]) atomicMin(b + 2, oz);
+    if (ox > b[3]) atomicMax(b + 3, ox);
+    if (oy > b[4]) atomicMax(b + 4, oy);
+    if (oz > b[5]) atomicMax(b + 5, oz);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < kMaxGroups * 6; k += blockDim.x) {
+    if (k % 6 < 3) { if (sb[k] != 0x7f7fffff) atomicMin(bbox + k, sb[k]); }
+    else { if (sb[k] != (int) (0xff7fffff ^ 0x7fffffff)) atomicMax(bbox + k, sb[k]); }
   }
 }
 

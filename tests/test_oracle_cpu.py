@@ -1,0 +1,231 @@
+"""CPU suite (-m "not gpu"): the oracle pinned against the reference's golden vectors and against the
+reference's own compiled sources (oracle/_ref, when present), the restatement (oracle/restate.c) against
+both, the host-side logic, and the C-ABI library's exported surface.  No CUDA compute here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ golden vectors of the reference
+def test_oracle_reproduces_published_polyhedron_result(poly_pair, poly_stages):
+    """sample_data/file_pairs_results.txt:3-7 (6 significant digits) and the ground truth file."""
+    from plade_b200.synth import transform_error
+    T = poly_stages["T"]
+    assert bool(poly_stages["ok"][0])
+    assert np.max(np.abs(T - poly_pair["published"])) < 2e-5
+    rot, tr = transform_error(T, poly_pair["gt"])
+    assert rot < 0.05 and tr < 1e-4
+
+
+def test_oracle_is_deterministic_for_fixed_seed(ref, poly_pair, poly_stages):
+    g = poly_stages
+    ref.set_seed(int(g["seed"][0]))
+    tp = ref.extract(poly_pair["tgt"], 10000, "t_")
+    assert np.array_equal(tp[0], g["t_off"]) and np.array_equal(tp[1], g["t_idx"]) and np.array_equal(tp[2], g["t_par"])
+    ok, T = ref.registration_planes(poly_pair["tgt"], poly_pair["src"], (g["t_off"], g["t_idx"], g["t_par"]),
+                                    (g["s_off"], g["s_idx"], g["s_par"]), dump=True)
+    assert ok and np.array_equal(T, g["T"])
+    assert np.array_equal(ref.blob("ver_score", np.float32), g["ver_score"])
+    assert np.array_equal(ref.blob("tgt_db_desc", np.float32), g["tgt_db_desc"])
+
+
+# ------------------------------------------------------------------ restatement vs the reference's own code
+def test_restate_verify_counts_vs_reference_flann(restate, poly_stages, synth_stages):
+    for g in (poly_stages, synth_stages):
+        src, tgt = g["src_ds"].reshape(-1, 3), g["tgt_ds"].reshape(-1, 3)
+        n = min(len(g["mr_nplanes"]), 12)
+        R, T, c = g["mr_R"].reshape(-1, 9)[:n], g["mr_T"].reshape(-1, 3)[:n], g["ver_center"].reshape(-1, 3)[:n]
+        cnt = restate.verify_counts(src, tgt, R, T, c, float(g["src_radius"][0]), float(g["downsample_distance"][0]))
+        overlap = (cnt.astype(np.float64) / min(len(src), len(tgt))).astype(np.float32)
+        assert np.array_equal(overlap, g["ver_overlap"][:n])      # the reference's float, bit for bit
+
+
+def test_restate_verify_counts_vs_live_reference(restate, ref):
+    rng = np.random.default_rng(0)
+    tgt = rng.uniform(0, 1, size=(3000, 3)).astype(np.float32)
+    src = (tgt[:2000] + rng.normal(0, 0.004, size=(2000, 3))).astype(np.float32)
+    R = np.repeat(np.eye(3, dtype=np.float32)[None], 6, axis=0)
+    T = rng.normal(0, 0.01, size=(6, 3)).astype(np.float32)
+    c = (src.mean(0) + T).astype(np.float32)
+    for ball, inl in ((0.5, 0.01), (0.2, 0.03)):
+        ov, cnt = ref.compute_overlap(src, tgt, R, T, c, ball, inl)
+        assert np.array_equal(restate.verify_counts(src, tgt, R, T, c, ball, inl), cnt.astype(np.uint32))
+
+
+def test_restate_voxel_vs_reference(restate, poly_pair, poly_stages, ref):
+    leaf = float(poly_stages["downsample_distance"][0])
+    got = restate.voxel_downsample(poly_pair["src"], leaf)
+    want = poly_stages["src_ds"].reshape(-1, 3)
+    assert got.shape == want.shape and np.array_equal(np.floor(got / leaf), np.floor(want / leaf))
+    assert np.max(np.abs(got - want)) <= 1e-6          # order of the float additions inside a voxel
+    rng = np.random.default_rng(1)
+    pts = rng.uniform(-1, 1, size=(4000, 3)).astype(np.float32)
+    live = ref.voxel_downsample(pts, 0.11)
+    mine = restate.voxel_downsample(pts, 0.11)
+    assert live.shape == mine.shape and np.max(np.abs(live - mine)) <= 1e-6
+
+
+def test_restate_average_spacing_vs_reference(restate, poly_pair, poly_stages, ref):
+    sub = poly_pair["src"][:20000]
+    assert restate.average_spacing(sub) == ref.average_spacing(sub)
+    assert ref.average_spacing(poly_pair["src"]) == float(poly_stages["average_space"][0])
+
+
+def test_restate_match_vs_reference_ann(restate, ref, poly_stages):
+    db = poly_stages["tgt_db_desc"].reshape(-1, 8)[:6000]
+    rng = np.random.default_rng(2)
+    q = db[rng.permutation(len(db))[:200]] + rng.normal(0, 0.01, size=(200, 8)).astype(np.float32)
+    off, idx, d2 = restate.match_descriptors(db, q, 0.04)
+    roff, ridx, rd = ref.match_descriptors(db, q, 0.04)
+    assert np.array_equal(off, roff) and len(idx) > 200
+    for a in range(len(q)):
+        s = slice(off[a], off[a + 1])
+        assert set(idx[s]) == set(ridx[s]) and np.array_equal(d2[s].astype(np.float32), rd[s])
+
+
+def test_restate_cluster_vs_reference_cec(restate, ref):
+    rng = np.random.default_rng(3)
+    n = 300
+    T = (rng.integers(0, 6, size=(n, 1)) * 0.05 + rng.normal(0, 0.002, size=(n, 3))).astype(np.float32)
+    ang = rng.normal(0, 0.01, size=n)
+    R = np.stack([np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]) for a in ang]).astype(np.float32)
+    lab = restate.cluster_transforms(R, T, 0.01, 0.0436)
+    nc, rlab = ref.cluster_transformations(R, T, 0.01, 0.0436)
+    assert len(np.unique(lab)) == nc
+    for c in range(nc):
+        m = np.where(rlab == c)[0]
+        assert len(np.unique(lab[m])) == 1 and lab[m[0]] == m.min()
+
+
+def test_restate_plane_predicate_on_reference_planes(restate, poly_pair, poly_stages):
+    """Every point the reference's RANSAC assigned to a plane satisfies its own global-score predicate
+    (3 * eps band + normal threshold) as restated in oracle_score_planes."""
+    g, cloud = poly_stages, poly_pair["tgt"]
+    eps = 0.005 * max(np.ptp(cloud[:, 0]), np.ptp(cloud[:, 1]))
+    for k in range(min(6, len(g["t_par"]))):
+        n, d = g["t_par"][k, :3], g["t_par"][k, 3]
+        members = g["t_idx"][g["t_off"][k]:g["t_off"][k + 1]]
+        cnt, mask = restate.score_planes(cloud, np.array([[*n, -d]], np.float32), 3 * eps, 0.8, want_mask=True)
+        assert mask[members].mean() > 0.995 and cnt[0] >= len(members) * 0.995
+
+
+# ------------------------------------------------------------------ host-side logic
+def test_synth_generator_is_deterministic_and_shaped():
+    from plade_b200.synth import make_pair, transform_error, perturbed_hypotheses
+    a = make_pair(n_points=20000, n_planes=20, seed=3)
+    b = make_pair(n_points=20000, n_planes=20, seed=3)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    tgt, src, gt = a
+    assert tgt.shape == (20000, 6) and src.shape[1] == 6 and abs(len(src) - 20000) < 3000
+    assert np.allclose(np.linalg.norm(tgt[:, 3:], axis=1), 1, atol=1e-5)
+    assert abs(np.linalg.norm(np.ptp(tgt[:, :3], axis=0)) - 2.0) < 0.3   # skewed shell faces stick out a little
+    assert np.allclose(gt[:3, :3] @ gt[:3, :3].T, np.eye(3), atol=1e-9)
+    assert transform_error(gt, gt) == (0.0, 0.0)
+    R, T, ti = perturbed_hypotheses(gt, 64)
+    assert np.allclose(R[ti], gt[:3, :3], atol=1e-6) and np.allclose(T[ti], gt[:3, 3], atol=1e-6)
+
+
+def test_shard_key_packing():
+    from plade_b200 import shard
+    assert shard.unpack_key(shard.pack_key(123, 7)) == (123, 7)
+    assert shard.pack_key(5, 3) > shard.pack_key(5, 4) > shard.pack_key(4, 0)         # ties -> lowest index
+    assert shard.float_bits(0.75) > shard.float_bits(0.5) > shard.float_bits(0.0)       # bit order == numeric order
+    assert np.array_equal(shard.shard_indices(10, 1, 4), [1, 5, 9])
+    assert shard.local_best_key([3, 9, 9], [2, 6, 10]) == shard.pack_key(9, 6)
+    assert shard.local_best_key([], []) == 0
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle.ref import Restate
+    from plade_b200 import shard
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)                       # same data on every rank (replicated clouds)
+    tgt = rng.uniform(0, 1, size=(1500, 3)).astype(np.float32)
+    src = (tgt[:900] + rng.normal(0, 0.003, size=(900, 3))).astype(np.float32)
+    H = 23
+    R = np.repeat(np.eye(3, dtype=np.float32)[None], H, axis=0)
+    T = rng.normal(0, 0.02, size=(H, 3)).astype(np.float32)
+    T[17] = 0
+    c = (src.mean(0) + T).astype(np.float32)
+    mine = shard.shard_indices(H, rank, world)
+    counts = Restate().verify_counts(src, tgt, R[mine], T[mine], c[mine], 0.8, 0.01)   # the CPU checker stands in for the kernel
+    key = shard.allreduce_max_key(shard.local_best_key(counts, mine), world)
+    full = Restate().verify_counts(src, tgt, R, T, c, 0.8, 0.01) if rank == 0 else None
+    q.put((rank, key, None if full is None else full.tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharded_best_hypothesis_gloo_world2():
+    """N > 1 path on CPU: two gloo ranks, each verifying its hypothesis shard, agree on the global best."""
+    import torch.multiprocessing as mp
+    from plade_b200 import shard
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    keys = {r[1] for r in res}
+    assert len(keys) == 1
+    full = np.array([r[2] for r in res if r[2] is not None][0])
+    value, index = shard.unpack_key(keys.pop())
+    assert value == full.max() and index == int(np.argmax(full)) == 17
+
+
+# ------------------------------------------------------------------ the C-ABI library (no compute without a GPU)
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "plade_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(plade_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import plade_b200
+    assert os.path.exists(plade_b200.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(plade_b200.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(declared) == set(plade_b200.SIGNATURES), set(declared) ^ set(plade_b200.SIGNATURES)
+    plade_b200.load_library()
+
+
+def test_library_is_sm100a_and_has_tma(tmp_path):
+    import plade_b200
+    out = subprocess.run(["cuobjdump", "-lelf", plade_b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", plade_b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS.ARRIVE.TRANS64" in sass     # cp.async.bulk (1-D TMA) tile staging + mbarrier
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import plade_b200
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        plade_b200.Context()
+
+
+def test_product_never_touches_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may use oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "plade_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle/" not in text.replace("oracle/restate.c)", "") or f == "voxel.cu", os.path.join(dirpath, f)
+                assert "libplade_oracle" not in text and "libplade_ref" not in text
