@@ -31,6 +31,8 @@ struct TargetGrid {
   DevBuf<int> order, order_alt;
   DevBuf<unsigned char> cub_tmp;
   DevBuf<float> mm;          // 6 ordered-int encoded bbox values
+  DevBuf<unsigned int> occ_raw, occ_dil;   // occupancy bits over the grid extended by one cell, and its 3x3x3 dilation
+  int ey = 0, ewords = 0;
   float minx = 0, miny = 0, minz = 0, inv_cell = 0, cell = 0;
   int nx = 0, ny = 0, nz = 0;
   size_t n = 0;

@@ -57,6 +57,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
 struct GridView {
   const float4 *pts;
   const int *cell_start;
+  const unsigned int *dil;     // dilated occupancy: bit set <=> some target point lies in the 27 cells around this one
+  int ey, ewords;
   float minx, miny, minz, inv_cell;
   int nx, ny, nz;
 };
@@ -82,6 +84,11 @@ __device__ __forceinline__ bool point_has_inlier(const GridView &g, const HypPar
         fz < (float) (g.nz + 1)))
     return false;
   int cx = (int) floorf(fx), cy = (int) floorf(fy), cz = (int) floorf(fz);
+  // one bit test rejects every point whose 27-cell neighbourhood is empty (most points of a wrong hypothesis)
+  {
+    unsigned int w = __ldg(g.dil + ((size_t) (cz + 1) * g.ey + (cy + 1)) * g.ewords + ((cx + 1) >> 5));
+    if (!((w >> ((cx + 1) & 31)) & 1u)) return false;
+  }
   int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
   int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
   int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
@@ -207,6 +214,41 @@ __global__ void gather_cells_kernel(const float4 *__restrict__ p, const int *__r
     for (unsigned int c = k + 1; c <= (unsigned int) ncells; ++c) cell_start[c] = n;
 }
 
+// raw occupancy bits over the grid extended by one empty cell on every side (bit xe = x + 1 of row (y + 1, z + 1))
+__global__ void occ_raw_kernel(const int *__restrict__ cell_start, int nx, int ny, int nz, int ey, int ewords,
+                               unsigned int *__restrict__ raw) {
+  long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long) nz * ny * ewords;
+  if (t >= total) return;
+  int w = (int) (t % ewords);
+  int y = (int) ((t / ewords) % ny), z = (int) (t / ((long long) ewords * ny));
+  unsigned int bits = 0;
+  const int *row = cell_start + ((size_t) z * ny + y) * nx;
+  for (int b = 0; b < 32; ++b) {
+    int x = 32 * w + b - 1;
+    if (x >= 0 && x < nx && row[x + 1] > row[x]) bits |= 1u << b;
+  }
+  raw[((size_t) (z + 1) * ey + (y + 1)) * ewords + w] = bits;
+}
+
+__global__ void occ_dilate_kernel(const unsigned int *__restrict__ raw, int ey, int ez, int ewords, unsigned int *__restrict__ dil) {
+  long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long) ez * ey * ewords;
+  if (t >= total) return;
+  int w = (int) (t % ewords);
+  int y = (int) ((t / ewords) % ey), z = (int) (t / ((long long) ewords * ey));
+  unsigned int acc = 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy) {
+      int yy = y + dy, zz = z + dz;
+      if (yy < 0 || yy >= ey || zz < 0 || zz >= ez) continue;
+      const unsigned int *r = raw + ((size_t) zz * ey + yy) * ewords;
+      unsigned int c = r[w], l = w > 0 ? r[w - 1] : 0u, rr = w + 1 < ewords ? r[w + 1] : 0u;
+      acc |= c | (c << 1) | (c >> 1) | (l >> 31) | (rr << 31);
+    }
+  dil[t] = acc;
+}
+
 inline float ordered_int_to_float(int v) {
   v = v >= 0 ? v : v ^ 0x7fffffff;
   float f;
@@ -278,6 +320,17 @@ void build_target_grid(Device &dev, const float4 *d_tgt, size_t n, float inlier_
   gather_cells_kernel<<<div_up((long long) n, 256), 256, 0, s>>>(d_tgt, ord2, keys2, (int) n, pts, cs, ncells);
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
+  // dilated occupancy bitmap
+  const int gex = grid.nx + 2, gey = grid.ny + 2, gez = grid.nz + 2;
+  grid.ey = gey;
+  grid.ewords = (gex + 31) / 32;
+  const size_t words = (size_t) gez * gey * grid.ewords;
+  unsigned int *raw = grid.occ_raw.ensure(words), *dil = grid.occ_dil.ensure(words);
+  PLADE_CUDA(cudaMemsetAsync(raw, 0, sizeof(unsigned int) * words, s));
+  occ_raw_kernel<<<div_up((long long) grid.nz * grid.ny * grid.ewords, 256), 256, 0, s>>>(cs, grid.nx, grid.ny, grid.nz, gey, grid.ewords, raw);
+  occ_dilate_kernel<<<div_up((long long) words, 256), 256, 0, s>>>(raw, gey, gez, grid.ewords, dil);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add(2);
 }
 
 void verify_hypotheses(Device &dev, const float4 *d_src, size_t ns, const TargetGrid &grid,
@@ -289,7 +342,7 @@ void verify_hypotheses(Device &dev, const float4 *d_src, size_t ns, const Target
   // static_cast<float>(radius * radius) with radius a double (kdtree_flann.hpp:193)
   float rball2 = (float) ((double) ball_radius * (double) ball_radius);
   float rin2 = (float) ((double) inlier_dist * (double) inlier_dist);
-  GridView g{grid.pts.p, grid.cell_start.p, grid.minx, grid.miny, grid.minz, grid.inv_cell, grid.nx, grid.ny, grid.nz};
+  GridView g{grid.pts.p, grid.cell_start.p, grid.occ_dil.p, grid.ey, grid.ewords, grid.minx, grid.miny, grid.minz, grid.inv_cell, grid.nx, grid.ny, grid.nz};
   int n_tiles = div_up((long long) ns, kTile);
   int n_chunks = div_up(H, kHypChunk);
   long long n_work = (long long) n_tiles * n_chunks;
