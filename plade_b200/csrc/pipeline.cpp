@@ -146,6 +146,25 @@ Registrar::Registrar(int device) {
   PLADE_CUDA(cudaEventCreate(&ev_user1));
 }
 
+void Registrar::mark(const char *name) {
+  static const bool on = getenv("PLADE_TIMING") != nullptr;
+  if (on) marks.emplace_back(name, now_s());
+}
+
+void Registrar::print_marks() {
+  if (marks.size() < 2) { marks.clear(); return; }
+  std::map<std::string, double> acc;
+  std::vector<std::string> order;
+  for (size_t i = 1; i < marks.size(); ++i) {
+    if (!acc.count(marks[i].first)) order.push_back(marks[i].first);
+    acc[marks[i].first] += marks[i].second - marks[i - 1].second;
+  }
+  fprintf(stderr, "[plade timing, ms]");
+  for (const std::string &k : order) fprintf(stderr, " %s=%.2f", k.c_str(), acc[k] * 1e3);
+  fprintf(stderr, "\n");
+  marks.clear();
+}
+
 Registrar::~Registrar() {
   for (cudaEvent_t e : {ev0, ev1, ev_user0, ev_user1}) if (e) cudaEventDestroy(e);
   if (dev.stream) cudaStreamDestroy(dev.stream);
@@ -247,6 +266,7 @@ bool Registrar::register_with_planes(const CloudDev &tgt, const CloudDev &src, c
 bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const std::vector<PlaneParam> &tplanes,
                               const std::vector<PlaneParam> &splanes, const int *d_group_t, const int *d_group_s, float out16[16]) {
   const double t_begin = now_s();
+  mark("core_begin");
   for (int i = 0; i < 16; ++i) out16[i] = (i % 5 == 0) ? 1.f : 0.f;
   cudaStream_t s = dev.stream;
   if (tgt.n == 0 || src.n == 0) { last_error = "empty cloud"; return false; }
@@ -255,6 +275,7 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
   double t0 = now_s();
   const float average_space = average_spacing(src);
   times.spacing = now_s() - t0;
+  mark("spacing");
   float downSampleDistance = average_space * 4;
   float lengthThreshold = average_space * 5;
   float angleThreshold = (float) (5.0 / 180 * M_PI);
@@ -280,15 +301,18 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     const CloudDev &C = *clouds[side];
     const std::vector<PlaneParam> &P = *planes_in[side];
     A.n_ds = voxel_downsample(dev, vox, C.pos.p, C.n, downSampleDistance, *ds_dev[side]);
+    mark("voxel_full");
     A.ds.resize(A.n_ds);
     PLADE_CUDA(cudaMemcpyAsync(A.ds.data(), ds_dev[side]->p, sizeof(float4) * A.n_ds, cudaMemcpyDeviceToHost, s));
     size_t nv = voxel_downsample_groups(dev, vox, C.pos.p, C.n, d_groups[side], (int) P.size(), downSampleDistance, *ds_pl[side], A.plane_ds_start);
     A.plane_ds.resize(nv);
     if (nv) PLADE_CUDA(cudaMemcpyAsync(A.plane_ds.data(), ds_pl[side]->p, sizeof(float4) * nv, cudaMemcpyDeviceToHost, s));
     PLADE_CUDA(cudaStreamSynchronize(s));
+    mark("voxel_planes+d2h");
     double w, h, d;
     if (0 != compute_bounding_box(A.ds.data(), A.n_ds, A.center, w, h, d, nullptr)) { last_error = "empty down-sampled cloud"; return false; }
     A.radius = std::max(std::max(w, h), d) / 2;
+    mark("obb_full");
     A.planes.resize(P.size());
     A.corners4.resize(P.size());
     A.plane_center.resize(P.size());
@@ -312,6 +336,7 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
       A.plane_center[i] = (A.corners4[i][0] + A.corners4[i][2]) / 2.f;
       A.plane_radius[i] = norm(A.corners4[i][0] - A.corners4[i][2]) / 2;
     }
+    mark("obb_planes");
   }
   times.downsample = now_s() - t0;
 
@@ -435,6 +460,7 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
       }
   }
   times.descriptors = now_s() - t0;
+  mark("lines+descriptors");
   if (debug) {
     put("tgt_db_desc", db_desc); put("tgt_db_pair", db_pair); put("src_q_desc", q_desc);
     std::vector<int> qp;
@@ -449,6 +475,7 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
   size_t n_match = match_descriptors(dev, match_sc, db_desc.data(), (int) (db_desc.size() / 8), q_desc.data(),
                                      (int) (q_desc.size() / 8), (float) params.descriptor_radius, m_off, m_idx, m_d2);
   times.match = now_s() - t0;
+  mark("match");
   if (debug) { put("match_offsets", m_off); put("match_idx", m_idx); put("match_dist2", m_d2); }
 
   // ---- K4a: one rigid transform per match, PLADE/util.cpp:303-327 -------------------------------------
@@ -538,6 +565,7 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     }
   }
   times.hypotheses = now_s() - t0;
+  mark("hypotheses");
 
   // ---- K4d: penetration filter, PLADE/util.cpp:447-519 ------------------------------------------------------
   t0 = now_s();
@@ -574,6 +602,7 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     }
   }
   times.penetration = now_s() - t0;
+  mark("penetration");
   if (debug) {
     std::vector<float> R, T;
     std::vector<int> np;
@@ -665,6 +694,8 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
   out16[12] = out16[13] = out16[14] = 0.f;
   out16[15] = 1.f;
   times.total = now_s() - t_begin;
+  mark("verify");
+  print_marks();
   return true;
 }
 

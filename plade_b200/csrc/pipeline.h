@@ -91,6 +91,10 @@ class Registrar {
   bool debug = false;
   std::map<std::string, std::vector<char>> blobs;
   std::string last_error;
+  // fine-grained wall-clock marks, printed to stderr at the end of a registration when PLADE_TIMING is set
+  std::vector<std::pair<std::string, double>> marks;
+  void mark(const char *name);
+  void print_marks();
   int shard_rank = 0, shard_world = 1;
   AllreduceMaxU64 allreduce = nullptr;
   void *allreduce_user = nullptr;

@@ -504,6 +504,7 @@ __global__ void remap_group_kernel(const int *__restrict__ assigned, int n, cons
 
 std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out) {
   std::vector<PlaneParam> result;
+  mark("ransac_begin");
   const int n = (int) c.n;
   if (n < 3) { std::cerr << "point set has less than 3 points" << std::endl; return result; }
   cudaStream_t s = dev.stream;
@@ -553,6 +554,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, order, order2, n, 0, 30, s);
   dev.launches.add(8);
   int *cur_order = order2, *alt_order = order;
+  mark("ransac_morton");
 
   int *assigned = rs.assigned.ensure(n);
   PLADE_CUDA(cudaMemsetAsync(assigned, 0xff, sizeof(int) * n, s));
@@ -603,6 +605,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     PLADE_CUDA(cudaMemcpyAsync(h_cand.data(), cand, sizeof(float4) * kCandPerRound, cudaMemcpyDeviceToHost, s));
     PLADE_CUDA(cudaMemcpyAsync(&n_valid, d_nvalid, sizeof(int), cudaMemcpyDeviceToHost, s));
     PLADE_CUDA(cudaStreamSynchronize(s));
+    mark("ransac_score_round");
     drawn += n_valid;
     // Candidate pool (the reference keeps its candidate list across iterations, RansacShapeDetector.cpp:
     // 548-855): the best distinct planes of this round are re-scored next round in the first slots, so a
@@ -610,10 +613,10 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     {
       std::vector<int> ord(kCandPerRound);
       for (int k = 0; k < kCandPerRound; ++k) ord[k] = k;
-      std::partial_sort(ord.begin(), ord.begin() + std::min(kCandPerRound, 1024), ord.end(),
+      std::partial_sort(ord.begin(), ord.begin() + std::min(kCandPerRound, 256), ord.end(),
                         [&](int a, int b) { return h_counts[a] != h_counts[b] ? h_counts[a] > h_counts[b] : a < b; });
       pool.clear();
-      for (int q = 0; q < std::min(kCandPerRound, 1024) && (int) pool.size() < kPoolSize; ++q) {
+      for (int q = 0; q < std::min(kCandPerRound, 256) && (int) pool.size() < kPoolSize; ++q) {
         const int k = ord[q];
         if (h_counts[k] == 0) break;
         const float4 &a = h_cand[k];
@@ -632,15 +635,22 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
         if (!dup) pool.push_back({(double) h_counts[k] * m / S, a});
       }
     }
+    mark("ransac_pool");
+    // Walk the pool best-first.  After an accepted plane the remaining entries keep their (now slightly
+    // stale, never too small) estimates: distinct planes share almost no points, and every candidate is
+    // fully re-evaluated on the current cloud before it is accepted, so no re-scoring round is needed.
+    bool stop_all = false, fresh = true;
+    for (;;) {
     best_est = pool.empty() ? 0.0 : pool[0].est;
     if (!pool.empty()) best_pl = pool[0].pl;
     const bool enough_for_min = failure_probability(min_support, m, drawn, nlevels) <= prob;
     const bool best_ok = best_est >= min_support && failure_probability(best_est, m, drawn, nlevels) <= prob;
     if (!best_ok) {
-      // nothing of min_support size left (w.h.p.): require the evidence in three consecutive rounds
-      if (enough_for_min && best_est < min_support) { if (++dry_rounds >= 3) break; } else dry_rounds = 0;
-      continue;
+      // nothing of min_support size left (w.h.p.): require the evidence in three consecutive scoring rounds
+      if (fresh) { if (enough_for_min && best_est < min_support) { if (++dry_rounds >= 3) stop_all = true; } else dry_rounds = 0; }
+      break;
     }
+    fresh = false;
     dry_rounds = 0;
     // --- refine the best candidate on the full cloud -------------------------------------------------------
     PlaneFrame fr;
@@ -749,13 +759,14 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       } while (newScore > oldScore && iter < 3);
     }
     best_est = 0;    // the pool is invalid once points are removed (or the candidate failed)
+    mark("ransac_refine");
     // the reference only accepts a candidate whose fully evaluated (connected-component) support
     // reaches min_support (FindBestCandidate, RansacShapeDetector.cpp:297,423-430)
     if (acc_size < min_support) {
       // its score can only shrink from here on: never look at this plane (or a duplicate of it) again
       banned.push_back(best_pl);
       if (!pool.empty()) pool.erase(pool.begin());
-      if (++rejects >= 256) break;
+      if (++rejects >= 256) { stop_all = true; break; }
       continue;
     }
     unsigned char *member = acc_member;
@@ -779,6 +790,11 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     PLADE_CUDA(cudaStreamSynchronize(s));
     std::swap(cur_order, alt_order);
     m = new_m;
+    if (!pool.empty()) pool.erase(pool.begin());
+    mark("ransac_accept");
+    if (m < min_support || m < 3) break;
+    }   // pool walk
+    if (stop_all) break;
   }
 
   // ---- output (PLADE/plane_extraction.cpp:115-160): drop shapes below min_support, unit normal, d = -n.p --------
@@ -803,6 +819,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
   PLADE_CUDA(cudaStreamSynchronize(s));
+  mark("ransac_output");
   return result;
 }
 

@@ -303,6 +303,73 @@ __global__ void knn_merge_kernel(const float *__restrict__ partial, int nsplit, 
   for (int j = 0; j < k; ++j) out[(size_t) q * k + j] = best[j];
 }
 
+// ---- grid-accelerated exact k nearest squared distances ------------------------------------------------
+__global__ void knn_key_kernel(const float4 *__restrict__ p, int n, float minx, float miny, float minz, float inv_c, int nx, int ny,
+                               int nz, unsigned int *__restrict__ keys, int *__restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 v = p[i];
+  int cx = min(max((int) floorf((v.x - minx) * inv_c), 0), nx - 1);
+  int cy = min(max((int) floorf((v.y - miny) * inv_c), 0), ny - 1);
+  int cz = min(max((int) floorf((v.z - minz) * inv_c), 0), nz - 1);
+  keys[i] = ((unsigned int) cz << 20) | ((unsigned int) cy << 10) | (unsigned int) cx;
+  idx[i] = i;
+}
+
+__global__ void knn_gather_kernel(const float4 *__restrict__ p, const int *__restrict__ idx, int n, float4 *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = p[idx[i]];
+}
+
+__device__ __forceinline__ int lower_bound_u32(const unsigned int *a, int n, unsigned int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// One thread per query: scan the cube of cells of radius rho around the query's cell, keep the k smallest
+// FLANN-L2_Simple distances; every point outside the cube is farther than rho * cell, so the list is exact
+// as soon as its k-th entry is below that bound (otherwise the cube grows).
+__global__ void knn_grid_kernel(const float4 *__restrict__ pts, const float4 *__restrict__ spts, const unsigned int *__restrict__ keys,
+                                int n, const int *__restrict__ qidx, int nq, int k, float minx, float miny, float minz, float cell,
+                                float inv_c, int nx, int ny, int nz, float *__restrict__ out) {
+  int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  const float4 q = pts[qidx[qi]];
+  const int cx = min(max((int) floorf((q.x - minx) * inv_c), 0), nx - 1);
+  const int cy = min(max((int) floorf((q.y - miny) * inv_c), 0), ny - 1);
+  const int cz = min(max((int) floorf((q.z - minz) * inv_c), 0), nz - 1);
+  float best[kKnnK];
+  for (int rho = 1;; ++rho) {
+#pragma unroll
+    for (int j = 0; j < kKnnK; ++j) best[j] = 3.4e38f;
+    const bool all = rho > 12 || (cx - rho <= 0 && cy - rho <= 0 && cz - rho <= 0 && cx + rho >= nx - 1 && cy + rho >= ny - 1 && cz + rho >= nz - 1);
+    const int z0 = all ? 0 : max(cz - rho, 0), z1 = all ? nz - 1 : min(cz + rho, nz - 1);
+    const int y0 = all ? 0 : max(cy - rho, 0), y1 = all ? ny - 1 : min(cy + rho, ny - 1);
+    const int x0 = all ? 0 : max(cx - rho, 0), x1 = all ? nx - 1 : min(cx + rho, nx - 1);
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        unsigned int base = ((unsigned int) z << 20) | ((unsigned int) y << 10);
+        int lo = lower_bound_u32(keys, n, base | (unsigned int) x0), hi = lower_bound_u32(keys, n, (base | (unsigned int) x1) + 1u);
+        for (int i = lo; i < hi; ++i) {
+          float4 t = __ldg(spts + i);
+          float dx = __fsub_rn(q.x, t.x), dy = __fsub_rn(q.y, t.y), dz = __fsub_rn(q.z, t.z);
+          float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          if (d < best[kKnnK - 1]) {
+            best[kKnnK - 1] = d;
+#pragma unroll
+            for (int j = kKnnK - 1; j > 0; --j)
+              if (best[j] < best[j - 1]) { float tsw = best[j]; best[j] = best[j - 1]; best[j - 1] = tsw; }
+          }
+        }
+      }
+    if (all) break;
+    float lim = (float) rho * cell * 0.999f;
+    if (best[k - 1] <= lim * lim) break;
+  }
+  for (int j = 0; j < k; ++j) out[(size_t) qi * k + j] = best[j];
+}
+
 }  // namespace
 
 size_t voxel_downsample(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n, float leaf,
@@ -320,19 +387,59 @@ void knn_sqdist(Device &dev, const float4 *d_pts, size_t n, const int *d_query_i
   if (k > kKnnK) throw std::runtime_error("knn_sqdist: k > 8");
   if (nq == 0) return;
   cudaStream_t s = dev.stream;
-  int qblocks = div_up(nq, kKnnThreads);
-  // split the point range so that the grid covers ~4 waves of the SMs
-  int nsplit = std::max(1, std::min(64, (dev.num_sms * 4 + qblocks - 1) / qblocks));
-  int chunk = div_up((long long) n, nsplit);
-  chunk = ((chunk + kKnnTile - 1) / kKnnTile) * kKnnTile;
-  nsplit = div_up((long long) n, chunk);
-  static thread_local DevBuf<float> partial;
-  float *d_partial = partial.ensure((size_t) nsplit * nq * k);
-  knn_partial_kernel<<<dim3(qblocks, nsplit), kKnnThreads, 0, s>>>(d_pts, (int) n, d_query_idx, nq, k, chunk, d_partial);
+  if (n <= 8192) {
+    // small clouds: plain brute force
+    int qblocks = div_up(nq, kKnnThreads);
+    int nsplit = std::max(1, std::min(64, (dev.num_sms * 4 + qblocks - 1) / qblocks));
+    int chunk = div_up((long long) n, nsplit);
+    chunk = ((chunk + kKnnTile - 1) / kKnnTile) * kKnnTile;
+    nsplit = div_up((long long) n, chunk);
+    static thread_local DevBuf<float> partial;
+    float *d_partial = partial.ensure((size_t) nsplit * nq * k);
+    knn_partial_kernel<<<dim3(qblocks, nsplit), kKnnThreads, 0, s>>>(d_pts, (int) n, d_query_idx, nq, k, chunk, d_partial);
+    PLADE_LAUNCH_CHECK();
+    knn_merge_kernel<<<div_up(nq, 128), 128, 0, s>>>(d_partial, nsplit, nq, k, d_out);
+    PLADE_LAUNCH_CHECK();
+    dev.launches.add(2);
+    return;
+  }
+  // uniform grid sized from a surface-density estimate (cell ~ 2.5 x expected spacing, <= 1023 cells per axis)
+  static thread_local DevBuf<int> bbox_buf, idx_a, idx_b;
+  static thread_local DevBuf<unsigned int> key_a, key_b;
+  static thread_local DevBuf<float4> sorted_pts;
+  static thread_local DevBuf<unsigned char> cub_tmp;
+  int *d_bbox = bbox_buf.ensure(8);
+  int h_bbox[6] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int) (0xff7fffff ^ 0x7fffffff), (int) (0xff7fffff ^ 0x7fffffff), (int) (0xff7fffff ^ 0x7fffffff)};
+  PLADE_CUDA(cudaMemcpyAsync(d_bbox, h_bbox, sizeof(h_bbox), cudaMemcpyHostToDevice, s));
+  single_bbox_kernel<<<std::min(div_up((long long) n, 256), dev.num_sms * 8), 256, 0, s>>>(d_pts, (int) n, d_bbox);
   PLADE_LAUNCH_CHECK();
-  knn_merge_kernel<<<div_up(nq, 128), 128, 0, s>>>(d_partial, nsplit, nq, k, d_out);
+  PLADE_CUDA(cudaMemcpyAsync(h_bbox, d_bbox, sizeof(h_bbox), cudaMemcpyDeviceToHost, s));
+  PLADE_CUDA(cudaStreamSynchronize(s));
+  float mn[3], mx[3];
+  for (int a = 0; a < 3; ++a) { mn[a] = o2f(h_bbox[a]); mx[a] = o2f(h_bbox[3 + a]); }
+  double ex = (double) mx[0] - mn[0], ey = (double) mx[1] - mn[1], ez = (double) mx[2] - mn[2];
+  double area = 2.0 * (ex * ey + ey * ez + ez * ex);
+  double maxext = std::max(ex, std::max(ey, ez));
+  double cell = 2.5 * std::sqrt(std::max(area, 1e-30) / (double) n);
+  if (!(cell > 0) || !std::isfinite(cell)) cell = 1e-6;
+  cell = std::max(cell, maxext / 1000.0);
+  if (!(cell > 0)) cell = 1e-6;
+  int nx = std::min(1023, (int) std::floor(ex / cell)) + 1, ny = std::min(1023, (int) std::floor(ey / cell)) + 1,
+      nz = std::min(1023, (int) std::floor(ez / cell)) + 1;
+  float fcell = (float) cell, inv_c = (float) (1.0 / cell);
+  unsigned int *ka = key_a.ensure(n), *kb = key_b.ensure(n);
+  int *ia = idx_a.ensure(n), *ib = idx_b.ensure(n);
+  knn_key_kernel<<<div_up((long long) n, 256), 256, 0, s>>>(d_pts, (int) n, mn[0], mn[1], mn[2], inv_c, nx, ny, nz, ka, ia);
   PLADE_LAUNCH_CHECK();
-  dev.launches.add(2);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, ka, kb, ia, ib, (int) n, 0, 30, s);
+  unsigned char *tmp = cub_tmp.ensure(tb);
+  cub::DeviceRadixSort::SortPairs(tmp, tb, ka, kb, ia, ib, (int) n, 0, 30, s);
+  float4 *sp = sorted_pts.ensure(n);
+  knn_gather_kernel<<<div_up((long long) n, 256), 256, 0, s>>>(d_pts, ib, (int) n, sp);
+  knn_grid_kernel<<<div_up(nq, 64), 64, 0, s>>>(d_pts, sp, kb, (int) n, d_query_idx, nq, k, mn[0], mn[1], mn[2], fcell, inv_c, nx, ny, nz, d_out);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add(9);
 }
 
 }  // namespace plade
