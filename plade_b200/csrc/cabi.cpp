@@ -348,13 +348,16 @@ long long plade_voxel_downsample(plade_ctx *ctx, const float *pts, size_t n, int
 
 int plade_bounding_box(plade_ctx *ctx, const float *xyz, size_t n, float *center, double *whd, float *corners) {
   PLADE_TRY(ctx, -1, {
-    std::vector<float4> h(n);
-    for (size_t i = 0; i < n; ++i) h[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
-    V3 c, c8[8];
-    int rc = compute_bounding_box(h.data(), n, c, whd[0], whd[1], whd[2], c8);
-    if (rc != 0) return rc;
-    center[0] = c.x; center[1] = c.y; center[2] = c.z;
-    for (int k = 0; k < 8; ++k) { corners[3 * k] = c8[k].x; corners[3 * k + 1] = c8[k].y; corners[3 * k + 2] = c8[k].z; }
+    Registrar &r = *ctx->reg;
+    if (n == 0) return -1;
+    upload_xyz(r, xyz, n, 3, ctx->stage_a);
+    std::vector<ObbSeg> segs(1, ObbSeg{ctx->stage_a.p, (int) n, 0});
+    std::vector<ObbResult> out;
+    obb_segments(r.dev, r.obb_sc, segs, out);
+    if (out[0].rc != 0) return out[0].rc;
+    center[0] = out[0].center.x; center[1] = out[0].center.y; center[2] = out[0].center.z;
+    whd[0] = out[0].width; whd[1] = out[0].height; whd[2] = out[0].depth;
+    for (int k = 0; k < 8; ++k) { corners[3 * k] = out[0].corners[k].x; corners[3 * k + 1] = out[0].corners[k].y; corners[3 * k + 2] = out[0].corners[k].z; }
     return 0;
   })
 }

@@ -138,4 +138,23 @@ struct PenScratch {
 void penetration_filter(Device &dev, PenScratch &sc, const PenSide &src, const PenSide &tgt, const float *h_hyp12, int H,
                         float lengthThreshold, float angleThreshold, std::vector<unsigned char> &pen_out);
 
+
+// ------------------------------------------------------------------------------------------------
+// Oriented bounding boxes (ComputeBoundingBox, PLADE/util.h:187-248) of many point segments at once
+// ------------------------------------------------------------------------------------------------
+struct ObbSeg { const float4 *p; int n; int pad; };
+struct ObbResult {
+  int rc = -1;
+  V3 center;
+  double width = 0, height = 0, depth = 0;
+  V3 corners[8];
+};
+struct ObbScratch {
+  DevBuf<unsigned char> segs, blocks;
+  DevBuf<double> acc;
+  DevBuf<float> frames;
+  DevBuf<int> mm;
+};
+void obb_segments(Device &dev, ObbScratch &sc, const std::vector<ObbSeg> &segs, std::vector<ObbResult> &out);
+
 }  // namespace plade

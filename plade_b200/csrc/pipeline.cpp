@@ -81,58 +81,6 @@ void pair_descriptor(const V3 &l1, const V3 &l2, const V3 &l1sp1, const V3 &l1sp
 
 }  // namespace
 
-int compute_bounding_box(const float4 *pts, size_t n, V3 &centerPoint, double &width, double &height, double &depth,
-                         V3 corners[8]) {
-  if (n == 0) return -1;
-  // compute3DCentroid (centroid.hpp:79-122): sequential float sums
-  float cx = 0, cy = 0, cz = 0;
-  for (size_t i = 0; i < n; ++i) { cx += pts[i].x; cy += pts[i].y; cz += pts[i].z; }
-  const float fn = (float) n;
-  cx /= fn; cy /= fn; cz /= fn;
-  // computeCovarianceMatrixNormalized (centroid.hpp:180-259)
-  float c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-  for (size_t i = 0; i < n; ++i) {
-    float px = pts[i].x - cx, py = pts[i].y - cy, pz = pts[i].z - cz;
-    c11 += py * py; c12 += py * pz; c22 += pz * pz;
-    c00 += px * px; c01 += py * px; c02 += pz * px;
-  }
-  c00 /= fn; c01 /= fn; c02 /= fn; c11 /= fn; c12 /= fn; c22 /= fn;
-  double A[3][3] = {{c00, c01, c02}, {c01, c11, c12}, {c02, c12, c22}}, w[3], V[3][3];
-  sym_eig3(A, w, V);
-  M3 E;   // eigDx, columns = eigenvectors (ascending eigenvalue); col2 := col0 x col1
-  V3 e0((float) V[0][0], (float) V[1][0], (float) V[2][0]), e1((float) V[0][1], (float) V[1][1], (float) V[2][1]);
-  V3 e2 = cross(e0, e1);
-  for (int r = 0; r < 3; ++r) { E(r, 0) = e0[r]; E(r, 1) = e1[r]; E(r, 2) = e2[r]; }
-  M3 Rt;  // eigDx^T
-  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Rt(r, c) = E(c, r);
-  V3 ctr(cx, cy, cz);
-  V3 t = -1.f * mul(Rt, ctr);
-  V3 mn(3.402823466e38f, 3.402823466e38f, 3.402823466e38f), mx(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f);
-  for (size_t i = 0; i < n; ++i) {
-    V3 q = xform(Rt, t, V3(pts[i].x, pts[i].y, pts[i].z));
-    mn.x = std::min(mn.x, q.x); mn.y = std::min(mn.y, q.y); mn.z = std::min(mn.z, q.z);
-    mx.x = std::max(mx.x, q.x); mx.y = std::max(mx.y, q.y); mx.z = std::max(mx.z, q.z);
-  }
-  V3 mean_diag = 0.5f * (mx + mn);
-  centerPoint = mul(E, mean_diag) + ctr;
-  width = mx.x - mn.x;
-  depth = mx.y - mn.y;
-  height = mx.z - mn.z;
-  if (corners) {
-    float x = mn.x, y = mn.y, z = mn.z;
-    V3 loc[8] = {mn,
-                 V3(x, (float) (y + depth), z),
-                 V3(x, (float) (y + depth), (float) (z + height)),
-                 V3(x, y, (float) (z + height)),
-                 V3((float) (x + width), y, (float) (z + height)),
-                 V3((float) (x + width), (float) (y + depth), z),
-                 V3((float) (x + width), y, z),
-                 V3((float) (x + width), (float) (y + depth), (float) (z + height))};
-    for (int k = 0; k < 8; ++k) corners[k] = xform(E, ctr, loc[k]);
-  }
-  return 0;
-}
-
 Registrar::Registrar(int device) {
   if (device >= 0) PLADE_CUDA(cudaSetDevice(device));
   PLADE_CUDA(cudaGetDevice(&dev.id));
@@ -302,41 +250,57 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     const std::vector<PlaneParam> &P = *planes_in[side];
     A.n_ds = voxel_downsample(dev, vox, C.pos.p, C.n, downSampleDistance, *ds_dev[side]);
     mark("voxel_full");
-    A.ds.resize(A.n_ds);
-    PLADE_CUDA(cudaMemcpyAsync(A.ds.data(), ds_dev[side]->p, sizeof(float4) * A.n_ds, cudaMemcpyDeviceToHost, s));
     size_t nv = voxel_downsample_groups(dev, vox, C.pos.p, C.n, d_groups[side], (int) P.size(), downSampleDistance, *ds_pl[side], A.plane_ds_start);
-    A.plane_ds.resize(nv);
-    if (nv) PLADE_CUDA(cudaMemcpyAsync(A.plane_ds.data(), ds_pl[side]->p, sizeof(float4) * nv, cudaMemcpyDeviceToHost, s));
-    PLADE_CUDA(cudaStreamSynchronize(s));
-    mark("voxel_planes+d2h");
-    double w, h, d;
-    if (0 != compute_bounding_box(A.ds.data(), A.n_ds, A.center, w, h, d, nullptr)) { last_error = "empty down-sampled cloud"; return false; }
-    A.radius = std::max(std::max(w, h), d) / 2;
-    mark("obb_full");
-    A.planes.resize(P.size());
-    A.corners4.resize(P.size());
-    A.plane_center.resize(P.size());
-    A.plane_radius.resize(P.size());
-    for (size_t i = 0; i < P.size(); ++i) {
-      A.planes[i] = {P[i].n[0], P[i].n[1], P[i].n[2], P[i].d};
-      V3 c8[8], ctr;
-      double pw, ph, pd;
-      size_t b = A.plane_ds_start[i], e = A.plane_ds_start[i + 1];
-      for (int k = 0; k < 4; ++k) A.corners4[i][k] = V3();
-      A.plane_center[i] = V3();
-      A.plane_radius[i] = 0;
-      if (e <= b || 0 != compute_bounding_box(A.plane_ds.data() + b, e - b, ctr, pw, ph, pd, c8)) continue;
-      // ProjectPoints2Plane on corners [0,4) (PLADE/util.h:293-329)
-      float Aa = P[i].n[0], B = P[i].n[1], Cc = P[i].n[2], D = P[i].d;
-      for (int k = 0; k < 4; ++k) {
-        const V3 &q = c8[k];
-        float kk = -(Aa * q.x + B * q.y + Cc * q.z + D) / (Aa * Aa + B * B + Cc * Cc);
-        A.corners4[i][k] = V3(q.x + kk * Aa, q.y + kk * B, q.z + kk * Cc);
-      }
-      A.plane_center[i] = (A.corners4[i][0] + A.corners4[i][2]) / 2.f;
-      A.plane_radius[i] = norm(A.corners4[i][0] - A.corners4[i][2]) / 2;
+    mark("voxel_planes");
+    if (debug) {     // host copies are only needed for the stage dumps
+      A.ds.resize(A.n_ds);
+      A.plane_ds.resize(nv);
+      if (A.n_ds) PLADE_CUDA(cudaMemcpyAsync(A.ds.data(), ds_dev[side]->p, sizeof(float4) * A.n_ds, cudaMemcpyDeviceToHost, s));
+      if (nv) PLADE_CUDA(cudaMemcpyAsync(A.plane_ds.data(), ds_pl[side]->p, sizeof(float4) * nv, cudaMemcpyDeviceToHost, s));
+      PLADE_CUDA(cudaStreamSynchronize(s));
     }
-    mark("obb_planes");
+  }
+  // oriented bounding boxes of both clouds and of every plane: one batch
+  {
+    std::vector<ObbSeg> segs;
+    for (int side = 0; side < 2; ++side) {
+      segs.push_back({ds_dev[side]->p, (int) S[side].n_ds, 0});
+      for (size_t i = 0; i < planes_in[side]->size(); ++i)
+        segs.push_back({ds_pl[side]->p + S[side].plane_ds_start[i], S[side].plane_ds_start[i + 1] - S[side].plane_ds_start[i], 0});
+    }
+    std::vector<ObbResult> obb;
+    obb_segments(dev, obb_sc, segs, obb);
+    size_t k = 0;
+    for (int side = 0; side < 2; ++side) {
+      Side &A = S[side];
+      const std::vector<PlaneParam> &P = *planes_in[side];
+      const ObbResult &full = obb[k++];
+      if (full.rc != 0) { last_error = "empty down-sampled cloud"; return false; }
+      A.center = full.center;
+      A.radius = std::max(std::max(full.width, full.height), full.depth) / 2;
+      A.planes.resize(P.size());
+      A.corners4.resize(P.size());
+      A.plane_center.resize(P.size());
+      A.plane_radius.resize(P.size());
+      for (size_t i = 0; i < P.size(); ++i) {
+        A.planes[i] = {P[i].n[0], P[i].n[1], P[i].n[2], P[i].d};
+        const ObbResult &o = obb[k++];
+        for (int c = 0; c < 4; ++c) A.corners4[i][c] = V3();
+        A.plane_center[i] = V3();
+        A.plane_radius[i] = 0;
+        if (o.rc != 0) continue;
+        // ProjectPoints2Plane on corners [0,4) (PLADE/util.h:293-329)
+        float Aa = P[i].n[0], B = P[i].n[1], Cc = P[i].n[2], D = P[i].d;
+        for (int c = 0; c < 4; ++c) {
+          const V3 &q = o.corners[c];
+          float kk = -(Aa * q.x + B * q.y + Cc * q.z + D) / (Aa * Aa + B * B + Cc * Cc);
+          A.corners4[i][c] = V3(q.x + kk * Aa, q.y + kk * B, q.z + kk * Cc);
+        }
+        A.plane_center[i] = (A.corners4[i][0] + A.corners4[i][2]) / 2.f;
+        A.plane_radius[i] = norm(A.corners4[i][0] - A.corners4[i][2]) / 2;
+      }
+    }
+    mark("obb");
   }
   times.downsample = now_s() - t0;
 

@@ -106,6 +106,7 @@ class Registrar {
   HypScratch hyp_sc;
   DevBuf<float4> ds_tgt, ds_src, ds_planes_t, ds_planes_s;
   PenScratch pen_sc;
+  ObbScratch obb_sc;
   DevBuf<int> group_t, group_s, qidx;
   DevBuf<float> knn_out;
   DevBuf<HypParams> d_hyp;
@@ -121,8 +122,5 @@ class Registrar {
   }
 };
 
-// Oriented bounding box exactly as ComputeBoundingBox (PLADE/util.h:187-248).
-int compute_bounding_box(const float4 *pts, size_t n, V3 &center, double &width, double &height, double &depth,
-                         V3 corners[8]);
 
 }  // namespace plade

@@ -37,8 +37,10 @@ namespace plade {
 
 namespace {
 
-constexpr int kCandPerRound = 4096;
-constexpr int kSubsample = 65536;
+constexpr int kCandPerRound = 16384;   // candidates drawn per round
+constexpr int kStage1Points = 4096;    // stage 1: every candidate against a small stratified subsample
+constexpr int kStage2Cand = 256;       // stage 2: the best stage-1 candidates ...
+constexpr int kSubsample = 65536;      // ... against the large subsample
 constexpr int kScoreTile = 512;       // points per TMA tile (pos + nrm = 16 KB)
 constexpr int kScoreThreads = 256;    // one candidate per thread
 
@@ -190,13 +192,13 @@ __global__ void gather_sub_kernel(const float4 *__restrict__ pos, const float4 *
 
 // K1a: every candidate of the round against the subsample.  grid = (tile groups, candidate groups).
 __global__ void __launch_bounds__(kScoreThreads)
-score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__restrict__ cand, int n_cand, float eps,
-                        float nthresh, int tiles_per_block, unsigned int *__restrict__ counts) {
+score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__restrict__ cand, const int *__restrict__ sel, int n_cand,
+                        float eps, float nthresh, int tiles_per_block, unsigned int *__restrict__ counts) {
   __shared__ __align__(128) float4 buf[2][2 * kScoreTile];
   __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x;
   const int c = blockIdx.y * kScoreThreads + tid;
-  const float4 pl = (c < n_cand) ? cand[c] : make_float4(0.f, 0.f, 0.f, 3.0e38f);
+  const float4 pl = (c < n_cand) ? cand[sel ? sel[c] : c] : make_float4(0.f, 0.f, 0.f, 3.0e38f);
   const int n_tiles = (S + kScoreTile - 1) / kScoreTile;
   const int t0 = blockIdx.x * tiles_per_block, t1 = min(n_tiles, t0 + tiles_per_block);
   if (tid == 0) {
@@ -230,6 +232,18 @@ score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__r
     __syncthreads();   // everyone done with buf[b] before it is refilled two iterations later
   }
   if (c < n_cand && cnt) atomicAdd(&counts[c], cnt);
+}
+
+// stage-1 keys: carried pool candidates are forced into stage 2; idx = iota
+__global__ void stage1_keys_kernel(unsigned int *__restrict__ counts1, int *__restrict__ idx, int n, int n_forced) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i < n_forced) counts1[i] = 0xFFFFFFFFu;
+  idx[i] = i;
+}
+__global__ void gather_planes_kernel(const float4 *__restrict__ cand, const int *__restrict__ sel, int n, float4 *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = cand[sel[i]];
 }
 
 // K1a/K1b stage API: n_planes planes against the whole cloud (assigned[i] == -1 only).
@@ -307,6 +321,159 @@ __global__ void raster_kernel(const float4 *__restrict__ pos, const unsigned cha
   int id = bu + bv * uext;
   pix[i] = id;
   bitmap[id] = 1;
+}
+
+// ---- device-side bitmap pipeline (no host round trip between the passes of one candidate evaluation) ----
+struct BmpInfo { float umin, vmin; int ue, ve; int ok; int overflow; int pad0, pad1; };
+constexpr int kBmpCap = 1 << 20;       // pixels; larger bitmaps take the host path
+
+__global__ void bmp_setup_kernel(const int *__restrict__ uvbox, float bmp_eps, BmpInfo *__restrict__ info) {
+  int a[4];
+  float uv[4];
+  for (int k = 0; k < 4; ++k) { a[k] = uvbox[k]; a[k] = a[k] >= 0 ? a[k] : a[k] ^ 0x7fffffff; uv[k] = __int_as_float(a[k]); }
+  BmpInfo r;
+  r.umin = uv[0]; r.vmin = uv[1]; r.ue = r.ve = 0; r.ok = 0; r.overflow = 0; r.pad0 = r.pad1 = 0;
+  if (uv[0] <= uv[2]) {
+    // BitmapExtent (R/PlanePrimitiveShape.cpp:192-198)
+    long long ue = (long long) ceilf(__fdiv_rn(__fsub_rn(uv[2], uv[0]), bmp_eps)) + 1, ve = (long long) ceilf(__fdiv_rn(__fsub_rn(uv[3], uv[1]), bmp_eps)) + 1;
+    if (ue < 2) ue = 2;
+    if (ve < 2) ve = 2;
+    if (ue * ve <= kBmpCap) { r.ue = (int) ue; r.ve = (int) ve; r.ok = 1; } else r.overflow = 1;
+  }
+  *info = r;
+}
+
+__global__ void raster_dev_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ flag, int n, PlaneFrame f, float bmp_eps,
+                                  const BmpInfo *__restrict__ info, int *__restrict__ pix, unsigned char *__restrict__ bitmap) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  const BmpInfo I = *info;
+  if (!I.ok) return;
+  float4 p = pos[i];
+  float px = __fsub_rn(p.x, f.pos.x), py = __fsub_rn(p.y, f.pos.y), pz = __fsub_rn(p.z, f.pos.z);
+  float u = __fadd_rn(__fadd_rn(__fmul_rn(px, f.u.x), __fmul_rn(py, f.u.y)), __fmul_rn(pz, f.u.z));
+  float v = __fadd_rn(__fadd_rn(__fmul_rn(px, f.v.x), __fmul_rn(py, f.v.y)), __fmul_rn(pz, f.v.z));
+  int bu = (int) floorf(__fdiv_rn(__fsub_rn(u, I.umin), bmp_eps));
+  int bv = (int) floorf(__fdiv_rn(__fsub_rn(v, I.vmin), bmp_eps));
+  bu = min(max(bu, 0), I.ue - 1);
+  bv = min(max(bv, 0), I.ve - 1);
+  int id = bu + bv * I.ue;
+  pix[i] = id;
+  bitmap[id] = 1;
+}
+
+// One block: cross closing (dilate, erode; R/Bitmap.cpp:154,459), 8-connected labelling by min-label
+// propagation with pointer jumping, largest component by PIXEL count (first in raster order on ties,
+// R/BitmapPrimitiveShape.cpp:170-173) -> mask.  Leaves the bitmap cleared for the next evaluation.
+__global__ void __launch_bounds__(1024)
+cc_kernel(unsigned char *__restrict__ bitmap, unsigned char *__restrict__ tmp, int *__restrict__ lab, int *__restrict__ cnt,
+          const BmpInfo *__restrict__ info, unsigned char *__restrict__ mask) {
+  __shared__ int changed;
+  __shared__ unsigned long long best;
+  const BmpInfo I = *info;
+  if (!I.ok) return;
+  const int ue = I.ue, ve = I.ve, P = ue * ve, tid = threadIdx.x, nt = blockDim.x;
+  for (int p = tid; p < P; p += nt) {
+    int x = p % ue, y = p / ue;
+    tmp[p] = bitmap[p] | (x > 0 ? bitmap[p - 1] : 0) | (x + 1 < ue ? bitmap[p + 1] : 0) | (y > 0 ? bitmap[p - ue] : 0) | (y + 1 < ve ? bitmap[p + ue] : 0);
+  }
+  __syncthreads();
+  for (int p = tid; p < P; p += nt) {
+    int x = p % ue, y = p / ue;
+    unsigned char e = tmp[p] & (x > 0 ? tmp[p - 1] : 1) & (x + 1 < ue ? tmp[p + 1] : 1) & (y > 0 ? tmp[p - ue] : 1) & (y + 1 < ve ? tmp[p + ue] : 1);
+    lab[p] = e ? p : -1;
+    cnt[p] = 0;
+  }
+  do {
+    __syncthreads();
+    if (tid == 0) changed = 0;
+    __syncthreads();
+    for (int p = tid; p < P; p += nt) {
+      int l = lab[p];
+      if (l < 0) continue;
+      int x = p % ue, y = p / ue, m = l;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          int xx = x + dx, yy = y + dy;
+          if (xx < 0 || yy < 0 || xx >= ue || yy >= ve) continue;
+          int lq = lab[yy * ue + xx];
+          if (lq >= 0 && lq < m) m = lq;
+        }
+      if (m < l) { lab[p] = m; changed = 1; }
+    }
+    __syncthreads();
+    for (int p = tid; p < P; p += nt) {
+      int l = lab[p];
+      if (l < 0) continue;
+      int r = l;
+      for (int it = 0; it < 64; ++it) { int nr = lab[r]; if (nr < 0 || nr >= r) break; r = nr; }
+      if (r < l) { lab[p] = r; changed = 1; }
+    }
+    __syncthreads();
+  } while (changed);
+  for (int p = tid; p < P; p += nt) { int l = lab[p]; if (l >= 0) atomicAdd(&cnt[l], 1); }
+  if (tid == 0) best = 0ull;
+  __syncthreads();
+  for (int p = tid; p < P; p += nt)
+    if (lab[p] == p) atomicMax(&best, ((unsigned long long) (unsigned int) cnt[p] << 32) | (unsigned long long) (0xFFFFFFFFu - (unsigned int) p));
+  __syncthreads();
+  const int bl = best ? (int) (0xFFFFFFFFu - (unsigned int) (best & 0xFFFFFFFFull)) : -2;
+  for (int p = tid; p < P; p += nt) { mask[p] = (lab[p] == bl) ? 1 : 0; bitmap[p] = 0; }
+}
+
+__global__ void mean_kernel(const double *__restrict__ acc, float *__restrict__ mean3) {
+  double c = acc[0];
+  if (c > 0) { mean3[0] = (float) (acc[1] / c); mean3[1] = (float) (acc[2] / c); mean3[2] = (float) (acc[3] / c); }
+  else { mean3[0] = mean3[1] = mean3[2] = 0.f; }
+}
+
+__global__ void cov_dev_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ member, int n, const float *__restrict__ mean3,
+                               double *__restrict__ acc6) {
+  const float mx = mean3[0], my = mean3[1], mz = mean3[2];
+  double c[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (!member[i]) continue;
+    float4 p = pos[i];
+    double dx = (double) (p.x - mx), dy = (double) (p.y - my), dz = (double) (p.z - mz);
+    c[0] += dx * dx; c[1] += dx * dy; c[2] += dx * dz; c[3] += dy * dy; c[4] += dy * dz; c[5] += dz * dz;
+  }
+  typedef cub::BlockReduce<double, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  for (int k = 0; k < 6; ++k) {
+    double r = BR(tmp).Sum(c[k]);
+    __syncthreads();
+    if (threadIdx.x == 0 && r != 0) atomicAdd(acc6 + k, r);
+  }
+}
+
+// select with the mask produced on the device (no-op when the bitmap stage was skipped)
+__global__ void select_dev_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ flag, const int *__restrict__ pix,
+                                  const unsigned char *__restrict__ comp_mask, const BmpInfo *__restrict__ info, int n, float4 pl, float eps3,
+                                  unsigned char *__restrict__ member, double *__restrict__ acc) {
+  const int ok = info->ok;
+  double cnt = 0, sx = 0, sy = 0, sz = 0, sc = 0;
+  const float denom = 2.f / 9.f * eps3 * eps3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    bool mem = ok && flag[i] && comp_mask[pix[i]];
+    member[i] = mem ? 1 : 0;
+    if (mem) {
+      float4 p = pos[i];
+      float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p.x), __fmul_rn(pl.y, p.y)), __fmul_rn(pl.z, p.z));
+      float d = fabsf(__fsub_rn(pl.w, dp));
+      cnt += 1; sx += p.x; sy += p.y; sz += p.z;
+      sc += (double) expf(-d * d / denom);
+    }
+  }
+  typedef cub::BlockReduce<double, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  double r0 = BR(tmp).Sum(cnt); __syncthreads();
+  double r1 = BR(tmp).Sum(sx); __syncthreads();
+  double r2 = BR(tmp).Sum(sy); __syncthreads();
+  double r3 = BR(tmp).Sum(sz); __syncthreads();
+  double r4 = BR(tmp).Sum(sc);
+  if (threadIdx.x == 0 && r0 > 0) {
+    atomicAdd(acc + 0, r0); atomicAdd(acc + 1, r1); atomicAdd(acc + 2, r2); atomicAdd(acc + 3, r3); atomicAdd(acc + 4, r4);
+  }
 }
 
 // pass E: members of the largest component; count, sum of positions, gaussian-weighted score
@@ -481,10 +648,14 @@ double failure_probability(double size, double n, double drawn, double levels) {
 }
 
 struct RansacScratch {
-  DevBuf<unsigned int> keys, keys_alt, counts;
+  DevBuf<unsigned int> keys, keys_alt, counts, counts_sorted, counts2;
   DevBuf<int> order, order_alt, assigned, pix, misc;
-  DevBuf<float4> cand, sub;
-  DevBuf<unsigned char> flag, member, member2, bitmap, mask, cub_tmp;
+  DevBuf<float4> cand, sub, sub1, cand_top;
+  DevBuf<int> cidx, cidx_sorted;
+  DevBuf<unsigned char> flag, member, member2, bitmap, mask, cub_tmp, bmp_dev, bmp_tmp, mask_dev;
+  DevBuf<int> cc_lab, cc_cnt;
+  DevBuf<float> mean3;
+  bool bmp_dev_clean = false;
   DevBuf<double> acc;
 };
 
@@ -569,8 +740,8 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   int m = n;                       // unassigned points
   double drawn = 0;
   unsigned long long round_seed = params.seed;
-  std::vector<unsigned int> h_counts(kCandPerRound);
-  std::vector<float4> h_cand(kCandPerRound);
+  std::vector<unsigned int> h_counts(kStage2Cand);
+  std::vector<float4> h_cand(kStage2Cand);
   float4 best_pl = make_float4(0, 0, 0, 0);
   double best_est = 0;
   const int max_rounds = 4000;
@@ -582,27 +753,48 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   for (int round = 0; round < max_rounds && m >= min_support && m >= 3; ++round) {
     int nlevels = 1;
     while ((8ll << nlevels) < m) ++nlevels;
-    // --- candidates + subsample + scores
-    const int S = std::min(m, kSubsample);
+    // --- candidates + two-stage scores: all candidates vs a small subsample, the best of them vs the large one
+    const int S = std::min(m, kSubsample), S1 = std::min(m, kStage1Points);
     float4 *sub = rs.sub.ensure((size_t) div_up(S, kScoreTile) * 2 * kScoreTile);
+    float4 *sub1 = rs.sub1.ensure((size_t) div_up(S1, kScoreTile) * 2 * kScoreTile);
+    unsigned int *counts_sorted = rs.counts_sorted.ensure(kCandPerRound), *counts2 = rs.counts2.ensure(kStage2Cand);
+    int *cidx = rs.cidx.ensure(kCandPerRound), *cidx_sorted = rs.cidx_sorted.ensure(kCandPerRound);
+    float4 *cand_top = rs.cand_top.ensure(kStage2Cand);
     PLADE_CUDA(cudaMemsetAsync(d_nvalid, 0, sizeof(int), s));
     PLADE_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * kCandPerRound, s));
+    PLADE_CUDA(cudaMemsetAsync(counts2, 0, sizeof(unsigned int) * kStage2Cand, s));
     round_seed = mix64(round_seed + 1);
     gen_candidates_kernel<<<div_up(kCandPerRound, 128), 128, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, nlevels, nthresh, round_seed, cand, d_nvalid);
     if (!pool.empty()) {   // carried candidates occupy the first slots
       for (size_t q = 0; q < pool.size(); ++q) h_pool[q] = pool[q].pl;
       PLADE_CUDA(cudaMemcpyAsync(cand, h_pool.data(), sizeof(float4) * pool.size(), cudaMemcpyHostToDevice, s));
     }
+    gather_sub_kernel<<<div_up(S1, 256), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S1, round_seed ^ 0x5bd1e995ull, sub1);
     gather_sub_kernel<<<div_up(S, 256), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S, round_seed, sub);
-    const int n_tiles = div_up(S, kScoreTile);
-    const int tiles_per_block = std::max(1, n_tiles / 32);
-    dim3 grid(div_up(n_tiles, tiles_per_block), kCandPerRound / kScoreThreads);
-    score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub, S, cand, kCandPerRound, eps, nthresh, tiles_per_block, counts);
+    {
+      const int n_tiles = div_up(S1, kScoreTile);
+      dim3 grid(n_tiles, kCandPerRound / kScoreThreads);
+      score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub1, S1, cand, nullptr, kCandPerRound, eps, nthresh, 1, counts);
+    }
+    stage1_keys_kernel<<<div_up(kCandPerRound, 256), 256, 0, s>>>(counts, cidx, kCandPerRound, (int) pool.size());
+    {
+      size_t tbs = 0;
+      cub::DeviceRadixSort::SortPairsDescending(nullptr, tbs, counts, counts_sorted, cidx, cidx_sorted, kCandPerRound, 0, 32, s);
+      unsigned char *t2 = rs.cub_tmp.ensure(tbs);
+      cub::DeviceRadixSort::SortPairsDescending(t2, tbs, counts, counts_sorted, cidx, cidx_sorted, kCandPerRound, 0, 32, s);
+    }
+    {
+      const int n_tiles = div_up(S, kScoreTile);
+      const int tiles_per_block = std::max(1, n_tiles / 128);
+      dim3 grid(div_up(n_tiles, tiles_per_block), kStage2Cand / kScoreThreads);
+      score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub, S, cand, cidx_sorted, kStage2Cand, eps, nthresh, tiles_per_block, counts2);
+    }
+    gather_planes_kernel<<<1, kStage2Cand, 0, s>>>(cand, cidx_sorted, kStage2Cand, cand_top);
     PLADE_LAUNCH_CHECK();
-    dev.launches.add(3);
+    dev.launches.add(9);
     int n_valid = 0;
-    PLADE_CUDA(cudaMemcpyAsync(h_counts.data(), counts, sizeof(unsigned int) * kCandPerRound, cudaMemcpyDeviceToHost, s));
-    PLADE_CUDA(cudaMemcpyAsync(h_cand.data(), cand, sizeof(float4) * kCandPerRound, cudaMemcpyDeviceToHost, s));
+    PLADE_CUDA(cudaMemcpyAsync(h_counts.data(), counts2, sizeof(unsigned int) * kStage2Cand, cudaMemcpyDeviceToHost, s));
+    PLADE_CUDA(cudaMemcpyAsync(h_cand.data(), cand_top, sizeof(float4) * kStage2Cand, cudaMemcpyDeviceToHost, s));
     PLADE_CUDA(cudaMemcpyAsync(&n_valid, d_nvalid, sizeof(int), cudaMemcpyDeviceToHost, s));
     PLADE_CUDA(cudaStreamSynchronize(s));
     mark("ransac_score_round");
@@ -611,12 +803,11 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     // 548-855): the best distinct planes of this round are re-scored next round in the first slots, so a
     // plane that lost against a bigger one is still there after the bigger one has been removed.
     {
-      std::vector<int> ord(kCandPerRound);
-      for (int k = 0; k < kCandPerRound; ++k) ord[k] = k;
-      std::partial_sort(ord.begin(), ord.begin() + std::min(kCandPerRound, 256), ord.end(),
-                        [&](int a, int b) { return h_counts[a] != h_counts[b] ? h_counts[a] > h_counts[b] : a < b; });
+      std::vector<int> ord(kStage2Cand);
+      for (int k = 0; k < kStage2Cand; ++k) ord[k] = k;
+      std::sort(ord.begin(), ord.end(), [&](int a, int b) { return h_counts[a] != h_counts[b] ? h_counts[a] > h_counts[b] : a < b; });
       pool.clear();
-      for (int q = 0; q < std::min(kCandPerRound, 256) && (int) pool.size() < kPoolSize; ++q) {
+      for (int q = 0; q < kStage2Cand && (int) pool.size() < kPoolSize; ++q) {
         const int k = ord[q];
         if (h_counts[k] == 0) break;
         const float4 &a = h_cand[k];
@@ -704,6 +895,49 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       e.size = (long long) h[0]; e.sum[0] = h[1]; e.sum[1] = h[2]; e.sum[2] = h[3]; e.score = h[4]; e.ok = e.size > 0;
       return e;
     };
+    // fused evaluation: flag/bbox -> raster -> closing + components -> select -> mean -> covariance, one sync.
+    // cov6 receives the covariance sums about float(mean) of the selected members (input of the LS refit).
+    auto evaluate_fused = [&](const PlaneFrame &f, unsigned char *member, double cov6[6], bool &overflow) -> Eval {
+      Eval e{0, 0, {0, 0, 0}, false};
+      unsigned char *bmp = rs.bmp_dev.ensure(kBmpCap), *btmp = rs.bmp_tmp.ensure(kBmpCap), *bmask = rs.mask_dev.ensure(kBmpCap);
+      int *lab = rs.cc_lab.ensure(kBmpCap), *ccnt = rs.cc_cnt.ensure(kBmpCap);
+      float *mean3 = rs.mean3.ensure(4);
+      BmpInfo *info = reinterpret_cast<BmpInfo *>(d_misc + 32);
+      if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
+      int init[4];
+      { float big = 3.4e38f, nb = -3.4e38f; int a, b; memcpy(&a, &big, 4); memcpy(&b, &nb, 4); b ^= 0x7fffffff; init[0] = init[1] = a; init[2] = init[3] = b; }
+      PLADE_CUDA(cudaMemcpyAsync(d_uvbox, init, sizeof(init), cudaMemcpyHostToDevice, s));
+      PLADE_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 16, s));
+      flag_uv_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, f, eps3, nthresh, flag, d_uvbox);
+      bmp_setup_kernel<<<1, 1, 0, s>>>(d_uvbox, bmp_eps, info);
+      raster_dev_kernel<<<div_up(n, 256), 256, 0, s>>>(c.pos.p, flag, n, f, bmp_eps, info, pix, bmp);
+      cc_kernel<<<1, 1024, 0, s>>>(bmp, btmp, lab, ccnt, info, bmask);
+      select_dev_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, flag, pix, bmask, info, n, f.pl, eps3, member, acc);
+      mean_kernel<<<1, 1, 0, s>>>(acc, mean3);
+      cov_dev_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, member, n, mean3, acc + 8);
+      PLADE_LAUNCH_CHECK();
+      dev.launches.add(7);
+      double h[16];
+      BmpInfo hi;
+      PLADE_CUDA(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, s));
+      PLADE_CUDA(cudaMemcpyAsync(&hi, info, sizeof(hi), cudaMemcpyDeviceToHost, s));
+      PLADE_CUDA(cudaStreamSynchronize(s));
+      overflow = hi.overflow != 0;
+      e.size = (long long) h[0]; e.sum[0] = h[1]; e.sum[1] = h[2]; e.sum[2] = h[3]; e.score = h[4]; e.ok = e.size > 0;
+      for (int k = 0; k < 6; ++k) cov6[k] = h[8 + k];
+      return e;
+    };
+    auto fit_from_cov = [&](const Eval &e, const double h[6], float nrm3[3], float pos3[3]) -> bool {
+      float a[3][3], d[3], v[3][3];
+      a[0][0] = (float) (h[0] / e.size); a[0][1] = a[1][0] = (float) (h[1] / e.size); a[0][2] = a[2][0] = (float) (h[2] / e.size);
+      a[1][1] = (float) (h[3] / e.size); a[1][2] = a[2][1] = (float) (h[4] / e.size); a[2][2] = (float) (h[5] / e.size);
+      if (!jacobi3f(a, d, v)) return false;
+      int k = 0;
+      for (int j = 1; j < 3; ++j) if (std::fabs(d[j]) < std::fabs(d[k])) k = j;
+      nrm3[0] = v[0][k]; nrm3[1] = v[1][k]; nrm3[2] = v[2][k];
+      pos3[0] = (float) (e.sum[0] / e.size); pos3[1] = (float) (e.sum[1] / e.size); pos3[2] = (float) (e.sum[2] / e.size);
+      return true;
+    };
     auto ls_fit = [&](const Eval &e, const unsigned char *member, float nrm3[3], float pos3[3]) -> bool {
       // Plane::LeastSquaresFit (R/Plane.h:66-74): mean, covariance, eigenvector of smallest |lambda|
       float3 mean = make_float3((float) (e.sum[0] / e.size), (float) (e.sum[1] / e.size), (float) (e.sum[2] / e.size));
@@ -731,11 +965,17 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     fr = make_frame(cn, cp);
     fr.pl.w = best_pl.w;
     unsigned char *acc_member = member_a, *work_member = member_b;
-    Eval cur = evaluate(fr, acc_member);   // GlobalScore + ConnectedComponent (+ weighted score of the clone)
+    double cov_cur[6];
+    bool ovf = false;
+    Eval cur = evaluate_fused(fr, acc_member, cov_cur, ovf);   // GlobalScore + ConnectedComponent (+ weighted score of the clone)
+    const bool host_path = ovf;                                // bitmap larger than the device cap: host labelling
+    if (host_path) cur = evaluate(fr, acc_member);
     float acc_n[3] = {cn[0], cn[1], cn[2]}, acc_p[3] = {cp[0], cp[1], cp[2]};
     long long acc_size = cur.ok ? cur.size : 0;
     if (cur.ok) {
       Eval clone = cur;
+      double cov_clone[6];
+      memcpy(cov_clone, cov_cur, sizeof(cov_cur));
       const unsigned char *clone_member = acc_member;
       double newScore = clone.score, oldScore;
       int iter = 0;
@@ -743,12 +983,17 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
         ++iter;
         oldScore = newScore;
         float fn[3], fp[3];
-        if (!ls_fit(clone, clone_member, fn, fp)) break;
+        if (host_path) { if (!ls_fit(clone, clone_member, fn, fp)) break; }
+        else if (!fit_from_cov(clone, cov_clone, fn, fp)) break;
         PlaneFrame f2 = make_frame(fn, fp);
-        Eval e2 = evaluate(f2, work_member);
+        double cov2[6];
+        bool ovf2 = false;
+        Eval e2 = host_path ? evaluate(f2, work_member) : evaluate_fused(f2, work_member, cov2, ovf2);
+        if (!host_path && ovf2) break;
         newScore = e2.score;
         if (!e2.ok) break;
         clone = e2;
+        memcpy(cov_clone, cov2, sizeof(cov2));
         clone_member = work_member;
         if (newScore > oldScore && e2.size > min_support) {
           memcpy(acc_n, fn, sizeof(fn)); memcpy(acc_p, fp, sizeof(fp));

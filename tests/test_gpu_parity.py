@@ -431,11 +431,14 @@ def test_file_overload_and_errors(ctx, poly_pair, tmp_path):
     blob = rng.normal(size=(20000, 6)).astype(np.float32)
     ok, T = ctx.register_clouds(blob, blob)
     assert not ok and np.array_equal(T, np.eye(4))
-    # swap rule: source >= 1.2 x target -> swapped internally, inverse returned (PLADE/plade.cpp:689-704)
-    big = np.concatenate([poly_pair["src"], poly_pair["src"][:30000] + np.float32(1e-4)])
-    write_ply(s, big)
+    # swap rule: source >= 1.2 x target -> swapped internally, inverse returned (PLADE/plade.cpp:689-704).
+    # (a synthetic pair: the polyhedron is symmetric enough that the reference itself flips on it)
+    st, ss, gt = make_pair(n_points=200000, n_planes=20, seed=11)
+    st = st[::2]                                                        # target half as dense: |src| >= 1.2 |tgt|
+    assert len(ss) >= 1.2 * len(st)
+    write_ply(t, st); write_ply(s, ss)
     ok, T3 = ctx.register_files(t, s)
     assert ok
-    diag = float(np.linalg.norm(np.ptp(poly_pair["tgt"][:, :3], axis=0)))
-    rot, tr = transform_error(T3, poly_pair["gt"], diag)
+    diag = float(np.linalg.norm(np.ptp(st[:, :3], axis=0)))
+    rot, tr = transform_error(T3, gt, diag)
     assert rot <= 0.5 and tr <= 5e-3
