@@ -9,6 +9,8 @@
 #include <cstring>
 #include <iostream>
 #include <numeric>
+#include <thread>
+#include <exception>
 
 namespace plade {
 
@@ -88,6 +90,9 @@ Registrar::Registrar(int device) {
   PLADE_CUDA(cudaGetDeviceProperties(&prop, dev.id));
   dev.num_sms = prop.multiProcessorCount;
   PLADE_CUDA(cudaStreamCreateWithFlags(&dev.stream, cudaStreamNonBlocking));
+  dev2 = dev;
+  dev2.launches.n = 0;
+  PLADE_CUDA(cudaStreamCreateWithFlags(&dev2.stream, cudaStreamNonBlocking));
   PLADE_CUDA(cudaEventCreate(&ev0));
   PLADE_CUDA(cudaEventCreate(&ev1));
   PLADE_CUDA(cudaEventCreate(&ev_user0));
@@ -114,8 +119,10 @@ void Registrar::print_marks() {
 }
 
 Registrar::~Registrar() {
+  free_ransac_scratch(*this);
   for (cudaEvent_t e : {ev0, ev1, ev_user0, ev_user1}) if (e) cudaEventDestroy(e);
   if (dev.stream) cudaStreamDestroy(dev.stream);
+  if (dev2.stream) cudaStreamDestroy(dev2.stream);
 }
 
 // defined in split.cu
@@ -164,13 +171,29 @@ float Registrar::average_spacing(const CloudDev &c) {
 bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float out16[16]) {
   double t0 = now_s();
   std::cout << "extracting planes for both point clouds...\n";
-  std::vector<PlaneParam> tp = extract_planes_dev(tgt, params.init_min_support, group_t);
+  // the two clouds are independent: the source's planes are extracted on a helper thread + stream while
+  // this thread does the target's (the kernels are small, so the two lanes overlap on the GPU and the
+  // host-side round trips of one lane hide behind the other's)
+  std::vector<PlaneParam> tp, sp;
+  std::exception_ptr helper_error;
+  std::thread helper([&] {
+    try {
+      PLADE_CUDA(cudaSetDevice(dev.id));
+      sp = extract_planes_dev(src, params.init_min_support, group_s, 1);
+    } catch (...) { helper_error = std::current_exception(); }
+  });
+  try {
+    tp = extract_planes_dev(tgt, params.init_min_support, group_t, 0);
+  } catch (...) { helper.join(); throw; }
+  helper.join();
+  dev.launches.n += dev2.launches.n;
+  dev2.launches.n = 0;
+  if (helper_error) std::rethrow_exception(helper_error);
   if ((int) tp.size() < params.min_planes) {
     std::cerr << "too few (only " << tp.size() << ") planes extracted from the target point cloud" << std::endl;
     last_error = "too few planes in target";
     return false;
   }
-  std::vector<PlaneParam> sp = extract_planes_dev(src, params.init_min_support, group_s);
   if ((int) sp.size() < params.min_planes) {
     std::cerr << "two few (only " << sp.size() << ") planes extracted from the source point cloud" << std::endl;
     last_error = "too few planes in source";

@@ -79,13 +79,14 @@ class Registrar {
   std::vector<PlaneRec> extract_planes(const CloudDev &c, int init_min_support);             // extract(), plade.cpp:602
   std::vector<PlaneRec> detect_planes(const CloudDev &c, int min_support);                   // PlaneExtraction::detect
   // device-resident variants used by the registration path: membership stays in HBM (group_out[n])
-  std::vector<PlaneParam> detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out);
-  std::vector<PlaneParam> extract_planes_dev(const CloudDev &c, int init_min_support, DevBuf<int> &group_out);
+  std::vector<PlaneParam> detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out, int lane = 0);
+  std::vector<PlaneParam> extract_planes_dev(const CloudDev &c, int init_min_support, DevBuf<int> &group_out, int lane = 0);
   std::vector<PlaneRec> planes_to_host(const CloudDev &c, const std::vector<PlaneParam> &pp, const DevBuf<int> &group);
   bool register_core(const CloudDev &tgt, const CloudDev &src, const std::vector<PlaneParam> &tp, const std::vector<PlaneParam> &sp,
                      const int *d_group_t, const int *d_group_s, float out16[16]);
 
   Device dev;
+  Device dev2;      // helper stream: plane extraction of the source cloud runs concurrently with the target's
   Params params;
   StageTimes times;
   bool debug = false;
@@ -107,6 +108,7 @@ class Registrar {
   DevBuf<float4> ds_tgt, ds_src, ds_planes_t, ds_planes_s;
   PenScratch pen_sc;
   ObbScratch obb_sc;
+  void *ransac_scratch[2] = {nullptr, nullptr};   // opaque, owned (ransac.cu)
   DevBuf<int> group_t, group_s, qidx;
   DevBuf<float> knn_out;
   DevBuf<HypParams> d_hyp;
@@ -122,5 +124,7 @@ class Registrar {
   }
 };
 
+
+void free_ransac_scratch(Registrar &r);
 
 }  // namespace plade

@@ -653,7 +653,7 @@ struct RansacScratch {
   DevBuf<float4> cand, sub, sub1, cand_top;
   DevBuf<int> cidx, cidx_sorted;
   DevBuf<unsigned char> flag, member, member2, bitmap, mask, cub_tmp, bmp_dev, bmp_tmp, mask_dev;
-  DevBuf<int> cc_lab, cc_cnt;
+  DevBuf<int> cc_lab, cc_cnt, remap;
   DevBuf<float> mean3;
   bool bmp_dev_clean = false;
   DevBuf<double> acc;
@@ -663,7 +663,15 @@ struct FoundPlane { float n[3]; float pos[3]; long long size; };
 
 }  // namespace
 
-static thread_local RansacScratch g_rs;
+// one scratch set per context and lane: lane 0 = the context's own stream, lane 1 = the helper stream used to
+// extract the planes of the second cloud concurrently
+static RansacScratch &scratch_of(Registrar &r, int lane) {
+  if (!r.ransac_scratch[lane]) r.ransac_scratch[lane] = new RansacScratch;
+  return *static_cast<RansacScratch *>(r.ransac_scratch[lane]);
+}
+void free_ransac_scratch(Registrar &r) {
+  for (int lane = 0; lane < 2; ++lane) { delete static_cast<RansacScratch *>(r.ransac_scratch[lane]); r.ransac_scratch[lane] = nullptr; }
+}
 
 __global__ void remap_group_kernel(const int *__restrict__ assigned, int n, const int *__restrict__ remap, int n_remap,
                                    int *__restrict__ group) {
@@ -673,13 +681,15 @@ __global__ void remap_group_kernel(const int *__restrict__ assigned, int n, cons
   group[i] = (a >= 0 && a < n_remap) ? remap[a] : -1;
 }
 
-std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out) {
+std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out, int lane) {
   std::vector<PlaneParam> result;
+  Device &dev = lane == 0 ? this->dev : this->dev2;          // shadows the member: everything below runs on the lane's stream
+  auto mark = [&](const char *name) { if (lane == 0) this->mark(name); };
   mark("ransac_begin");
   const int n = (int) c.n;
   if (n < 3) { std::cerr << "point set has less than 3 points" << std::endl; return result; }
   cudaStream_t s = dev.stream;
-  RansacScratch &rs = g_rs;
+  RansacScratch &rs = scratch_of(*this, lane);
   const int blocks_n = std::min(div_up(n, 256), dev.num_sms * 8);
 
   // bounding box -> scale (bug-compatible: z ignored)
@@ -1069,9 +1079,10 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
 }
 
 // extract(), PLADE/plade.cpp:602-635
-std::vector<PlaneParam> Registrar::extract_planes_dev(const CloudDev &c, int init_min_support, DevBuf<int> &group_out) {
+std::vector<PlaneParam> Registrar::extract_planes_dev(const CloudDev &c, int init_min_support, DevBuf<int> &group_out, int lane) {
+  Device &dev = lane == 0 ? this->dev : this->dev2;
   const int min_num = params.min_planes, max_num = params.max_planes, min_allowed_support = params.min_allowed_support;
-  std::vector<PlaneParam> planes = detect_planes_dev(c, init_min_support, group_out);
+  std::vector<PlaneParam> planes = detect_planes_dev(c, init_min_support, group_out, lane);
   if ((int) planes.size() >= min_num && (int) planes.size() <= max_num) return planes;
   if ((int) planes.size() > max_num) {
     // the reference sorts with a (non-strict) `>=` comparator; a stable descending sort is the defined equivalent
@@ -1081,8 +1092,7 @@ std::vector<PlaneParam> Registrar::extract_planes_dev(const CloudDev &c, int ini
     std::vector<int> remap(planes.size(), -1);
     std::vector<PlaneParam> kept;
     for (int r = 0; r < max_num; ++r) { remap[ord[r]] = r; kept.push_back(planes[ord[r]]); }
-    static thread_local DevBuf<int> d_remap;
-    int *dr = d_remap.ensure(remap.size());
+    int *dr = scratch_of(*this, lane).remap.ensure(remap.size());
     PLADE_CUDA(cudaMemcpyAsync(dr, remap.data(), sizeof(int) * remap.size(), cudaMemcpyHostToDevice, dev.stream));
     remap_group_kernel<<<div_up((long long) c.n, 256), 256, 0, dev.stream>>>(group_out.p, (int) c.n, dr, (int) remap.size(), group_out.p);
     PLADE_LAUNCH_CHECK();
@@ -1094,7 +1104,7 @@ std::vector<PlaneParam> Registrar::extract_planes_dev(const CloudDev &c, int ini
   int min_support = init_min_support / 2;
   int trials = 1;
   while ((int) planes.size() < min_num && trials < max_trials && min_support >= min_allowed_support) {
-    planes = detect_planes_dev(c, min_support, group_out);
+    planes = detect_planes_dev(c, min_support, group_out, lane);
     min_support /= 2;
     ++trials;
   }
