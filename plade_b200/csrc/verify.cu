@@ -54,6 +54,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
   } while (!ok);
 }
 
+__constant__ int c_row_dy[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+__constant__ int c_row_dz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+
 struct GridView {
   const float4 *pts;
   const int *cell_start;
@@ -93,16 +96,27 @@ __device__ __forceinline__ bool point_has_inlier(const GridView &g, const HypPar
   int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
   int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
   if (x0 > x1) return false;
-  for (int zz = z0; zz <= z1; ++zz) {
-    for (int yy = y0; yy <= y1; ++yy) {
-      int row = (zz * g.ny + yy) * g.nx;
-      int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
-      for (int i = b; i < e; ++i) {
-        float4 t = __ldg(g.pts + i);
-        if (dist2_l2simple(x, y, z, t.x, t.y, t.z) < rin2) {
-          // coarse-overlap ball: target point must be inside ball(c, ball_radius)
-          if (dist2_l2simple(hp.c[0], hp.c[1], hp.c[2], t.x, t.y, t.z) < rball2) return true;
-        }
+  // rows (dy, dz) nearest-first: a true inlier is usually found in the centre row, and a corner row can only
+  // hold a point within one cell edge (>= the inlier distance... the cell is 2^-10 larger) of the query if the
+  // query's in-cell offsets towards it satisfy oy^2 + oz^2 < 1 (in cell units; 1.01 leaves room for rounding)
+  const float ry = fy - (float) cy, rz = fz - (float) cz;          // in-cell position, [0, 1)
+  // (rolled loop on purpose: unrolling it leaves the lanes of a warp on nine different code paths)
+#pragma unroll 1
+  for (int k = 0; k < 9; ++k) {
+    const int dy = c_row_dy[k], dz = c_row_dz[k];
+    const int yy = cy + dy, zz = cz + dz;
+    if (yy < y0 || yy > y1 || zz < z0 || zz > z1) continue;
+    if (k >= 5) {
+      const float oy = dy < 0 ? ry : 1.0f - ry, oz = dz < 0 ? rz : 1.0f - rz;
+      if (oy * oy + oz * oz > 1.01f) continue;
+    }
+    const int row = (zz * g.ny + yy) * g.nx;
+    const int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
+    for (int i = b; i < e; ++i) {
+      float4 t = __ldg(g.pts + i);
+      if (dist2_l2simple(x, y, z, t.x, t.y, t.z) < rin2) {
+        // coarse-overlap ball: target point must be inside ball(c, ball_radius)
+        if (dist2_l2simple(hp.c[0], hp.c[1], hp.c[2], t.x, t.y, t.z) < rball2) return true;
       }
     }
   }
