@@ -142,7 +142,7 @@ def run_ours(args):
     quiet = open(os.devnull, "w")
     saved = os.dup(1)
 
-    def hush(on):   # the library prints the reference's progress lines on stdout; keep the JSON line clean
+    def hush(on):   # the library prints the reference's progress lines (one per stage) on stdout: drop them while timing
         sys.stdout.flush()
         os.dup2(quiet.fileno() if on else saved, 1)
 
@@ -174,8 +174,8 @@ def run_ours(args):
     rot, tr = transform_error(T, gt, diag)
     if args.profile:     # short run under ncu: never a bench value
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": t_step * 1e3, "gpu_launches": int(launches), "ok": bool(ok),
-                              "rot_err_deg": rot, "stage_ms": {k: 1e3 * v / args.steps for k, v in stage_acc.items()}}), flush=True)
+            emit({"profile_run": True, "ms_per_step": t_step * 1e3, "gpu_launches": int(launches), "ok": bool(ok),
+                  "rot_err_deg": rot, "stage_ms": {k: 1e3 * v / args.steps for k, v in stage_acc.items()}})
         return
 
     # ---- end to end through the C ABI with host buffers ("e2e") -------------------------------------------
@@ -273,7 +273,7 @@ def run_ours(args):
     ctx.free_cloud(hs)
     ctx.close()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -317,7 +317,7 @@ def run_reference(args):
     import multiprocessing as mp
     import tempfile
     if not oref.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libplade_ref.so missing (built only where /root/reference is mounted)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libplade_ref.so missing (built only where /root/reference is mounted)"})
         return
     tgt, src, gt = workload(args.points)
     diag = float(np.linalg.norm(np.ptp(tgt[:, :3], axis=0)))
@@ -352,10 +352,23 @@ def run_reference(args):
         "gpu_launches": 0,
         "result": {"ok": bool(all(oks)), "rot_err_deg": float(np.median([e[0] for e in errs])), "trans_err_rel_diag": float(np.median([e[1] for e in errs]))},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line goes to the process's original stdout; everything else (library progress lines,
+    NCCL's version banner, ...) was routed to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
