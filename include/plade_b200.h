@@ -100,6 +100,11 @@ float plade_average_spacing(plade_ctx *ctx, const float *xyzn, size_t n);
 long long plade_voxel_downsample(plade_ctx *ctx, const float *pts, size_t n, int stride, float leaf, float *out_xyz);
 /* ComputeBoundingBox PLADE/util.h:187-248: center[3], whd[3] = width, height, depth, corners[24] */
 int plade_bounding_box(plade_ctx *ctx, const float *xyz, size_t n, float *center, double *whd, float *corners);
+/* ComputeNearstTwoPointsOfTwo3DLine PLADE/util.cpp:1167-1229 for n line pairs at once: lines12 holds
+ * v1[3] p1[3] v2[3] p2[3] per pair; directions are normalised as the reference does, the 9x9 float
+ * cv::solve(DECOMP_SVD) is restated on the GPU.  points6 = point1[3] point2[3]; length[i] = |point1-point2|
+ * or -1 where the reference returns -1 (identical directions).  Returns 0 or -1. */
+int plade_nearest_points_two_lines(plade_ctx *ctx, const float *lines12, int n, float *points6, double *length);
 /* descriptor radius search, KdTreeSearchNDim<.,8>::find_neighbors(q, 0, radius) ANN.h:979-1029.
  * offsets[nq+1]; returns the total number of matches M (or -1); plade_match_results copies the M
  * (db index, squared distance) pairs, per query ascending in (distance, index). */

@@ -55,6 +55,7 @@ SIGNATURES = {
     "plade_average_spacing": (ctypes.c_float, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t]),
     "plade_voxel_downsample": (ctypes.c_longlong, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, _c_float_p]),
     "plade_bounding_box": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, _c_float_p, _c_double_p, _c_float_p]),
+    "plade_nearest_points_two_lines": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_int, _c_float_p, _c_double_p]),
     "plade_match_descriptors": (ctypes.c_longlong, [ctypes.c_void_p, _c_float_p, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_float, _c_int_p]),
     "plade_match_results": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, _c_double_p]),
     "plade_transforms_from_matches": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p]),
@@ -286,6 +287,16 @@ class Context:
         corners = np.zeros((8, 3), dtype=np.float32)
         rc = self.lib.plade_bounding_box(self.h, _p(a, _c_float_p), len(a), _p(c, _c_float_p), _p(whd, _c_double_p), _p(corners, _c_float_p))
         return rc, c, whd, corners
+
+    def nearest_points_two_lines(self, lines12):
+        """lines12: (n, 12) = v1 p1 v2 p2 -> (points (n, 2, 3), length (n,)), PLADE/util.cpp:1167-1229."""
+        a = _f32(lines12).reshape(-1, 12)
+        pts = np.zeros((len(a), 2, 3), dtype=np.float32)
+        length = np.zeros(len(a), dtype=np.float64)
+        rc = self.lib.plade_nearest_points_two_lines(self.h, _p(a, _c_float_p), len(a), _p(pts, _c_float_p), _p(length, _c_double_p))
+        if rc != 0:
+            raise RuntimeError(self.last_error())
+        return pts, length
 
     def match_descriptors(self, db8, q8, radius=0.04):
         db, q = _f32(db8).reshape(-1, 8), _f32(q8).reshape(-1, 8)

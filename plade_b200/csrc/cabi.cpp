@@ -362,6 +362,34 @@ int plade_bounding_box(plade_ctx *ctx, const float *xyz, size_t n, float *center
   })
 }
 
+int plade_nearest_points_two_lines(plade_ctx *ctx, const float *lines12, int n, float *points6, double *length) {
+  PLADE_TRY(ctx, -1, {
+    Registrar &r = *ctx->reg;
+    std::vector<float> in, out;
+    std::vector<int> slot(n, -1);
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+      const float *q = lines12 + 12 * (size_t) i;
+      V3 v1(q[0], q[1], q[2]), v2(q[6], q[7], q[8]);
+      normalize(v1);
+      normalize(v2);
+      if (v1.x == v2.x && v1.y == v2.y && v1.z == v2.z) continue;
+      const float e[12] = {v1.x, v1.y, v1.z, q[3], q[4], q[5], v2.x, v2.y, v2.z, q[9], q[10], q[11]};
+      in.insert(in.end(), e, e + 12);
+      slot[i] = m++;
+    }
+    out.resize((size_t) 6 * m);
+    nearest_points_batch(r.dev, r.svd_sc, in.data(), m, out.data());
+    for (int i = 0; i < n; ++i) {
+      float *o = points6 + 6 * (size_t) i;
+      if (slot[i] < 0) { for (int k = 0; k < 6; ++k) o[k] = 0.f; length[i] = -1; continue; }
+      memcpy(o, &out[6 * (size_t) slot[i]], sizeof(float) * 6);
+      length[i] = norm(V3(o[0], o[1], o[2]) - V3(o[3], o[4], o[5]));
+    }
+    return 0;
+  })
+}
+
 long long plade_match_descriptors(plade_ctx *ctx, const float *db8, int ndb, const float *q8, int nq, float radius, int *offsets) {
   PLADE_TRY(ctx, -1, {
     Registrar &r = *ctx->reg;

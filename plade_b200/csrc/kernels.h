@@ -157,4 +157,12 @@ struct ObbScratch {
 };
 void obb_segments(Device &dev, ObbScratch &sc, const std::vector<ObbSeg> &segs, std::vector<ObbResult> &out);
 
+// ------------------------------------------------------------------------------------------------
+// Closest points of line pairs through the reference's own float Jacobi-SVD solve
+// (ComputeNearstTwoPointsOfTwo3DLine, PLADE/util.cpp:1167-1229), one thread per pair.
+// h_in12: v1 p1 v2 p2 per pair (directions normalised); h_out6: point1 point2 per pair.
+// ------------------------------------------------------------------------------------------------
+struct SvdScratch { DevBuf<float> in, out; };
+void nearest_points_batch(Device &dev, SvdScratch &sc, const float *h_in12, int n, float *h_out6);
+
 }  // namespace plade

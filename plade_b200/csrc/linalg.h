@@ -28,8 +28,9 @@ PLADE_HD V3 operator*(const V3 &a, float s) { return V3(a.x * s, a.y * s, a.z * 
 PLADE_HD V3 operator*(float s, const V3 &a) { return V3(s * a.x, s * a.y, s * a.z); }
 PLADE_HD V3 operator/(const V3 &a, float s) { return V3(a.x / s, a.y / s, a.z / s); }
 PLADE_HD V3 operator-(const V3 &a) { return V3(-a.x, -a.y, -a.z); }
-// Eigen fixed-size dot / squaredNorm: ((a0*b0 + a1*b1) + a2*b2)
-PLADE_HD float dot(const V3 &a, const V3 &b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+// Eigen 3.4 fixed-size dot / squaredNorm / sum of 3 terms: the unrolled reduction splits the range in
+// halves (Core/Redux.h redux_novec_unroller), i.e. a0*b0 + (a1*b1 + a2*b2) -- checked against Eigen itself
+PLADE_HD float dot(const V3 &a, const V3 &b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
 PLADE_HD float sqnorm(const V3 &a) { return dot(a, a); }
 PLADE_HD float norm(const V3 &a) { return sqrtf(sqnorm(a)); }
 PLADE_HD V3 cross(const V3 &a, const V3 &b) {
@@ -46,10 +47,10 @@ struct M3 {           // row-major
   PLADE_HD float operator()(int r, int c) const { return m[3 * r + c]; }
   PLADE_HD float &operator()(int r, int c) { return m[3 * r + c]; }
 };
-// Eigen lazy 3x3 * 3x1 coefficient product: row dot, left to right
+// Eigen lazy 3x3 * 3x1 coefficient product: row . vector with the same halving reduction as dot()
 PLADE_HD V3 mul(const M3 &R, const V3 &v) {
-  return V3((R.m[0] * v.x + R.m[1] * v.y) + R.m[2] * v.z, (R.m[3] * v.x + R.m[4] * v.y) + R.m[5] * v.z,
-            (R.m[6] * v.x + R.m[7] * v.y) + R.m[8] * v.z);
+  return V3(R.m[0] * v.x + (R.m[1] * v.y + R.m[2] * v.z), R.m[3] * v.x + (R.m[4] * v.y + R.m[5] * v.z),
+            R.m[6] * v.x + (R.m[7] * v.y + R.m[8] * v.z));
 }
 // pcl::transformPointCloud formula (common/impl/transforms.hpp:69-71)
 PLADE_HD V3 xform(const M3 &R, const V3 &T, const V3 &p) {

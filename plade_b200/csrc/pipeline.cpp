@@ -49,16 +49,28 @@ struct Side {            // MatchInformation, PLADE/util.h:80-102
   std::vector<Line> lines;
 };
 
-// ComputeNearstTwoPointsOfTwo3DLine (PLADE/util.cpp:1167-1229): normalises both directions IN PLACE,
-// fails on identical directions, closest points (closed form here), length = |p1 - p2| (float norm).
-int nearest_two_lines(V3 &v1, const V3 &p1, V3 &v2, const V3 &p2, V3 &q1, V3 &q2, double &len) {
-  normalize(v1);
-  normalize(v2);
-  if (v1.x == v2.x && v1.y == v2.y && v1.z == v2.z) return -1;
-  if (!closest_points_two_lines(v1, p1, v2, p2, q1, q2)) { q1 = p1; q2 = p2; }
-  len = norm(q1 - q2);
-  return 0;
-}
+// ComputeNearstTwoPointsOfTwo3DLine (PLADE/util.cpp:1167-1229), split in two: the host part normalises both
+// directions IN PLACE and rejects identical directions (util.cpp:1170-1176); the 9x9 float SVD solve of all
+// accepted pairs then runs as one batch on the GPU (svdsolve.cu), and length = |p1 - p2| (float norm).
+struct PairSolve {
+  std::vector<float> in, out;    // 12 / 6 floats per accepted pair
+  int count = 0;
+  int add(V3 &v1, const V3 &p1, V3 &v2, const V3 &p2) {
+    normalize(v1);
+    normalize(v2);
+    if (v1.x == v2.x && v1.y == v2.y && v1.z == v2.z) return -1;
+    const float q[12] = {v1.x, v1.y, v1.z, p1.x, p1.y, p1.z, v2.x, v2.y, v2.z, p2.x, p2.y, p2.z};
+    in.insert(in.end(), q, q + 12);
+    return count++;
+  }
+  void get(int k, V3 &a, V3 &b, double &len) const {
+    if (k < 0) { len = -1; return; }
+    const float *o = &out[6 * (size_t) k];
+    a = V3(o[0], o[1], o[2]);
+    b = V3(o[3], o[4], o[5]);
+    len = norm(a - b);
+  }
+};
 
 // ComputeDescriptorVectorForPairLines, method22 (PLADE/util.cpp:533-602)
 void pair_descriptor(const V3 &l1, const V3 &l2, const V3 &l1sp1, const V3 &l1sp2, const V3 &l2sp1, const V3 &l2sp2,
@@ -386,6 +398,22 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
   // ---- target descriptor table "22", ConstructPairLinesKdTree (PLADE/util.cpp:706-1165) -------------
   t0 = now_s();
   const float angleThresh10 = (float) std::cos(10.0 / 180 * M_PI);
+  // pass 1: play both sides' in-place normalisations in the reference's order and collect every line pair
+  // whose closest points the reference solves for (all i < j), then solve them in one launch
+  PairSolve solve;
+  std::vector<int> t_slot(mainLinesNum * mainLinesNum, -1), s_slot(currentLinesNum * currentLinesNum, -1);
+  {
+    std::vector<Line> keep = M.lines;
+    for (size_t i = 0; i < mainLinesNum; ++i)
+      for (size_t j = i + 1; j < mainLinesNum; ++j)
+        t_slot[i * mainLinesNum + j] = solve.add(M.lines[i].vec, M.lines[i].pt, M.lines[j].vec, M.lines[j].pt);
+    M.lines = keep;                  // pass 2 replays the normalisations interleaved with the descriptor tests
+    for (size_t i = 0; i < currentLinesNum; ++i)
+      for (size_t j = i + 1; j < currentLinesNum; ++j)
+        s_slot[i * currentLinesNum + j] = solve.add(Cu.lines[i].vec, Cu.lines[i].pt, Cu.lines[j].vec, Cu.lines[j].pt);
+    solve.out.resize((size_t) 6 * solve.count);
+    nearest_points_batch(dev, svd_sc, solve.in.data(), solve.count, solve.out.data());
+  }
   std::vector<float> db_desc;                 // 8 per entry
   struct DbRec { V3 v1, v2, p1; };
   std::vector<DbRec> db;
@@ -404,7 +432,9 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
           const NearPts &o = tab[j * mainLinesNum + i];
           e.a = o.b; e.b = o.a; e.length = o.length;
         } else {
-          if (0 != nearest_two_lines(l1.vec, l1.pt, l2.vec, l2.pt, e.a, e.b, e.length)) e.length = -1;
+          normalize(l1.vec);          // replays the in-place normalisation of pass 1
+          normalize(l2.vec);
+          solve.get(t_slot[i * mainLinesNum + j], e.a, e.b, e.length);
           e.length = e.length / scale;
         }
         if (std::fabs(dot(l1.vec, l2.vec)) > angleThresh10) continue;
@@ -429,7 +459,7 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     for (size_t i = 0; i < currentLinesNum; ++i)
       for (size_t j = i + 1; j < currentLinesNum; ++j) {
         NearPts &e = tab[i * currentLinesNum + j];
-        if (0 != nearest_two_lines(Cu.lines[i].vec, Cu.lines[i].pt, Cu.lines[j].vec, Cu.lines[j].pt, e.a, e.b, e.length)) e.length = -1;
+        solve.get(s_slot[i * currentLinesNum + j], e.a, e.b, e.length);
         e.length = e.length / scale;
       }
     for (size_t i = 0; i < currentLinesNum; ++i)

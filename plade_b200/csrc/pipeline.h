@@ -108,6 +108,7 @@ class Registrar {
   DevBuf<float4> ds_tgt, ds_src, ds_planes_t, ds_planes_s;
   PenScratch pen_sc;
   ObbScratch obb_sc;
+  SvdScratch svd_sc;
   void *ransac_scratch[2] = {nullptr, nullptr};   // opaque, owned (ransac.cu)
   DevBuf<int> group_t, group_s, qidx;
   DevBuf<float> knn_out;

@@ -275,6 +275,36 @@ def test_match_descriptors_vs_ann(ctx, ref, poly_stages):
 
 
 # ---------------------------------------------------------------------------------------------- K4
+def test_nearest_points_two_lines_bit_exact_vs_cv_solve(ctx, ref, poly_stages):
+    """K3a: closest points of line pairs.  The reference solves a 9x9 system with cv::solve(DECOMP_SVD) in
+    float (PLADE/util.cpp:1167-1229); the GPU kernel restates OpenCV's Jacobi SVD + back-substitution
+    operation for operation, so points and length must be IDENTICAL to the compiled reference's."""
+    rng = np.random.default_rng(5)
+    n = 300
+    v1, v2 = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    v2[:20] = v1[:20] + 1e-3 * rng.normal(size=(20, 3))          # nearly parallel: ill-conditioned solve
+    p1, p2 = rng.uniform(-5, 5, size=(n, 3)), rng.uniform(-5, 5, size=(n, 3))
+    p2[20:40] = p1[20:40] + v1[20:40] * 0.7 - v2[20:40] * 1.3       # intersecting lines
+    rows = [np.concatenate([v1[i], p1[i], v2[i], p2[i]]) for i in range(n)]
+    L = poly_stages["tgt_lines"].reshape(-1, 6)                     # the reference's own intersection lines
+    for i in range(len(L)):
+        for j in range(i + 1, len(L)):
+            rows.append(np.concatenate([L[i], L[j]]))
+    rows.append(np.concatenate([[0, 0, 2], [1, 2, 3], [0, 0, 5], [4, 5, 6]]))   # identical directions -> -1
+    lines12 = np.asarray(rows, dtype=np.float32)
+    pts, length = ctx.nearest_points_two_lines(lines12)
+    worst = 0.0
+    for i, r in enumerate(lines12):
+        rc, q1, q2, ln = ref.nearest_points_two_lines(r[0:3], r[3:6], r[6:9], r[9:12])
+        if rc != 0:
+            assert length[i] == -1
+            continue
+        worst = max(worst, float(np.abs(pts[i, 0] - q1).max()), float(np.abs(pts[i, 1] - q2).max()))
+        assert np.array_equal(pts[i, 0], q1) and np.array_equal(pts[i, 1], q2), (i, pts[i], q1, q2)
+        assert length[i] == ln
+    assert length[-1] == -1 and worst == 0.0
+
+
 def test_transforms_from_matches_vs_eigen_umeyama(ctx, ref):
     """Tolerance: |dR|_max <= 3e-5, |dT| <= 5e-5 against the reference (Eigen's FLOAT JacobiSVD inside
     umeyama carries ~1e-5 of its own error; ours evaluates the same rotation in fp64 and rounds once)."""
@@ -349,12 +379,10 @@ def test_registration_with_reference_planes(ctx, poly_pair, poly_stages, synth_s
         assert np.array_equal(ctx.blob(side + "_line_planes", np.int32), g[side + "_line_planes"])
         assert np.allclose(ctx.blob(side + "_lines", np.float32), g[side + "_lines"], atol=2e-5)
     assert np.array_equal(ctx.blob("tgt_db_pair", np.int32), g["tgt_db_pair"])
-    # descriptor[0] = line-pair distance / scale: the reference gets it from a 9x9 FLOAT SVD solve
-    # (cv::solve, PLADE/util.cpp:1219) whose own error reaches ~4e-4 in the closest points (2e-3 in
-    # descriptor units: it reports 0.002 for lines that intersect); ours is the closed form in double.  Components 1..7 (dot products of plane normals) agree to float rounding.
+    # all 8 descriptor components are bit-identical to the reference's: component 0 (line-pair distance / scale)
+    # comes from the restated 9x9 float SVD solve (K3a, svdsolve.cu), 1..7 are Eigen-ordered dot products
     ours_d, ref_d = ctx.blob("tgt_db_desc", np.float32).reshape(-1, 8), g["tgt_db_desc"].reshape(-1, 8)
-    assert np.allclose(ours_d[:, 1:], ref_d[:, 1:], atol=2e-6)
-    assert np.allclose(ours_d[:, 0], ref_d[:, 0], rtol=1e-3, atol=5e-3)
+    assert np.array_equal(ours_d, ref_d)
     assert np.array_equal(ctx.blob("lines_to_match", np.int32), g["lines_to_match"])
     # hypothesis list: cluster representatives can differ where a cluster boundary sits within that
     # float noise, so: same winner, same winning score, and >= 90 % of the reference's hypotheses have a

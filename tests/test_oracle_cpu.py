@@ -117,6 +117,32 @@ def test_restate_plane_predicate_on_reference_planes(restate, poly_pair, poly_st
 
 
 # ------------------------------------------------------------------ host-side logic
+def test_host_restatement_of_cv_solve_vs_reference(ref, poly_stages, tmp_path):
+    """plade_b200/csrc/svdsolve.h (the float Jacobi-SVD solve the K3a kernel runs per line pair) compiled for the
+    HOST must give the compiled reference's ComputeNearstTwoPointsOfTwo3DLine (PLADE/util.cpp:1167-1229) bit
+    for bit, ill-conditioned pairs included; the same header compiled by nvcc is checked by the GPU suite."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "svd_host_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + os.path.join(root, "plade_b200", "csrc"),
+                    "-o", exe, os.path.join(root, "tests", "host", "svd_host_check.cpp")], check=True)
+    rng = np.random.default_rng(5)
+    n = 600
+    v1, v2 = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    v2[:60] = v1[:60] + 1e-3 * rng.normal(size=(60, 3))
+    p1, p2 = rng.uniform(-5, 5, size=(n, 3)), rng.uniform(-5, 5, size=(n, 3))
+    p2[60:120] = p1[60:120] + v1[60:120] * 0.7 - v2[60:120] * 1.3
+    rows = np.concatenate([v1, p1, v2, p2], axis=1).astype(np.float32)
+    L = poly_stages["tgt_lines"].reshape(-1, 6)
+    extra = [np.concatenate([L[i], L[j]]) for i in range(len(L)) for j in range(i + 1, len(L))]
+    rows = np.concatenate([rows, np.asarray(extra, np.float32)])
+    r = subprocess.run([exe], input=np.int32(len(rows)).tobytes() + rows.tobytes(), capture_output=True, check=True)
+    out = np.frombuffer(r.stdout, np.float32).reshape(-1, 2, 3)
+    assert len(out) == len(rows)
+    for i, q in enumerate(rows):
+        rc, q1, q2, _ = ref.nearest_points_two_lines(q[0:3], q[3:6], q[6:9], q[9:12])
+        assert rc == 0 and np.array_equal(out[i, 0], q1) and np.array_equal(out[i, 1], q2), i
+
+
 def test_synth_generator_is_deterministic_and_shaped():
     from plade_b200.synth import make_pair, transform_error, perturbed_hypotheses
     a = make_pair(n_points=20000, n_planes=20, seed=3)
