@@ -105,6 +105,16 @@ int plade_bounding_box(plade_ctx *ctx, const float *xyz, size_t n, float *center
  * cv::solve(DECOMP_SVD) is restated on the GPU.  points6 = point1[3] point2[3]; length[i] = |point1-point2|
  * or -1 where the reference returns -1 (identical directions).  Returns 0 or -1. */
 int plade_nearest_points_two_lines(plade_ctx *ctx, const float *lines12, int n, float *points6, double *length);
+/* Penetration filter of MatchingLines, PLADE/util.cpp:466-511 around AreTwoPlanesPenetrable PLADE/util.cpp:
+ * 1279-1458, for n_hyp candidate transforms (hyp12: R row-major, T).  Per side: planes4 (n, d), corners12 = the
+ * 4 bounding-rectangle corners of each plane in the reference's order, centers3, the per-plane down-sampled
+ * points xyz with offsets[P+1].  flags[h] = 1 iff the reference would drop hypothesis h.  Returns 0 or -1. */
+int plade_penetration_filter(plade_ctx *ctx,
+                             const float *src_planes4, int n_src_planes, const float *src_corners12, const float *src_centers3,
+                             const float *src_xyz, const int *src_offsets,
+                             const float *tgt_planes4, int n_tgt_planes, const float *tgt_corners12, const float *tgt_centers3,
+                             const float *tgt_xyz, const int *tgt_offsets,
+                             const float *hyp12, int n_hyp, float length_threshold, float angle_threshold, unsigned char *flags);
 /* descriptor radius search, KdTreeSearchNDim<.,8>::find_neighbors(q, 0, radius) ANN.h:979-1029.
  * offsets[nq+1]; returns the total number of matches M (or -1); plade_match_results copies the M
  * (db index, squared distance) pairs, per query ascending in (distance, index). */

@@ -247,6 +247,35 @@ class Ref:
         rc = self.lib.ref_plane_intersection(_p(a, _fp), _p(b, _fp), _p(v, _fp), _p(p, _fp))
         return rc, v, p
 
+    def self_adjoint_eig3(self, A):
+        a = _f32(A).reshape(9)
+        w, V = np.zeros(3, np.float32), np.zeros(9, np.float32)
+        self.lib.ref_self_adjoint_eig3(_p(a, _fp), _p(w, _fp), _p(V, _fp))
+        return w, V.reshape(3, 3)
+
+    def line_line_intersection(self, v1, p1, v2, p2):
+        a, b, c, d = _f32(v1), _f32(p1), _f32(v2), _f32(p2)
+        o = np.zeros(3, np.float32)
+        rc = self.lib.ref_line_line_intersection(_p(a, _fp), _p(b, _fp), _p(c, _fp), _p(d, _fp), _p(o, _fp))
+        return rc, o
+
+    def penetration_filter(self, src, tgt, hyp12, length_threshold, angle_threshold):
+        """src / tgt: dicts with planes (P,4), corners4 (P,4,3), center (P,3), pts (n,3), off (P+1,).  Returns flags (H,)."""
+        def side(d):
+            return (_f32(d["planes"]).reshape(-1, 4), _f32(d["corners4"]).reshape(-1, 12), _f32(d["center"]).reshape(-1, 3),
+                    _f32(d["pts"]).reshape(-1, 3), np.ascontiguousarray(d["off"], dtype=np.int32))
+        sp, sc, sce, spt, so = side(src)
+        tp, tc, tce, tpt, to = side(tgt)
+        h = _f32(hyp12).reshape(-1, 12)
+        flags = np.zeros(len(h), np.uint8)
+        self.lib.ref_penetration_filter.restype = None
+        self.lib.ref_penetration_filter.argtypes = None
+        self.lib.ref_penetration_filter(_p(sp, _fp), ctypes.c_int(len(sp)), _p(sc, _fp), _p(sce, _fp), _p(spt, _fp), _p(so, _ip),
+                                        _p(tp, _fp), ctypes.c_int(len(tp)), _p(tc, _fp), _p(tce, _fp), _p(tpt, _fp), _p(to, _ip),
+                                        _p(h, _fp), ctypes.c_int(len(h)), ctypes.c_float(length_threshold), ctypes.c_float(angle_threshold),
+                                        flags.ctypes.data_as(ctypes.c_void_p))
+        return flags
+
     def nearest_points_two_lines(self, v1, p1, v2, p2):
         a, b, c, d = _f32(v1), _f32(p1), _f32(v2), _f32(p2)
         q1, q2 = np.zeros(3, np.float32), np.zeros(3, np.float32)

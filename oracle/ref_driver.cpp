@@ -433,6 +433,81 @@ int ref_cluster_transformations(const float *R9, const float *T3, int n, float d
   return (int) clusters.size();
 }
 
+// Eigen::SelfAdjointEigenSolver<Eigen::Matrix3f>, the solver ComputeBoundingBox uses (PLADE/util.h:199-200).
+void ref_self_adjoint_eig3(const float *A9, float *w3, float *V9) {
+  Eigen::Matrix3f A;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) A(r, c) = A9[3 * r + c];
+  Eigen::SelfAdjointEigenSolver<Eigen::Matrix3f> es(A, Eigen::ComputeEigenvectors);
+  Eigen::Matrix3f V = es.eigenvectors();
+  for (int r = 0; r < 3; ++r) { w3[r] = es.eigenvalues()(r); for (int c = 0; c < 3; ++c) V9[3 * r + c] = V(r, c); }
+}
+
+// Penetration filter of MatchingLines, PLADE/util.cpp:466-511, for H hypotheses (12 floats each: R row-major,
+// T): the loop over (source plane i1, target plane j1) as written there -- same statements, same order --
+// around the reference's own AreTwoPlanesPenetrable (PLADE/util.cpp:1279-1458), pcl::transformPointCloud and
+// pcl::search::KdTree.  flags[h] = 1 iff the reference would drop hypothesis h.
+void ref_penetration_filter(const float *s_planes4, int Ps, const float *s_corners12, const float *s_centers3,
+                            const float *s_pts, const int *s_off,
+                            const float *t_planes4, int Pt, const float *t_corners12, const float *t_centers3,
+                            const float *t_pts, const int *t_off,
+                            const float *hyp12, int H, float lengthThreshold, float angleThreshold, unsigned char *flags) {
+  std::vector<Eigen::Vector4f> planes(Ps), mainPlanes(Pt);
+  std::vector<std::vector<Eigen::Vector3f> > sc(Ps), tc(Pt);
+  std::vector<Eigen::Vector3f> scen(Ps), tcen(Pt);
+  std::vector<CloudXYZ::Ptr> sp(Ps), tp(Pt);
+  std::vector<pcl::search::KdTree<pcl::PointXYZ>::Ptr> ttree(Pt);
+  for (int i = 0; i < Ps; ++i) {
+    planes[i] = Eigen::Vector4f(s_planes4[4 * i], s_planes4[4 * i + 1], s_planes4[4 * i + 2], s_planes4[4 * i + 3]);
+    for (int k = 0; k < 4; ++k) sc[i].push_back(Eigen::Vector3f(s_corners12[12 * i + 3 * k], s_corners12[12 * i + 3 * k + 1], s_corners12[12 * i + 3 * k + 2]));
+    scen[i] = Eigen::Vector3f(s_centers3[3 * i], s_centers3[3 * i + 1], s_centers3[3 * i + 2]);
+    sp[i] = make_xyz(s_pts + 3 * (size_t) s_off[i], s_off[i + 1] - s_off[i]);
+  }
+  for (int j = 0; j < Pt; ++j) {
+    mainPlanes[j] = Eigen::Vector4f(t_planes4[4 * j], t_planes4[4 * j + 1], t_planes4[4 * j + 2], t_planes4[4 * j + 3]);
+    for (int k = 0; k < 4; ++k) tc[j].push_back(Eigen::Vector3f(t_corners12[12 * j + 3 * k], t_corners12[12 * j + 3 * k + 1], t_corners12[12 * j + 3 * k + 2]));
+    tcen[j] = Eigen::Vector3f(t_centers3[3 * j], t_centers3[3 * j + 1], t_centers3[3 * j + 2]);
+    tp[j] = make_xyz(t_pts + 3 * (size_t) t_off[j], t_off[j + 1] - t_off[j]);
+    ttree[j].reset(new pcl::search::KdTree<pcl::PointXYZ>);
+    ttree[j]->setInputCloud(tp[j]);
+  }
+  for (int h = 0; h < H; ++h) {
+    Eigen::Matrix3f R;
+    Eigen::Vector3f T;
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R(r, c) = hyp12[12 * h + 3 * r + c]; T(r) = hyp12[12 * h + 9 + r]; }
+    Eigen::Matrix4f transformation = Eigen::Matrix4f::Identity();
+    transformation.block(0, 0, 3, 3) = R;
+    transformation.block(0, 3, 3, 1) = T;
+    bool isPentrable = false;
+    pcl::search::KdTree<pcl::PointXYZ>::Ptr tempKdtree(new pcl::search::KdTree<pcl::PointXYZ>);
+    for (int i1 = 0; i1 < Ps; i1++) {
+      isPentrable = false;
+      Eigen::Vector4f plane1;
+      plane1.block(0, 0, 3, 1) = R * planes[i1].block(0, 0, 3, 1);
+      plane1(3) = -(-planes[i1](3) + (plane1.block(0, 0, 3, 1).transpose() * T)(0));
+      CloudXYZ::Ptr tempTransPoints(new CloudXYZ);
+      pcl::transformPointCloud(*sp[i1], *tempTransPoints, transformation);
+      pcl::PointCloud<pcl::PointXYZ> tempPclFourCorner;
+      ExchnageBetweentPCLPointXYZwithEigenVector3f(tempPclFourCorner, sc[i1]);
+      pcl::transformPointCloud(tempPclFourCorner, tempPclFourCorner, transformation);
+      std::vector<Eigen::Vector3f> tempEigenFourCorner;
+      ExchnageBetweentPCLPointXYZwithEigenVector3f(tempPclFourCorner, tempEigenFourCorner);
+      tempKdtree->setInputCloud(tempTransPoints);
+      Eigen::Vector3f currentCenter2Main = R * scen[i1] + T;
+      for (int j1 = 0; j1 < Pt; j1++) {
+        Eigen::Vector3f plane_A = mainPlanes[j1].block(0, 0, 3, 1);
+        Eigen::Vector3f plane_B = plane1.block(0, 0, 3, 1);
+        double center2PlaneDistance = (abs(plane_A.dot(currentCenter2Main) + mainPlanes[j1](3)) + abs(plane_B.dot(tcen[j1]) + plane1(3))) / 2;
+        if (center2PlaneDistance < lengthThreshold && plane_B.dot(plane_A) > angleThreshold) continue;
+        if (0 != AreTwoPlanesPenetrable(plane1, mainPlanes[j1], tempEigenFourCorner, tc[j1], tempKdtree, ttree[j1], isPentrable,
+                                        lengthThreshold, 10, lengthThreshold / 2)) continue;
+        if (isPentrable) break;
+      }
+      if (isPentrable) break;
+    }
+    flags[h] = isPentrable ? 1 : 0;
+  }
+}
+
 // Verification body PLADE/plade.cpp:547-560 + ComputeOverlap PLADE/util.h:612-647 for H hypotheses.
 // centers[3H] are the ball centres (R*c+T) as the caller computed them; out: overlap ratio (float) and
 // the integer inlier count recovered from it is NOT exposed by the reference, so counts[] is the

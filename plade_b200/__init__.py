@@ -56,6 +56,9 @@ SIGNATURES = {
     "plade_voxel_downsample": (ctypes.c_longlong, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, _c_float_p]),
     "plade_bounding_box": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, _c_float_p, _c_double_p, _c_float_p]),
     "plade_nearest_points_two_lines": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_int, _c_float_p, _c_double_p]),
+    "plade_penetration_filter": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_int_p,
+                                                _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_int_p,
+                                                _c_float_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
     "plade_match_descriptors": (ctypes.c_longlong, [ctypes.c_void_p, _c_float_p, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_float, _c_int_p]),
     "plade_match_results": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, _c_double_p]),
     "plade_transforms_from_matches": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p]),
@@ -297,6 +300,23 @@ class Context:
         if rc != 0:
             raise RuntimeError(self.last_error())
         return pts, length
+
+    def penetration_filter(self, src, tgt, hyp12, length_threshold, angle_threshold):
+        """K4d (PLADE/util.cpp:466-511).  src / tgt: dicts with planes (P,4), corners4 (P,4,3), center (P,3),
+        pts (n,3), off (P+1,); hyp12 (H,12) = R row-major, T.  Returns flags (H,) uint8, 1 = dropped."""
+        def side(d):
+            return (_f32(d["planes"]).reshape(-1, 4), _f32(d["corners4"]).reshape(-1, 12), _f32(d["center"]).reshape(-1, 3),
+                    _f32(d["pts"]).reshape(-1, 3), np.ascontiguousarray(d["off"], dtype=np.int32))
+        sp, sc, sce, spt, so = side(src)
+        tp, tc, tce, tpt, to = side(tgt)
+        h = _f32(hyp12).reshape(-1, 12)
+        flags = np.zeros(len(h), dtype=np.uint8)
+        rc = self.lib.plade_penetration_filter(self.h, _p(sp, _c_float_p), len(sp), _p(sc, _c_float_p), _p(sce, _c_float_p), _p(spt, _c_float_p), _p(so, _c_int_p),
+                                               _p(tp, _c_float_p), len(tp), _p(tc, _c_float_p), _p(tce, _c_float_p), _p(tpt, _c_float_p), _p(to, _c_int_p),
+                                               _p(h, _c_float_p), len(h), float(length_threshold), float(angle_threshold), flags.ctypes.data_as(ctypes.c_void_p))
+        if rc != 0:
+            raise RuntimeError(self.last_error())
+        return flags
 
     def match_descriptors(self, db8, q8, radius=0.04):
         db, q = _f32(db8).reshape(-1, 8), _f32(q8).reshape(-1, 8)

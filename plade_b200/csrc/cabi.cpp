@@ -4,6 +4,7 @@
 #include "../../include/plade_b200.h"
 #include "pipeline.h"
 #include "ply.h"
+#include "libm_flt32.h"
 #include <cstring>
 #include <iostream>
 #include <memory>
@@ -390,6 +391,37 @@ int plade_nearest_points_two_lines(plade_ctx *ctx, const float *lines12, int n, 
   })
 }
 
+static void fill_pen_side(Registrar &r, PenSide &ps, const float *planes4, int P, const float *corners12, const float *centers3,
+                          const float *xyz, const int *off, DevBuf<float4> &stage) {
+  ps.planes.resize(P); ps.corners4.resize(P); ps.center.resize(P);
+  for (int i = 0; i < P; ++i) {
+    ps.planes[i] = {planes4[4 * i], planes4[4 * i + 1], planes4[4 * i + 2], planes4[4 * i + 3]};
+    for (int k = 0; k < 4; ++k) ps.corners4[i][k] = V3(corners12[12 * i + 3 * k], corners12[12 * i + 3 * k + 1], corners12[12 * i + 3 * k + 2]);
+    ps.center[i] = V3(centers3[3 * i], centers3[3 * i + 1], centers3[3 * i + 2]);
+  }
+  ps.ds_start.assign(off, off + P + 1);
+  upload_xyz(r, xyz, (size_t) off[P], 3, stage);
+  ps.d_pts = stage.p;
+}
+
+int plade_penetration_filter(plade_ctx *ctx,
+                             const float *src_planes4, int n_src_planes, const float *src_corners12, const float *src_centers3,
+                             const float *src_xyz, const int *src_offsets,
+                             const float *tgt_planes4, int n_tgt_planes, const float *tgt_corners12, const float *tgt_centers3,
+                             const float *tgt_xyz, const int *tgt_offsets,
+                             const float *hyp12, int n_hyp, float length_threshold, float angle_threshold, unsigned char *flags) {
+  PLADE_TRY(ctx, -1, {
+    Registrar &r = *ctx->reg;
+    PenSide ps, pt;
+    fill_pen_side(r, ps, src_planes4, n_src_planes, src_corners12, src_centers3, src_xyz, src_offsets, ctx->stage_a);
+    fill_pen_side(r, pt, tgt_planes4, n_tgt_planes, tgt_corners12, tgt_centers3, tgt_xyz, tgt_offsets, ctx->stage_b);
+    std::vector<unsigned char> pen;
+    penetration_filter(r.dev, r.pen_sc, ps, pt, hyp12, n_hyp, length_threshold, angle_threshold, pen);
+    for (int h = 0; h < n_hyp; ++h) flags[h] = pen[h];
+    return 0;
+  })
+}
+
 long long plade_match_descriptors(plade_ctx *ctx, const float *db8, int ndb, const float *q8, int nq, float radius, int *offsets) {
   PLADE_TRY(ctx, -1, {
     Registrar &r = *ctx->reg;
@@ -427,9 +459,9 @@ int plade_cluster_transforms(plade_ctx *ctx, const float *R9, const float *T3, i
       memcpy(rt[i].R, R9 + 9 * i, sizeof(float) * 9);
       memcpy(rt[i].T, T3 + 3 * i, sizeof(float) * 3);
       // pcl::getEulerAngles on the float rotation (same expression as the K4a kernel)
-      rt[i].euler[0] = (float) std::atan2((double) rt[i].R[7], (double) rt[i].R[8]);
-      rt[i].euler[1] = (float) std::asin(-(double) rt[i].R[6]);
-      rt[i].euler[2] = (float) std::atan2((double) rt[i].R[3], (double) rt[i].R[0]);
+      rt[i].euler[0] = atan2f_glibc(rt[i].R[7], rt[i].R[8]);
+      rt[i].euler[1] = asinf_glibc(-rt[i].R[6]);
+      rt[i].euler[2] = atan2f_glibc(rt[i].R[3], rt[i].R[0]);
       rt[i].pad = 0;
     }
     std::vector<int> label;

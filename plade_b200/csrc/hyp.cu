@@ -5,11 +5,9 @@
 // (registration/impl/transformation_estimation_svd.hpp:121-148) = Eigen::umeyama(src, dst, false):
 //   sigma = (1/3) * sum (dst_i - mean_dst)(src_i - mean_src)^T ; sigma = U S V^T ;
 //   R = U diag(1, 1, sign(det U det V)) V^T ;  then T = targetPoint - R * sourcePoint.
-// Here R is evaluated in fp64 from the two dominant singular triplets,
-//   R = u1 v1^T + u2 v2^T + (u1 x u2)(v1 x v2)^T,
-// which equals the umeyama rotation for every sign choice of the third singular pair (the demeaned
-// triangle has rank 2), then rounded to float; T uses the reference's float expression order.
-// Float-parity with Eigen's float JacobiSVD is tolerance-level (|dR| ~ 1e-7), see DESIGN.md.
+// One thread per match runs umeyama.h, a statement-for-statement float restatement of Eigen 3.4's umeyama +
+// two-sided JacobiSVD<Matrix3f>, so R, T and the Euler angles equal the reference's bit for bit (the later
+// stages threshold on them: clustering, the penetration filter's sample lattice, the verification ball).
 //
 // K4b replaces ClusterTransformation (PLADE/util.cpp:1245-1277) = pcl ConditionalEuclideanClustering
 // (segmentation/impl/conditional_euclidean_clustering.hpp:43-148) over points (T, euler(R)): region
@@ -19,6 +17,8 @@
 // element is its smallest index.  Here: spatial hash on T + lock-free union-find (atomicMin hooking,
 // smaller index wins), label = smallest member index.
 #include "kernels.h"
+#include "umeyama.h"
+#include "libm_flt32.h"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
@@ -27,100 +27,28 @@ namespace plade {
 
 namespace {
 
-__device__ __forceinline__ void cross3(const double *a, const double *b, double *o) {
-  o[0] = a[1] * b[2] - a[2] * b[1];
-  o[1] = a[2] * b[0] - a[0] * b[2];
-  o[2] = a[0] * b[1] - a[1] * b[0];
-}
-
-// cyclic Jacobi eigen-decomposition of a symmetric 3x3 (double); V columns = eigenvectors
-__device__ void jacobi_eig3(double A[3][3], double V[3][3], double w[3]) {
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
-    double diag = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
-    if (off <= 1e-300 || off <= 1e-17 * diag) break;
-    for (int p = 0; p < 2; ++p)
-      for (int q = p + 1; q < 3; ++q) {
-        double apq = A[p][q];
-        if (fabs(apq) < 1e-300) continue;
-        double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < 3; ++k) {
-          double akp = A[k][p], akq = A[k][q];
-          A[k][p] = c * akp - s * akq;
-          A[k][q] = s * akp + c * akq;
-        }
-        for (int k = 0; k < 3; ++k) {
-          double apk = A[p][k], aqk = A[q][k];
-          A[p][k] = c * apk - s * aqk;
-          A[q][k] = s * apk + c * aqk;
-        }
-        for (int k = 0; k < 3; ++k) {
-          double vkp = V[k][p], vkq = V[k][q];
-          V[k][p] = c * vkp - s * vkq;
-          V[k][q] = s * vkp + c * vkq;
-        }
-      }
-  }
-  w[0] = A[0][0]; w[1] = A[1][1]; w[2] = A[2][2];
-}
-
 __global__ void transform_kernel(const MatchPairIn *__restrict__ in, int m, RigidOut *__restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   MatchPairIn mp = in[i];
-  // PLADE/util.cpp:609-616: third point = cross product, float arithmetic (Eigen cross, no FMA)
-  float s3[3], d3[3];
-  s3[0] = __fsub_rn(__fmul_rn(mp.sv1[1], mp.sv2[2]), __fmul_rn(mp.sv1[2], mp.sv2[1]));
-  s3[1] = __fsub_rn(__fmul_rn(mp.sv1[2], mp.sv2[0]), __fmul_rn(mp.sv1[0], mp.sv2[2]));
-  s3[2] = __fsub_rn(__fmul_rn(mp.sv1[0], mp.sv2[1]), __fmul_rn(mp.sv1[1], mp.sv2[0]));
-  d3[0] = __fsub_rn(__fmul_rn(mp.dv1[1], mp.dv2[2]), __fmul_rn(mp.dv1[2], mp.dv2[1]));
-  d3[1] = __fsub_rn(__fmul_rn(mp.dv1[2], mp.dv2[0]), __fmul_rn(mp.dv1[0], mp.dv2[2]));
-  d3[2] = __fsub_rn(__fmul_rn(mp.dv1[0], mp.dv2[1]), __fmul_rn(mp.dv1[1], mp.dv2[0]));
-  double S[3][3], D[3][3];   // rows = points
-  for (int k = 0; k < 3; ++k) { S[0][k] = mp.sv1[k]; S[1][k] = mp.sv2[k]; S[2][k] = s3[k]; D[0][k] = mp.dv1[k]; D[1][k] = mp.dv2[k]; D[2][k] = d3[k]; }
-  double ms[3], md[3];
-  for (int k = 0; k < 3; ++k) { ms[k] = (S[0][k] + S[1][k] + S[2][k]) / 3.0; md[k] = (D[0][k] + D[1][k] + D[2][k]) / 3.0; }
-  double sig[3][3];
-  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
-    double a = 0;
-    for (int p = 0; p < 3; ++p) a += (D[p][r] - md[r]) * (S[p][c] - ms[c]);
-    sig[r][c] = a / 3.0;
-  }
-  double A[3][3], V[3][3], w[3];
-  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) A[r][c] = sig[0][r] * sig[0][c] + sig[1][r] * sig[1][c] + sig[2][r] * sig[2][c];
-  jacobi_eig3(A, V, w);
-  int i0 = 0;
-  if (w[1] > w[i0]) i0 = 1;
-  if (w[2] > w[i0]) i0 = 2;
-  int i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
-  if (w[i2] > w[i1]) { int t = i1; i1 = i2; i2 = t; }
-  double v1[3] = {V[0][i0], V[1][i0], V[2][i0]}, v2[3] = {V[0][i1], V[1][i1], V[2][i1]};
-  double u1[3], u2[3];
-  for (int r = 0; r < 3; ++r) { u1[r] = sig[r][0] * v1[0] + sig[r][1] * v1[1] + sig[r][2] * v1[2]; u2[r] = sig[r][0] * v2[0] + sig[r][1] * v2[1] + sig[r][2] * v2[2]; }
-  double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
-  for (int r = 0; r < 3; ++r) u1[r] /= (n1 > 0 ? n1 : 1.0);
-  double dp = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
-  for (int r = 0; r < 3; ++r) u2[r] -= dp * u1[r];
-  double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
-  for (int r = 0; r < 3; ++r) u2[r] /= (n2 > 0 ? n2 : 1.0);
-  double u3[3], v3[3];
-  cross3(u1, u2, u3);
-  cross3(v1, v2, v3);
+  // PLADE/util.cpp:609-616: the third point of each triple is the cross product (Eigen float cross)
+  V3 sv1(mp.sv1[0], mp.sv1[1], mp.sv1[2]), sv2(mp.sv2[0], mp.sv2[1], mp.sv2[2]);
+  V3 dv1(mp.dv1[0], mp.dv1[1], mp.dv1[2]), dv2(mp.dv2[0], mp.dv2[1], mp.dv2[2]);
+  V3 s3 = cross(sv1, sv2), d3 = cross(dv1, dv2);
+  const float src[3][3] = {{sv1.x, sv1.y, sv1.z}, {sv2.x, sv2.y, sv2.z}, {s3.x, s3.y, s3.z}};
+  const float dst[3][3] = {{dv1.x, dv1.y, dv1.z}, {dv2.x, dv2.y, dv2.z}, {d3.x, d3.y, d3.z}};
+  float Rm[3][3];
+  umeyama3_rotation_eigen(src, dst, Rm);
   RigidOut o;
-  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
-    o.R[3 * r + c] = (float) (u1[r] * v1[c] + u2[r] * v2[c] + u3[r] * v3[c]);
-  // T = targetPoint - R * sourcePoint (Eigen float, row dot products left to right)
-  for (int r = 0; r < 3; ++r) {
-    float rs = __fadd_rn(__fadd_rn(__fmul_rn(o.R[3 * r], mp.sp[0]), __fmul_rn(o.R[3 * r + 1], mp.sp[1])), __fmul_rn(o.R[3 * r + 2], mp.sp[2]));
-    o.T[r] = __fsub_rn(mp.tp[r], rs);
-  }
-  // pcl::getEulerAngles (common/impl/eigen.hpp:664-669), float results
-  o.euler[0] = (float) atan2((double) o.R[7], (double) o.R[8]);
-  o.euler[1] = (float) asin(-(double) o.R[6]);
-  o.euler[2] = (float) atan2((double) o.R[3], (double) o.R[0]);
+  M3 R;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { R(r, c) = Rm[r][c]; o.R[3 * r + c] = Rm[r][c]; }
+  // T = targetPoint - R * sourcePoint (PLADE/util.cpp:621)
+  V3 T = V3(mp.tp[0], mp.tp[1], mp.tp[2]) - mul(R, V3(mp.sp[0], mp.sp[1], mp.sp[2]));
+  o.T[0] = T.x; o.T[1] = T.y; o.T[2] = T.z;
+  // pcl::getEulerAngles<float> (common/impl/eigen.hpp:664-669) with the reference's libm, see libm_flt32.h
+  o.euler[0] = atan2f_glibc(o.R[7], o.R[8]);
+  o.euler[1] = asinf_glibc(-o.R[6]);
+  o.euler[2] = atan2f_glibc(o.R[3], o.R[0]);
   o.pad = 0.f;
   out[i] = o;
 }

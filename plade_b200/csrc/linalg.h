@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <limits>
 
 #if defined(__CUDACC__)
 #define PLADE_HD __host__ __device__ inline
@@ -66,62 +67,116 @@ PLADE_HD float l2simple(const V3 &a, const V3 &b) {
   return r;
 }
 
-// Symmetric 3x3 eigen-decomposition (cyclic Jacobi in double), eigenvalues ascending, eigenvectors
-// in the columns of V (unit length).  Stands in for Eigen::SelfAdjointEigenSolver<Matrix3f>
-// (PLADE/util.h:199); eigenvector signs are arbitrary there as well.
-inline void sym_eig3(const double Ain[3][3], double w[3], double V[3][3]) {
-  double A[3][3];
-  memcpy(A, Ain, sizeof(A));
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = (i == j);
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = std::fabs(A[0][1]) + std::fabs(A[0][2]) + std::fabs(A[1][2]);
-    double diag = std::fabs(A[0][0]) + std::fabs(A[1][1]) + std::fabs(A[2][2]);
-    if (off == 0.0 || off <= 1e-18 * diag) break;
-    for (int p = 0; p < 2; ++p)
-      for (int q = p + 1; q < 3; ++q) {
-        double apq = A[p][q];
-        if (apq == 0.0) continue;
-        double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < 3; ++k) { double a = A[k][p], b = A[k][q]; A[k][p] = c * a - s * b; A[k][q] = s * a + c * b; }
-        for (int k = 0; k < 3; ++k) { double a = A[p][k], b = A[q][k]; A[p][k] = c * a - s * b; A[q][k] = s * a + c * b; }
-        for (int k = 0; k < 3; ++k) { double a = V[k][p], b = V[k][q]; V[k][p] = c * a - s * b; V[k][q] = s * a + c * b; }
-      }
+// Eigen::SelfAdjointEigenSolver<Matrix3f>(A, ComputeEigenvectors) restated in float, statement for statement
+// (Eigen 3.4: Eigenvalues/SelfAdjointEigenSolver.h compute() :414-466, computeFromTridiagonal_impl :502-573,
+// tridiagonal_qr_step :837-898; Tridiagonalization.h 3x3 real special case :464-504; Jacobi.h makeGivens
+// :231-267).  The bounding-box frame of ComputeBoundingBox (PLADE/util.h:199-201) -- hence the ORDER and the
+// orientation of the rectangle corners the penetration filter walks -- depends on the signs this algorithm
+// happens to produce, so a generic solver is not a substitute.  Only the lower triangle of A is read.
+// Eigenvalues ascending in w, eigenvectors in the columns of V.
+inline void sym_eig3f_eigen(const float A[3][3], float w[3], float V[3][3]) {
+  float m[3][3] = {{A[0][0], 0.f, 0.f}, {A[1][0], A[1][1], 0.f}, {A[2][0], A[2][1], A[2][2]}};
+  float scale = 0.f;
+  for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) scale = std::max(scale, std::fabs(m[r][c]));
+  if (scale == 0.f) scale = 1.f;
+  for (int c = 0; c < 3; ++c) for (int r = c; r < 3; ++r) m[r][c] /= scale;
+  float diag[3], sub[2];
+  // tridiagonalization of a real 3x3
+  const float tol = std::numeric_limits<float>::min();
+  diag[0] = m[0][0];
+  float v1norm2 = m[2][0] * m[2][0];
+  float Q[3][3];
+  if (v1norm2 <= tol) {
+    diag[1] = m[1][1]; diag[2] = m[2][2];
+    sub[0] = m[1][0]; sub[1] = m[2][1];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Q[r][c] = r == c ? 1.f : 0.f;
+  } else {
+    float beta = std::sqrt(m[1][0] * m[1][0] + v1norm2);
+    float invBeta = 1.f / beta;
+    float m01 = m[1][0] * invBeta, m02 = m[2][0] * invBeta;
+    float q = 2.f * m01 * m[2][1] + m02 * (m[2][2] - m[1][1]);
+    diag[1] = m[1][1] + m02 * q;
+    diag[2] = m[2][2] - m02 * q;
+    sub[0] = beta;
+    sub[1] = m[2][1] - m01 * q;
+    const float Qi[3][3] = {{1.f, 0.f, 0.f}, {0.f, m01, m02}, {0.f, m02, -m01}};
+    memcpy(Q, Qi, sizeof(Q));
   }
-  int ord[3] = {0, 1, 2};
-  double ev[3] = {A[0][0], A[1][1], A[2][2]};
-  std::sort(ord, ord + 3, [&](int a, int b) { return ev[a] < ev[b]; });
-  double Vs[3][3];
-  for (int k = 0; k < 3; ++k) { w[k] = ev[ord[k]]; for (int r = 0; r < 3; ++r) Vs[r][k] = V[r][ord[k]]; }
-  memcpy(V, Vs, sizeof(Vs));
-}
-
-// Closest points of two 3-D lines, closed form in double; stands in for the 9x9 float
-// cv::solve(DECOMP_SVD) of ComputeNearstTwoPointsOfTwo3DLine (PLADE/util.cpp:1167-1229).
-// Returns false for (numerically) parallel lines.
-PLADE_HD bool closest_points_two_lines(const V3 &d1, const V3 &p1, const V3 &d2, const V3 &p2, V3 &q1, V3 &q2) {
-  double a = (double) d1.x * d2.x + (double) d1.y * d2.y + (double) d1.z * d2.z;
-  double b = (double) d1.x * d1.x + (double) d1.y * d1.y + (double) d1.z * d1.z;
-  double c = (double) d2.x * d2.x + (double) d2.y * d2.y + (double) d2.z * d2.z;
-  double den = b * c - a * a;
-  if (!(den > 1e-14 * b * c)) return false;
-  double wx = (double) p2.x - p1.x, wy = (double) p2.y - p1.y, wz = (double) p2.z - p1.z;
-  double w1 = wx * d1.x + wy * d1.y + wz * d1.z, w2 = wx * d2.x + wy * d2.y + wz * d2.z;
-  double t1 = (c * w1 - a * w2) / den, t2 = (a * w1 - b * w2) / den;
-  q1 = V3((float) (p1.x + t1 * d1.x), (float) (p1.y + t1 * d1.y), (float) (p1.z + t1 * d1.z));
-  q2 = V3((float) (p2.x + t2 * d2.x), (float) (p2.y + t2 * d2.y), (float) (p2.z + t2 * d2.z));
-  return true;
-}
-
-// ComputeIntersectionPointOf23DLine (PLADE/util.cpp:1461-1500): least-squares "intersection" of two
-// lines (6x5 float SVD solve in the reference) = midpoint of their closest points, closed form.
-PLADE_HD int line_line_point(const V3 &v1, const V3 &p1, const V3 &v2, const V3 &p2, V3 &out) {
-  if (fabsf(dot(v1, v2)) > 0.9999) return -1;
-  V3 q1, q2;
-  if (!closest_points_two_lines(v1, p1, v2, p2, q1, q2)) return -1;
-  out = V3((float) (0.5 * ((double) q1.x + q2.x)), (float) (0.5 * ((double) q1.y + q2.y)), (float) (0.5 * ((double) q1.z + q2.z)));
-  return 0;
+  // implicit symmetric QR with Wilkinson shift
+  const int n = 3, maxIterations = 30;
+  int end = n - 1, start = 0, iter = 0;
+  const float considerAsZero = std::numeric_limits<float>::min();
+  const float precision_inv = 1.f / std::numeric_limits<float>::epsilon();
+  while (end > 0) {
+    for (int i = start; i < end; ++i) {
+      if (std::fabs(sub[i]) < considerAsZero) sub[i] = 0.f;
+      else {
+        const float scaled = precision_inv * sub[i];
+        if (scaled * scaled <= (std::fabs(diag[i]) + std::fabs(diag[i + 1]))) sub[i] = 0.f;
+      }
+    }
+    while (end > 0 && sub[end - 1] == 0.f) end--;
+    if (end <= 0) break;
+    iter++;
+    if (iter > maxIterations * n) break;
+    start = end - 1;
+    while (start > 0 && sub[start - 1] != 0.f) start--;
+    // one QR step on [start, end]
+    float td = (diag[end - 1] - diag[end]) * 0.5f;
+    float e = sub[end - 1];
+    float mu = diag[end];
+    if (td == 0.f) mu -= std::fabs(e);
+    else if (e != 0.f) {
+      const float e2 = e * e;
+      float hx = std::fabs(td), hy = std::fabs(e);            // numext::hypot -> positive_real_hypot
+      float hp = std::max(hx, hy), h;
+      if (hp == 0.f) h = 0.f;
+      else { float qp = std::min(hy, hx) / hp; h = hp * std::sqrt(1.f + qp * qp); }
+      if (e2 == 0.f) mu -= e / ((td + (td > 0.f ? h : -h)) / e);
+      else mu -= e2 / (td + (td > 0.f ? h : -h));
+    }
+    float x = diag[start] - mu, z = sub[start];
+    for (int k = start; k < end && z != 0.f; ++k) {
+      float c, sn;                                             // JacobiRotation::makeGivens(x, z)
+      if (z == 0.f) { c = x < 0.f ? -1.f : 1.f; sn = 0.f; }
+      else if (x == 0.f) { c = 0.f; sn = z < 0.f ? 1.f : -1.f; }
+      else if (std::fabs(x) > std::fabs(z)) {
+        float t = z / x, u = std::sqrt(1.f + t * t);
+        if (x < 0.f) u = -u;
+        c = 1.f / u; sn = -t * c;
+      } else {
+        float t = x / z, u = std::sqrt(1.f + t * t);
+        if (z < 0.f) u = -u;
+        sn = -1.f / u; c = -t * sn;
+      }
+      float sdk = sn * diag[k] + c * sub[k];
+      float dkp1 = sn * sub[k] + c * diag[k + 1];
+      diag[k] = c * (c * diag[k] - sn * sub[k]) - sn * (c * sub[k] - sn * diag[k + 1]);
+      diag[k + 1] = sn * sdk + c * dkp1;
+      sub[k] = c * sdk - sn * dkp1;
+      if (k > start) sub[k - 1] = c * sub[k - 1] - sn * z;
+      x = sub[k];
+      if (k < end - 1) { z = -sn * sub[k + 1]; sub[k + 1] = c * sub[k + 1]; }
+      // Q = Q * G : applyOnTheRight(k, k+1, rot) = rotation (c, -sn) on the two columns
+      if (!(c == 1.f && -sn == 0.f))
+        for (int r = 0; r < 3; ++r) {
+          float xi = Q[r][k], yi = Q[r][k + 1];
+          Q[r][k] = c * xi + (-sn) * yi;
+          Q[r][k + 1] = -(-sn) * xi + c * yi;
+        }
+    }
+  }
+  if (iter <= maxIterations * n)
+    for (int i = 0; i < n - 1; ++i) {
+      int k = 0;
+      for (int j = 1; j < n - i; ++j) if (diag[i + j] < diag[i + k]) k = j;      // minCoeff: first minimum
+      if (k > 0) {
+        std::swap(diag[i], diag[k + i]);
+        for (int r = 0; r < 3; ++r) std::swap(Q[r][i], Q[r][k + i]);
+      }
+    }
+  for (int i = 0; i < 3; ++i) w[i] = diag[i] * scale;
+  memcpy(V, Q, sizeof(Q));
 }
 
 // ComputeIntersectionLineOfTwoPlanes (PLADE/util.cpp:626-676); planes are (n, d) with n.x + d = 0.

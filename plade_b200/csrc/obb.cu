@@ -126,9 +126,11 @@ void obb_segments(Device &dev, ObbScratch &sc, const std::vector<ObbSeg> &segs, 
     const double *a = &acc[16 * i];
     V3 ctr((float) a[0] / fn, (float) a[1] / fn, (float) a[2] / fn);
     float c00 = (float) a[4] / fn, c01 = (float) a[5] / fn, c02 = (float) a[6] / fn, c11 = (float) a[7] / fn, c12 = (float) a[8] / fn, c22 = (float) a[9] / fn;
-    double A[3][3] = {{c00, c01, c02}, {c01, c11, c12}, {c02, c12, c22}}, w[3], V[3][3];
-    sym_eig3(A, w, V);
-    V3 e0((float) V[0][0], (float) V[1][0], (float) V[2][0]), e1((float) V[0][1], (float) V[1][1], (float) V[2][1]);
+    // same solver, statement for statement, as Eigen::SelfAdjointEigenSolver<Matrix3f>: the signs of the frame
+    // axes decide the order / orientation of the corner loop the penetration filter later walks
+    float A[3][3] = {{c00, c01, c02}, {c01, c11, c12}, {c02, c12, c22}}, w[3], V[3][3];
+    sym_eig3f_eigen(A, w, V);
+    V3 e0(V[0][0], V[1][0], V[2][0]), e1(V[0][1], V[1][1], V[2][1]);
     V3 e2 = cross(e0, e1);
     M3 E, Rt;
     for (int r = 0; r < 3; ++r) { E(r, 0) = e0[r]; E(r, 1) = e1[r]; E(r, 2) = e2[r]; }

@@ -15,6 +15,7 @@
 //     bookkeeping replaced by evaluating each probe point once.
 #include "kernels.h"
 #include "linalg.h"
+#include "svdsolve.h"
 #include <algorithm>
 #include <cmath>
 
@@ -57,7 +58,7 @@ __device__ int segment_of_pair(const float plane1[4], const float plane2[4], con
     V3 tl = c1[i % 4] - c1[(i - 1) % 4];
     normalize(tl);
     V3 ip;
-    if (0 != line_line_point(lineVec, linePoint, tl, c1[i - 1], ip)) continue;
+    if (0 != line_line_point_cv(lineVec, linePoint, tl, c1[i - 1], ip)) continue;
     if (dot(c1[(i - 1) % 4] - ip, c1[i % 4] - ip) > 0) continue;
     ip1[n1++] = ip;
   }
@@ -65,7 +66,7 @@ __device__ int segment_of_pair(const float plane1[4], const float plane2[4], con
     V3 tl = c2[i % 4] - c2[(i - 1) % 4];
     normalize(tl);
     V3 ip;
-    if (0 != line_line_point(lineVec, linePoint, tl, c2[i - 1], ip)) continue;
+    if (0 != line_line_point_cv(lineVec, linePoint, tl, c2[i - 1], ip)) continue;
     if (dot(c2[(i - 1) % 4] - ip, c2[i % 4] - ip) > 0) continue;
     ip2[n2++] = ip;
   }

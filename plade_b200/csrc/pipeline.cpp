@@ -531,6 +531,10 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     std::vector<float> R, T;
     for (const RigidOut &r : rt) { R.insert(R.end(), r.R, r.R + 9); T.insert(T.end(), r.T, r.T + 3); }
     put("init_R", R); put("init_T", T); put("cluster_label", label);
+    std::vector<float> in18;
+    for (const MatchPairIn &m : mp) in18.insert(in18.end(), m.sv1, m.sv1 + 18);
+    put("match_in18", in18);
+    put("cluster_params", std::vector<float>{(float) ((double) lengthThreshold / 2), (float) ((double) angleThreshold / 2)});
   }
   // sort by cluster size, same struct / comparator / algorithm as PLADE/util.cpp:335-347
   std::vector<LenIdx> sortVec(rep.size());
@@ -608,6 +612,11 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     pt.planes = M.planes; pt.corners4 = M.corners4; pt.center = M.plane_center; pt.ds_start = M.plane_ds_start; pt.d_pts = ds_planes_t.p;
     std::vector<unsigned char> pen;
     penetration_filter(dev, pen_sc, ps, pt, hyp12.data(), (int) cand.size(), lengthThreshold, angleThreshold, pen);
+    if (debug) {
+      std::vector<int> c_rt, c_np, flag(pen.begin(), pen.end());
+      for (int index : cand) { c_rt.push_back(cand_rt[index]); c_np.push_back((int) matches[index].size()); }
+      put("cand_rt", c_rt); put("cand_nplanes", c_np); put("cand_pen", flag);
+    }
     for (size_t c = 0; c < cand.size(); ++c) {
       if (pen[c]) continue;
       const int index = cand[c], k = cand_rt[index];

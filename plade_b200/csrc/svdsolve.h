@@ -134,4 +134,23 @@ PLADE_HD void nearest_points_cv_solve(const V3 &v1, const V3 &p1, const V3 &v2, 
   point2 = V3(x[4], x[5], x[6]);
 }
 
+// ComputeIntersectionPointOf23DLine (PLADE/util.cpp:1461-1500): least-squares "intersection" point of two lines
+// from the reference's 6x5 float cv::solve(DECOMP_SVD):  x - t1 v1 = p1,  x - t2 v2 = p2.
+PLADE_HD int line_line_point_cv(const V3 &v1, const V3 &p1, const V3 &v2, const V3 &p2, V3 &out) {
+  if (fabsf(dot(v1, v2)) > 0.9999) return -1;      // parallel
+  float At[5][6];
+  for (int i = 0; i < 5; ++i) for (int k = 0; k < 6; ++k) At[i][k] = 0.f;
+  At[0][0] = 1; At[3][0] = -v1.x;
+  At[1][1] = 1; At[3][1] = -v1.y;
+  At[2][2] = 1; At[3][2] = -v1.z;
+  At[0][3] = 1; At[4][3] = -v2.x;
+  At[1][4] = 1; At[4][4] = -v2.y;
+  At[2][5] = 1; At[4][5] = -v2.z;
+  float b[6] = {p1.x, p1.y, p1.z, p2.x, p2.y, p2.z};
+  float x[5];
+  jacobi_svd_solve<6, 5>(At, b, x);
+  out = V3(x[0], x[1], x[2]);
+  return 0;
+}
+
 }  // namespace plade

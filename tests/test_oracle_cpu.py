@@ -117,30 +117,92 @@ def test_restate_plane_predicate_on_reference_planes(restate, poly_pair, poly_st
 
 
 # ------------------------------------------------------------------ host-side logic
-def test_host_restatement_of_cv_solve_vs_reference(ref, poly_stages, tmp_path):
-    """plade_b200/csrc/svdsolve.h (the float Jacobi-SVD solve the K3a kernel runs per line pair) compiled for the
-    HOST must give the compiled reference's ComputeNearstTwoPointsOfTwo3DLine (PLADE/util.cpp:1167-1229) bit
-    for bit, ill-conditioned pairs included; the same header compiled by nvcc is checked by the GPU suite."""
+@pytest.fixture(scope="module")
+def host_check(tmp_path_factory):
+    """tests/host/svd_host_check.cpp: the host build of the product's restated numeric kernels (svdsolve.h,
+    umeyama.h, linalg.h, libm_flt32.h -- the same headers nvcc compiles into the CUDA kernels)."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = str(tmp_path / "svd_host_check")
+    exe = str(tmp_path_factory.mktemp("host") / "svd_host_check")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + os.path.join(root, "plade_b200", "csrc"),
                     "-o", exe, os.path.join(root, "tests", "host", "svd_host_check.cpp")], check=True)
-    rng = np.random.default_rng(5)
-    n = 600
+
+    def run(mode, records, out_width):
+        rec = np.ascontiguousarray(records, dtype=np.float32)
+        r = subprocess.run([exe], input=np.int32(mode).tobytes() + np.int32(len(rec)).tobytes() + rec.tobytes(), capture_output=True, check=True)
+        return np.frombuffer(r.stdout, np.float32).reshape(-1, out_width)
+    run.exe = exe
+    return run
+
+
+def _line_pairs(rng, n, poly_stages):
     v1, v2 = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
-    v2[:60] = v1[:60] + 1e-3 * rng.normal(size=(60, 3))
+    v2[:n // 10] = v1[:n // 10] + 1e-3 * rng.normal(size=(n // 10, 3))              # nearly parallel: ill-conditioned
     p1, p2 = rng.uniform(-5, 5, size=(n, 3)), rng.uniform(-5, 5, size=(n, 3))
-    p2[60:120] = p1[60:120] + v1[60:120] * 0.7 - v2[60:120] * 1.3
+    p2[n // 10:n // 5] = p1[n // 10:n // 5] + v1[n // 10:n // 5] * 0.7 - v2[n // 10:n // 5] * 1.3   # intersecting
     rows = np.concatenate([v1, p1, v2, p2], axis=1).astype(np.float32)
     L = poly_stages["tgt_lines"].reshape(-1, 6)
     extra = [np.concatenate([L[i], L[j]]) for i in range(len(L)) for j in range(i + 1, len(L))]
-    rows = np.concatenate([rows, np.asarray(extra, np.float32)])
-    r = subprocess.run([exe], input=np.int32(len(rows)).tobytes() + rows.tobytes(), capture_output=True, check=True)
-    out = np.frombuffer(r.stdout, np.float32).reshape(-1, 2, 3)
+    return np.concatenate([rows, np.asarray(extra, np.float32)])
+
+
+def test_host_restatement_of_cv_solve_vs_reference(ref, poly_stages, host_check):
+    """svdsolve.h (OpenCV's float Jacobi-SVD solve, run per line pair by K3a and per rectangle edge by K4d) must
+    give the compiled reference's ComputeNearstTwoPointsOfTwo3DLine (PLADE/util.cpp:1167-1229) and
+    ComputeIntersectionPointOf23DLine (PLADE/util.cpp:1461-1500) bit for bit, ill-conditioned pairs included."""
+    rows = _line_pairs(np.random.default_rng(5), 600, poly_stages)
+    out = host_check(0, rows, 6).reshape(-1, 2, 3)
     assert len(out) == len(rows)
     for i, q in enumerate(rows):
         rc, q1, q2, _ = ref.nearest_points_two_lines(q[0:3], q[3:6], q[6:9], q[9:12])
         assert rc == 0 and np.array_equal(out[i, 0], q1) and np.array_equal(out[i, 1], q2), i
+    rows[:, 0:3] /= np.linalg.norm(rows[:, 0:3], axis=1, keepdims=True)
+    rows[:, 6:9] /= np.linalg.norm(rows[:, 6:9], axis=1, keepdims=True)
+    out = host_check(1, rows, 4)
+    n_parallel = 0
+    for i, q in enumerate(rows):
+        rc, o = ref.line_line_intersection(q[0:3], q[3:6], q[6:9], q[9:12])
+        n_parallel += rc != 0
+        assert rc == int(out[i, 0]) and (rc != 0 or np.array_equal(out[i, 1:], o)), i
+    assert n_parallel > 0
+
+
+def test_host_restatement_of_eigen_solvers_vs_reference(ref, host_check):
+    """linalg.h sym_eig3f_eigen == Eigen::SelfAdjointEigenSolver<Matrix3f> (PLADE/util.h:199) and umeyama.h ==
+    ComputeTransformationUsingTwoVecAndOnePoint (PLADE/util.cpp:604-624), bit for bit (signs included)."""
+    rng = np.random.default_rng(2)
+    mats = []
+    for i in range(1500):
+        k = i % 5
+        scale = ([1, 1, 0.01], [3, 0.2, 0.001], [1, 1.0001, 0.005], [1, 1, 1], [1, 0, 0.1])[k]
+        P = rng.normal(size=(60, 3)) * scale
+        if k != 4 or i % 2:
+            P = P @ np.linalg.qr(rng.normal(size=(3, 3)))[0].T
+        mats.append(np.cov(P.T).astype(np.float32))
+    mats += [np.zeros((3, 3), np.float32), np.diag([3, 1, 2]).astype(np.float32)]
+    rows = np.zeros((len(mats), 12), np.float32)
+    rows[:, :9] = np.asarray(mats).reshape(-1, 9)
+    out = host_check(2, rows, 12)
+    for i, m in enumerate(mats):
+        w, V = ref.self_adjoint_eig3(m)
+        assert np.array_equal(out[i, :3], w) and np.array_equal(out[i, 3:].reshape(3, 3), V), i
+    n = 3000
+    a, b = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    Q = np.array([np.linalg.qr(rng.normal(size=(3, 3)))[0] for _ in range(n)])
+    c = np.einsum("nij,nj->ni", Q, a) + 1e-3 * rng.normal(size=(n, 3))
+    d = np.einsum("nij,nj->ni", Q, b) + 1e-3 * rng.normal(size=(n, 3))
+    in18 = np.concatenate([a, b, c, d, rng.uniform(-2, 2, size=(n, 3)), rng.uniform(-2, 2, size=(n, 3))], axis=1).astype(np.float32)
+    out = host_check(3, in18, 12)
+    rR, rT = ref.transform_from_two_vecs(in18)
+    assert np.array_equal(out[:, :9], rR.reshape(-1, 9)) and np.array_equal(out[:, 9:], rT)
+
+
+def test_host_libm_flt32_matches_system_libm(host_check):
+    """libm_flt32.h (atan2f / asinf / atanf of glibc's flt-32 libm, which pcl::getEulerAngles<float> ends up in)
+    against the libm of this image, bit for bit over a fixed 3e6-argument sweep."""
+    r = subprocess.run([host_check.exe], input=np.int32(4).tobytes() + np.int32(3000000).tobytes(), capture_output=True, check=True)
+    assert int(r.stdout.decode().strip()) == 0
 
 
 def test_synth_generator_is_deterministic_and_shaped():
