@@ -274,14 +274,16 @@ struct PlaneFrame {      // plane + in-plane frame (PlanePrimitiveShape: m_plane
 
 __device__ __forceinline__ int f2o(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 
-// pass A: inlier flags at eps3 + (u, v) bounding box
+// pass A: inlier flags at eps3 + (u, v) bounding box.  `assigned` may be null (all points free) and the point
+// count may come from device memory (d_count), as for the compacted band of a candidate (see band_compact_kernel).
 __global__ void flag_uv_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const int *__restrict__ assigned,
-                               int n, PlaneFrame f, float eps3, float nthresh, unsigned char *__restrict__ flag,
+                               int n, const int *__restrict__ d_count, PlaneFrame f, float eps3, float nthresh, unsigned char *__restrict__ flag,
                                int *__restrict__ uvbox /* 4 ordered ints: umin vmin umax vmax */) {
+  if (d_count) n = *d_count;
   float umin = 3.4e38f, vmin = 3.4e38f, umax = -3.4e38f, vmax = -3.4e38f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = pos[i];
-    bool in = assigned[i] == -1 && compatible(f.pl, p, nrm[i], eps3, nthresh);
+    bool in = (assigned == nullptr || assigned[i] == -1) && compatible(f.pl, p, nrm[i], eps3, nthresh);
     flag[i] = in ? 1 : 0;
     if (in) {
       // PlanePrimitiveShape::ParametersImpl (R/PlanePrimitiveShape.h:97-109)
@@ -300,6 +302,35 @@ __global__ void flag_uv_kernel(const float4 *__restrict__ pos, const float4 *__r
   if (threadIdx.x == 0) {
     atomicMin(uvbox + 0, f2o(a)); atomicMin(uvbox + 1, f2o(b));
     atomicMax(uvbox + 2, f2o(c)); atomicMax(uvbox + 3, f2o(d));
+  }
+}
+
+// Band of a candidate: the still-unassigned points within `band` of the candidate's plane (band = +inf: all of
+// them), compacted into contiguous copies.  Every evaluation of the candidate and of its least-squares refits
+// then touches the band only (a few % of the cloud) instead of the whole cloud; the host proves before each
+// evaluation that no point outside the band can be an inlier of the plane being evaluated (see band_covers).
+__global__ void band_compact_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const int *__restrict__ assigned, int n,
+                                    float4 pl, float band, float4 *__restrict__ posB, float4 *__restrict__ nrmB, int *__restrict__ idxB,
+                                    int *__restrict__ d_nb) {
+  const unsigned lane = threadIdx.x & 31;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + lane;
+    bool in = false;
+    float4 p;
+    if (i < n && assigned[i] == -1) {
+      p = pos[i];
+      float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p.x), __fmul_rn(pl.y, p.y)), __fmul_rn(pl.z, p.z));
+      in = fabsf(__fsub_rn(pl.w, dp)) < band;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    if (!bal) continue;
+    int start = 0;
+    if (lane == 0) start = atomicAdd(d_nb, __popc(bal));
+    start = __shfl_sync(0xffffffffu, start, 0);
+    if (in) {
+      const int k = start + __popc(bal & ((1u << lane) - 1));
+      posB[k] = p; nrmB[k] = nrm[i]; idxB[k] = i;
+    }
   }
 }
 
@@ -326,6 +357,7 @@ __global__ void raster_kernel(const float4 *__restrict__ pos, const unsigned cha
 // ---- device-side bitmap pipeline (no host round trip between the passes of one candidate evaluation) ----
 struct BmpInfo { float umin, vmin; int ue, ve; int ok; int overflow; int pad0, pad1; };
 constexpr int kBmpCap = 1 << 20;       // pixels; larger bitmaps take the host path
+constexpr float kBandMul = 3.f;        // half-width of a candidate's band in units of eps3 (= 3 eps)
 
 __global__ void bmp_setup_kernel(const int *__restrict__ uvbox, float bmp_eps, BmpInfo *__restrict__ info) {
   int a[4];
@@ -343,23 +375,26 @@ __global__ void bmp_setup_kernel(const int *__restrict__ uvbox, float bmp_eps, B
   *info = r;
 }
 
-__global__ void raster_dev_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ flag, int n, PlaneFrame f, float bmp_eps,
-                                  const BmpInfo *__restrict__ info, int *__restrict__ pix, unsigned char *__restrict__ bitmap) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !flag[i]) return;
+__global__ void raster_dev_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ flag, const int *__restrict__ d_count,
+                                  PlaneFrame f, float bmp_eps, const BmpInfo *__restrict__ info, int *__restrict__ pix,
+                                  unsigned char *__restrict__ bitmap) {
   const BmpInfo I = *info;
   if (!I.ok) return;
-  float4 p = pos[i];
-  float px = __fsub_rn(p.x, f.pos.x), py = __fsub_rn(p.y, f.pos.y), pz = __fsub_rn(p.z, f.pos.z);
-  float u = __fadd_rn(__fadd_rn(__fmul_rn(px, f.u.x), __fmul_rn(py, f.u.y)), __fmul_rn(pz, f.u.z));
-  float v = __fadd_rn(__fadd_rn(__fmul_rn(px, f.v.x), __fmul_rn(py, f.v.y)), __fmul_rn(pz, f.v.z));
-  int bu = (int) floorf(__fdiv_rn(__fsub_rn(u, I.umin), bmp_eps));
-  int bv = (int) floorf(__fdiv_rn(__fsub_rn(v, I.vmin), bmp_eps));
-  bu = min(max(bu, 0), I.ue - 1);
-  bv = min(max(bv, 0), I.ve - 1);
-  int id = bu + bv * I.ue;
-  pix[i] = id;
-  bitmap[id] = 1;
+  const int n = *d_count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (!flag[i]) continue;
+    float4 p = pos[i];
+    float px = __fsub_rn(p.x, f.pos.x), py = __fsub_rn(p.y, f.pos.y), pz = __fsub_rn(p.z, f.pos.z);
+    float u = __fadd_rn(__fadd_rn(__fmul_rn(px, f.u.x), __fmul_rn(py, f.u.y)), __fmul_rn(pz, f.u.z));
+    float v = __fadd_rn(__fadd_rn(__fmul_rn(px, f.v.x), __fmul_rn(py, f.v.y)), __fmul_rn(pz, f.v.z));
+    int bu = (int) floorf(__fdiv_rn(__fsub_rn(u, I.umin), bmp_eps));
+    int bv = (int) floorf(__fdiv_rn(__fsub_rn(v, I.vmin), bmp_eps));
+    bu = min(max(bu, 0), I.ue - 1);
+    bv = min(max(bv, 0), I.ve - 1);
+    int id = bu + bv * I.ue;
+    pix[i] = id;
+    bitmap[id] = 1;
+  }
 }
 
 // One block: cross closing (dilate, erode; R/Bitmap.cpp:154,459), 8-connected labelling by min-label
@@ -427,12 +462,13 @@ __global__ void mean_kernel(const double *__restrict__ acc, float *__restrict__ 
   else { mean3[0] = mean3[1] = mean3[2] = 0.f; }
 }
 
-__global__ void cov_dev_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ member, int n, const float *__restrict__ mean3,
-                               double *__restrict__ acc6) {
+__global__ void cov_dev_kernel(const float4 *__restrict__ pos, const int *__restrict__ idx, const unsigned char *__restrict__ member,
+                               const int *__restrict__ d_count, const float *__restrict__ mean3, double *__restrict__ acc6) {
+  const int n = *d_count;
   const float mx = mean3[0], my = mean3[1], mz = mean3[2];
   double c[6] = {0, 0, 0, 0, 0, 0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (!member[i]) continue;
+    if (!member[idx[i]]) continue;
     float4 p = pos[i];
     double dx = (double) (p.x - mx), dy = (double) (p.y - my), dz = (double) (p.z - mz);
     c[0] += dx * dx; c[1] += dx * dy; c[2] += dx * dz; c[3] += dy * dy; c[4] += dy * dz; c[5] += dz * dz;
@@ -447,15 +483,16 @@ __global__ void cov_dev_kernel(const float4 *__restrict__ pos, const unsigned ch
 }
 
 // select with the mask produced on the device (no-op when the bitmap stage was skipped)
-__global__ void select_dev_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ flag, const int *__restrict__ pix,
-                                  const unsigned char *__restrict__ comp_mask, const BmpInfo *__restrict__ info, int n, float4 pl, float eps3,
-                                  unsigned char *__restrict__ member, double *__restrict__ acc) {
-  const int ok = info->ok;
+__global__ void select_dev_kernel(const float4 *__restrict__ pos, const int *__restrict__ idx, const unsigned char *__restrict__ flag,
+                                  const int *__restrict__ pix, const unsigned char *__restrict__ comp_mask, const BmpInfo *__restrict__ info,
+                                  const int *__restrict__ d_count, float4 pl, float eps3, unsigned char *__restrict__ member /* by point index */,
+                                  double *__restrict__ acc) {
+  const int ok = info->ok, n = *d_count;
   double cnt = 0, sx = 0, sy = 0, sz = 0, sc = 0;
   const float denom = 2.f / 9.f * eps3 * eps3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     bool mem = ok && flag[i] && comp_mask[pix[i]];
-    member[i] = mem ? 1 : 0;
+    member[idx[i]] = mem ? 1 : 0;
     if (mem) {
       float4 p = pos[i];
       float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p.x), __fmul_rn(pl.y, p.y)), __fmul_rn(pl.z, p.z));
@@ -473,6 +510,19 @@ __global__ void select_dev_kernel(const float4 *__restrict__ pos, const unsigned
   double r4 = BR(tmp).Sum(sc);
   if (threadIdx.x == 0 && r0 > 0) {
     atomicAdd(acc + 0, r0); atomicAdd(acc + 1, r1); atomicAdd(acc + 2, r2); atomicAdd(acc + 3, r3); atomicAdd(acc + 4, r4);
+  }
+}
+
+// end of a candidate: accept (assign the members of `member` to shape_id) and/or clear both membership maps
+// over the band, restoring the all-zero invariant they have between candidates
+__global__ void band_finish_kernel(const int *__restrict__ idx, const int *__restrict__ d_count, unsigned char *__restrict__ member,
+                                   unsigned char *__restrict__ other, int shape_id, int *__restrict__ assigned) {
+  const int n = *d_count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int g = idx[i];
+    if (shape_id >= 0 && member[g]) assigned[g] = shape_id;
+    member[g] = 0;
+    other[g] = 0;
   }
 }
 
@@ -650,7 +700,8 @@ double failure_probability(double size, double n, double drawn, double levels) {
 struct RansacScratch {
   DevBuf<unsigned int> keys, keys_alt, counts, counts_sorted, counts2;
   DevBuf<int> order, order_alt, assigned, pix, misc;
-  DevBuf<float4> cand, sub, sub1, cand_top;
+  DevBuf<float4> cand, sub, sub1, cand_top, band_pos, band_nrm;
+  DevBuf<int> band_idx;
   DevBuf<int> cidx, cidx_sorted;
   DevBuf<unsigned char> flag, member, member2, bitmap, mask, cub_tmp, bmp_dev, bmp_tmp, mask_dev;
   DevBuf<int> cc_lab, cc_cnt, remap;
@@ -740,11 +791,17 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   int *assigned = rs.assigned.ensure(n);
   PLADE_CUDA(cudaMemsetAsync(assigned, 0xff, sizeof(int) * n, s));
   unsigned char *flag = rs.flag.ensure(n), *member_a = rs.member.ensure(n), *member_b = rs.member2.ensure(n);
+  PLADE_CUDA(cudaMemsetAsync(member_a, 0, n, s));       // membership maps over all points; all-zero between candidates
+  PLADE_CUDA(cudaMemsetAsync(member_b, 0, n, s));
   int *pix = rs.pix.ensure(n);
+  float4 *posB = rs.band_pos.ensure(n), *nrmB = rs.band_nrm.ensure(n);
+  int *idxB = rs.band_idx.ensure(n);
+  const int blocks_b = std::min(blocks_n, dev.num_sms * 4);
+  int n_band_builds = 0, n_band_full = 0;
   float4 *cand = rs.cand.ensure(kCandPerRound);
   unsigned int *counts = rs.counts.ensure(kCandPerRound);
   double *acc = rs.acc.ensure(16);
-  int *d_nvalid = d_misc + 8, *d_uvbox = d_misc + 16, *d_nsel = d_misc + 24;
+  int *d_nvalid = d_misc + 8, *d_uvbox = d_misc + 16, *d_nsel = d_misc + 24, *d_nb = d_misc + 28;
 
   std::vector<FoundPlane> found;
   int m = n;                       // unassigned points
@@ -872,7 +929,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       int init[4];
       { float big = 3.4e38f, nb = -3.4e38f; int a, b; memcpy(&a, &big, 4); memcpy(&b, &nb, 4); b ^= 0x7fffffff; init[0] = init[1] = a; init[2] = init[3] = b; }
       PLADE_CUDA(cudaMemcpyAsync(d_uvbox, init, sizeof(init), cudaMemcpyHostToDevice, s));
-      flag_uv_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, f, eps3, nthresh, flag, d_uvbox);
+      flag_uv_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, nullptr, f, eps3, nthresh, flag, d_uvbox);
       PLADE_LAUNCH_CHECK();
       dev.launches.add();
       int hb[4];
@@ -905,8 +962,44 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       e.size = (long long) h[0]; e.sum[0] = h[1]; e.sum[1] = h[2]; e.sum[2] = h[3]; e.score = h[4]; e.ok = e.size > 0;
       return e;
     };
-    // fused evaluation: flag/bbox -> raster -> closing + components -> select -> mean -> covariance, one sync.
-    // cov6 receives the covariance sums about float(mean) of the selected members (input of the LS refit).
+    // clears both membership maps over the current band; with shape_id >= 0 first assigns the members of `acc`
+    auto band_finish = [&](int shape_id, unsigned char *acc_map) {
+      band_finish_kernel<<<blocks_b, 256, 0, s>>>(idxB, d_nb, acc_map ? acc_map : member_a, acc_map == member_a ? member_b : member_a,
+                                                 acc_map ? shape_id : -1, assigned);
+      PLADE_LAUNCH_CHECK();
+      dev.launches.add();
+    };
+    // ---- band of this candidate (see band_compact_kernel) -------------------------------------------------------
+    float4 band_pl = make_float4(0, 0, 0, 0);
+    bool band_full = false;
+    auto build_band = [&](const float4 &pl, bool full) {
+      PLADE_CUDA(cudaMemsetAsync(d_nb, 0, sizeof(int), s));
+      band_compact_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, pl, full ? INFINITY : kBandMul * eps3, posB, nrmB, idxB, d_nb);
+      PLADE_LAUNCH_CHECK();
+      dev.launches.add();
+      band_pl = pl;
+      band_full = full;
+      ++n_band_builds;
+    };
+    // Can a point outside the band be within eps3 of plane `pl`?  d_pl(x) - d_band(x) is affine in x, so over the
+    // bounding box of the cloud its extreme values sit at the corners; if they stay below (kBandMul - 1) * eps3
+    // (minus float slack) every inlier of `pl` lies inside the band.  The fitted normal may come out flipped.
+    auto band_covers = [&](const float4 &pl) -> bool {
+      if (band_full) return true;
+      double worst[2] = {0, 0};
+      for (int k = 0; k < 8; ++k) {
+        const double x = (k & 1) ? mx[0] : mn[0], y = (k & 2) ? mx[1] : mn[1], z = (k & 4) ? mx[2] : mn[2];
+        const double db = band_pl.w - (band_pl.x * x + band_pl.y * y + band_pl.z * z);
+        const double dp = pl.w - (pl.x * x + pl.y * y + pl.z * z);
+        worst[0] = std::max(worst[0], std::fabs(dp - db));
+        worst[1] = std::max(worst[1], std::fabs(-dp - db));
+      }
+      const double slack = 1e-5 * (double) ext + 1e-3 * eps3;
+      return std::min(worst[0], worst[1]) + eps3 + slack <= (double) kBandMul * eps3;
+    };
+    // fused evaluation on the band: flag/bbox -> raster -> closing + components -> select -> mean -> covariance,
+    // one sync.  cov6 receives the covariance sums about float(mean) of the selected members (input of the LS
+    // refit); member is a map over ALL points (zero outside the band).
     auto evaluate_fused = [&](const PlaneFrame &f, unsigned char *member, double cov6[6], bool &overflow) -> Eval {
       Eval e{0, 0, {0, 0, 0}, false};
       unsigned char *bmp = rs.bmp_dev.ensure(kBmpCap), *btmp = rs.bmp_tmp.ensure(kBmpCap), *bmask = rs.mask_dev.ensure(kBmpCap);
@@ -914,17 +1007,19 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       float *mean3 = rs.mean3.ensure(4);
       BmpInfo *info = reinterpret_cast<BmpInfo *>(d_misc + 32);
       if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
+      // widening keeps both membership maps: they are indexed by point, and the full band is a superset of the old one
+      if (!band_covers(f.pl)) { build_band(f.pl, true); ++n_band_full; }
       int init[4];
       { float big = 3.4e38f, nb = -3.4e38f; int a, b; memcpy(&a, &big, 4); memcpy(&b, &nb, 4); b ^= 0x7fffffff; init[0] = init[1] = a; init[2] = init[3] = b; }
       PLADE_CUDA(cudaMemcpyAsync(d_uvbox, init, sizeof(init), cudaMemcpyHostToDevice, s));
       PLADE_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 16, s));
-      flag_uv_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, f, eps3, nthresh, flag, d_uvbox);
+      flag_uv_kernel<<<blocks_b, 256, 0, s>>>(posB, nrmB, nullptr, 0, d_nb, f, eps3, nthresh, flag, d_uvbox);
       bmp_setup_kernel<<<1, 1, 0, s>>>(d_uvbox, bmp_eps, info);
-      raster_dev_kernel<<<div_up(n, 256), 256, 0, s>>>(c.pos.p, flag, n, f, bmp_eps, info, pix, bmp);
+      raster_dev_kernel<<<blocks_b, 256, 0, s>>>(posB, flag, d_nb, f, bmp_eps, info, pix, bmp);
       cc_kernel<<<1, 1024, 0, s>>>(bmp, btmp, lab, ccnt, info, bmask);
-      select_dev_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, flag, pix, bmask, info, n, f.pl, eps3, member, acc);
+      select_dev_kernel<<<blocks_b, 256, 0, s>>>(posB, idxB, flag, pix, bmask, info, d_nb, f.pl, eps3, member, acc);
       mean_kernel<<<1, 1, 0, s>>>(acc, mean3);
-      cov_dev_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, member, n, mean3, acc + 8);
+      cov_dev_kernel<<<blocks_b, 256, 0, s>>>(posB, idxB, member, d_nb, mean3, acc + 8);
       PLADE_LAUNCH_CHECK();
       dev.launches.add(7);
       double h[16];
@@ -977,6 +1072,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     unsigned char *acc_member = member_a, *work_member = member_b;
     double cov_cur[6];
     bool ovf = false;
+    build_band(fr.pl, false);
     Eval cur = evaluate_fused(fr, acc_member, cov_cur, ovf);   // GlobalScore + ConnectedComponent (+ weighted score of the clone)
     const bool host_path = ovf;                                // bitmap larger than the device cap: host labelling
     if (host_path) cur = evaluate(fr, acc_member);
@@ -1018,6 +1114,8 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     // the reference only accepts a candidate whose fully evaluated (connected-component) support
     // reaches min_support (FindBestCandidate, RansacShapeDetector.cpp:297,423-430)
     if (acc_size < min_support) {
+      if (host_path) { PLADE_CUDA(cudaMemsetAsync(member_a, 0, n, s)); PLADE_CUDA(cudaMemsetAsync(member_b, 0, n, s)); }
+      else band_finish(-1, nullptr);
       // its score can only shrink from here on: never look at this plane (or a duplicate of it) again
       banned.push_back(best_pl);
       if (!pool.empty()) pool.erase(pool.begin());
@@ -1026,8 +1124,12 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     }
     unsigned char *member = acc_member;
     // --- accept: remove the points (RansacShapeDetector.cpp:659-675) ---------------------------------------------
-    mark_kernel<<<div_up(n, 256), 256, 0, s>>>(member, n, (int) found.size(), assigned);
-    PLADE_LAUNCH_CHECK();
+    if (host_path) {
+      mark_kernel<<<div_up(n, 256), 256, 0, s>>>(member, n, (int) found.size(), assigned);
+      PLADE_LAUNCH_CHECK();
+      PLADE_CUDA(cudaMemsetAsync(member_a, 0, n, s));
+      PLADE_CUDA(cudaMemsetAsync(member_b, 0, n, s));
+    } else band_finish((int) found.size(), member);
     FoundPlane fp;
     memcpy(fp.n, acc_n, sizeof(acc_n)); memcpy(fp.pos, acc_p, sizeof(acc_p));
     fp.size = acc_size;
@@ -1075,6 +1177,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   dev.launches.add();
   PLADE_CUDA(cudaStreamSynchronize(s));
   mark("ransac_output");
+  if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade ransac lane %d] candidates evaluated on a band: %d, widened to all points: %d\n", lane, n_band_builds - n_band_full, n_band_full);
   return result;
 }
 
