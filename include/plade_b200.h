@@ -38,6 +38,7 @@ plade_ctx *plade_ctx_create(int device);          /* device < 0: current device;
 void plade_ctx_destroy(plade_ctx *ctx);
 const char *plade_last_error(plade_ctx *ctx);
 const char *plade_create_error(void);             /* why the last plade_ctx_create returned NULL */
+int plade_device_count(void);                     /* visible CUDA devices (0 when there is none) */
 /* tunables; names = fields of plade::Params (defaults are the reference's literals). 1 if known. */
 int plade_set_param(plade_ctx *ctx, const char *name, double value);
 /* hypothesis sharding for multi-GPU verification (PLADE/plade.cpp:547-564 iterations are independent):
@@ -68,6 +69,15 @@ int plade_register_with_planes(plade_ctx *ctx, const float *tgt_xyzn, size_t nt,
 /* registration(T, target_cloud, source_cloud, min_support, min_support)   PLADE/plade.cpp:583-599 */
 int plade_register_min_support(plade_ctx *ctx, const float *tgt_xyzn, size_t nt, const float *src_xyzn, size_t ns,
                                int min_support_target, int min_support_source, float out16[16]);
+
+/* Batch mode of the reference CLI (PLADE/main.cpp:97-159: a list of (target, source) file pairs registered one
+ * after the other) spread over the GPUs of one box.  Pairs are independent: one worker thread +
+ * context per entry of devices[] (NULL => 0..n_devices-1) takes the next unclaimed pair, and parses the
+ * following pair's PLY files into page-locked memory while the current one is on the GPU.  No collective.
+ * out16 = n_pairs row-major 4x4 (identity where ok[p] == 0), same per-pair semantics as plade_register_files.
+ * Returns the number of successful pairs, or -1 when no device could be used. */
+int plade_register_batch(const int *devices, int n_devices, const char *const *target_files,
+                         const char *const *source_files, int n_pairs, float *out16, int *ok);
 
 /* HBM-resident variants (inputs uploaded once; used for the device-resident throughput figure) */
 plade_cloud *plade_cloud_upload(plade_ctx *ctx, const float *xyzn, size_t n);

@@ -26,6 +26,7 @@ SIGNATURES = {
     "plade_ctx_destroy": (None, [ctypes.c_void_p]),
     "plade_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "plade_create_error": (ctypes.c_char_p, []),
+    "plade_device_count": (ctypes.c_int, []),
     "plade_set_param": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]),
     "plade_set_shard": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ALLREDUCE_FN, ctypes.c_void_p]),
     "plade_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
@@ -39,6 +40,8 @@ SIGNATURES = {
                                                   _c_int_p, _c_int_p, _c_float_p, ctypes.c_int, _c_float_p]),
     "plade_register_min_support": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, _c_float_p, ctypes.c_size_t,
                                                   ctypes.c_int, ctypes.c_int, _c_float_p]),
+    "plade_register_batch": (ctypes.c_int, [_c_int_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p),
+                                            ctypes.c_int, _c_float_p, _c_int_p]),
     "plade_cloud_upload": (ctypes.c_void_p, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t]),
     "plade_cloud_free": (None, [ctypes.c_void_p, ctypes.c_void_p]),
     "plade_cloud_size": (ctypes.c_size_t, [ctypes.c_void_p]),
@@ -370,6 +373,22 @@ class Context:
         if not ok:
             raise RuntimeError(self.last_error())
         return counts, float(ms.value)
+
+
+def register_batch(pairs, devices=None):
+    """Batch mode of the reference CLI (PLADE/main.cpp:97-159) over the GPUs of one box: ``pairs`` is a list of
+    (target_ply, source_ply); ``devices`` a list of CUDA ordinals (default: device 0).  Returns (ok[n], T[n,4,4])."""
+    lib = load_library()
+    devices = _i32([0] if devices is None else devices)
+    n = len(pairs)
+    tf = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(p[0]) for p in pairs])
+    sf = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(p[1]) for p in pairs])
+    out = np.zeros((n, 16), dtype=np.float32)
+    ok = np.zeros(n, dtype=np.int32)
+    rc = lib.plade_register_batch(_p(devices, _c_int_p), len(devices), tf, sf, n, _p(out, _c_float_p), _p(ok, _c_int_p))
+    if rc < 0:
+        raise RuntimeError("plade_b200: no usable CUDA device (%s); there is no CPU fallback" % lib.plade_create_error().decode())
+    return ok.astype(bool), out.reshape(n, 4, 4)
 
 
 def registration(target, source, ctx=None):

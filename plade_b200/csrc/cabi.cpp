@@ -5,9 +5,13 @@
 #include "pipeline.h"
 #include "ply.h"
 #include "libm_flt32.h"
+#include <atomic>
+#include <condition_variable>
 #include <cstring>
 #include <iostream>
 #include <memory>
+#include <mutex>
+#include <thread>
 
 using namespace plade;
 
@@ -26,6 +30,7 @@ struct plade_ctx {
   std::vector<int> match_idx;
   std::vector<double> match_d2;
   CloudDev tmp_t, tmp_s;
+  PinBuf<float> pin_t, pin_s;            // PLY records of the file overload (page-locked)
   // resident buffers for plade_verify_upload / plade_verify_resident
   DevBuf<float4> v_src, v_tgt;
   size_t v_ns = 0, v_nt = 0;
@@ -94,6 +99,11 @@ plade_ctx *plade_ctx_create(int device) {
 void plade_ctx_destroy(plade_ctx *ctx) { delete ctx; }
 const char *plade_last_error(plade_ctx *ctx) { return ctx ? (ctx->err.empty() ? ctx->reg->last_error.c_str() : ctx->err.c_str()) : ""; }
 const char *plade_create_error(void) { return g_create_error.c_str(); }
+int plade_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return count;
+}
 
 int plade_set_param(plade_ctx *ctx, const char *name, double v) {
   if (!ctx) return 0;
@@ -166,6 +176,36 @@ int plade_register_clouds(plade_ctx *ctx, const float *tgt, size_t nt, const flo
   })
 }
 
+// swap rule + registration + inverse-on-swap of the file overload (PLADE/plade.cpp:689-704) on loaded clouds
+static int register_loaded(plade_ctx *ctx, const float *t, size_t nt, const float *s, size_t ns, float out16[16], bool announce) {
+  bool switched = false;
+  if (ns >= nt * 1.2f) {
+    std::swap(t, s);
+    std::swap(nt, ns);
+    switched = true;
+    if (announce) std::cout << "---->>> ATTENTION: target and source have been switched for efficiency <<<----" << std::endl;
+  }
+  Registrar &r = *ctx->reg;
+  r.upload(t, nt, ctx->tmp_t);
+  r.upload(s, ns, ctx->tmp_s);
+  if (!r.register_clouds(ctx->tmp_t, ctx->tmp_s, out16)) { std::cerr << "registration failed" << std::endl; return 0; }
+  if (switched) {
+    // the reference calls Matrix4f::inverse() (general 4x4 inverse); here the general inverse of the 3x3 block
+    // via its adjugate in double (R need not be exactly orthonormal in float), equal up to rounding
+    double R[9], T[3];
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[3 * i + j] = out16[4 * i + j]; T[i] = out16[4 * i + 3]; }
+    double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+    double inv[9] = {(R[4] * R[8] - R[5] * R[7]) / det, (R[2] * R[7] - R[1] * R[8]) / det, (R[1] * R[5] - R[2] * R[4]) / det,
+                     (R[5] * R[6] - R[3] * R[8]) / det, (R[0] * R[8] - R[2] * R[6]) / det, (R[2] * R[3] - R[0] * R[5]) / det,
+                     (R[3] * R[7] - R[4] * R[6]) / det, (R[1] * R[6] - R[0] * R[7]) / det, (R[0] * R[4] - R[1] * R[3]) / det};
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) out16[4 * i + j] = (float) inv[3 * i + j];
+      out16[4 * i + 3] = (float) -(inv[3 * i] * T[0] + inv[3 * i + 1] * T[1] + inv[3 * i + 2] * T[2]);
+    }
+  }
+  return 1;
+}
+
 int plade_register_files(plade_ctx *ctx, const char *target_ply, const char *source_ply, float out16[16]) {
   identity16(out16);
   PLADE_TRY(ctx, 0, {
@@ -177,36 +217,105 @@ int plade_register_files(plade_ctx *ctx, const char *target_ply, const char *sou
       ctx->err = "only PLY format is accepted";
       return 0;
     }
-    std::vector<float> t, s;
-    if (!load_ply_xyzn(target_ply, t)) { std::cerr << "loading target point cloud failed" << std::endl; ctx->err = "loading target point cloud failed"; return 0; }
-    if (!load_ply_xyzn(source_ply, s)) { std::cerr << "loading source point cloud failed" << std::endl; ctx->err = "loading source point cloud failed"; return 0; }
-    // swap rule, PLADE/plade.cpp:689-704
-    bool switched = false;
-    if (s.size() / 6 >= (t.size() / 6) * 1.2f) {
-      std::swap(t, s);
-      switched = true;
-      std::cout << "---->>> ATTENTION: target and source have been switched for efficiency <<<----" << std::endl;
-    }
-    Registrar &r = *ctx->reg;
-    r.upload(t.data(), t.size() / 6, ctx->tmp_t);
-    r.upload(s.data(), s.size() / 6, ctx->tmp_s);
-    if (!r.register_clouds(ctx->tmp_t, ctx->tmp_s, out16)) { std::cerr << "registration failed" << std::endl; return 0; }
-    if (switched) {
-      // rigid inverse of [R | T]; the reference calls Matrix4f::inverse() (general 4x4 inverse), equal up to rounding
-      double R[9], T[3];
-      for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[3 * i + j] = out16[4 * i + j]; T[i] = out16[4 * i + 3]; }
-      // general inverse of the 3x3 block via adjugate (R need not be exactly orthonormal in float)
-      double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
-      double inv[9] = {(R[4] * R[8] - R[5] * R[7]) / det, (R[2] * R[7] - R[1] * R[8]) / det, (R[1] * R[5] - R[2] * R[4]) / det,
-                       (R[5] * R[6] - R[3] * R[8]) / det, (R[0] * R[8] - R[2] * R[6]) / det, (R[2] * R[3] - R[0] * R[5]) / det,
-                       (R[3] * R[7] - R[4] * R[6]) / det, (R[1] * R[6] - R[0] * R[7]) / det, (R[0] * R[4] - R[1] * R[3]) / det};
-      for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j) out16[4 * i + j] = (float) inv[3 * i + j];
-        out16[4 * i + 3] = (float) -(inv[3 * i] * T[0] + inv[3 * i + 1] * T[1] + inv[3 * i + 2] * T[2]);
-      }
-    }
-    return 1;
+    // the records are read straight into page-locked memory so the H2D copy is one DMA
+    struct Pin {
+      static float *alloc(size_t n, void *user) { return static_cast<PinBuf<float> *>(user)->ensure(std::max<size_t>(n, 1)); }
+    };
+    size_t nt = 0, ns = 0;
+    if (!load_ply_xyzn_into(target_ply, &Pin::alloc, &ctx->pin_t, nt)) { std::cerr << "loading target point cloud failed" << std::endl; ctx->err = "loading target point cloud failed"; return 0; }
+    if (!load_ply_xyzn_into(source_ply, &Pin::alloc, &ctx->pin_s, ns)) { std::cerr << "loading source point cloud failed" << std::endl; ctx->err = "loading source point cloud failed"; return 0; }
+    return register_loaded(ctx, ctx->pin_t.p, nt, ctx->pin_s.p, ns, out16, true);
   })
+}
+
+// Batch mode of the reference CLI (PLADE/main.cpp:97-159) over the GPUs of one box: pairs are independent, so
+// worker g (one host thread + one context on devices[g]) takes the next unclaimed pair from a shared counter;
+// each worker has a loader thread that parses the NEXT pair's PLY files into its second pair of pinned
+// buffers while the current pair is on the GPU.  No data-path collective; results are written by pair index.
+int plade_register_batch(const int *devices, int n_devices, const char *const *target_files, const char *const *source_files,
+                         int n_pairs, float *out16, int *ok) {
+  if (n_pairs < 0 || n_devices < 1 || !target_files || !source_files || !out16 || !ok) return -1;
+  for (int p = 0; p < n_pairs; ++p) { identity16(out16 + 16 * p); ok[p] = 0; }
+  struct Slot {
+    PinBuf<float> t, s;
+    size_t nt = 0, ns = 0;
+    int pair = -1;          // -1: end of work
+    bool loaded = false;    // both files parsed
+    std::string why;
+  };
+  struct Pin {
+    static float *alloc(size_t n, void *user) { return static_cast<PinBuf<float> *>(user)->ensure(std::max<size_t>(n, 1)); }
+  };
+  std::atomic<int> next(0), successes(0), workers_up(0);
+  std::mutex io;     // one pair's messages at a time
+  auto worker = [&](int g) {
+    int device = devices ? devices[g] : g;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
+    plade_ctx *ctx = plade_ctx_create(device);
+    if (!ctx) return;
+    workers_up.fetch_add(1);
+    Slot slots[2];
+    std::mutex m;
+    std::condition_variable cv;
+    int ready[2] = {0, 0};    // 0 = free for the loader, 1 = filled for the worker
+    std::thread loader([&] {
+      cudaSetDevice(device);
+      for (int k = 0;; k ^= 1) {
+        { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return ready[k] == 0; }); }
+        Slot &sl = slots[k];
+        sl.pair = next.fetch_add(1);
+        sl.loaded = false;
+        sl.why.clear();
+        if (sl.pair >= n_pairs) sl.pair = -1;
+        else {
+          const char *tf = target_files[sl.pair], *sf = source_files[sl.pair];
+          try {
+            if (file_extension(tf) != "ply" || file_extension(sf) != "ply") sl.why = "only PLY format is accepted";
+            else if (!load_ply_xyzn_into(tf, &Pin::alloc, &sl.t, sl.nt)) sl.why = "loading target point cloud failed";
+            else if (!load_ply_xyzn_into(sf, &Pin::alloc, &sl.s, sl.ns)) sl.why = "loading source point cloud failed";
+            else sl.loaded = true;
+          } catch (const std::exception &e) { sl.why = e.what(); }
+        }
+        { std::lock_guard<std::mutex> l(m); ready[k] = 1; }
+        cv.notify_all();
+        if (sl.pair < 0) break;
+      }
+    });
+    for (int k = 0;; k ^= 1) {
+      { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return ready[k] == 1; }); }
+      Slot &sl = slots[k];
+      if (sl.pair < 0) break;
+      int good = 0;
+      if (!sl.loaded) {
+        std::lock_guard<std::mutex> l(io);
+        std::cerr << sl.why << " (pair " << sl.pair << ")" << std::endl;
+      } else {
+        try {
+          ctx->err.clear();
+          good = register_loaded(ctx, sl.t.p, sl.nt, sl.s.p, sl.ns, out16 + 16 * sl.pair, false);
+        } catch (const std::exception &e) {
+          std::lock_guard<std::mutex> l(io);
+          std::cerr << "plade_b200: " << e.what() << " (pair " << sl.pair << ")" << std::endl;
+          identity16(out16 + 16 * sl.pair);
+          good = 0;
+        }
+      }
+      ok[sl.pair] = good;
+      if (good) successes.fetch_add(1);
+      { std::lock_guard<std::mutex> l(m); ready[k] = 0; }
+      cv.notify_all();
+    }
+    loader.join();
+    plade_ctx_destroy(ctx);
+  };
+  std::vector<std::thread> th;
+  for (int g = 0; g < n_devices; ++g) th.emplace_back(worker, g);
+  for (std::thread &t : th) t.join();
+  if (workers_up.load() == 0) {
+    std::cerr << "plade_b200: no usable CUDA device for the batch: " << g_create_error << std::endl;
+    return -1;
+  }
+  return successes.load();
 }
 
 int plade_register_with_planes(plade_ctx *ctx, const float *tgt, size_t nt, const float *src, size_t ns, const int *t_off,

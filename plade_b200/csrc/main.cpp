@@ -5,6 +5,7 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <algorithm>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -37,10 +38,10 @@ int main(int argc, char **argv) {
               << "Usage 2:  plade_b200_cli  file_pairs.txt  results.txt   (two lines per pair: target, source)\n";
     return EXIT_FAILURE;
   }
-  plade_ctx *ctx = plade_ctx_create(-1);
-  if (!ctx) { std::cerr << "no usable CUDA device: " << plade_create_error() << std::endl; return EXIT_FAILURE; }
   float T[16];
   if (argc == 4) {
+    plade_ctx *ctx = plade_ctx_create(-1);
+    if (!ctx) { std::cerr << "no usable CUDA device: " << plade_create_error() << std::endl; return EXIT_FAILURE; }
     std::ofstream output(argv[3]);
     if (!output.is_open()) { std::cerr << "failed opening the result file: " << argv[3] << std::endl; return EXIT_FAILURE; }
     int ok = plade_register_files(ctx, argv[1], argv[2], T);
@@ -59,24 +60,51 @@ int main(int argc, char **argv) {
     return EXIT_FAILURE;
   }
   std::ifstream input(argv[1]);
-  if (!input.is_open()) { std::cerr << "failed opening the file pairs file: " << argv[1] << std::endl; return EXIT_FAILURE; }
+  if (!input.is_open()) { std::cerr << "failed opening the file containing pairs of point cloud names: " << argv[1] << std::endl; return EXIT_FAILURE; }
   std::ofstream output(argv[2]);
   if (!output.is_open()) { std::cerr << "failed opening the result file: " << argv[2] << std::endl; return EXIT_FAILURE; }
-  std::string t, s;
-  int success = 0, fail = 0;
+  // The pair list is read first, exactly as PLADE/main.cpp:117-134 walks it: one name per line, empty lines and
+  // names that cannot be opened are skipped ("file doesn't exist"), every two surviving names form a pair, a
+  // trailing single name is dropped.  The pairs are then spread over the GPUs (PLADE_DEVICES=n limits how many;
+  // default: all visible) and the results written in list order with the reference's text format (:136-147).
+  auto is_file = [](const std::string &filename) -> bool { std::ifstream fin(filename); return fin.is_open(); };
+  std::vector<std::string> tf, sf;
   while (!input.eof()) {
-    std::getline(input, t);
-    if (t.empty()) continue;
-    std::getline(input, s);
-    if (s.empty()) continue;
-    int ok = plade_register_files(ctx, t.c_str(), s.c_str(), T);
-    output << "target: " << t << "\nsource: " << s << "\n";
-    if (ok) { output << "transformation:\n"; ++success; }
-    else { output << "registration failed, an identity matrix is recorded:\n"; ++fail; }
-    write_matrix(output, T);
-    output << "\n" << std::endl;
+    std::vector<std::string> file_pair;
+    while (!input.eof() && file_pair.size() < 2) {
+      std::string file_name;
+      std::getline(input, file_name);
+      if (!file_name.empty()) {
+        if (is_file(file_name)) file_pair.push_back(file_name);
+        else std::cerr << "file doesn't exist: " << file_name << std::endl;
+      }
+    }
+    if (file_pair.size() == 2) { tf.push_back(file_pair[0]); sf.push_back(file_pair[1]); }
   }
-  std::cout << success << " pairs succeeded, " << fail << " failed. results written into: " << argv[2] << std::endl;
-  plade_ctx_destroy(ctx);
-  return fail ? EXIT_FAILURE : EXIT_SUCCESS;
+  int n_dev = plade_device_count();
+  if (const char *e = getenv("PLADE_DEVICES")) n_dev = std::max(1, std::min(n_dev, atoi(e)));
+  if (n_dev < 1) { std::cerr << "no usable CUDA device (plade_b200 has no CPU fallback)" << std::endl; return EXIT_FAILURE; }
+  const int n = (int) tf.size();
+  std::vector<const char *> tp(n), sp(n);
+  for (int i = 0; i < n; ++i) { tp[i] = tf[i].c_str(); sp[i] = sf[i].c_str(); }
+  std::vector<float> Ts(16 * (size_t) std::max(n, 1));
+  std::vector<int> oks(std::max(n, 1), 0);
+  if (plade_register_batch(nullptr, std::min(n_dev, std::max(n, 1)), tp.data(), sp.data(), n, Ts.data(), oks.data()) < 0) return EXIT_FAILURE;
+  int count_success = 0, count_failure = 0;
+  for (int i = 0; i < n; ++i) {
+    output << "target: " << tf[i] << std::endl;
+    output << "source: " << sf[i] << std::endl;
+    if (oks[i]) { output << "transformation:\n"; ++count_success; }
+    else { output << "registration failed, an identity matrix is recorded:\n"; ++count_failure; }
+    write_matrix(output, &Ts[16 * (size_t) i]);
+    output << std::endl << std::endl;
+  }
+  if (count_success == 0) {
+    std::cerr << "registration all failed (" << count_failure << " pairs)" << std::endl;
+    return EXIT_FAILURE;
+  }
+  if (count_failure > 0)
+    std::cerr << "registration of " << count_failure << " (out of " << count_failure + count_success << ") pairs failed" << std::endl;
+  std::cout << "the registration result has been written into file: " << argv[2] << std::endl;
+  return EXIT_SUCCESS;
 }

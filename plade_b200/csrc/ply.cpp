@@ -44,6 +44,20 @@ std::string file_extension(const std::string &file_name) {      // extension(), 
 
 bool load_ply_xyzn(const std::string &file_name, std::vector<float> &out) {
   out.clear();
+  struct Grow {
+    static float *alloc(size_t n_floats, void *user) {
+      std::vector<float> *v = static_cast<std::vector<float> *>(user);
+      v->resize(n_floats);
+      return v->data();
+    }
+  };
+  size_t n = 0;
+  if (!load_ply_xyzn_into(file_name, &Grow::alloc, &out, n)) { out.clear(); return false; }
+  return true;
+}
+
+bool load_ply_xyzn_into(const std::string &file_name, PlyAlloc alloc, void *user, size_t &n_points) {
+  n_points = 0;
   FILE *f = fopen(file_name.c_str(), "rb");
   if (!f) { std::cerr << "failed to open ply file: " << file_name << std::endl; return false; }
   char line[1024];
@@ -86,13 +100,14 @@ bool load_ply_xyzn(const std::string &file_name, std::vector<float> &out) {
     std::cerr << "the number of points does not equal to the number of normals in the file" << std::endl;
     return false;
   }
-  out.resize(n_vertex * 6);
+  float *out = alloc(n_vertex * 6, user);
+  if (!out && n_vertex) { fclose(f); std::cerr << "failed to read ply file: " << file_name << std::endl; return false; }
   bool ok = true;
   if (binary_le) {
     bool fast = props.size() == 6;
     for (int k = 0; k < 6 && fast; ++k) fast = ix[k] == k && (props[k].type == "float" || props[k].type == "float32");
     if (fast) {
-      ok = fread(out.data(), sizeof(float) * 6, n_vertex, f) == n_vertex;
+      ok = fread(out, sizeof(float) * 6, n_vertex, f) == n_vertex;
     } else {
       size_t rec = 0;
       std::vector<size_t> off(props.size());
@@ -115,7 +130,8 @@ bool load_ply_xyzn(const std::string &file_name, std::vector<float> &out) {
     }
   }
   fclose(f);
-  if (!ok) { out.clear(); std::cerr << "failed to read ply file: " << file_name << std::endl; return false; }
+  if (!ok) { std::cerr << "failed to read ply file: " << file_name << std::endl; return false; }
+  n_points = n_vertex;
   return n_vertex > 0;
 }
 

@@ -12,6 +12,7 @@ from plade_b200 import Planes
 from plade_b200.synth import make_pair, perturbed_hypotheses, transform_error
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _rand_rigid(rng, n, rot_deg=20.0, trans=0.3):
@@ -518,3 +519,67 @@ def test_file_overload_and_errors(ctx, poly_pair, tmp_path):
     diag = float(np.linalg.norm(np.ptp(st[:, :3], axis=0)))
     rot, tr = transform_error(T3, gt, diag)
     assert rot <= 0.5 and tr <= 5e-3
+
+
+def test_batch_mode_matches_single_registrations(ctx, poly_pair, tmp_path):
+    """plade_register_batch (reference CLI batch mode, PLADE/main.cpp:97-159, spread over worker threads) gives, pair
+    by pair, exactly what plade_register_files gives; bad entries fail alone and leave the identity."""
+    import plade_b200
+    from tests.plyio import write_ply
+    pairs, want = [], []
+    for k, seed in enumerate([11, 12, 13]):
+        st, ss, gt = make_pair(n_points=120000, n_planes=20, seed=seed)
+        t, s = str(tmp_path / ("t%d.ply" % k)), str(tmp_path / ("s%d.ply" % k))
+        write_ply(t, st); write_ply(s, ss)
+        pairs.append((t, s))
+        want.append(ctx.register_files(t, s))
+    pairs.insert(1, (str(tmp_path / "missing.ply"), pairs[0][1]))
+    want.insert(1, (False, np.eye(4, dtype=np.float32)))
+    # two workers on the same device: exercises the per-thread contexts and the loader threads
+    ok, T = plade_b200.register_batch(pairs, devices=[0, 0])
+    assert ok.tolist() == [bool(w[0]) for w in want]
+    for k in range(len(pairs)):
+        assert np.array_equal(T[k], want[k][1]), k
+    ok0, T0 = plade_b200.register_batch([], devices=[0])
+    assert len(ok0) == 0 and T0.shape == (0, 4, 4)
+
+
+def test_cli_result_file_format(poly_pair, tmp_path):
+    """plade_b200_cli keeps both usages of PLADE/main.cpp and its result-file text format (main.cpp:84-91,139-146)."""
+    import subprocess
+    from tests.plyio import write_ply
+    cli = os.path.join(ROOT, "plade_b200", "plade_b200_cli")
+    st, ss, gt = make_pair(n_points=120000, n_planes=20, seed=11)
+    t, s = str(tmp_path / "t.ply"), str(tmp_path / "s.ply")
+    write_ply(t, st); write_ply(s, ss)
+    res = str(tmp_path / "result.txt")
+    r = subprocess.run([cli, t, s, res], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = open(res).read().split("\n")
+    assert lines[0] == "target: " + t and lines[1] == "source: " + s and lines[2] == "transformation:"
+    M = np.array([[float(x) for x in l.split()] for l in lines[3:7]])
+    diag = float(np.linalg.norm(np.ptp(st[:, :3], axis=0)))
+    rot, tr = transform_error(M, gt, diag)
+    assert rot <= 0.5 and tr <= 5e-3
+    # usage 2: pair list -> blocks separated by a blank line; a name that cannot be opened is skipped with a message
+    # and the pairing continues with the next existing name (main.cpp:117-134); a failed registration records the
+    # identity; exit code is failure only when every pair failed (main.cpp:150-158)
+    rng = np.random.default_rng(3)
+    blob = str(tmp_path / "blob.ply")
+    write_ply(blob, rng.normal(size=(20000, 6)).astype(np.float32))       # no planes -> registration fails
+    lst = str(tmp_path / "file_pairs.txt")
+    open(lst, "w").write("%s\n%s\n\n%s\n%s\n%s\n" % (t, str(tmp_path / "nope.ply"), s, blob, blob))
+    res2 = str(tmp_path / "results.txt")
+    r = subprocess.run([cli, lst, res2], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "file doesn't exist: " + str(tmp_path / "nope.ply") in r.stderr
+    assert "registration of 1 (out of 2) pairs failed" in r.stderr
+    assert "the registration result has been written into file: " + res2 in r.stdout
+    blocks = open(res2).read().strip("\n").split("\n\n")
+    assert len(blocks) == 2
+    b0, b1 = blocks[0].split("\n"), blocks[1].split("\n")
+    assert b0[:3] == ["target: " + t, "source: " + s, "transformation:"]
+    assert b1[:3] == ["target: " + blob, "source: " + blob, "registration failed, an identity matrix is recorded:"]
+    assert [l.split() for l in b1[3:7]] == [["1", "0", "0", "0"], ["0", "1", "0", "0"], ["0", "0", "1", "0"], ["0", "0", "0", "1"]]
+    M2 = np.array([[float(x) for x in l.split()] for l in b0[3:7]])
+    assert np.array_equal(M, M2)
