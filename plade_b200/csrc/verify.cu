@@ -22,9 +22,11 @@ namespace plade {
 
 namespace {
 
-constexpr int kTile = 2048;          // source points per shared-memory tile (32 KB)
+constexpr int kTile = 1024;          // source points per shared-memory tile (16 KB)
 constexpr int kThreads = 256;
-constexpr int kHypChunk = 32;        // hypotheses per work item
+constexpr int kHypChunk = 32;        // hypotheses per work item (the tile is reused for all of them)
+constexpr int kHypGroup = 8;         // hypotheses per filter/search pass; the queue holds every (hypothesis, point) of a pass
+static_assert(kTile <= 1024 && kHypChunk <= 64, "queue entries pack (hypothesis << 10 | point) into 16 bits");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -60,6 +62,7 @@ __constant__ int c_row_dz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
 struct GridView {
   const float4 *pts;
   const int *cell_start;
+  const unsigned int *raw;     // occupancy: bit set <=> the cell holds a target point (grid extended by one empty cell per side)
   const unsigned int *dil;     // dilated occupancy: bit set <=> some target point lies in the 27 cells around this one
   int ey, ewords;
   float minx, miny, minz, inv_cell;
@@ -75,27 +78,42 @@ __device__ __forceinline__ float dist2_l2simple(float ax, float ay, float az, fl
   return r;
 }
 
-__device__ __forceinline__ bool point_has_inlier(const GridView &g, const HypParams &hp, float rball2, float rin2,
-                                                 float sx, float sy, float sz) {
-  // pcl::transformPointCloud: x' = ((m00*x + m01*y) + m02*z) + m03, plain float, left to right.
-  float x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.R[0], sx), __fmul_rn(hp.R[1], sy)), __fmul_rn(hp.R[2], sz)), hp.T[0]);
-  float y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.R[3], sx), __fmul_rn(hp.R[4], sy)), __fmul_rn(hp.R[5], sz)), hp.T[1]);
-  float z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.R[6], sx), __fmul_rn(hp.R[7], sy)), __fmul_rn(hp.R[8], sz)), hp.T[2]);
+// pcl::transformPointCloud: x' = ((m00*x + m01*y) + m02*z) + m03, plain float, left to right.
+__device__ __forceinline__ void transform_point(const HypParams &hp, float sx, float sy, float sz, float &x, float &y, float &z) {
+  x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.R[0], sx), __fmul_rn(hp.R[1], sy)), __fmul_rn(hp.R[2], sz)), hp.T[0]);
+  y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.R[3], sx), __fmul_rn(hp.R[4], sy)), __fmul_rn(hp.R[5], sz)), hp.T[1]);
+  z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.R[6], sx), __fmul_rn(hp.R[7], sy)), __fmul_rn(hp.R[8], sz)), hp.T[2]);
+}
+
+// Filter pass: can the transformed point have a target point within the inlier distance at all?  One bit test of
+// the dilated occupancy rejects every point whose 27-cell neighbourhood is empty (most points of a wrong hypothesis).
+__device__ __forceinline__ bool point_may_have_inlier(const GridView &g, const HypParams &hp, float sx, float sy, float sz) {
+  float x, y, z;
+  transform_point(hp, sx, sy, sz, x, y, z);
   float fx = (x - g.minx) * g.inv_cell, fy = (y - g.miny) * g.inv_cell, fz = (z - g.minz) * g.inv_cell;
   // outside the grid by more than one cell (or NaN) => no target point can be within the inlier radius
   if (!(fx >= -1.0f && fy >= -1.0f && fz >= -1.0f && fx < (float) (g.nx + 1) && fy < (float) (g.ny + 1) &&
         fz < (float) (g.nz + 1)))
     return false;
   int cx = (int) floorf(fx), cy = (int) floorf(fy), cz = (int) floorf(fz);
-  // one bit test rejects every point whose 27-cell neighbourhood is empty (most points of a wrong hypothesis)
-  {
-    unsigned int w = __ldg(g.dil + ((size_t) (cz + 1) * g.ey + (cy + 1)) * g.ewords + ((cx + 1) >> 5));
-    if (!((w >> ((cx + 1) & 31)) & 1u)) return false;
-  }
+  unsigned int w = __ldg(g.dil + ((size_t) (cz + 1) * g.ey + (cy + 1)) * g.ewords + ((cx + 1) >> 5));
+  return (w >> ((cx + 1) & 31)) & 1u;
+}
+
+// Search pass, for a point that passed the filter: exact test against the target points of the 27 cells around it.
+__device__ __forceinline__ bool point_has_inlier(const GridView &g, const HypParams &hp, float rball2, float rin2,
+                                                 float sx, float sy, float sz) {
+  float x, y, z;
+  transform_point(hp, sx, sy, sz, x, y, z);
+  float fx = (x - g.minx) * g.inv_cell, fy = (y - g.miny) * g.inv_cell, fz = (z - g.minz) * g.inv_cell;
+  int cx = (int) floorf(fx), cy = (int) floorf(fy), cz = (int) floorf(fz);
   int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
   int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.ny - 1);
   int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
   if (x0 > x1) return false;
+  const unsigned int xmask = (2u << (x1 - x0)) - 1u;     // x1 - x0 + 1 bits
+  const int xe0 = x0 + 1, xw = xe0 >> 5, xs = xe0 & 31;
+  const bool two_words = xs + (x1 - x0) > 31;
   // rows (dy, dz) nearest-first: a true inlier is usually found in the centre row, and a corner row can only
   // hold a point within one cell edge (>= the inlier distance... the cell is 2^-10 larger) of the query if the
   // query's in-cell offsets towards it satisfy oy^2 + oz^2 < 1 (in cell units; 1.01 leaves room for rounding)
@@ -110,8 +128,14 @@ __device__ __forceinline__ bool point_has_inlier(const GridView &g, const HypPar
       const float oy = dy < 0 ? ry : 1.0f - ry, oz = dz < 0 ? rz : 1.0f - rz;
       if (oy * oy + oz * oz > 1.01f) continue;
     }
-    const int row = (zz * g.ny + yy) * g.nx;
-    const int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
+    // occupancy bits of the (up to) three cells of this row: the 1.2 MB bitmap answers "empty row" from L1/L2
+    // without touching the 4-byte-per-cell CSR table
+    const unsigned int *orow = g.raw + ((size_t) (zz + 1) * g.ey + (yy + 1)) * g.ewords + xw;
+    const unsigned int lo = __ldg(orow), hi = two_words ? __ldg(orow + 1) : 0u;
+    const unsigned int occ = __funnelshift_r(lo, hi, xs) & xmask;
+    if (!occ) continue;
+    const int row = (zz * g.ny + yy) * g.nx + x0;
+    const int b = __ldg(g.cell_start + row + (__ffs(occ) - 1)), e = __ldg(g.cell_start + row + (32 - __clz(occ)));
     for (int i = b; i < e; ++i) {
       float4 t = __ldg(g.pts + i);
       if (dist2_l2simple(x, y, z, t.x, t.y, t.z) < rin2) {
@@ -123,15 +147,22 @@ __device__ __forceinline__ bool point_has_inlier(const GridView &g, const HypPar
   return false;
 }
 
+// Persistent kernel over (source tile, hypothesis chunk) work items.  Per group of kHypGroup hypotheses the block
+// runs two passes over the tile: a FILTER pass (transform + one occupancy bit) in which all lanes do the same
+// cheap work and the survivors are appended to a shared-memory queue, then a SEARCH pass in which consecutive
+// lanes take consecutive queue entries — so the expensive, data-dependent grid walk runs with full warps instead
+// of the ~1 lane in 5 that survives the filter.
 __global__ void __launch_bounds__(kThreads)
 verify_kernel(const float4 *__restrict__ src, int ns, GridView g, const HypParams *__restrict__ hyps, int H,
               float rball2, float rin2, unsigned int *__restrict__ counts, int n_tiles, int n_chunks) {
   __shared__ __align__(128) float4 tile[kTile];
   __shared__ __align__(16) HypParams hp_s[kHypChunk];
+  __shared__ unsigned short queue[kHypGroup * kTile];
   __shared__ unsigned int cnt_s[kHypChunk];
+  __shared__ unsigned int q_n;
   __shared__ __align__(8) uint64_t bar;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -150,6 +181,7 @@ verify_kernel(const float4 *__restrict__ src, int ns, GridView g, const HypParam
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&bar, (uint32_t) np * 16u);
       tma_load_1d(tile, src + p0, (uint32_t) np * 16u, &bar);
+      q_n = 0;
     }
     for (int i = tid; i < nh * 16; i += kThreads)
       reinterpret_cast<float *>(hp_s)[i] = __ldg(reinterpret_cast<const float *>(hyps + h0) + i);
@@ -157,17 +189,42 @@ verify_kernel(const float4 *__restrict__ src, int ns, GridView g, const HypParam
     mbar_wait(&bar, phase);
     phase ^= 1;
     __syncthreads();
-    for (int h = 0; h < nh; ++h) {
-      const HypParams hp = hp_s[h];
-      int c = 0;
-      for (int i = tid; i < np; i += kThreads) {
-        float4 s = tile[i];
-        c += point_has_inlier(g, hp, rball2, rin2, s.x, s.y, s.z) ? 1 : 0;
+    for (int hg = 0; hg < nh; hg += kHypGroup) {
+      const int hg_end = min(hg + kHypGroup, nh);
+      // ---- filter pass
+      for (int h = hg; h < hg_end; ++h) {
+        const HypParams hp = hp_s[h];
+        for (int i0 = 0; i0 < np; i0 += kThreads) {
+          const int i = i0 + tid;
+          bool pass = false;
+          if (i < np) {
+            const float4 s = tile[i];
+            pass = point_may_have_inlier(g, hp, s.x, s.y, s.z);
+          }
+          const unsigned int m = __ballot_sync(0xffffffffu, pass);
+          if (m) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&q_n, (unsigned int) __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short) (((h - hg) << 10) | i);
+          }
+        }
       }
-      c = __reduce_add_sync(0xffffffffu, c);
-      if ((tid & 31) == 0 && c) atomicAdd(&cnt_s[h], (unsigned int) c);
+      __syncthreads();
+      // ---- search pass
+      const int qn = (int) q_n;
+      for (int j = tid; j < qn; j += kThreads) {
+        const unsigned int e = queue[j];
+        const int h = hg + (int) (e >> 10);
+        const float4 s = tile[e & 1023u];
+        if (point_has_inlier(g, hp_s[h], rball2, rin2, s.x, s.y, s.z)) atomicAdd(&cnt_s[h], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) q_n = 0;
+      // (the next filter pass only appends after its first ballot; q_n = 0 is ordered by the barrier below or by
+      //  the end-of-item barriers)
+      __syncthreads();
     }
-    __syncthreads();
     if (tid < nh && cnt_s[tid]) atomicAdd(&counts[h0 + tid], cnt_s[tid]);
     __syncthreads();
   }
@@ -356,11 +413,17 @@ void verify_hypotheses(Device &dev, const float4 *d_src, size_t ns, const Target
   // static_cast<float>(radius * radius) with radius a double (kdtree_flann.hpp:193)
   float rball2 = (float) ((double) ball_radius * (double) ball_radius);
   float rin2 = (float) ((double) inlier_dist * (double) inlier_dist);
-  GridView g{grid.pts.p, grid.cell_start.p, grid.occ_dil.p, grid.ey, grid.ewords, grid.minx, grid.miny, grid.minz, grid.inv_cell, grid.nx, grid.ny, grid.nz};
+  GridView g{grid.pts.p, grid.cell_start.p, grid.occ_raw.p, grid.occ_dil.p, grid.ey, grid.ewords, grid.minx, grid.miny, grid.minz, grid.inv_cell, grid.nx, grid.ny, grid.nz};
   int n_tiles = div_up((long long) ns, kTile);
   int n_chunks = div_up(H, kHypChunk);
   long long n_work = (long long) n_tiles * n_chunks;
-  int blocks = (int) std::min<long long>(n_work, (long long) dev.num_sms * 4);
+  // persistent grid: every SM filled to the occupancy the kernel's registers / shared memory allow
+  static thread_local int per_sm = 0;
+  if (per_sm == 0) {
+    PLADE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, verify_kernel, kThreads, 0));
+    per_sm = std::max(per_sm, 1);
+  }
+  int blocks = (int) std::min<long long>(n_work, (long long) dev.num_sms * per_sm);
   verify_kernel<<<blocks, kThreads, 0, s>>>(d_src, (int) ns, g, d_hyp, H, rball2, rin2, d_counts, n_tiles, n_chunks);
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
