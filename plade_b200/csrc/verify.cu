@@ -56,8 +56,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
   } while (!ok);
 }
 
-__constant__ int c_row_dy[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
-__constant__ int c_row_dz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+// the nine (dy, dz) rows of the 3x3x3 neighbourhood, nearest first: centre, four edge-adjacent, four corners
+__device__ constexpr int kRowDy[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+__device__ constexpr int kRowDz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
 
 struct GridView {
   const float4 *pts;
@@ -101,6 +102,11 @@ __device__ __forceinline__ bool point_may_have_inlier(const GridView &g, const H
 }
 
 // Search pass, for a point that passed the filter: exact test against the target points of the 27 cells around it.
+// Two steps so that the lanes of a warp stay together: (1) a fixed nine-iteration loop gathers the occupancy bits
+// of the nine rows into one 27-bit mask (rows outside the grid, and corner rows that cannot hold a point within
+// the inlier distance, contribute nothing) — the 1.2 MB bitmap answers "empty" without touching the 4-byte-per-
+// cell CSR table; (2) a loop over the NON-EMPTY rows only, nearest row first (a true inlier is usually found in
+// the centre row), with early exit.
 __device__ __forceinline__ bool point_has_inlier(const GridView &g, const HypParams &hp, float rball2, float rin2,
                                                  float sx, float sy, float sz) {
   float x, y, z;
@@ -114,27 +120,33 @@ __device__ __forceinline__ bool point_has_inlier(const GridView &g, const HypPar
   const unsigned int xmask = (2u << (x1 - x0)) - 1u;     // x1 - x0 + 1 bits
   const int xe0 = x0 + 1, xw = xe0 >> 5, xs = xe0 & 31;
   const bool two_words = xs + (x1 - x0) > 31;
-  // rows (dy, dz) nearest-first: a true inlier is usually found in the centre row, and a corner row can only
-  // hold a point within one cell edge (>= the inlier distance... the cell is 2^-10 larger) of the query if the
-  // query's in-cell offsets towards it satisfy oy^2 + oz^2 < 1 (in cell units; 1.01 leaves room for rounding)
+  // a corner row (dy != 0 and dz != 0) can only hold a point within one cell edge (>= the inlier distance: the cell
+  // is 2^-10 larger) of the query if the query's in-cell offsets towards it satisfy oy^2 + oz^2 < 1 (in cell
+  // units; 1.01 leaves room for rounding)
   const float ry = fy - (float) cy, rz = fz - (float) cz;          // in-cell position, [0, 1)
-  // (rolled loop on purpose: unrolling it leaves the lanes of a warp on nine different code paths)
-#pragma unroll 1
+  unsigned int m27 = 0;
+#pragma unroll
   for (int k = 0; k < 9; ++k) {
-    const int dy = c_row_dy[k], dz = c_row_dz[k];
+    const int dy = kRowDy[k], dz = kRowDz[k];
     const int yy = cy + dy, zz = cz + dz;
-    if (yy < y0 || yy > y1 || zz < z0 || zz > z1) continue;
+    bool ok = yy >= y0 && yy <= y1 && zz >= z0 && zz <= z1;
     if (k >= 5) {
       const float oy = dy < 0 ? ry : 1.0f - ry, oz = dz < 0 ? rz : 1.0f - rz;
-      if (oy * oy + oz * oz > 1.01f) continue;
+      ok = ok && !(oy * oy + oz * oz > 1.01f);
     }
-    // occupancy bits of the (up to) three cells of this row: the 1.2 MB bitmap answers "empty row" from L1/L2
-    // without touching the 4-byte-per-cell CSR table
-    const unsigned int *orow = g.raw + ((size_t) (zz + 1) * g.ey + (yy + 1)) * g.ewords + xw;
-    const unsigned int lo = __ldg(orow), hi = two_words ? __ldg(orow + 1) : 0u;
-    const unsigned int occ = __funnelshift_r(lo, hi, xs) & xmask;
-    if (!occ) continue;
-    const int row = (zz * g.ny + yy) * g.nx + x0;
+    if (ok) {
+      const unsigned int *orow = g.raw + ((size_t) (zz + 1) * g.ey + (yy + 1)) * g.ewords + xw;
+      const unsigned int lo = __ldg(orow), hi = two_words ? __ldg(orow + 1) : 0u;
+      m27 |= (__funnelshift_r(lo, hi, xs) & xmask) << (3 * k);
+    }
+  }
+  while (m27) {
+    const int k = (__ffs(m27) - 1) / 3;
+    const unsigned int occ = (m27 >> (3 * k)) & 7u;
+    m27 &= ~(7u << (3 * k));
+    // dy + 1 and dz + 1 of row k, two bits each, packed (same order as kRowDy / kRowDz)
+    const int dy = (int) ((0x22161u >> (2 * k)) & 3u) - 1, dz = (int) ((0x28215u >> (2 * k)) & 3u) - 1;
+    const int row = ((cz + dz) * g.ny + (cy + dy)) * g.nx + x0;
     const int b = __ldg(g.cell_start + row + (__ffs(occ) - 1)), e = __ldg(g.cell_start + row + (32 - __clz(occ)));
     for (int i = b; i < e; ++i) {
       float4 t = __ldg(g.pts + i);
@@ -159,7 +171,7 @@ verify_kernel(const float4 *__restrict__ src, int ns, GridView g, const HypParam
   __shared__ __align__(16) HypParams hp_s[kHypChunk];
   __shared__ unsigned short queue[kHypGroup * kTile];
   __shared__ unsigned int cnt_s[kHypChunk];
-  __shared__ unsigned int q_n;
+  __shared__ unsigned int q_n[2];
   __shared__ __align__(8) uint64_t bar;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -181,7 +193,7 @@ verify_kernel(const float4 *__restrict__ src, int ns, GridView g, const HypParam
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&bar, (uint32_t) np * 16u);
       tma_load_1d(tile, src + p0, (uint32_t) np * 16u, &bar);
-      q_n = 0;
+      q_n[0] = 0;
     }
     for (int i = tid; i < nh * 16; i += kThreads)
       reinterpret_cast<float *>(hp_s)[i] = __ldg(reinterpret_cast<const float *>(hyps + h0) + i);
@@ -189,7 +201,7 @@ verify_kernel(const float4 *__restrict__ src, int ns, GridView g, const HypParam
     mbar_wait(&bar, phase);
     phase ^= 1;
     __syncthreads();
-    for (int hg = 0; hg < nh; hg += kHypGroup) {
+    for (int hg = 0, par = 0; hg < nh; hg += kHypGroup, par ^= 1) {
       const int hg_end = min(hg + kHypGroup, nh);
       // ---- filter pass
       for (int h = hg; h < hg_end; ++h) {
@@ -204,7 +216,7 @@ verify_kernel(const float4 *__restrict__ src, int ns, GridView g, const HypParam
           const unsigned int m = __ballot_sync(0xffffffffu, pass);
           if (m) {
             unsigned int base = 0;
-            if (lane == 0) base = atomicAdd(&q_n, (unsigned int) __popc(m));
+            if (lane == 0) base = atomicAdd(&q_n[par], (unsigned int) __popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (pass) queue[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short) (((h - hg) << 10) | i);
           }
@@ -212,17 +224,14 @@ verify_kernel(const float4 *__restrict__ src, int ns, GridView g, const HypParam
       }
       __syncthreads();
       // ---- search pass
-      const int qn = (int) q_n;
+      const int qn = (int) q_n[par];
+      if (tid == 0) q_n[par ^ 1] = 0;       // the next group's counter: nobody touches it before the barrier below
       for (int j = tid; j < qn; j += kThreads) {
         const unsigned int e = queue[j];
         const int h = hg + (int) (e >> 10);
         const float4 s = tile[e & 1023u];
         if (point_has_inlier(g, hp_s[h], rball2, rin2, s.x, s.y, s.z)) atomicAdd(&cnt_s[h], 1u);
       }
-      __syncthreads();
-      if (tid == 0) q_n = 0;
-      // (the next filter pass only appends after its first ballot; q_n = 0 is ordered by the barrier below or by
-      //  the end-of-item barriers)
       __syncthreads();
     }
     if (tid < nh && cnt_s[tid]) atomicAdd(&counts[h0 + tid], cnt_s[tid]);
