@@ -50,6 +50,10 @@ long long plade_launch_count(plade_ctx *ctx);     /* kernels launched by this co
  * hypotheses, penetration, verify, total, then the verification kernel of that call as timed with
  * CUDA events on the context stream: kernel_ms, hypotheses, source ds points, target ds points (15 values) */
 int plade_stage_times(plade_ctx *ctx, double *out, int n);
+/* Device time of one kernel family during the last plade_register_* call, measured with CUDA events recorded on
+ * the launching stream around every launch: out = { total ms, launches, algorithmic bytes }.
+ * kernel = "score_candidates" (K1a, 28 B per subsample point per pass) or "verify" (K5).  1 if known. */
+int plade_kernel_times(plade_ctx *ctx, const char *kernel, double out[3]);
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of this context is
  * launched on): start records an event, stop records a second one, waits for it and returns the
  * elapsed device time in milliseconds. */

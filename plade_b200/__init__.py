@@ -31,6 +31,7 @@ SIGNATURES = {
     "plade_set_shard": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ALLREDUCE_FN, ctypes.c_void_p]),
     "plade_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
     "plade_stage_times": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int]),
+    "plade_kernel_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, _c_double_p]),
     "plade_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
     "plade_timer_stop_ms": (ctypes.c_float, [ctypes.c_void_p]),
     "plade_register_files": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, _c_float_p]),
@@ -174,6 +175,13 @@ class Context:
         out = np.zeros(15, dtype=np.float64)
         self.lib.plade_stage_times(self.h, _p(out, _c_double_p), 15)
         return dict(zip(STAGE_NAMES, out.tolist()))
+
+    def kernel_times(self, kernel):
+        """{ms, launches, algorithmic_bytes} of one kernel family during the last registration (CUDA events)."""
+        out = np.zeros(3, dtype=np.float64)
+        if not self.lib.plade_kernel_times(self.h, kernel.encode(), _p(out, _c_double_p)):
+            raise KeyError(kernel)
+        return {"ms": float(out[0]), "launches": int(out[1]), "algorithmic_bytes": float(out[2])}
 
     def timer_start(self):
         self.lib.plade_timer_start(self.h)

@@ -141,6 +141,25 @@ int plade_stage_times(plade_ctx *ctx, double *out, int n) {
   for (int i = 0; i < n && i < 15; ++i) out[i] = v[i];
   return 15;
 }
+int plade_kernel_times(plade_ctx *ctx, const char *kernel, double out[3]) {
+  if (!ctx || !kernel || !out) return 0;
+  out[0] = out[1] = out[2] = 0;
+  const std::string k(kernel);
+  const Registrar &r = *ctx->reg;
+  if (k == "score_candidates") {
+    out[0] = r.dev.clock.ms[KernelClock::kScoreCandidates];
+    out[1] = (double) r.dev.clock.launches[KernelClock::kScoreCandidates];
+    out[2] = r.dev.clock.bytes[KernelClock::kScoreCandidates];
+    return 1;
+  }
+  if (k == "verify") {
+    out[0] = r.times.verify_kernel_ms;
+    out[1] = 1;
+    out[2] = r.times.verify_h * 16.0 * r.times.verify_ns + 16.0 * r.times.verify_nt;
+    return 1;
+  }
+  return 0;
+}
 int plade_timer_start(plade_ctx *ctx) {
   PLADE_TRY(ctx, 0, { PLADE_CUDA(cudaEventRecord(ctx->reg->ev_user0, ctx->reg->dev.stream)); return 1; })
 }

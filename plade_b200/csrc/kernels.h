@@ -7,11 +7,45 @@
 
 namespace plade {
 
+// CUDA-event stopwatch around selected launches of one stream.  begin/end only record events (no host wait);
+// collect() is called once the stream is idle and adds the elapsed device times to the totals that bench.py
+// reads through plade_kernel_times (the roofline figure of the dominant kernel is measured live this way).
+struct KernelClock {
+  enum { kScoreCandidates = 0, kKinds = 1 };
+  struct Span { cudaEvent_t a = nullptr, b = nullptr; int kind = 0; };
+  std::vector<Span> spans;
+  size_t used = 0;
+  double ms[kKinds] = {0}, bytes[kKinds] = {0};
+  long long launches[kKinds] = {0};
+  void begin(int kind, double algorithmic_bytes, cudaStream_t s) {
+    if (used == spans.size()) {
+      Span sp;
+      PLADE_CUDA(cudaEventCreate(&sp.a));
+      PLADE_CUDA(cudaEventCreate(&sp.b));
+      spans.push_back(sp);
+    }
+    spans[used].kind = kind;
+    bytes[kind] += algorithmic_bytes;
+    PLADE_CUDA(cudaEventRecord(spans[used].a, s));
+  }
+  void end(cudaStream_t s) { PLADE_CUDA(cudaEventRecord(spans[used].b, s)); ++used; }
+  void collect() {          // the stream must be idle
+    for (size_t i = 0; i < used; ++i) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, spans[i].a, spans[i].b) == cudaSuccess) { ms[spans[i].kind] += t; ++launches[spans[i].kind]; }
+    }
+    used = 0;
+  }
+  void reset() { used = 0; for (int k = 0; k < kKinds; ++k) { ms[k] = bytes[k] = 0; launches[k] = 0; } }
+  void destroy() { for (Span &sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); } spans.clear(); used = 0; }
+};
+
 struct Device {
   int id = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   LaunchCounter launches;
+  KernelClock clock;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -133,6 +133,8 @@ void Registrar::print_marks() {
 Registrar::~Registrar() {
   free_ransac_scratch(*this);
   for (cudaEvent_t e : {ev0, ev1, ev_user0, ev_user1}) if (e) cudaEventDestroy(e);
+  dev.clock.destroy();
+  dev2.clock.destroy();
   if (dev.stream) cudaStreamDestroy(dev.stream);
   if (dev2.stream) cudaStreamDestroy(dev2.stream);
 }
@@ -182,6 +184,8 @@ float Registrar::average_spacing(const CloudDev &c) {
 
 bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float out16[16]) {
   double t0 = now_s();
+  dev.clock.reset();
+  dev2.clock.reset();
   std::cout << "extracting planes for both point clouds...\n";
   // the two clouds are independent: the source's planes are extracted on a helper thread + stream while
   // this thread does the target's (the kernels are small, so the two lanes overlap on the GPU and the
@@ -200,6 +204,9 @@ bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float 
   helper.join();
   dev.launches.n += dev2.launches.n;
   dev2.launches.n = 0;
+  for (int k = 0; k < KernelClock::kKinds; ++k) {     // fold the helper lane's kernel times into the context's
+    dev.clock.ms[k] += dev2.clock.ms[k]; dev.clock.bytes[k] += dev2.clock.bytes[k]; dev.clock.launches[k] += dev2.clock.launches[k];
+  }
   if (helper_error) std::rethrow_exception(helper_error);
   if ((int) tp.size() < params.min_planes) {
     std::cerr << "too few (only " << tp.size() << ") planes extracted from the target point cloud" << std::endl;

@@ -841,7 +841,9 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     {
       const int n_tiles = div_up(S1, kScoreTile);
       dim3 grid(n_tiles, kCandPerRound / kScoreThreads);
+      dev.clock.begin(KernelClock::kScoreCandidates, 28.0 * S1, s);     // 28 B per point per pass
       score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub1, S1, cand, nullptr, kCandPerRound, eps, nthresh, 1, counts);
+      dev.clock.end(s);
     }
     stage1_keys_kernel<<<div_up(kCandPerRound, 256), 256, 0, s>>>(counts, cidx, kCandPerRound, (int) pool.size());
     {
@@ -854,7 +856,9 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       const int n_tiles = div_up(S, kScoreTile);
       const int tiles_per_block = std::max(1, n_tiles / 128);
       dim3 grid(div_up(n_tiles, tiles_per_block), kStage2Cand / kScoreThreads);
+      dev.clock.begin(KernelClock::kScoreCandidates, 28.0 * S, s);
       score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub, S, cand, cidx_sorted, kStage2Cand, eps, nthresh, tiles_per_block, counts2);
+      dev.clock.end(s);
     }
     gather_planes_kernel<<<1, kStage2Cand, 0, s>>>(cand, cidx_sorted, kStage2Cand, cand_top);
     PLADE_LAUNCH_CHECK();
@@ -1176,6 +1180,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
   PLADE_CUDA(cudaStreamSynchronize(s));
+  dev.clock.collect();
   mark("ransac_output");
   if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade ransac lane %d] candidates evaluated on a band: %d, widened to all points: %d\n", lane, n_band_builds - n_band_full, n_band_full);
   return result;

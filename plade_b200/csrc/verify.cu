@@ -97,7 +97,8 @@ __device__ __forceinline__ bool point_may_have_inlier(const GridView &g, const H
         fz < (float) (g.nz + 1)))
     return false;
   int cx = (int) floorf(fx), cy = (int) floorf(fy), cz = (int) floorf(fz);
-  unsigned int w = __ldg(g.dil + ((size_t) (cz + 1) * g.ey + (cy + 1)) * g.ewords + ((cx + 1) >> 5));
+  // (the bitmap has at most 2^26 / 32 words: 32-bit index arithmetic)
+  unsigned int w = __ldg(g.dil + (unsigned int) (((cz + 1) * g.ey + (cy + 1)) * g.ewords + ((cx + 1) >> 5)));
   return (w >> ((cx + 1) & 31)) & 1u;
 }
 
@@ -135,7 +136,7 @@ __device__ __forceinline__ bool point_has_inlier(const GridView &g, const HypPar
       ok = ok && !(oy * oy + oz * oz > 1.01f);
     }
     if (ok) {
-      const unsigned int *orow = g.raw + ((size_t) (zz + 1) * g.ey + (yy + 1)) * g.ewords + xw;
+      const unsigned int *orow = g.raw + (unsigned int) (((zz + 1) * g.ey + (yy + 1)) * g.ewords + xw);
       const unsigned int lo = __ldg(orow), hi = two_words ? __ldg(orow + 1) : 0u;
       m27 |= (__funnelshift_r(lo, hi, xs) & xmask) << (3 * k);
     }
