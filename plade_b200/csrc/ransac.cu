@@ -43,6 +43,9 @@ constexpr int kStage2Cand = 256;       // stage 2: the best stage-1 candidates .
 constexpr int kSubsample = 65536;      // ... against the large subsample
 constexpr int kScoreTile = 512;       // points per TMA tile (pos + nrm = 16 KB)
 constexpr int kScoreThreads = 256;    // one candidate per thread
+constexpr unsigned int kForcedKey = 2u * kStage1Points;   // stage-1 key of a carried candidate: above every real count
+constexpr int kStage1KeyBits = 14;    // bits of the stage-1 keys (counts <= 4096 < kForcedKey = 8192 < 2^14)
+static_assert(kForcedKey < (1u << kStage1KeyBits) && kStage1Points < (int) kForcedKey, "stage-1 sort key range");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -238,7 +241,7 @@ score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__r
 __global__ void stage1_keys_kernel(unsigned int *__restrict__ counts1, int *__restrict__ idx, int n, int n_forced) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (i < n_forced) counts1[i] = 0xFFFFFFFFu;
+  if (i < n_forced) counts1[i] = kForcedKey;
   idx[i] = i;
 }
 __global__ void gather_planes_kernel(const float4 *__restrict__ cand, const int *__restrict__ sel, int n, float4 *__restrict__ out) {
@@ -312,24 +315,47 @@ __global__ void flag_uv_kernel(const float4 *__restrict__ pos, const float4 *__r
 __global__ void band_compact_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const int *__restrict__ assigned, int n,
                                     float4 pl, float band, float4 *__restrict__ posB, float4 *__restrict__ nrmB, int *__restrict__ idxB,
                                     int *__restrict__ d_nb) {
+  // HBM streaming pass (20 B per point: assigned + pos): four independent loads in flight per thread, the warp's
+  // survivors are appended with one atomic per 4 x 32 points
+  constexpr int kU = 4;
   const unsigned lane = threadIdx.x & 31;
-  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
-    const int i = base + lane;
-    bool in = false;
-    float4 p;
-    if (i < n && assigned[i] == -1) {
-      p = pos[i];
-      float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p.x), __fmul_rn(pl.y, p.y)), __fmul_rn(pl.z, p.z));
-      in = fabsf(__fsub_rn(pl.w, dp)) < band;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (long long base = (long long) warp * (32 * kU); base < n; base += (long long) n_warps * (32 * kU)) {
+    int a[kU];
+    float4 p[kU];
+    bool in[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = base + u * 32 + lane;
+      a[u] = i < n ? __ldg(assigned + i) : 0;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, in);
-    if (!bal) continue;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = base + u * 32 + lane;
+      p[u] = (i < n && a[u] == -1) ? __ldg(pos + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    unsigned bal[kU];
+    int total = 0;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = base + u * 32 + lane;
+      float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p[u].x), __fmul_rn(pl.y, p[u].y)), __fmul_rn(pl.z, p[u].z));
+      in[u] = i < n && a[u] == -1 && fabsf(__fsub_rn(pl.w, dp)) < band;
+      bal[u] = __ballot_sync(0xffffffffu, in[u]);
+      total += __popc(bal[u]);
+    }
+    if (!total) continue;
     int start = 0;
-    if (lane == 0) start = atomicAdd(d_nb, __popc(bal));
+    if (lane == 0) start = atomicAdd(d_nb, total);
     start = __shfl_sync(0xffffffffu, start, 0);
-    if (in) {
-      const int k = start + __popc(bal & ((1u << lane) - 1));
-      posB[k] = p; nrmB[k] = nrm[i]; idxB[k] = i;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (in[u]) {
+        const int i = (int) (base + u * 32 + lane);
+        const int k = start + __popc(bal[u] & ((1u << lane) - 1));
+        posB[k] = p[u]; nrmB[k] = __ldg(nrm + i); idxB[k] = i;
+      }
+      start += __popc(bal[u]);
     }
   }
 }
@@ -359,7 +385,7 @@ struct BmpInfo { float umin, vmin; int ue, ve; int ok; int overflow; int pad0, p
 constexpr int kBmpCap = 1 << 20;       // pixels; larger bitmaps take the host path
 constexpr float kBandMul = 3.f;        // half-width of a candidate's band in units of eps3 (= 3 eps)
 
-__global__ void bmp_setup_kernel(const int *__restrict__ uvbox, float bmp_eps, BmpInfo *__restrict__ info) {
+__device__ __forceinline__ BmpInfo bmp_info_from_box(const int *uvbox, float bmp_eps) {
   int a[4];
   float uv[4];
   for (int k = 0; k < 4; ++k) { a[k] = uvbox[k]; a[k] = a[k] >= 0 ? a[k] : a[k] ^ 0x7fffffff; uv[k] = __int_as_float(a[k]); }
@@ -372,13 +398,15 @@ __global__ void bmp_setup_kernel(const int *__restrict__ uvbox, float bmp_eps, B
     if (ve < 2) ve = 2;
     if (ue * ve <= kBmpCap) { r.ue = (int) ue; r.ve = (int) ve; r.ok = 1; } else r.overflow = 1;
   }
-  *info = r;
+  return r;
 }
 
+// (the bitmap geometry is derived from the (u, v) box by every thread; block 0 publishes it for the later passes)
 __global__ void raster_dev_kernel(const float4 *__restrict__ pos, const unsigned char *__restrict__ flag, const int *__restrict__ d_count,
-                                  PlaneFrame f, float bmp_eps, const BmpInfo *__restrict__ info, int *__restrict__ pix,
+                                  PlaneFrame f, float bmp_eps, const int *__restrict__ uvbox, BmpInfo *__restrict__ info, int *__restrict__ pix,
                                   unsigned char *__restrict__ bitmap) {
-  const BmpInfo I = *info;
+  const BmpInfo I = bmp_info_from_box(uvbox, bmp_eps);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *info = I;
   if (!I.ok) return;
   const int n = *d_count;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -400,12 +428,9 @@ __global__ void raster_dev_kernel(const float4 *__restrict__ pos, const unsigned
 // One block: cross closing (dilate, erode; R/Bitmap.cpp:154,459), 8-connected labelling by min-label
 // propagation with pointer jumping, largest component by PIXEL count (first in raster order on ties,
 // R/BitmapPrimitiveShape.cpp:170-173) -> mask.  Leaves the bitmap cleared for the next evaluation.
-__global__ void __launch_bounds__(1024)
-cc_kernel(unsigned char *__restrict__ bitmap, unsigned char *__restrict__ tmp, int *__restrict__ lab, int *__restrict__ cnt,
-          const BmpInfo *__restrict__ info, unsigned char *__restrict__ mask) {
+__device__ void cc_block(unsigned char *bitmap, unsigned char *tmp, int *lab, int *cnt, const BmpInfo I, unsigned char *mask) {
   __shared__ int changed;
   __shared__ unsigned long long best;
-  const BmpInfo I = *info;
   if (!I.ok) return;
   const int ue = I.ue, ve = I.ve, P = ue * ve, tid = threadIdx.x, nt = blockDim.x;
   for (int p = tid; p < P; p += nt) {
@@ -455,17 +480,18 @@ cc_kernel(unsigned char *__restrict__ bitmap, unsigned char *__restrict__ tmp, i
   const int bl = best ? (int) (0xFFFFFFFFu - (unsigned int) (best & 0xFFFFFFFFull)) : -2;
   for (int p = tid; p < P; p += nt) { mask[p] = (lab[p] == bl) ? 1 : 0; bitmap[p] = 0; }
 }
-
-__global__ void mean_kernel(const double *__restrict__ acc, float *__restrict__ mean3) {
-  double c = acc[0];
-  if (c > 0) { mean3[0] = (float) (acc[1] / c); mean3[1] = (float) (acc[2] / c); mean3[2] = (float) (acc[3] / c); }
-  else { mean3[0] = mean3[1] = mean3[2] = 0.f; }
+__global__ void __launch_bounds__(1024)
+cc_kernel(unsigned char *bitmap, unsigned char *tmp, int *lab, int *cnt, const BmpInfo *__restrict__ info, unsigned char *mask) {
+  cc_block(bitmap, tmp, lab, cnt, *info, mask);
 }
 
 __global__ void cov_dev_kernel(const float4 *__restrict__ pos, const int *__restrict__ idx, const unsigned char *__restrict__ member,
-                               const int *__restrict__ d_count, const float *__restrict__ mean3, double *__restrict__ acc6) {
+                               const int *__restrict__ d_count, const double *__restrict__ acc, double *__restrict__ acc6) {
   const int n = *d_count;
-  const float mx = mean3[0], my = mean3[1], mz = mean3[2];
+  // float mean of the members (GfxTL::Mean) from the sums of the select pass: acc = {count, sx, sy, sz}
+  const double cnt = acc[0];
+  if (!(cnt > 0)) return;
+  const float mx = (float) (acc[1] / cnt), my = (float) (acc[2] / cnt), mz = (float) (acc[3] / cnt);
   double c[6] = {0, 0, 0, 0, 0, 0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (!member[idx[i]]) continue;
@@ -586,9 +612,9 @@ struct IsUnassigned {
 
 // ---- host pieces ----------------------------------------------------------------------------------------
 // HyperplaneCoordinateSystem::FromNormal (R/GfxTL/HyperplaneCoordinateSystem.h:81-93), AutoCAD arbitrary axis
-void frame_from_normal(const float n[3], float u[3], float v[3]) {
+__host__ __device__ void frame_from_normal(const float n[3], float u[3], float v[3]) {
   V3 N(n[0], n[1], n[2]), a0;
-  if (std::fabs(n[0]) < 0.015625f && std::fabs(n[1]) < 0.015625f) a0 = cross(V3(0, 1, 0), N);
+  if (fabsf(n[0]) < 0.015625f && fabsf(n[1]) < 0.015625f) a0 = cross(V3(0, 1, 0), N);
   else a0 = cross(V3(0, 0, 1), N);
   normalize(a0);
   V3 a1 = cross(N, a0);
@@ -649,47 +675,416 @@ void largest_component(std::vector<unsigned char> &bmp, int ue, int ve, std::vec
 // Jacobi eigen-solver for symmetric 3x3 (float), the textbook cyclic algorithm started from V = I that
 // R/GfxTL/Jacobi.h implements; the eigenvector of smallest |eigenvalue| is the plane normal and its
 // sign is whatever the rotation sequence produces (it is never flipped afterwards).
-bool jacobi3f(float a[3][3], float d[3], float v[3][3]) {
+__host__ __device__ bool jacobi3f(float a[3][3], float d[3], float v[3][3]) {
   float b[3], z[3];
   for (int ip = 0; ip < 3; ++ip) { for (int iq = 0; iq < 3; ++iq) v[ip][iq] = 0.f; v[ip][ip] = 1.f; }
   for (int ip = 0; ip < 3; ++ip) { b[ip] = d[ip] = a[ip][ip]; z[ip] = 0.f; }
   for (int i = 1; i <= 200; ++i) {
     float sm = 0.f;
-    for (int ip = 0; ip < 2; ++ip) for (int iq = ip + 1; iq < 3; ++iq) sm += std::fabs(a[ip][iq]);
+    for (int ip = 0; ip < 2; ++ip) for (int iq = ip + 1; iq < 3; ++iq) sm += fabsf(a[ip][iq]);
     if (sm == 0.f) return true;
     float tresh = i < 4 ? 0.2f * sm / 9.f : 0.f;
     for (int ip = 0; ip < 2; ++ip)
       for (int iq = ip + 1; iq < 3; ++iq) {
-        float g = 100.f * std::fabs(a[ip][iq]);
-        volatile float t1 = std::fabs(d[ip]) + g, t2 = std::fabs(d[iq]) + g;
-        if (i > 4 && t1 == std::fabs(d[ip]) && t2 == std::fabs(d[iq])) a[ip][iq] = 0.f;
-        else if (std::fabs(a[ip][iq]) > tresh) {
+        float g = 100.f * fabsf(a[ip][iq]);
+        volatile float t1 = fabsf(d[ip]) + g, t2 = fabsf(d[iq]) + g;
+        if (i > 4 && t1 == fabsf(d[ip]) && t2 == fabsf(d[iq])) a[ip][iq] = 0.f;
+        else if (fabsf(a[ip][iq]) > tresh) {
           float h = d[iq] - d[ip], t;
-          volatile float t3 = std::fabs(h) + g;
-          if (t3 == std::fabs(h)) t = a[ip][iq] / h;
+          volatile float t3 = fabsf(h) + g;
+          if (t3 == fabsf(h)) t = a[ip][iq] / h;
           else {
             float theta = 0.5f * h / a[ip][iq];
-            t = 1.f / (std::fabs(theta) + std::sqrt(1.f + theta * theta));
+            t = 1.f / (fabsf(theta) + sqrtf(1.f + theta * theta));
             if (theta < 0.f) t = -t;
           }
-          float c = 1.f / std::sqrt(1.f + t * t), s = t * c, tau = s / (1.f + c);
+          float c = 1.f / sqrtf(1.f + t * t), s = t * c, tau = s / (1.f + c);
           h = t * a[ip][iq];
           z[ip] -= h; z[iq] += h; d[ip] -= h; d[iq] += h;
           a[ip][iq] = 0.f;
-          auto rot = [&](float m[3][3], int i1, int j1, int i2, int j2) {
-            float gg = m[i1][j1], hh = m[i2][j2];
-            m[i1][j1] = gg - s * (hh + gg * tau);
-            m[i2][j2] = hh + s * (gg - hh * tau);
-          };
-          for (int j = 0; j <= ip - 1; ++j) rot(a, j, ip, j, iq);
-          for (int j = ip + 1; j <= iq - 1; ++j) rot(a, ip, j, j, iq);
-          for (int j = iq + 1; j < 3; ++j) rot(a, ip, j, iq, j);
-          for (int j = 0; j < 3; ++j) rot(v, j, ip, j, iq);
+#define PLADE_JROT(m, i1, j1, i2, j2) { float gg = m[i1][j1], hh = m[i2][j2]; m[i1][j1] = gg - s * (hh + gg * tau); m[i2][j2] = hh + s * (gg - hh * tau); }
+          for (int j = 0; j <= ip - 1; ++j) PLADE_JROT(a, j, ip, j, iq)
+          for (int j = ip + 1; j <= iq - 1; ++j) PLADE_JROT(a, ip, j, j, iq)
+          for (int j = iq + 1; j < 3; ++j) PLADE_JROT(a, ip, j, iq, j)
+          for (int j = 0; j < 3; ++j) PLADE_JROT(v, j, ip, j, iq)
+#undef PLADE_JROT
         }
       }
     for (int ip = 0; ip < 3; ++ip) { b[ip] += z[ip]; d[ip] = b[ip]; z[ip] = 0.f; }
   }
   return false;
+}
+
+// result of one full evaluation of a plane: support of the largest connected component, gaussian-weighted score,
+// position sums of its members
+struct Eval { long long size; double score; double sum[3]; bool ok; };
+
+// PlanePrimitiveShape(normal, position): plane + in-plane frame
+__host__ __device__ PlaneFrame make_plane_frame(const float nrm3[3], const float pos3[3]) {
+  PlaneFrame f;
+  float u[3], v[3];
+  frame_from_normal(nrm3, u, v);
+  float dist = (pos3[0] * nrm3[0] + pos3[1] * nrm3[1]) + pos3[2] * nrm3[2];   // m_pos.dot(m_normal)
+  f.pl = make_float4(nrm3[0], nrm3[1], nrm3[2], dist);
+  f.pos = make_float3(pos3[0], pos3[1], pos3[2]);
+  f.u = make_float3(u[0], u[1], u[2]);
+  f.v = make_float3(v[0], v[1], v[2]);
+  return f;
+}
+
+// Plane::LeastSquaresFit (R/Plane.h:66-74) from the member sums: mean, covariance about float(mean), eigenvector
+// of the smallest |eigenvalue| (sign as the Jacobi rotations leave it)
+__host__ __device__ bool fit_plane_from_cov(const Eval &e, const double h[6], float nrm3[3], float pos3[3]) {
+  float a[3][3], d[3], v[3][3];
+  a[0][0] = (float) (h[0] / e.size); a[0][1] = a[1][0] = (float) (h[1] / e.size); a[0][2] = a[2][0] = (float) (h[2] / e.size);
+  a[1][1] = (float) (h[3] / e.size); a[1][2] = a[2][1] = (float) (h[4] / e.size); a[2][2] = (float) (h[5] / e.size);
+  if (!jacobi3f(a, d, v)) return false;
+  int k = 0;
+  for (int j = 1; j < 3; ++j) if (fabsf(d[j]) < fabsf(d[k])) k = j;
+  nrm3[0] = v[0][k]; nrm3[1] = v[1][k]; nrm3[2] = v[2][k];
+  pos3[0] = (float) (e.sum[0] / e.size); pos3[1] = (float) (e.sum[1] / e.size); pos3[2] = (float) (e.sum[2] / e.size);
+  return true;
+}
+
+// Can a point outside the band (|d_band(x)| < halfwidth) be within eps3 of plane `pl`?  d_pl(x) - d_band(x) is affine
+// in x, so over the bounding box of the cloud its extreme values sit at the corners; if they stay below
+// halfwidth - eps3 (minus float slack) every inlier of `pl` lies inside the band.  The fitted normal may be flipped.
+__host__ __device__ bool band_covers_plane(const float4 &band_pl, float halfwidth, const float4 &pl, const float mn[3], const float mx[3],
+                                           float ext, float eps3) {
+  double worst[2] = {0, 0};
+  for (int k = 0; k < 8; ++k) {
+    const double x = (k & 1) ? mx[0] : mn[0], y = (k & 2) ? mx[1] : mn[1], z = (k & 4) ? mx[2] : mn[2];
+    const double db = band_pl.w - (band_pl.x * x + band_pl.y * y + band_pl.z * z);
+    const double dp = pl.w - (pl.x * x + pl.y * y + pl.z * z);
+    worst[0] = fmax(worst[0], fabs(dp - db));
+    worst[1] = fmax(worst[1], fabs(-dp - db));
+  }
+  const double slack = 1e-5 * (double) ext + 1e-3 * eps3;
+  return fmin(worst[0], worst[1]) + eps3 + slack <= (double) halfwidth;
+}
+
+// ---- candidate refinement as ONE thread-block-cluster kernel --------------------------------------------------
+// The acceptance test of a candidate (RansacShapeDetector.cpp:619-655) is a chain of up to four full evaluations
+// -- inlier flags + (u, v) box -> bitmap -> closing + connected components -> members + score -> covariance ->
+// least-squares refit -> next evaluation -- each a handful of passes over the candidate's band (10^5 points) with
+// a tiny serial decision in between.  As separate launches that is ~20 kernels and 3-4 host round trips per
+// candidate, all latency.  Here one cluster of kRefCluster CTAs (hardware co-scheduled, barrier.cluster between
+// the passes) runs the whole chain, the refit and the accept logic included, on 16 of the 148 SMs, so the other
+// lane / other contexts keep the rest of the GPU busy and the host synchronises once per candidate.
+constexpr int kRefThreads = 1024;
+constexpr int kRefUnroll = 4;        // band points per thread and batch
+constexpr int kRefUnroll1 = 2;       // ... in the first pass (position + normal per point)
+
+struct RefineCtl {        // written by the boss thread between evaluations, read by every thread after the barrier
+  PlaneFrame frame;
+  int go;                 // 1: evaluate `frame` into membership map `member_sel`
+  int member_sel;
+  int pad0, pad1;
+};
+struct RefineOut {
+  long long acc_size;     // support of the accepted (possibly refitted) plane; 0 if the candidate has no inliers
+  float acc_n[3], acc_p[3];
+  int acc_sel;            // membership map that holds its members (0 = A, 1 = B)
+  int status;             // 0 = done, 1 = bitmap larger than the device cap (host path), 2 = a refit left the band
+  int evals;
+  int pad;
+};
+struct RefineArgs {
+  const float4 *posB, *nrmB;
+  const int *idxB, *d_nb;
+  unsigned char *flag;
+  int *pix;
+  unsigned char *bmp, *btmp, *bmask;
+  int *lab, *ccnt;
+  unsigned char *member_a, *member_b;
+  int *uvbox;
+  double *acc;
+  RefineCtl *ctl;
+  RefineOut *out;
+  float4 cand_pl, band_pl;
+  float eps3, nthresh, bmp_eps, band_halfwidth, ext;
+  float mn[3], mx[3];
+  int min_support, band_full;
+};
+
+__device__ __forceinline__ double block_sum(double v, double *sh /* 32 */) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;      // valid in thread 0
+}
+__device__ __forceinline__ float block_minmax(float v, bool is_min, float *sh /* 32 */) {
+  for (int o = 16; o > 0; o >>= 1) { float t = __shfl_down_sync(0xffffffffu, v, o); v = is_min ? fminf(v, t) : fmaxf(v, t); }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : (is_min ? 3.4e38f : -3.4e38f);
+  if (w == 0) for (int o = 16; o > 0; o >>= 1) { float t = __shfl_down_sync(0xffffffffu, v, o); v = is_min ? fminf(v, t) : fmaxf(v, t); }
+  return v;      // valid in thread 0
+}
+__device__ __forceinline__ unsigned int cluster_rank() { unsigned int r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned int cluster_size() { unsigned int r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// barrier over all threads of the cluster; release/acquire at cluster scope orders the global-memory traffic of the passes
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const RefineArgs a) {
+  __shared__ double sh_d[32];
+  __shared__ float sh_f[32];
+  const int rank = (int) cluster_rank(), nth = (int) cluster_size() * kRefThreads;
+  const int gt = rank * kRefThreads + threadIdx.x;
+  const bool boss = gt == 0;
+  const int n = *a.d_nb;
+  const float denom = 2.f / 9.f * a.eps3 * a.eps3;
+  volatile RefineCtl *ctl = a.ctl;
+
+  // boss-only state of the refinement loop (RansacShapeDetector.cpp:619-655; the host version is in detect_planes_dev),
+  // kept in shared memory so that it does not occupy registers of the 16K threads that never touch it
+  struct Boss {
+    Eval clone;
+    double cov_clone[6], newScore, oldScore;
+    float acc_n[3], acc_p[3], fn[3], fp[3];
+    long long acc_size;
+    int acc_sel, work_sel, iter, status, evals;
+  };
+  __shared__ Boss B;
+  if (boss) {
+    B.clone = Eval{0, 0, {0, 0, 0}, false};
+    for (int k = 0; k < 6; ++k) B.cov_clone[k] = 0;
+    B.newScore = B.oldScore = 0;
+    B.acc_n[0] = a.cand_pl.x; B.acc_n[1] = a.cand_pl.y; B.acc_n[2] = a.cand_pl.z;
+    // position of the 3-point plane: any point on it (the reference keeps the first sample); n * dist lies on the plane
+    B.acc_p[0] = a.cand_pl.x * a.cand_pl.w; B.acc_p[1] = a.cand_pl.y * a.cand_pl.w; B.acc_p[2] = a.cand_pl.z * a.cand_pl.w;
+    for (int k = 0; k < 3; ++k) B.fn[k] = B.fp[k] = 0;
+    B.acc_size = 0;
+    B.acc_sel = 0; B.work_sel = 1; B.iter = 0; B.status = 0; B.evals = 0;
+  }
+
+  auto publish = [&](const PlaneFrame &f, int sel, int go) {     // boss: next evaluation + clean accumulators
+    RefineCtl c;
+    c.frame = f; c.go = go; c.member_sel = sel; c.pad0 = c.pad1 = 0;
+    *a.ctl = c;
+    a.uvbox[0] = a.uvbox[1] = f2o(3.4e38f);
+    a.uvbox[2] = a.uvbox[3] = f2o(-3.4e38f);
+    for (int k = 0; k < 16; ++k) a.acc[k] = 0.0;
+    __threadfence();
+  };
+  // boss: top of the do-loop body -- refit the clone and, if the refit stays inside the band, evaluate it next
+  auto try_next = [&]() -> bool {
+    ++B.iter;
+    B.oldScore = B.newScore;
+    if (!fit_plane_from_cov(B.clone, B.cov_clone, B.fn, B.fp)) return false;
+    PlaneFrame f2 = make_plane_frame(B.fn, B.fp);
+    if (!a.band_full && !band_covers_plane(a.band_pl, a.band_halfwidth, f2.pl, a.mn, a.mx, a.ext, a.eps3)) { B.status = 2; return false; }
+    publish(f2, B.work_sel, 1);
+    return true;
+  };
+  if (boss) {
+    PlaneFrame f0 = make_plane_frame(B.acc_n, B.acc_p);
+    f0.pl.w = a.cand_pl.w;
+    publish(f0, B.acc_sel, 1);
+  }
+  cluster_barrier();
+
+  for (int ev = 0; ev < 4; ++ev) {
+    if (!ctl->go) break;                       // uniform over the cluster
+    PlaneFrame f;
+    f.pl = make_float4(ctl->frame.pl.x, ctl->frame.pl.y, ctl->frame.pl.z, ctl->frame.pl.w);
+    f.pos = make_float3(ctl->frame.pos.x, ctl->frame.pos.y, ctl->frame.pos.z);
+    f.u = make_float3(ctl->frame.u.x, ctl->frame.u.y, ctl->frame.u.z);
+    f.v = make_float3(ctl->frame.v.x, ctl->frame.v.y, ctl->frame.v.z);
+    unsigned char *member = ctl->member_sel ? a.member_b : a.member_a;
+
+    // Every pass walks the band in batches of kRefUnroll points per thread with all loads of a batch issued before
+    // the first use: a pass is a dependent-latency chain (a dozen points per thread), not a bandwidth problem.
+    // pass 1: inlier flags at eps3 + (u, v) box (flag_uv_kernel)
+    {
+      float umin = 3.4e38f, vmin = 3.4e38f, umax = -3.4e38f, vmax = -3.4e38f;
+      for (int base = gt; base < n; base += kRefUnroll1 * nth) {
+        float4 p[kRefUnroll1], nr[kRefUnroll1];
+#pragma unroll
+        for (int u = 0; u < kRefUnroll1; ++u) {
+          const int ic = min(base + u * nth, n - 1);          // clamped: the loads are unconditional (no partially
+          p[u] = __ldg(a.posB + ic); nr[u] = __ldg(a.nrmB + ic);   // defined arrays, which would live in local memory)
+        }
+#pragma unroll
+        for (int u = 0; u < kRefUnroll1; ++u) {
+          const int i = base + u * nth;
+          if (i >= n) continue;
+          const bool in = compatible(f.pl, p[u], nr[u], a.eps3, a.nthresh);
+          a.flag[i] = in ? 1 : 0;
+          if (in) {
+            float px = __fsub_rn(p[u].x, f.pos.x), py = __fsub_rn(p[u].y, f.pos.y), pz = __fsub_rn(p[u].z, f.pos.z);
+            float uu = __fadd_rn(__fadd_rn(__fmul_rn(px, f.u.x), __fmul_rn(py, f.u.y)), __fmul_rn(pz, f.u.z));
+            float vv = __fadd_rn(__fadd_rn(__fmul_rn(px, f.v.x), __fmul_rn(py, f.v.y)), __fmul_rn(pz, f.v.z));
+            umin = fminf(umin, uu); umax = fmaxf(umax, uu); vmin = fminf(vmin, vv); vmax = fmaxf(vmax, vv);
+          }
+        }
+      }
+      float r0 = block_minmax(umin, true, sh_f), r1 = block_minmax(vmin, true, sh_f);
+      float r2 = block_minmax(umax, false, sh_f), r3 = block_minmax(vmax, false, sh_f);
+      if (threadIdx.x == 0) {
+        atomicMin(a.uvbox + 0, f2o(r0)); atomicMin(a.uvbox + 1, f2o(r1));
+        atomicMax(a.uvbox + 2, f2o(r2)); atomicMax(a.uvbox + 3, f2o(r3));
+      }
+    }
+    cluster_barrier();
+    // pass 2: bitmap geometry + rasterisation (raster_dev_kernel)
+    int box[4];
+    for (int k = 0; k < 4; ++k) box[k] = __ldcg(a.uvbox + k);
+    const BmpInfo I = bmp_info_from_box(box, a.bmp_eps);
+    if (I.ok) {
+      for (int base = gt; base < n; base += kRefUnroll * nth) {
+        float4 p[kRefUnroll];
+        unsigned int fl[kRefUnroll];
+#pragma unroll
+        for (int u = 0; u < kRefUnroll; ++u) {
+          const int i = base + u * nth, ic = min(i, n - 1);
+          fl[u] = a.flag[ic]; p[u] = __ldg(a.posB + ic);
+          if (i >= n) fl[u] = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kRefUnroll; ++u) {
+          const int i = base + u * nth;
+          if (!fl[u]) continue;
+          float px = __fsub_rn(p[u].x, f.pos.x), py = __fsub_rn(p[u].y, f.pos.y), pz = __fsub_rn(p[u].z, f.pos.z);
+          float uu = __fadd_rn(__fadd_rn(__fmul_rn(px, f.u.x), __fmul_rn(py, f.u.y)), __fmul_rn(pz, f.u.z));
+          float vv = __fadd_rn(__fadd_rn(__fmul_rn(px, f.v.x), __fmul_rn(py, f.v.y)), __fmul_rn(pz, f.v.z));
+          int bu = (int) floorf(__fdiv_rn(__fsub_rn(uu, I.umin), a.bmp_eps));
+          int bv = (int) floorf(__fdiv_rn(__fsub_rn(vv, I.vmin), a.bmp_eps));
+          bu = min(max(bu, 0), I.ue - 1);
+          bv = min(max(bv, 0), I.ve - 1);
+          const int id = bu + bv * I.ue;
+          a.pix[i] = id;
+          a.bmp[id] = 1;
+        }
+      }
+    }
+    cluster_barrier();
+    // pass 3: closing + connected components on CTA 0 (cc_kernel); leaves the bitmap cleared
+    if (rank == 0) cc_block(a.bmp, a.btmp, a.lab, a.ccnt, I, a.bmask);
+    cluster_barrier();
+    // pass 4: members of the largest component, their count / position sums / weighted score (select_dev_kernel);
+    // the member bit is also kept next to the flag (bit 1) for pass 5
+    {
+      double cnt = 0, sx = 0, sy = 0, sz = 0, sc = 0;
+      for (int base = gt; base < n; base += kRefUnroll * nth) {
+        float4 p[kRefUnroll];
+        int gi[kRefUnroll], px[kRefUnroll];
+        unsigned int fl[kRefUnroll], mk[kRefUnroll];
+#pragma unroll
+        for (int u = 0; u < kRefUnroll; ++u) {
+          const int i = base + u * nth, ic = min(i, n - 1);
+          fl[u] = a.flag[ic]; px[u] = a.pix[ic];
+          gi[u] = __ldg(a.idxB + ic);
+          p[u] = __ldg(a.posB + ic);
+          if (i >= n || !I.ok) fl[u] = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kRefUnroll; ++u) mk[u] = fl[u] ? (unsigned int) __ldcg(a.bmask + px[u]) : 0u;   // pix is only defined where flagged
+#pragma unroll
+        for (int u = 0; u < kRefUnroll; ++u) {
+          const int i = base + u * nth;
+          if (i >= n) continue;
+          const bool mem = fl[u] && mk[u];
+          member[gi[u]] = mem ? 1 : 0;
+          a.flag[i] = (unsigned char) ((fl[u] & 1) | (mem ? 2 : 0));
+          if (mem) {
+            float dp = __fadd_rn(__fadd_rn(__fmul_rn(f.pl.x, p[u].x), __fmul_rn(f.pl.y, p[u].y)), __fmul_rn(f.pl.z, p[u].z));
+            float d = fabsf(__fsub_rn(f.pl.w, dp));
+            cnt += 1; sx += p[u].x; sy += p[u].y; sz += p[u].z;
+            sc += (double) expf(-d * d / denom);
+          }
+        }
+      }
+      double r0 = block_sum(cnt, sh_d), r1 = block_sum(sx, sh_d), r2 = block_sum(sy, sh_d), r3 = block_sum(sz, sh_d), r4 = block_sum(sc, sh_d);
+      if (threadIdx.x == 0 && r0 > 0) {
+        atomicAdd(a.acc + 0, r0); atomicAdd(a.acc + 1, r1); atomicAdd(a.acc + 2, r2); atomicAdd(a.acc + 3, r3); atomicAdd(a.acc + 4, r4);
+      }
+    }
+    cluster_barrier();
+    // pass 5: covariance about float(mean) of the members (cov_dev_kernel)
+    {
+      const double cnt = __ldcg(a.acc + 0);
+      if (cnt > 0) {
+        const float mx = (float) (__ldcg(a.acc + 1) / cnt), my = (float) (__ldcg(a.acc + 2) / cnt), mz = (float) (__ldcg(a.acc + 3) / cnt);
+        double c[6] = {0, 0, 0, 0, 0, 0};
+        for (int base = gt; base < n; base += kRefUnroll * nth) {
+          float4 p[kRefUnroll];
+          unsigned int fl[kRefUnroll];
+#pragma unroll
+          for (int u = 0; u < kRefUnroll; ++u) {
+            const int i = base + u * nth, ic = min(i, n - 1);
+            fl[u] = a.flag[ic]; p[u] = __ldg(a.posB + ic);
+            if (i >= n) fl[u] = 0;
+          }
+#pragma unroll
+          for (int u = 0; u < kRefUnroll; ++u) {
+            if (!(fl[u] & 2)) continue;
+            double dx = (double) (p[u].x - mx), dy = (double) (p[u].y - my), dz = (double) (p[u].z - mz);
+            c[0] += dx * dx; c[1] += dx * dy; c[2] += dx * dz; c[3] += dy * dy; c[4] += dy * dz; c[5] += dz * dz;
+          }
+        }
+        for (int k = 0; k < 6; ++k) {
+          double r = block_sum(c[k], sh_d);
+          if (threadIdx.x == 0 && r != 0) atomicAdd(a.acc + 8 + k, r);
+        }
+      }
+    }
+    cluster_barrier();
+    // decision (boss thread): the loop of RansacShapeDetector.cpp:619-655
+    if (boss) {
+      ++B.evals;
+      Eval e;
+      double cov[6];
+      e.size = (long long) __ldcg(a.acc + 0);
+      e.sum[0] = __ldcg(a.acc + 1); e.sum[1] = __ldcg(a.acc + 2); e.sum[2] = __ldcg(a.acc + 3);
+      e.score = __ldcg(a.acc + 4);
+      e.ok = e.size > 0;
+      for (int k = 0; k < 6; ++k) cov[k] = __ldcg(a.acc + 8 + k);
+      bool go = false;
+      if (ev == 0) {
+        if (I.overflow) B.status = 1;
+        else {
+          B.acc_size = e.ok ? e.size : 0;
+          if (e.ok) {
+            B.clone = e;
+            for (int k = 0; k < 6; ++k) B.cov_clone[k] = cov[k];
+            B.newScore = B.clone.score;
+            B.iter = 0;
+            go = try_next();
+          }
+        }
+      } else if (!I.overflow) {
+        B.newScore = e.score;
+        if (e.ok) {
+          B.clone = e;
+          for (int k = 0; k < 6; ++k) B.cov_clone[k] = cov[k];
+          if (B.newScore > B.oldScore && e.size > a.min_support) {
+            for (int k = 0; k < 3; ++k) { B.acc_n[k] = B.fn[k]; B.acc_p[k] = B.fp[k]; }
+            B.acc_size = e.size;
+            const int t = B.acc_sel; B.acc_sel = B.work_sel; B.work_sel = t;      // the B.clone becomes the candidate
+          }
+          if (B.newScore > B.oldScore && B.iter < 3) go = try_next();
+        }
+      }
+      if (!go) { a.ctl->go = 0; __threadfence(); }
+    }
+    cluster_barrier();
+  }
+  if (boss) {
+    RefineOut o;
+    o.acc_size = B.acc_size;
+    for (int k = 0; k < 3; ++k) { o.acc_n[k] = B.acc_n[k]; o.acc_p[k] = B.acc_p[k]; }
+    o.acc_sel = B.acc_sel; o.status = B.status; o.evals = B.evals; o.pad = 0;
+    *a.out = o;
+  }
 }
 
 double failure_probability(double size, double n, double drawn, double levels) {
@@ -708,7 +1103,30 @@ struct RansacScratch {
   DevBuf<float> mean3;
   bool bmp_dev_clean = false;
   DevBuf<double> acc;
+  DevBuf<double> refine_mem;      // RefineCtl at +0, RefineOut at +128 bytes
 };
+
+// cluster size of refine_cluster_kernel on this device: 16 (non-portable) when the GPU can co-schedule it, else 8
+int refine_cluster_size() {
+  static const int cached = [] {       // (thread-safe: the two lanes of a context ask concurrently)
+  int size = 0;
+  if (getenv("PLADE_NO_CLUSTER_REFINE")) return size;
+  for (int want : {16, 8}) {
+    if (want > 8 && cudaFuncSetAttribute(refine_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(want); cfg.blockDim = dim3(kRefThreads);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, refine_cluster_kernel, &cfg) == cudaSuccess && n_clusters >= 1) { size = want; break; }
+    cudaGetLastError();
+  }
+  return size;
+  }();
+  return cached;
+}
 
 struct FoundPlane { float n[3]; float pos[3]; long long size; };
 
@@ -797,7 +1215,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   float4 *posB = rs.band_pos.ensure(n), *nrmB = rs.band_nrm.ensure(n);
   int *idxB = rs.band_idx.ensure(n);
   const int blocks_b = std::min(blocks_n, dev.num_sms * 4);
-  int n_band_builds = 0, n_band_full = 0;
+  int n_band_builds = 0, n_band_full = 0, n_cluster_fallbacks = 0;
   float4 *cand = rs.cand.ensure(kCandPerRound);
   unsigned int *counts = rs.counts.ensure(kCandPerRound);
   double *acc = rs.acc.ensure(16);
@@ -848,9 +1266,9 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     stage1_keys_kernel<<<div_up(kCandPerRound, 256), 256, 0, s>>>(counts, cidx, kCandPerRound, (int) pool.size());
     {
       size_t tbs = 0;
-      cub::DeviceRadixSort::SortPairsDescending(nullptr, tbs, counts, counts_sorted, cidx, cidx_sorted, kCandPerRound, 0, 32, s);
+      cub::DeviceRadixSort::SortPairsDescending(nullptr, tbs, counts, counts_sorted, cidx, cidx_sorted, kCandPerRound, 0, kStage1KeyBits, s);
       unsigned char *t2 = rs.cub_tmp.ensure(tbs);
-      cub::DeviceRadixSort::SortPairsDescending(t2, tbs, counts, counts_sorted, cidx, cidx_sorted, kCandPerRound, 0, 32, s);
+      cub::DeviceRadixSort::SortPairsDescending(t2, tbs, counts, counts_sorted, cidx, cidx_sorted, kCandPerRound, 0, kStage1KeyBits, s);
     }
     {
       const int n_tiles = div_up(S, kScoreTile);
@@ -916,18 +1334,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     dry_rounds = 0;
     // --- refine the best candidate on the full cloud -------------------------------------------------------
     PlaneFrame fr;
-    auto make_frame = [&](const float nrm3[3], const float pos3[3]) {
-      PlaneFrame f;
-      float u[3], v[3];
-      frame_from_normal(nrm3, u, v);
-      float dist = (pos3[0] * nrm3[0] + pos3[1] * nrm3[1]) + pos3[2] * nrm3[2];   // m_pos.dot(m_normal)
-      f.pl = make_float4(nrm3[0], nrm3[1], nrm3[2], dist);
-      f.pos = make_float3(pos3[0], pos3[1], pos3[2]);
-      f.u = make_float3(u[0], u[1], u[2]);
-      f.v = make_float3(v[0], v[1], v[2]);
-      return f;
-    };
-    struct Eval { long long size; double score; double sum[3]; bool ok; };
+    auto make_frame = [&](const float nrm3[3], const float pos3[3]) { return make_plane_frame(nrm3, pos3); };
     auto evaluate = [&](const PlaneFrame &f, unsigned char *member) -> Eval {
       Eval e{0, 0, {0, 0, 0}, false};
       int init[4];
@@ -985,21 +1392,8 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       band_full = full;
       ++n_band_builds;
     };
-    // Can a point outside the band be within eps3 of plane `pl`?  d_pl(x) - d_band(x) is affine in x, so over the
-    // bounding box of the cloud its extreme values sit at the corners; if they stay below (kBandMul - 1) * eps3
-    // (minus float slack) every inlier of `pl` lies inside the band.  The fitted normal may come out flipped.
     auto band_covers = [&](const float4 &pl) -> bool {
-      if (band_full) return true;
-      double worst[2] = {0, 0};
-      for (int k = 0; k < 8; ++k) {
-        const double x = (k & 1) ? mx[0] : mn[0], y = (k & 2) ? mx[1] : mn[1], z = (k & 4) ? mx[2] : mn[2];
-        const double db = band_pl.w - (band_pl.x * x + band_pl.y * y + band_pl.z * z);
-        const double dp = pl.w - (pl.x * x + pl.y * y + pl.z * z);
-        worst[0] = std::max(worst[0], std::fabs(dp - db));
-        worst[1] = std::max(worst[1], std::fabs(-dp - db));
-      }
-      const double slack = 1e-5 * (double) ext + 1e-3 * eps3;
-      return std::min(worst[0], worst[1]) + eps3 + slack <= (double) kBandMul * eps3;
+      return band_full || band_covers_plane(band_pl, kBandMul * eps3, pl, mn, mx, ext, eps3);
     };
     // fused evaluation on the band: flag/bbox -> raster -> closing + components -> select -> mean -> covariance,
     // one sync.  cov6 receives the covariance sums about float(mean) of the selected members (input of the LS
@@ -1008,7 +1402,6 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       Eval e{0, 0, {0, 0, 0}, false};
       unsigned char *bmp = rs.bmp_dev.ensure(kBmpCap), *btmp = rs.bmp_tmp.ensure(kBmpCap), *bmask = rs.mask_dev.ensure(kBmpCap);
       int *lab = rs.cc_lab.ensure(kBmpCap), *ccnt = rs.cc_cnt.ensure(kBmpCap);
-      float *mean3 = rs.mean3.ensure(4);
       BmpInfo *info = reinterpret_cast<BmpInfo *>(d_misc + 32);
       if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
       // widening keeps both membership maps: they are indexed by point, and the full band is a superset of the old one
@@ -1018,14 +1411,12 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       PLADE_CUDA(cudaMemcpyAsync(d_uvbox, init, sizeof(init), cudaMemcpyHostToDevice, s));
       PLADE_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 16, s));
       flag_uv_kernel<<<blocks_b, 256, 0, s>>>(posB, nrmB, nullptr, 0, d_nb, f, eps3, nthresh, flag, d_uvbox);
-      bmp_setup_kernel<<<1, 1, 0, s>>>(d_uvbox, bmp_eps, info);
-      raster_dev_kernel<<<blocks_b, 256, 0, s>>>(posB, flag, d_nb, f, bmp_eps, info, pix, bmp);
+      raster_dev_kernel<<<blocks_b, 256, 0, s>>>(posB, flag, d_nb, f, bmp_eps, d_uvbox, info, pix, bmp);
       cc_kernel<<<1, 1024, 0, s>>>(bmp, btmp, lab, ccnt, info, bmask);
       select_dev_kernel<<<blocks_b, 256, 0, s>>>(posB, idxB, flag, pix, bmask, info, d_nb, f.pl, eps3, member, acc);
-      mean_kernel<<<1, 1, 0, s>>>(acc, mean3);
-      cov_dev_kernel<<<blocks_b, 256, 0, s>>>(posB, idxB, member, d_nb, mean3, acc + 8);
+      cov_dev_kernel<<<blocks_b, 256, 0, s>>>(posB, idxB, member, d_nb, acc, acc + 8);
       PLADE_LAUNCH_CHECK();
-      dev.launches.add(7);
+      dev.launches.add(5);
       double h[16];
       BmpInfo hi;
       PLADE_CUDA(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -1036,17 +1427,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       for (int k = 0; k < 6; ++k) cov6[k] = h[8 + k];
       return e;
     };
-    auto fit_from_cov = [&](const Eval &e, const double h[6], float nrm3[3], float pos3[3]) -> bool {
-      float a[3][3], d[3], v[3][3];
-      a[0][0] = (float) (h[0] / e.size); a[0][1] = a[1][0] = (float) (h[1] / e.size); a[0][2] = a[2][0] = (float) (h[2] / e.size);
-      a[1][1] = (float) (h[3] / e.size); a[1][2] = a[2][1] = (float) (h[4] / e.size); a[2][2] = (float) (h[5] / e.size);
-      if (!jacobi3f(a, d, v)) return false;
-      int k = 0;
-      for (int j = 1; j < 3; ++j) if (std::fabs(d[j]) < std::fabs(d[k])) k = j;
-      nrm3[0] = v[0][k]; nrm3[1] = v[1][k]; nrm3[2] = v[2][k];
-      pos3[0] = (float) (e.sum[0] / e.size); pos3[1] = (float) (e.sum[1] / e.size); pos3[2] = (float) (e.sum[2] / e.size);
-      return true;
-    };
+    auto fit_from_cov = [&](const Eval &e, const double h[6], float nrm3[3], float pos3[3]) -> bool { return fit_plane_from_cov(e, h, nrm3, pos3); };
     auto ls_fit = [&](const Eval &e, const unsigned char *member, float nrm3[3], float pos3[3]) -> bool {
       // Plane::LeastSquaresFit (R/Plane.h:66-74): mean, covariance, eigenvector of smallest |lambda|
       float3 mean = make_float3((float) (e.sum[0] / e.size), (float) (e.sum[1] / e.size), (float) (e.sum[2] / e.size));
@@ -1074,15 +1455,58 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     fr = make_frame(cn, cp);
     fr.pl.w = best_pl.w;
     unsigned char *acc_member = member_a, *work_member = member_b;
+    float acc_n[3] = {cn[0], cn[1], cn[2]}, acc_p[3] = {cp[0], cp[1], cp[2]};
+    long long acc_size = 0;
+    bool host_path = false, refined = false;
+    build_band(fr.pl, false);
+    // ---- the whole acceptance chain in one cluster kernel, one host round trip (refine_cluster_kernel) -----------
+    if (const int csize = refine_cluster_size()) {
+      unsigned char *rm = reinterpret_cast<unsigned char *>(rs.refine_mem.ensure(64));
+      RefineArgs ra;
+      ra.posB = posB; ra.nrmB = nrmB; ra.idxB = idxB; ra.d_nb = d_nb;
+      ra.flag = flag; ra.pix = pix;
+      ra.bmp = rs.bmp_dev.ensure(kBmpCap); ra.btmp = rs.bmp_tmp.ensure(kBmpCap); ra.bmask = rs.mask_dev.ensure(kBmpCap);
+      ra.lab = rs.cc_lab.ensure(kBmpCap); ra.ccnt = rs.cc_cnt.ensure(kBmpCap);
+      ra.member_a = member_a; ra.member_b = member_b;
+      ra.uvbox = d_uvbox; ra.acc = acc;
+      ra.ctl = reinterpret_cast<RefineCtl *>(rm); ra.out = reinterpret_cast<RefineOut *>(rm + 128);
+      ra.cand_pl = best_pl; ra.band_pl = band_pl;
+      ra.eps3 = eps3; ra.nthresh = nthresh; ra.bmp_eps = bmp_eps; ra.band_halfwidth = kBandMul * eps3; ra.ext = ext;
+      for (int k = 0; k < 3; ++k) { ra.mn[k] = mn[k]; ra.mx[k] = mx[k]; }
+      ra.min_support = min_support; ra.band_full = band_full ? 1 : 0;
+      if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(ra.bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(csize); cfg.blockDim = dim3(kRefThreads); cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      PLADE_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel, ra));
+      dev.launches.add();
+      RefineOut ro;
+      PLADE_CUDA(cudaMemcpyAsync(&ro, ra.out, sizeof(ro), cudaMemcpyDeviceToHost, s));
+      PLADE_CUDA(cudaStreamSynchronize(s));
+      if (ro.status == 0) {
+        refined = true;
+        acc_size = ro.acc_size;
+        memcpy(acc_n, ro.acc_n, sizeof(acc_n)); memcpy(acc_p, ro.acc_p, sizeof(acc_p));
+        if (ro.acc_sel) std::swap(acc_member, work_member);
+      } else {
+        band_finish(-1, nullptr);      // restore the all-zero membership maps, then take the multi-kernel path below
+        ++n_cluster_fallbacks;
+      }
+    }
     double cov_cur[6];
     bool ovf = false;
-    build_band(fr.pl, false);
-    Eval cur = evaluate_fused(fr, acc_member, cov_cur, ovf);   // GlobalScore + ConnectedComponent (+ weighted score of the clone)
-    const bool host_path = ovf;                                // bitmap larger than the device cap: host labelling
-    if (host_path) cur = evaluate(fr, acc_member);
-    float acc_n[3] = {cn[0], cn[1], cn[2]}, acc_p[3] = {cp[0], cp[1], cp[2]};
-    long long acc_size = cur.ok ? cur.size : 0;
-    if (cur.ok) {
+    Eval cur{0, 0, {0, 0, 0}, false};
+    if (!refined) {
+      build_band(fr.pl, false);
+      cur = evaluate_fused(fr, acc_member, cov_cur, ovf);      // GlobalScore + ConnectedComponent (+ weighted score of the clone)
+      host_path = ovf;                                         // bitmap larger than the device cap: host labelling
+      if (host_path) cur = evaluate(fr, acc_member);
+      acc_size = cur.ok ? cur.size : 0;
+    }
+    if (!refined && cur.ok) {
       Eval clone = cur;
       double cov_clone[6];
       memcpy(cov_clone, cov_cur, sizeof(cov_cur));
@@ -1146,11 +1570,9 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     tmp = rs.cub_tmp.ensure(tb3);
     cub::DeviceSelect::If(tmp, tb3, cur_order, alt_order, d_nsel, m, pr, s);
     dev.launches.add(3);
-    int new_m = 0;
-    PLADE_CUDA(cudaMemcpyAsync(&new_m, d_nsel, sizeof(int), cudaMemcpyDeviceToHost, s));
-    PLADE_CUDA(cudaStreamSynchronize(s));
+    // the accepted members are exactly acc_size previously unassigned points: no round trip for the new count
     std::swap(cur_order, alt_order);
-    m = new_m;
+    m = (int) (m - acc_size);
     if (!pool.empty()) pool.erase(pool.begin());
     mark("ransac_accept");
     if (m < min_support || m < 3) break;
@@ -1182,7 +1604,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   PLADE_CUDA(cudaStreamSynchronize(s));
   dev.clock.collect();
   mark("ransac_output");
-  if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade ransac lane %d] candidates evaluated on a band: %d, widened to all points: %d\n", lane, n_band_builds - n_band_full, n_band_full);
+  if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade ransac lane %d] candidates evaluated on a band: %d, widened to all points: %d, cluster-kernel fallbacks: %d\n", lane, n_band_builds - n_band_full, n_band_full, n_cluster_fallbacks);
   return result;
 }
 

@@ -3,11 +3,19 @@ Prints pairs/s for B = 1..Bmax contexts on the same resident 2M pair.  Diagnosti
 import os, sys, threading, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes
 import plade_b200
 from plade_b200.synth import make_pair
+if os.environ.get("PLADE_AB_LIB"):       # A/B runs against an older build of the library (tools/_ab/*.so)
+    plade_b200.LIB_PATH = os.path.abspath(os.environ["PLADE_AB_LIB"])
+    _l = ctypes.CDLL(plade_b200.LIB_PATH)
+    for _n in list(plade_b200.SIGNATURES):
+        if not hasattr(_l, _n):
+            del plade_b200.SIGNATURES[_n]
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
-bmax = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+bs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 4]
+bmax = max(bs)
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 tgt, src, gt = make_pair(n_points=n, n_planes=20, seed=20240611)
 devnull = os.open(os.devnull, os.O_WRONLY)
@@ -18,7 +26,7 @@ for b in range(bmax):
     ctxs.append(c)
     clouds.append((c.upload(tgt), c.upload(src)))
 res = {}
-for B in range(1, bmax + 1):
+for B in bs:
     def work(k):
         for _ in range(reps):
             ctxs[k].register_resident(*clouds[k])
