@@ -107,6 +107,11 @@ int plade_planes_get(plade_ctx *ctx, int *offsets, int *indices, float *params);
  * if inlier_mask != NULL (n bytes) it receives the mask of plane 0. */
 int plade_score_planes(plade_ctx *ctx, const float *xyzn, size_t n, const int *assigned, const float *planes4,
                        int n_planes, float eps, float normal_thresh, unsigned int *counts, unsigned char *inlier_mask);
+/* Connected-component step of the RANSAC acceptance test (BitmapPrimitiveShape::ConnectedComponent,
+ * 3rd_party/ransac/BitmapPrimitiveShape.cpp:155-205 with Bitmap.cpp:154,459,633): cross closing (dilate, erode) of
+ * the ue x ve bitmap (row-major, ue fastest, non-zero = set), 8-connected labelling, mask (0/1) of the component
+ * with the most pixels (first in raster order on ties).  ue * ve <= 2^20.  Returns 1, or 0 on error. */
+int plade_largest_component(plade_ctx *ctx, const unsigned char *bitmap, int ue, int ve, unsigned char *mask);
 /* average_spacing(cloud, 6) PLADE/util.cpp:1619-1648 */
 float plade_average_spacing(plade_ctx *ctx, const float *xyzn, size_t n);
 /* DownSamplePointCloud / pcl::VoxelGrid  PLADE/util.h:162-184; xyz has `stride` floats per point

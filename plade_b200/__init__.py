@@ -56,6 +56,7 @@ SIGNATURES = {
     "plade_planes_get": (ctypes.c_int, [ctypes.c_void_p, _c_int_p, _c_int_p, _c_float_p]),
     "plade_score_planes": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, _c_int_p, _c_float_p, ctypes.c_int,
                                           ctypes.c_float, ctypes.c_float, _c_uint_p, _c_ubyte_p]),
+    "plade_largest_component": (ctypes.c_int, [ctypes.c_void_p, _c_ubyte_p, ctypes.c_int, ctypes.c_int, _c_ubyte_p]),
     "plade_average_spacing": (ctypes.c_float, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t]),
     "plade_voxel_downsample": (ctypes.c_longlong, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, _c_float_p]),
     "plade_bounding_box": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, _c_float_p, _c_double_p, _c_float_p]),
@@ -267,6 +268,14 @@ class Context:
     def detect_planes(self, xyzn, min_support):
         a = _f32(xyzn).reshape(-1, 6)
         return self._planes(self.lib.plade_detect_planes(self.h, _p(a, _c_float_p), len(a), int(min_support)))
+
+    def largest_component(self, bitmap):
+        """closing + largest 8-connected component of a (ve, ue) uint8 bitmap, as the RANSAC acceptance test runs it"""
+        b = np.ascontiguousarray(bitmap, dtype=np.uint8)
+        mask = np.zeros_like(b)
+        if not self.lib.plade_largest_component(self.h, _p(b, _c_ubyte_p), b.shape[1], b.shape[0], _p(mask, _c_ubyte_p)):
+            raise RuntimeError(self.last_error())
+        return mask
 
     def score_planes(self, xyzn, planes4, eps, normal_thresh, assigned=None, want_mask=False):
         a = _f32(xyzn).reshape(-1, 6)

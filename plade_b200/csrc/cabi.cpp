@@ -16,6 +16,7 @@
 using namespace plade;
 
 namespace plade {
+void largest_component_device(Device &dev, const unsigned char *h_bitmap, int ue, int ve, unsigned char *h_mask);
 void score_planes_full(Device &dev, const float4 *pos, const float4 *nrm, const int *assigned, size_t n, const float4 *d_planes,
                        int n_planes, float eps, float nthresh, unsigned int *d_counts, unsigned char *d_mask0);
 }
@@ -429,6 +430,13 @@ int plade_planes_get(plade_ctx *ctx, int *offsets, int *indices, float *params) 
     params[4 * i] = p.n[0]; params[4 * i + 1] = p.n[1]; params[4 * i + 2] = p.n[2]; params[4 * i + 3] = p.d;
   }
   return 1;
+}
+
+int plade_largest_component(plade_ctx *ctx, const unsigned char *bitmap, int ue, int ve, unsigned char *mask) {
+  PLADE_TRY(ctx, 0, {
+    largest_component_device(ctx->reg->dev, bitmap, ue, ve, mask);
+    return 1;
+  })
 }
 
 int plade_score_planes(plade_ctx *ctx, const float *xyzn, size_t n, const int *assigned, const float *planes4, int n_planes,

@@ -426,7 +426,8 @@ __global__ void raster_dev_kernel(const float4 *__restrict__ pos, const unsigned
 }
 
 // One block: cross closing (dilate, erode; R/Bitmap.cpp:154,459), 8-connected labelling by min-label
-// propagation with pointer jumping, largest component by PIXEL count (first in raster order on ties,
+// propagation with pointer jumping (a union-find with L2 atomics was tried and is 3x slower on the nearly full
+// bitmaps of real planes), largest component by PIXEL count (first in raster order on ties,
 // R/BitmapPrimitiveShape.cpp:170-173) -> mask.  Leaves the bitmap cleared for the next evaluation.
 __device__ void cc_block(unsigned char *bitmap, unsigned char *tmp, int *lab, int *cnt, const BmpInfo I, unsigned char *mask) {
   __shared__ int changed;
@@ -550,6 +551,14 @@ __global__ void band_finish_kernel(const int *__restrict__ idx, const int *__res
     member[g] = 0;
     other[g] = 0;
   }
+}
+
+// accept after refine_cluster_kernel: its membership map is indexed by band position
+__global__ void band_assign_kernel(const int *__restrict__ idx, const int *__restrict__ d_count, const unsigned char *__restrict__ member_band,
+                                   int shape_id, int *__restrict__ assigned) {
+  const int n = *d_count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (member_band[i]) assigned[idx[i]] = shape_id;
 }
 
 // pass E: members of the largest component; count, sum of positions, gaussian-weighted score
@@ -774,6 +783,7 @@ __host__ __device__ bool band_covers_plane(const float4 &band_pl, float halfwidt
 constexpr int kRefThreads = 1024;
 constexpr int kRefUnroll = 4;        // band points per thread and batch
 constexpr int kRefUnroll1 = 2;       // ... in the first pass (position + normal per point)
+constexpr int kRefSmemPix = 1 << 16;  // bitmaps up to this many pixels are rasterised / looked up through shared-memory bits
 
 struct RefineCtl {        // written by the boss thread between evaluations, read by every thread after the barrier
   PlaneFrame frame;
@@ -788,6 +798,7 @@ struct RefineOut {
   int status;             // 0 = done, 1 = bitmap larger than the device cap (host path), 2 = a refit left the band
   int evals;
   int pad;
+  unsigned int phase_ns[6];   // device time per phase summed over the evaluations (flags, raster, components, select, covariance, decision)
 };
 struct RefineArgs {
   const float4 *posB, *nrmB;
@@ -796,7 +807,7 @@ struct RefineArgs {
   int *pix;
   unsigned char *bmp, *btmp, *bmask;
   int *lab, *ccnt;
-  unsigned char *member_a, *member_b;
+  unsigned char *member_a, *member_b;     // membership of the band points, by BAND position (two maps: candidate / clone)
   int *uvbox;
   double *acc;
   RefineCtl *ctl;
@@ -837,8 +848,9 @@ __device__ __forceinline__ void cluster_barrier() {
 __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const RefineArgs a) {
   __shared__ double sh_d[32];
   __shared__ float sh_f[32];
-  const int rank = (int) cluster_rank(), nth = (int) cluster_size() * kRefThreads;
-  const int gt = rank * kRefThreads + threadIdx.x;
+  __shared__ unsigned int sbits[kRefSmemPix / 32];     // per-CTA bit image of the bitmap (pass 2) / of the component mask (pass 4)
+  const int rank = (int) cluster_rank(), nthr = (int) blockDim.x, nth = (int) cluster_size() * nthr;
+  const int gt = rank * nthr + threadIdx.x;
   const bool boss = gt == 0;
   const int n = *a.d_nb;
   const float denom = 2.f / 9.f * a.eps3 * a.eps3;
@@ -852,8 +864,16 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
     float acc_n[3], acc_p[3], fn[3], fp[3];
     long long acc_size;
     int acc_sel, work_sel, iter, status, evals;
+    unsigned long long t_prev;
+    unsigned int phase_ns[6];
   };
   __shared__ Boss B;
+  auto lap = [&](int phase) {       // boss: %globaltimer at the phase boundaries (PLADE_TIMING prints the sums)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    B.phase_ns[phase] += (unsigned int) (t - B.t_prev);
+    B.t_prev = t;
+  };
   if (boss) {
     B.clone = Eval{0, 0, {0, 0, 0}, false};
     for (int k = 0; k < 6; ++k) B.cov_clone[k] = 0;
@@ -864,6 +884,8 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
     for (int k = 0; k < 3; ++k) B.fn[k] = B.fp[k] = 0;
     B.acc_size = 0;
     B.acc_sel = 0; B.work_sel = 1; B.iter = 0; B.status = 0; B.evals = 0;
+    for (int k = 0; k < 6; ++k) B.phase_ns[k] = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(B.t_prev));
   }
 
   auto publish = [&](const PlaneFrame &f, int sel, int go) {     // boss: next evaluation + clean accumulators
@@ -935,11 +957,18 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
       }
     }
     cluster_barrier();
+    if (boss) lap(0);
     // pass 2: bitmap geometry + rasterisation (raster_dev_kernel)
     int box[4];
     for (int k = 0; k < 4; ++k) box[k] = __ldcg(a.uvbox + k);
     const BmpInfo I = bmp_info_from_box(box, a.bmp_eps);
-    if (I.ok) {
+    const int P = I.ok ? I.ue * I.ve : 0;
+    const bool small = P <= kRefSmemPix;     // (thousands of band points fall on each pixel: setting bits in shared memory
+    if (I.ok) {                              //  and flushing once per CTA avoids ~10^5 same-address stores in L2)
+      if (small) {
+        for (int w = threadIdx.x; w < (P + 31) / 32; w += nthr) sbits[w] = 0u;
+        __syncthreads();
+      }
       for (int base = gt; base < n; base += kRefUnroll * nth) {
         float4 p[kRefUnroll];
         unsigned int fl[kRefUnroll];
@@ -962,38 +991,54 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
           bv = min(max(bv, 0), I.ve - 1);
           const int id = bu + bv * I.ue;
           a.pix[i] = id;
-          a.bmp[id] = 1;
+          if (small) atomicOr(&sbits[id >> 5], 1u << (id & 31));
+          else a.bmp[id] = 1;
+        }
+      }
+      if (small) {
+        __syncthreads();
+        for (int w = threadIdx.x; w < (P + 31) / 32; w += nthr) {
+          unsigned int bits = sbits[w];
+          while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; a.bmp[32 * w + b] = 1; }
         }
       }
     }
     cluster_barrier();
+    if (boss) lap(1);
     // pass 3: closing + connected components on CTA 0 (cc_kernel); leaves the bitmap cleared
     if (rank == 0) cc_block(a.bmp, a.btmp, a.lab, a.ccnt, I, a.bmask);
     cluster_barrier();
+    if (boss) lap(2);
     // pass 4: members of the largest component, their count / position sums / weighted score (select_dev_kernel);
     // the member bit is also kept next to the flag (bit 1) for pass 5
     {
+      if (I.ok && small) {      // component mask -> shared-memory bits (one L2 read per pixel and CTA instead of one per band point)
+        for (int w = threadIdx.x; w < (P + 31) / 32; w += nthr) sbits[w] = 0u;
+        __syncthreads();
+        for (int q = threadIdx.x; q < P; q += nthr) if (__ldcg(a.bmask + q)) atomicOr(&sbits[q >> 5], 1u << (q & 31));
+        __syncthreads();
+      }
       double cnt = 0, sx = 0, sy = 0, sz = 0, sc = 0;
       for (int base = gt; base < n; base += kRefUnroll * nth) {
         float4 p[kRefUnroll];
-        int gi[kRefUnroll], px[kRefUnroll];
+        int px[kRefUnroll];
         unsigned int fl[kRefUnroll], mk[kRefUnroll];
 #pragma unroll
         for (int u = 0; u < kRefUnroll; ++u) {
           const int i = base + u * nth, ic = min(i, n - 1);
           fl[u] = a.flag[ic]; px[u] = a.pix[ic];
-          gi[u] = __ldg(a.idxB + ic);
           p[u] = __ldg(a.posB + ic);
           if (i >= n || !I.ok) fl[u] = 0;
         }
 #pragma unroll
-        for (int u = 0; u < kRefUnroll; ++u) mk[u] = fl[u] ? (unsigned int) __ldcg(a.bmask + px[u]) : 0u;   // pix is only defined where flagged
+        for (int u = 0; u < kRefUnroll; ++u)       // pix is only defined where flagged
+          mk[u] = !fl[u] ? 0u : small ? ((sbits[px[u] >> 5] >> (px[u] & 31)) & 1u) : (unsigned int) __ldcg(a.bmask + px[u]);
 #pragma unroll
         for (int u = 0; u < kRefUnroll; ++u) {
           const int i = base + u * nth;
           if (i >= n) continue;
           const bool mem = fl[u] && mk[u];
-          member[gi[u]] = mem ? 1 : 0;
+          member[i] = mem ? 1 : 0;
           a.flag[i] = (unsigned char) ((fl[u] & 1) | (mem ? 2 : 0));
           if (mem) {
             float dp = __fadd_rn(__fadd_rn(__fmul_rn(f.pl.x, p[u].x), __fmul_rn(f.pl.y, p[u].y)), __fmul_rn(f.pl.z, p[u].z));
@@ -1009,6 +1054,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
       }
     }
     cluster_barrier();
+    if (boss) lap(3);
     // pass 5: covariance about float(mean) of the members (cov_dev_kernel)
     {
       const double cnt = __ldcg(a.acc + 0);
@@ -1040,6 +1086,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
     cluster_barrier();
     // decision (boss thread): the loop of RansacShapeDetector.cpp:619-655
     if (boss) {
+      lap(4);
       ++B.evals;
       Eval e;
       double cov[6];
@@ -1077,12 +1124,14 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
       if (!go) { a.ctl->go = 0; __threadfence(); }
     }
     cluster_barrier();
+    if (boss) lap(5);
   }
   if (boss) {
     RefineOut o;
     o.acc_size = B.acc_size;
     for (int k = 0; k < 3; ++k) { o.acc_n[k] = B.acc_n[k]; o.acc_p[k] = B.acc_p[k]; }
     o.acc_sel = B.acc_sel; o.status = B.status; o.evals = B.evals; o.pad = 0;
+    for (int k = 0; k < 6; ++k) o.phase_ns[k] = B.phase_ns[k];
     *a.out = o;
   }
 }
@@ -1104,17 +1153,25 @@ struct RansacScratch {
   bool bmp_dev_clean = false;
   DevBuf<double> acc;
   DevBuf<double> refine_mem;      // RefineCtl at +0, RefineOut at +128 bytes
+  DevBuf<unsigned char> memb_a, memb_b;   // band-local membership maps of refine_cluster_kernel
 };
 
 // cluster size of refine_cluster_kernel on this device: 16 (non-portable) when the GPU can co-schedule it, else 8
+int refine_block_threads() {
+  static const int t = [] { const char *e = getenv("PLADE_REFINE_THREADS"); int v = e ? atoi(e) : kRefThreads; return (v == 256 || v == 512 || v == 1024) ? v : kRefThreads; }();
+  return t;
+}
 int refine_cluster_size() {
   static const int cached = [] {       // (thread-safe: the two lanes of a context ask concurrently)
   int size = 0;
   if (getenv("PLADE_NO_CLUSTER_REFINE")) return size;
-  for (int want : {16, 8}) {
+  const char *e = getenv("PLADE_REFINE_CLUSTER");
+  const int first = e ? atoi(e) : 16;
+  for (int want : {first, 8}) {
+    if (want < 1 || want > 16) continue;
     if (want > 8 && cudaFuncSetAttribute(refine_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(want); cfg.blockDim = dim3(kRefThreads);
+    cfg.gridDim = dim3(want); cfg.blockDim = dim3(refine_block_threads());
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1215,7 +1272,8 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   float4 *posB = rs.band_pos.ensure(n), *nrmB = rs.band_nrm.ensure(n);
   int *idxB = rs.band_idx.ensure(n);
   const int blocks_b = std::min(blocks_n, dev.num_sms * 4);
-  int n_band_builds = 0, n_band_full = 0, n_cluster_fallbacks = 0;
+  int n_band_builds = 0, n_band_full = 0, n_cluster_fallbacks = 0, refine_evals = 0;
+  double refine_phase_ns[6] = {0, 0, 0, 0, 0, 0};
   float4 *cand = rs.cand.ensure(kCandPerRound);
   unsigned int *counts = rs.counts.ensure(kCandPerRound);
   double *acc = rs.acc.ensure(16);
@@ -1458,6 +1516,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     float acc_n[3] = {cn[0], cn[1], cn[2]}, acc_p[3] = {cp[0], cp[1], cp[2]};
     long long acc_size = 0;
     bool host_path = false, refined = false;
+    const unsigned char *band_member = nullptr;      // members of the accepted plane by band position (cluster path)
     build_band(fr.pl, false);
     // ---- the whole acceptance chain in one cluster kernel, one host round trip (refine_cluster_kernel) -----------
     if (const int csize = refine_cluster_size()) {
@@ -1467,7 +1526,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       ra.flag = flag; ra.pix = pix;
       ra.bmp = rs.bmp_dev.ensure(kBmpCap); ra.btmp = rs.bmp_tmp.ensure(kBmpCap); ra.bmask = rs.mask_dev.ensure(kBmpCap);
       ra.lab = rs.cc_lab.ensure(kBmpCap); ra.ccnt = rs.cc_cnt.ensure(kBmpCap);
-      ra.member_a = member_a; ra.member_b = member_b;
+      ra.member_a = rs.memb_a.ensure(n); ra.member_b = rs.memb_b.ensure(n);
       ra.uvbox = d_uvbox; ra.acc = acc;
       ra.ctl = reinterpret_cast<RefineCtl *>(rm); ra.out = reinterpret_cast<RefineOut *>(rm + 128);
       ra.cand_pl = best_pl; ra.band_pl = band_pl;
@@ -1476,7 +1535,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       ra.min_support = min_support; ra.band_full = band_full ? 1 : 0;
       if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(ra.bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(csize); cfg.blockDim = dim3(kRefThreads); cfg.stream = s;
+      cfg.gridDim = dim3(csize); cfg.blockDim = dim3(refine_block_threads()); cfg.stream = s;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1486,14 +1545,15 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       RefineOut ro;
       PLADE_CUDA(cudaMemcpyAsync(&ro, ra.out, sizeof(ro), cudaMemcpyDeviceToHost, s));
       PLADE_CUDA(cudaStreamSynchronize(s));
+      for (int k = 0; k < 6; ++k) refine_phase_ns[k] += ro.phase_ns[k];
+      refine_evals += ro.evals;
       if (ro.status == 0) {
         refined = true;
         acc_size = ro.acc_size;
         memcpy(acc_n, ro.acc_n, sizeof(acc_n)); memcpy(acc_p, ro.acc_p, sizeof(acc_p));
-        if (ro.acc_sel) std::swap(acc_member, work_member);
+        band_member = ro.acc_sel ? ra.member_b : ra.member_a;
       } else {
-        band_finish(-1, nullptr);      // restore the all-zero membership maps, then take the multi-kernel path below
-        ++n_cluster_fallbacks;
+        ++n_cluster_fallbacks;         // (the cluster kernel never touches the per-point maps: they are still all zero)
       }
     }
     double cov_cur[6];
@@ -1543,7 +1603,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     // reaches min_support (FindBestCandidate, RansacShapeDetector.cpp:297,423-430)
     if (acc_size < min_support) {
       if (host_path) { PLADE_CUDA(cudaMemsetAsync(member_a, 0, n, s)); PLADE_CUDA(cudaMemsetAsync(member_b, 0, n, s)); }
-      else band_finish(-1, nullptr);
+      else if (!refined) band_finish(-1, nullptr);
       // its score can only shrink from here on: never look at this plane (or a duplicate of it) again
       banned.push_back(best_pl);
       if (!pool.empty()) pool.erase(pool.begin());
@@ -1557,6 +1617,10 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       PLADE_LAUNCH_CHECK();
       PLADE_CUDA(cudaMemsetAsync(member_a, 0, n, s));
       PLADE_CUDA(cudaMemsetAsync(member_b, 0, n, s));
+    } else if (refined) {
+      band_assign_kernel<<<blocks_b, 256, 0, s>>>(idxB, d_nb, band_member, (int) found.size(), assigned);
+      PLADE_LAUNCH_CHECK();
+      dev.launches.add();
     } else band_finish((int) found.size(), member);
     FoundPlane fp;
     memcpy(fp.n, acc_n, sizeof(acc_n)); memcpy(fp.pos, acc_p, sizeof(acc_p));
@@ -1604,7 +1668,9 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   PLADE_CUDA(cudaStreamSynchronize(s));
   dev.clock.collect();
   mark("ransac_output");
-  if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade ransac lane %d] candidates evaluated on a band: %d, widened to all points: %d, cluster-kernel fallbacks: %d\n", lane, n_band_builds - n_band_full, n_band_full, n_cluster_fallbacks);
+  if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade ransac lane %d] candidates evaluated on a band: %d, widened to all points: %d, cluster-kernel fallbacks: %d; cluster kernel: %d evaluations, us per phase: flags %.0f raster %.0f components %.0f select %.0f covariance %.0f decision %.0f\n",
+                                   lane, n_band_builds - n_band_full, n_band_full, n_cluster_fallbacks, refine_evals, refine_phase_ns[0] / 1e3, refine_phase_ns[1] / 1e3,
+                                   refine_phase_ns[2] / 1e3, refine_phase_ns[3] / 1e3, refine_phase_ns[4] / 1e3, refine_phase_ns[5] / 1e3);
   return result;
 }
 
@@ -1668,6 +1734,27 @@ std::vector<PlaneRec> Registrar::extract_planes(const CloudDev &c, int init_min_
   static thread_local DevBuf<int> g;
   std::vector<PlaneParam> pp = extract_planes_dev(c, init_min_support, g);
   return planes_to_host(c, pp, g);
+}
+
+// stage API: closing + largest 8-connected component of a ue x ve bitmap on the device (cc_kernel), as the RANSAC
+// acceptance test runs it (BitmapPrimitiveShape::ConnectedComponent, R/BitmapPrimitiveShape.cpp:155-205)
+void largest_component_device(Device &dev, const unsigned char *h_bitmap, int ue, int ve, unsigned char *h_mask) {
+  const size_t P = (size_t) ue * ve;
+  if (P == 0 || P > (size_t) kBmpCap) throw std::runtime_error("largest_component_device: bitmap size out of range");
+  static thread_local DevBuf<unsigned char> bmp, tmp, mask;
+  static thread_local DevBuf<int> lab, cnt, info;
+  unsigned char *d_bmp = bmp.ensure(P), *d_tmp = tmp.ensure(P), *d_mask = mask.ensure(P);
+  int *d_lab = lab.ensure(P), *d_cnt = cnt.ensure(P);
+  BmpInfo hi{0.f, 0.f, ue, ve, 1, 0, 0, 0};
+  BmpInfo *d_info = reinterpret_cast<BmpInfo *>(info.ensure(8));
+  cudaStream_t s = dev.stream;
+  PLADE_CUDA(cudaMemcpyAsync(d_bmp, h_bitmap, P, cudaMemcpyHostToDevice, s));
+  PLADE_CUDA(cudaMemcpyAsync(d_info, &hi, sizeof(hi), cudaMemcpyHostToDevice, s));
+  cc_kernel<<<1, 1024, 0, s>>>(d_bmp, d_tmp, d_lab, d_cnt, d_info, d_mask);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add();
+  PLADE_CUDA(cudaMemcpyAsync(h_mask, d_mask, P, cudaMemcpyDeviceToHost, s));
+  PLADE_CUDA(cudaStreamSynchronize(s));
 }
 
 // stage API: plane consensus counts over the whole cloud (K1a/K1b predicate)

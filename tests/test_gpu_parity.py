@@ -583,3 +583,66 @@ def test_cli_result_file_format(poly_pair, tmp_path):
     assert [l.split() for l in b1[3:7]] == [["1", "0", "0", "0"], ["0", "1", "0", "0"], ["0", "0", "1", "0"], ["0", "0", "0", "1"]]
     M2 = np.array([[float(x) for x in l.split()] for l in b0[3:7]])
     assert np.array_equal(M, M2)
+
+
+def test_kernel_times_and_cluster_path_parity(ctx):
+    """plade_kernel_times reports the CUDA-event clock of the last registration, and the one-launch cluster
+    refinement (refine_cluster_kernel) extracts exactly the planes of the multi-kernel path it replaces."""
+    import subprocess, sys, json
+    tgt, src, gt = make_pair(n_points=150000, n_planes=20, seed=21)
+    ok, T = ctx.register_clouds(tgt, src)
+    assert ok
+    k1, k5 = ctx.kernel_times("score_candidates"), ctx.kernel_times("verify")
+    assert k1["launches"] >= 2 and k1["ms"] > 0 and k1["algorithmic_bytes"] > 0
+    assert k5["launches"] == 1 and k5["ms"] > 0
+    with pytest.raises(KeyError):
+        ctx.kernel_times("no_such_kernel")
+    planes = ctx.extract_planes(tgt, 10000)
+    # the same extraction in a fresh process with the cluster kernel disabled (the switch is read once per process)
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import plade_b200; from plade_b200.synth import make_pair;"
+            "t, s, g = make_pair(n_points=150000, n_planes=20, seed=21); c = plade_b200.Context();"
+            "p = c.extract_planes(t, 10000); ok, T = c.register_clouds(t, s);"
+            "print(json.dumps({'params': p.params.tolist(), 'sizes': p.sizes().tolist(), 'T': T.tolist()}))" % ROOT)
+    env = dict(os.environ, PLADE_NO_CLUSTER_REFINE="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    other = json.loads(r.stdout.strip().split("\n")[-1])
+    assert planes.sizes().tolist() == other["sizes"]
+    assert np.array_equal(planes.params, np.asarray(other["params"], dtype=np.float32))
+    assert np.array_equal(T, np.asarray(other["T"], dtype=np.float32))
+
+
+def _largest_component_numpy(bmp):
+    """cross closing without wrapping (out-of-range = 0 for the dilation, 1 for the erosion), 8-connected labels,
+    largest by pixel count, first in raster order on ties (R/Bitmap.cpp:154,459,633; R/BitmapPrimitiveShape.cpp:170-173)"""
+    from scipy import ndimage
+    b = bmp.astype(bool)
+    pad = np.pad(b, 1, constant_values=False)
+    dil = pad[1:-1, 1:-1] | pad[1:-1, :-2] | pad[1:-1, 2:] | pad[:-2, 1:-1] | pad[2:, 1:-1]
+    pad = np.pad(dil, 1, constant_values=True)
+    ero = pad[1:-1, 1:-1] & pad[1:-1, :-2] & pad[1:-1, 2:] & pad[:-2, 1:-1] & pad[2:, 1:-1]
+    lab, n = ndimage.label(ero, structure=np.ones((3, 3), dtype=int))     # labels in raster order of first pixel
+    if n == 0:
+        return np.zeros_like(bmp, dtype=np.uint8)
+    sizes = np.bincount(lab.ravel(), minlength=n + 1)[1:]
+    return (lab == (1 + int(np.argmax(sizes)))).astype(np.uint8)          # argmax: first maximum
+
+
+def test_largest_component_bit_exact(ctx):
+    """K1c: the device labelling (union-find, cc_kernel) against an independent numpy/scipy restatement of the
+    reference's closing + Components + largest-label rule, on sparse, dense, tied and degenerate bitmaps."""
+    rng = np.random.default_rng(5)
+    cases = []
+    for (ve, ue, dens) in [(2, 2, 0.5), (7, 13, 0.3), (40, 55, 0.45), (100, 100, 0.55), (64, 200, 0.62), (300, 257, 0.5), (1000, 1000, 0.58), (1, 500, 0.7), (500, 1, 0.7)]:
+        cases.append((rng.uniform(size=(ve, ue)) < dens).astype(np.uint8))
+    cases.append(np.zeros((20, 30), np.uint8))
+    cases.append(np.ones((33, 65), np.uint8))
+    tie = np.zeros((20, 40), np.uint8); tie[2:8, 2:10] = 1; tie[12:18, 20:28] = 1          # two equal components: first wins
+    cases.append(tie)
+    spiral = np.zeros((101, 101), np.uint8)                                                 # long thin component (deep union chains)
+    for k in range(0, 50, 4):
+        spiral[k, k:101 - k] = 1; spiral[k:101 - k, 100 - k] = 1; spiral[100 - k, k + 4:101 - k] = 1; spiral[k + 4:101 - k, k + 4] = 1
+    cases.append(spiral)
+    for b in cases:
+        got, want = ctx.largest_component(b), _largest_component_numpy(b)
+        assert np.array_equal(got, want), (b.shape, int(got.sum()), int(want.sum()))
