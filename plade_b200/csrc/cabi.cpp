@@ -47,9 +47,10 @@ struct plade_ctx {
 
 static std::string g_create_error;
 
+// (a context may be driven from any host thread: make its device current first -- a new thread starts on device 0)
 #define PLADE_TRY(ctx, fail, ...)                                                      \
   if (!(ctx)) return fail;                                                             \
-  try { __VA_ARGS__ } catch (const std::exception &e) {                                     \
+  try { PLADE_CUDA(cudaSetDevice((ctx)->reg->dev.id)); __VA_ARGS__ } catch (const std::exception &e) {                                     \
     (ctx)->err = e.what();                                                             \
     (ctx)->reg->last_error = e.what();                                                 \
     std::cerr << "plade_b200: " << e.what() << std::endl;                              \

@@ -168,8 +168,7 @@ void cluster_transforms(Device &dev, HypScratch &sc, const std::vector<RigidOut>
   float cell = dist_thresh * 1.001f;
   if (!(cell > 0)) cell = 1e-6f;
   float inv_cell = 1.0f / cell;
-  static thread_local DevBuf<unsigned long long> k_a, k_b;
-  unsigned long long *keys = k_a.ensure(m), *keys2 = k_b.ensure(m);
+  unsigned long long *keys = sc.key64_a.ensure(m), *keys2 = sc.key64_b.ensure(m);
   int *order = sc.cell_order.ensure(m), *order2 = sc.order_alt.ensure(m);
   int *parent = sc.label.ensure(m), *d_label = sc.misc.ensure(m);
   int blocks = div_up((long long) m, 256);

@@ -108,13 +108,21 @@ size_t voxel_downsample_groups(Device &dev, VoxelScratch &sc, const float4 *d_pt
 
 // k nearest squared distances (ascending, float, FLANN L2_Simple arithmetic) of nq query points
 // (indices into d_pts) against all n points.  d_out: nq * k floats.
-void knn_sqdist(Device &dev, const float4 *d_pts, size_t n, const int *d_query_idx, int nq, int k,
+struct KnnScratch {      // grow-only scratch of knn_sqdist (owned by the context: nothing is allocated per call or per thread)
+  DevBuf<float> partial;
+  DevBuf<int> bbox_buf, idx_a, idx_b;
+  DevBuf<unsigned int> key_a, key_b;
+  DevBuf<float4> sorted_pts;
+  DevBuf<unsigned char> cub_tmp;
+};
+void knn_sqdist(Device &dev, KnnScratch &ks, const float4 *d_pts, size_t n, const int *d_query_idx, int nq, int k,
                 float *d_out);
 
 // ------------------------------------------------------------------------------------------------
 // K3c — descriptor radius matching (KdTreeSearchNDim<.,8>::find_neighbors, ANN.h:979-1029)
 // ------------------------------------------------------------------------------------------------
 struct MatchScratch {
+  DevBuf<unsigned long long> sort_a, sort_b;
   DevBuf<float> db, q;
   DevBuf<int> counts, offsets;
   DevBuf<int> out_idx, out_idx_alt;
@@ -136,6 +144,7 @@ struct MatchPairIn {    // one (query pair, db pair) match, PLADE/util.cpp:316-3
 struct RigidOut { float R[9]; float T[3]; float euler[3]; float pad; };
 
 struct HypScratch {
+  DevBuf<unsigned long long> key64_a, key64_b;
   DevBuf<MatchPairIn> in;
   DevBuf<RigidOut> rt;
   DevBuf<int> label, cell_key, cell_order, cell_start;

@@ -106,8 +106,7 @@ size_t match_descriptors(Device &dev, MatchScratch &sc, const float *h_db, int n
   if (m == 0) return 0;
   // canonical order (query asc, dist asc, db index asc): three stable LSD radix passes
   unsigned long long *qi = sc.out_key.p, *di = sc.out_key_alt.p;
-  static thread_local DevBuf<unsigned long long> t_a, t_b;
-  unsigned long long *qi2 = t_a.ensure(capacity), *di2 = t_b.ensure(capacity);
+  unsigned long long *qi2 = sc.sort_a.ensure(capacity), *di2 = sc.sort_b.ensure(capacity);
   size_t tb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tb, qi, qi2, di, di2, (int) m, 0, 64, s);
   unsigned char *tmp = sc.cub_tmp.ensure(tb);

@@ -145,8 +145,7 @@ void split_cloud(Device &dev, const float *d_xyzn, size_t n, float4 *pos, float4
 void Registrar::upload(const float *xyzn, size_t n, CloudDev &out) {
   out.n = n;
   if (n == 0) return;
-  static thread_local DevBuf<float> staging;
-  float *d_in = staging.ensure(n * 6);
+  float *d_in = upload_stage.ensure(n * 6);
   PLADE_CUDA(cudaMemcpyAsync(d_in, xyzn, sizeof(float) * n * 6, cudaMemcpyHostToDevice, dev.stream));
   split_cloud(dev, d_in, n, out.pos.ensure(n), out.nrm.ensure(n));
   PLADE_CUDA(cudaStreamSynchronize(dev.stream));
@@ -165,7 +164,7 @@ float Registrar::average_spacing(const CloudDev &c) {
   int *d_q = qidx.ensure(q.size());
   float *d_o = knn_out.ensure(q.size() * kk);
   PLADE_CUDA(cudaMemcpyAsync(d_q, q.data(), sizeof(int) * q.size(), cudaMemcpyHostToDevice, dev.stream));
-  knn_sqdist(dev, c.pos.p, num, d_q, (int) q.size(), kk, d_o);
+  knn_sqdist(dev, knn_sc, c.pos.p, num, d_q, (int) q.size(), kk, d_o);
   std::vector<float> h(q.size() * kk);
   PLADE_CUDA(cudaMemcpyAsync(h.data(), d_o, sizeof(float) * h.size(), cudaMemcpyDeviceToHost, dev.stream));
   PLADE_CUDA(cudaStreamSynchronize(dev.stream));

@@ -109,6 +109,9 @@ class Registrar {
   PenScratch pen_sc;
   ObbScratch obb_sc;
   SvdScratch svd_sc;
+  KnnScratch knn_sc;
+  DevBuf<float> upload_stage;                     // interleaved records of the cloud being uploaded
+  DevBuf<int> stage_group;                        // plane membership of the stage API (extract_planes / detect_planes)
   void *ransac_scratch[2] = {nullptr, nullptr};   // opaque, owned (ransac.cu)
   DevBuf<int> group_t, group_s, qidx;
   DevBuf<float> knn_out;

@@ -1725,13 +1725,13 @@ std::vector<PlaneRec> Registrar::planes_to_host(const CloudDev &c, const std::ve
 }
 
 std::vector<PlaneRec> Registrar::detect_planes(const CloudDev &c, int min_support) {
-  static thread_local DevBuf<int> g;
+  DevBuf<int> &g = stage_group;
   std::vector<PlaneParam> pp = detect_planes_dev(c, min_support, g);
   return planes_to_host(c, pp, g);
 }
 
 std::vector<PlaneRec> Registrar::extract_planes(const CloudDev &c, int init_min_support) {
-  static thread_local DevBuf<int> g;
+  DevBuf<int> &g = stage_group;
   std::vector<PlaneParam> pp = extract_planes_dev(c, init_min_support, g);
   return planes_to_host(c, pp, g);
 }

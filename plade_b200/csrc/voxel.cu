@@ -383,7 +383,7 @@ size_t voxel_downsample_groups(Device &dev, VoxelScratch &sc, const float4 *d_pt
   return voxel_impl(dev, sc, d_pts, n, d_group, ngroups, leaf, out, &out_group_start);
 }
 
-void knn_sqdist(Device &dev, const float4 *d_pts, size_t n, const int *d_query_idx, int nq, int k, float *d_out) {
+void knn_sqdist(Device &dev, KnnScratch &ks, const float4 *d_pts, size_t n, const int *d_query_idx, int nq, int k, float *d_out) {
   if (k > kKnnK) throw std::runtime_error("knn_sqdist: k > 8");
   if (nq == 0) return;
   cudaStream_t s = dev.stream;
@@ -394,8 +394,7 @@ void knn_sqdist(Device &dev, const float4 *d_pts, size_t n, const int *d_query_i
     int chunk = div_up((long long) n, nsplit);
     chunk = ((chunk + kKnnTile - 1) / kKnnTile) * kKnnTile;
     nsplit = div_up((long long) n, chunk);
-    static thread_local DevBuf<float> partial;
-    float *d_partial = partial.ensure((size_t) nsplit * nq * k);
+    float *d_partial = ks.partial.ensure((size_t) nsplit * nq * k);
     knn_partial_kernel<<<dim3(qblocks, nsplit), kKnnThreads, 0, s>>>(d_pts, (int) n, d_query_idx, nq, k, chunk, d_partial);
     PLADE_LAUNCH_CHECK();
     knn_merge_kernel<<<div_up(nq, 128), 128, 0, s>>>(d_partial, nsplit, nq, k, d_out);
@@ -404,10 +403,10 @@ void knn_sqdist(Device &dev, const float4 *d_pts, size_t n, const int *d_query_i
     return;
   }
   // uniform grid sized from a surface-density estimate (cell ~ 2.5 x expected spacing, <= 1023 cells per axis)
-  static thread_local DevBuf<int> bbox_buf, idx_a, idx_b;
-  static thread_local DevBuf<unsigned int> key_a, key_b;
-  static thread_local DevBuf<float4> sorted_pts;
-  static thread_local DevBuf<unsigned char> cub_tmp;
+  DevBuf<int> &bbox_buf = ks.bbox_buf, &idx_a = ks.idx_a, &idx_b = ks.idx_b;
+  DevBuf<unsigned int> &key_a = ks.key_a, &key_b = ks.key_b;
+  DevBuf<float4> &sorted_pts = ks.sorted_pts;
+  DevBuf<unsigned char> &cub_tmp = ks.cub_tmp;
   int *d_bbox = bbox_buf.ensure(8);
   int h_bbox[6] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int) (0xff7fffff ^ 0x7fffffff), (int) (0xff7fffff ^ 0x7fffffff), (int) (0xff7fffff ^ 0x7fffffff)};
   PLADE_CUDA(cudaMemcpyAsync(d_bbox, h_bbox, sizeof(h_bbox), cudaMemcpyHostToDevice, s));
