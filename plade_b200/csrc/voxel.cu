@@ -81,13 +81,13 @@ __global__ void single_bbox_kernel(const float4 *__restrict__ p, int n, int *__r
 }
 
 __global__ void voxel_key_kernel(const float4 *__restrict__ p, int n, const int *__restrict__ group,
-                                 const GroupParams *__restrict__ gp, unsigned long long *__restrict__ keys,
-                                 int *__restrict__ idx, int *__restrict__ n_selected) {
+                                 const GroupParams *__restrict__ gp, int vbits, unsigned long long unselected_key,
+                                 unsigned long long *__restrict__ keys, int *__restrict__ idx, int *__restrict__ n_selected) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool sel = false;
   if (i < n) {
     int g = group ? group[i] : 0;
-    unsigned long long key = ~0ull;
+    unsigned long long key = unselected_key;      // sorts behind every (group, voxel) key
     if (g >= 0) {
       GroupParams q = gp[g];
       float4 v = p[i];
@@ -97,7 +97,7 @@ __global__ void voxel_key_kernel(const float4 *__restrict__ p, int n, const int 
       int id = i0 + i1 * q.div0 + i2 * q.div01;
       // a group whose grid would overflow int32 keeps every point: one "voxel" per point
       if (!q.valid) id = i;
-      key = ((unsigned long long) (unsigned int) g << 32) | (unsigned int) id;
+      key = ((unsigned long long) (unsigned int) g << vbits) | (unsigned int) id;     // only vbits + gbits key bits are sorted
       sel = true;
     }
     keys[i] = key;
@@ -114,7 +114,7 @@ __global__ void head_flag_kernel(const unsigned long long *__restrict__ keys, in
 }
 
 // flags holds the inclusive scan (voxel id + 1).  seg_start[v] = first sorted position of voxel v.
-__global__ void seg_start_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ scan, int m,
+__global__ void seg_start_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ scan, int m, int vbits,
                                  int *__restrict__ seg_start, int *__restrict__ group_first_voxel) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
@@ -122,8 +122,8 @@ __global__ void seg_start_kernel(const unsigned long long *__restrict__ keys, co
   if (head) {
     int v = scan[i] - 1;
     seg_start[v] = i;
-    int g = (int) (keys[i] >> 32);
-    if (i == 0 || (int) (keys[i - 1] >> 32) != g) group_first_voxel[g] = v;
+    int g = (int) (keys[i] >> vbits);
+    if (i == 0 || (int) (keys[i - 1] >> vbits) != g) group_first_voxel[g] = v;
   }
 }
 
@@ -163,6 +163,7 @@ size_t voxel_impl(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n, 
 
   // 2. per-group grid parameters, exactly as voxel_grid.hpp:237-262
   std::vector<GroupParams> gp(ngroups);
+  long long max_id = 0;        // largest voxel index any group can produce -> number of key bits to sort
   const float inv = 1.0f / leaf;
   for (int g = 0; g < ngroups; ++g) {
     GroupParams &q = gp[g];
@@ -180,10 +181,13 @@ size_t voxel_impl(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n, 
       q.min_b[k] = (int) std::floor(mn[k] * inv);
       maxb[k] = (int) std::floor(mx[k] * inv);
     }
-    int d0 = maxb[0] - q.min_b[0] + 1, d1 = maxb[1] - q.min_b[1] + 1;
+    int d0 = maxb[0] - q.min_b[0] + 1, d1 = maxb[1] - q.min_b[1] + 1, d2 = maxb[2] - q.min_b[2] + 1;
     q.div0 = d0;
     q.div01 = d0 * d1;
+    max_id = std::max(max_id, q.valid ? (long long) d0 * d1 * d2 - 1 : (long long) n - 1);
   }
+  int vbits = 1;
+  while (vbits < 32 && (1ll << vbits) <= max_id) ++vbits;
   static_assert(sizeof(GroupParams) == 28, "GroupParams layout");
   // layout of sc.counter: [0] selected-point counter | [16..) GroupParams[kMaxGroups] | first voxel per group
   int *d_counter = sc.counter.ensure(16 + kMaxGroups * 8 + kMaxGroups);
@@ -196,14 +200,16 @@ size_t voxel_impl(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n, 
   // 3. keys, 4. stable sort
   unsigned long long *keys = sc.keys.ensure(n), *keys2 = sc.keys_alt.ensure(n);
   int *idx = sc.idx.ensure(n), *idx2 = sc.idx_alt.ensure(n);
-  voxel_key_kernel<<<div_up((long long) n, 256), 256, 0, s>>>(d_pts, (int) n, d_group, d_params, keys, idx, d_counter);
-  PLADE_LAUNCH_CHECK();
-  dev.launches.add();
   int gbits = 1;
   while ((1 << gbits) < ngroups + 1) ++gbits;
+  // key = group << vbits | voxel; unselected points carry the (unused) group 2^gbits - 1 and sort to the end.
+  // Only the vbits + gbits significant bits are sorted (32 instead of 64 for the per-plane grids of a 2 M cloud).
+  const unsigned long long unselected_key = (((1ull << gbits) - 1) << vbits) | ((1ull << vbits) - 1);
+  voxel_key_kernel<<<div_up((long long) n, 256), 256, 0, s>>>(d_pts, (int) n, d_group, d_params, vbits, unselected_key, keys, idx, d_counter);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add();
   size_t tmp_bytes = 0;
-  // unselected points carry key ~0 and sort to the end: sort on all 64 bits only if there are any
-  int end_bit = d_group ? 64 : 32;
+  int end_bit = vbits + gbits;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, idx2, (int) n, 0, end_bit, s);
   unsigned char *tmp = sc.cub_tmp.ensure(tmp_bytes);
   cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, idx2, (int) n, 0, end_bit, s);
@@ -226,7 +232,7 @@ size_t voxel_impl(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n, 
   PLADE_CUDA(cudaMemcpyAsync(&nvox, flags + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
   PLADE_CUDA(cudaStreamSynchronize(s));
   int *seg = sc.seg_start.ensure((size_t) nvox + 1);
-  seg_start_kernel<<<div_up(m, 256), 256, 0, s>>>(keys2, flags, m, seg, d_group_first);
+  seg_start_kernel<<<div_up(m, 256), 256, 0, s>>>(keys2, flags, m, vbits, seg, d_group_first);
   PLADE_LAUNCH_CHECK();
   // 6. centroids
   float4 *o = out.ensure(nvox);
