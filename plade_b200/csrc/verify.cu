@@ -22,10 +22,10 @@ namespace plade {
 
 namespace {
 
-constexpr int kTile = 1024;          // source points per shared-memory tile (16 KB)
+constexpr int kTile = 512;           // source points per shared-memory tile (8 KB)
 constexpr int kThreads = 256;
 constexpr int kHypChunk = 32;        // hypotheses per work item (the tile is reused for all of them)
-constexpr int kHypGroup = 8;         // hypotheses per filter/search pass; the queue holds every (hypothesis, point) of a pass
+constexpr int kHypGroup = 16;        // hypotheses per filter/search pass; the queue holds every (hypothesis, point) of a pass
 static_assert(kTile <= 1024 && kHypChunk <= 64, "queue entries pack (hypothesis << 10 | point) into 16 bits");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
