@@ -18,6 +18,8 @@
 #include "svdsolve.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 namespace plade {
 
@@ -261,6 +263,7 @@ void penetration_filter(Device &dev, PenScratch &sc, const PenSide &src, const P
   PLADE_CUDA(cudaMemcpyAsync(h2, d_n, sizeof(h2), cudaMemcpyDeviceToHost, s));
   PLADE_CUDA(cudaStreamSynchronize(s));
   if (h2[1]) throw std::runtime_error("penetration filter: segment longer than 4096 search radii");
+  if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade penetration] hypotheses %d, planes %d x %d, (hypothesis, plane, plane) triples to sample: %d\n", H, Ps, Pt, h2[0]);
   if (h2[0] > 0) {
     int blocks = std::min(h2[0], dev.num_sms * 8);
     pen_sample_kernel<<<blocks, kPenThreads, 0, s>>>(a, d_tr, h2[0], d_flags);
