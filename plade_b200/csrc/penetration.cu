@@ -150,6 +150,18 @@ pen_sample_kernel(PenArgs a, const Triple *__restrict__ triples, int n_triples, 
     const float r2 = (float) ((double) r * (double) r), rh2 = (float) ((double) rh * (double) rh);
     const float inv_r = 1.0f / r;
     const int sb = a.off_s[tr.i1], se = a.off_s[tr.i1 + 1], tb = a.off_t[tr.j1], te = a.off_t[tr.j1 + 1];
+    // Conservative pre-test: a sample point start + d * direc can only be within radius rr of p if p is within rr of
+    // the LINE.  The squared distance to the line is evaluated in double (no cancellation at the 1e-5 scale of rr^2)
+    // and compared with a 1 % margin, far above the float rounding of the sample positions, so every point the
+    // exact float tests below would accept still reaches them; most plane points are rejected here.
+    const double sdx = start.x, sdy = start.y, sdz = start.z, ddx = direc.x, ddy = direc.y, ddz = direc.z;
+    const double inv_dd = 1.0 / (ddx * ddx + ddy * ddy + ddz * ddz);
+    auto far_from_line = [&](const V3 &p, double lim) {
+      const double vx = (double) p.x - sdx, vy = (double) p.y - sdy, vz = (double) p.z - sdz;
+      const double t = vx * ddx + vy * ddy + vz * ddz;
+      return (vx * vx + vy * vy + vz * vz) - t * t * inv_dd > lim;
+    };
+    const double lim_gate = 1.01 * (double) rh2, lim_probe = 1.01 * (double) r2;
     bool penetrable = true;
     for (int pass = 0; pass < 2 && penetrable; ++pass) {
       // pass 0: gate = target plane cloud, probe = transformed source plane cloud, classified against plane2
@@ -164,6 +176,7 @@ pen_sample_kernel(PenArgs a, const Triple *__restrict__ triples, int n_triples, 
         float4 q = gate_is_tgt ? a.pts_t[i] : a.pts_s[i];
         V3 p(q.x, q.y, q.z);
         if (!gate_is_tgt) p = xform(R, T, p);
+        if (far_from_line(p, lim_gate)) continue;
         int k0 = (int) floorf(dot(p - start, direc) * inv_r);
         for (int k = k0 - 1; k <= k0 + 2; ++k) {
           if (k < 0 || k >= tr.nsteps) continue;
@@ -180,6 +193,7 @@ pen_sample_kernel(PenArgs a, const Triple *__restrict__ triples, int n_triples, 
         float4 q = gate_is_tgt ? a.pts_s[i] : a.pts_t[i];
         V3 p(q.x, q.y, q.z);
         if (gate_is_tgt) p = xform(R, T, p);
+        if (far_from_line(p, lim_probe)) continue;
         int k0 = (int) floorf(dot(p - start, direc) * inv_r);
         bool hit = false;
         for (int k = k0 - 2; k <= k0 + 3 && !hit; ++k) {
