@@ -244,6 +244,88 @@ __global__ void stage1_keys_kernel(unsigned int *__restrict__ counts1, int *__re
   if (i < n_forced) counts1[i] = kForcedKey;
   idx[i] = i;
 }
+// Stage-1 selection: the kStage2Cand candidates a stable descending sort of the stage-1 counts would put first
+// (carried pool candidates forced to the front, ties by ascending candidate index), in that order, without
+// sorting all kCandPerRound of them: one block builds the histogram of the counts (<= kStage1Points), finds the
+// threshold count by a suffix scan, compacts the candidates above it plus the lowest-index ties, and bitonic-sorts
+// the kStage2Cand survivors.  Replaces four library sort kernels per round by one 1-SM kernel.
+constexpr int kSelThreads = 1024;
+__global__ void __launch_bounds__(kSelThreads)
+select_top_kernel(const unsigned int *__restrict__ counts, int n, int n_forced, int *__restrict__ out /* kStage2Cand */) {
+  constexpr int K = kStage2Cand, kBins = kStage1Points + 1, kPerThread = (kBins + kSelThreads - 1) / kSelThreads;
+  __shared__ unsigned int hist[kSelThreads * kPerThread];
+  __shared__ unsigned long long keys[K];
+  __shared__ int s_thr, s_above, s_fill;
+  typedef cub::BlockScan<int, kSelThreads> Scan;
+  __shared__ typename Scan::TempStorage scan_tmp;
+  const int tid = threadIdx.x;
+  n_forced = min(n_forced, K);
+  const int need = K - n_forced;                         // slots left for the ranked candidates
+  for (int b = tid; b < kSelThreads * kPerThread; b += kSelThreads) hist[b] = 0u;
+  if (tid < K) keys[tid] = 0ull;
+  if (tid == 0) { s_thr = -1; s_above = 0; s_fill = 0; }
+  __syncthreads();
+  for (int i = n_forced + tid; i < n; i += kSelThreads) atomicAdd(&hist[min(counts[i], (unsigned int) kStage1Points)], 1u);
+  __syncthreads();
+  // suffix scan over the bins, highest count first: thread t owns bins top - t*kPerThread - j
+  {
+    const int top = kSelThreads * kPerThread - 1;
+    int mine = 0;
+    for (int j = 0; j < kPerThread; ++j) mine += (int) hist[top - (tid * kPerThread + j)];
+    int incl;
+    Scan(scan_tmp).InclusiveSum(mine, incl);
+    const int excl = incl - mine;                        // candidates in bins above this thread's
+    if (excl < need && incl >= need) {                   // the threshold bin is one of mine (exactly one thread)
+      int run = excl;
+      for (int j = 0; j < kPerThread; ++j) {
+        const int b = top - (tid * kPerThread + j), c = (int) hist[b];
+        if (run + c >= need) { s_thr = b; s_above = run; break; }
+        run += c;
+      }
+    }
+  }
+  __syncthreads();
+  const int thr = s_thr, above = s_above;                // thr < 0: fewer than `need` candidates in total -> take all
+  const int quota = thr < 0 ? 0 : need - above;          // ties at the threshold to take, lowest index first
+  // ordered compaction: every thread walks a contiguous index range
+  const int per = (n - n_forced + kSelThreads - 1) / kSelThreads;
+  const int i0 = n_forced + tid * per, i1 = min(n, i0 + per);
+  int ties = 0;
+  for (int i = i0; i < i1; ++i) ties += (thr >= 0 && (int) min(counts[i], (unsigned int) kStage1Points) == thr) ? 1 : 0;
+  int tie_rank;
+  __syncthreads();
+  Scan(scan_tmp).ExclusiveSum(ties, tie_rank);
+  for (int i = i0; i < i1; ++i) {
+    const int c = (int) min(counts[i], (unsigned int) kStage1Points);
+    bool take = thr < 0 || c > thr;
+    if (thr >= 0 && c == thr) { take = tie_rank < quota; ++tie_rank; }
+    if (take) {
+      const int slot = atomicAdd(&s_fill, 1);
+      if (slot < need) keys[n_forced + slot] = ((unsigned long long) (unsigned int) c << 32) | (unsigned long long) (0xFFFFFFFFu - (unsigned int) i);
+    }
+  }
+  if (tid < n_forced) keys[tid] = ((unsigned long long) kForcedKey << 32) | (unsigned long long) (0xFFFFFFFFu - (unsigned int) tid);
+  __syncthreads();
+  // bitonic sort, descending: (count desc, index asc) == the order of the stable descending radix sort it replaces
+  for (int k = 2; k <= K; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (tid < K) {
+        const int ixj = tid ^ j;
+        if (ixj > tid) {
+          const unsigned long long a = keys[tid], b = keys[ixj];
+          const bool desc = (tid & k) == 0;
+          if (desc ? a < b : a > b) { keys[tid] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  // unfilled slots (fewer than K candidates) keep key 0 -> index 0xFFFFFFFF: point them at candidate 0 as the sort did not exist for them
+  if (tid < K) {
+    const unsigned long long kx = keys[tid];
+    out[tid] = kx ? (int) (0xFFFFFFFFu - (unsigned int) (kx & 0xFFFFFFFFull)) : 0;
+  }
+}
+
 __global__ void gather_planes_kernel(const float4 *__restrict__ cand, const int *__restrict__ sel, int n, float4 *__restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = cand[sel[i]];
@@ -1321,13 +1403,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub1, S1, cand, nullptr, kCandPerRound, eps, nthresh, 1, counts);
       dev.clock.end(s);
     }
-    stage1_keys_kernel<<<div_up(kCandPerRound, 256), 256, 0, s>>>(counts, cidx, kCandPerRound, (int) pool.size());
-    {
-      size_t tbs = 0;
-      cub::DeviceRadixSort::SortPairsDescending(nullptr, tbs, counts, counts_sorted, cidx, cidx_sorted, kCandPerRound, 0, kStage1KeyBits, s);
-      unsigned char *t2 = rs.cub_tmp.ensure(tbs);
-      cub::DeviceRadixSort::SortPairsDescending(t2, tbs, counts, counts_sorted, cidx, cidx_sorted, kCandPerRound, 0, kStage1KeyBits, s);
-    }
+    select_top_kernel<<<1, kSelThreads, 0, s>>>(counts, kCandPerRound, (int) pool.size(), cidx_sorted);
     {
       const int n_tiles = div_up(S, kScoreTile);
       const int tiles_per_block = std::max(1, n_tiles / 128);
@@ -1338,7 +1414,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     }
     gather_planes_kernel<<<1, kStage2Cand, 0, s>>>(cand, cidx_sorted, kStage2Cand, cand_top);
     PLADE_LAUNCH_CHECK();
-    dev.launches.add(9);
+    dev.launches.add(7);
     int n_valid = 0;
     PLADE_CUDA(cudaMemcpyAsync(h_counts.data(), counts2, sizeof(unsigned int) * kStage2Cand, cudaMemcpyDeviceToHost, s));
     PLADE_CUDA(cudaMemcpyAsync(h_cand.data(), cand_top, sizeof(float4) * kStage2Cand, cudaMemcpyDeviceToHost, s));
