@@ -178,10 +178,17 @@ __global__ void gen_candidates_kernel(const float4 *__restrict__ pos, const floa
   if ((threadIdx.x & 31) == 0 && mk) atomicAdd(n_valid, __popc(mk));
 }
 
+// (both subsamples of a round in one launch: threads [0, Sa) build `sub_a` with seed_a, threads [Sa, Sa + Sb) build `sub_b`)
 __global__ void gather_sub_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const int *__restrict__ order,
-                                  int m, int S, unsigned long long seed, float4 *__restrict__ sub /* [2*S]: pos | nrm interleaved per tile */) {
+                                  int m, int Sa, unsigned long long seed_a, float4 *__restrict__ sub_a, int Sb, unsigned long long seed_b,
+                                  float4 *__restrict__ sub_b /* [2*S]: pos | nrm interleaved per tile */) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= S) return;
+  if (k >= Sa + Sb) return;
+  const bool first = k < Sa;
+  const int S = first ? Sa : Sb;
+  const unsigned long long seed = first ? seed_a : seed_b;
+  float4 *sub = first ? sub_a : sub_b;
+  if (!first) k -= Sa;
   // stratified: one point from each of S equal strata of the Morton-ordered list
   long long b = (long long) k * m / S, e = (long long) (k + 1) * m / S;
   if (e <= b) e = b + 1;
@@ -250,8 +257,13 @@ __global__ void stage1_keys_kernel(unsigned int *__restrict__ counts1, int *__re
 // threshold count by a suffix scan, compacts the candidates above it plus the lowest-index ties, and bitonic-sorts
 // the kStage2Cand survivors.  Replaces four library sort kernels per round by one 1-SM kernel.
 constexpr int kSelThreads = 1024;
+// layout of RansacScratch::round_buf in 32-bit words: one memset clears [0, kRoundTop), one copy fetches [kRoundCounts2, kRoundEnd)
+constexpr int kRoundCounts2 = kCandPerRound, kRoundNValid = kRoundCounts2 + kStage2Cand, kRoundTop = kRoundNValid + 4,
+              kRoundEnd = kRoundTop + 4 * kStage2Cand;
+static_assert((kRoundTop * 4) % 16 == 0, "selected planes must be float4-aligned");
 __global__ void __launch_bounds__(kSelThreads)
-select_top_kernel(const unsigned int *__restrict__ counts, int n, int n_forced, int *__restrict__ out /* kStage2Cand */) {
+select_top_kernel(const unsigned int *__restrict__ counts, int n, int n_forced, int *__restrict__ out /* kStage2Cand */,
+                  const float4 *__restrict__ cand, float4 *__restrict__ cand_top /* the selected planes, in order */) {
   constexpr int K = kStage2Cand, kBins = kStage1Points + 1, kPerThread = (kBins + kSelThreads - 1) / kSelThreads;
   __shared__ unsigned int hist[kSelThreads * kPerThread];
   __shared__ unsigned long long keys[K];
@@ -322,13 +334,10 @@ select_top_kernel(const unsigned int *__restrict__ counts, int n, int n_forced, 
   // unfilled slots (fewer than K candidates) keep key 0 -> index 0xFFFFFFFF: point them at candidate 0 as the sort did not exist for them
   if (tid < K) {
     const unsigned long long kx = keys[tid];
-    out[tid] = kx ? (int) (0xFFFFFFFFu - (unsigned int) (kx & 0xFFFFFFFFull)) : 0;
+    const int sel = kx ? (int) (0xFFFFFFFFu - (unsigned int) (kx & 0xFFFFFFFFull)) : 0;
+    out[tid] = sel;
+    cand_top[tid] = cand[sel];
   }
-}
-
-__global__ void gather_planes_kernel(const float4 *__restrict__ cand, const int *__restrict__ sel, int n, float4 *__restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = cand[sel[i]];
 }
 
 // K1a/K1b stage API: n_planes planes against the whole cloud (assigned[i] == -1 only).
@@ -1235,6 +1244,9 @@ struct RansacScratch {
   bool bmp_dev_clean = false;
   DevBuf<double> acc;
   DevBuf<double> refine_mem;      // RefineCtl at +0, RefineOut at +128 bytes
+  DevBuf<unsigned int> round_buf;  // one scoring round: counts | counts2 | n_valid | selected planes (see kRound* offsets)
+  PinBuf<unsigned int> round_host; // page-locked landing zone of the round's results and of the cluster kernel's verdict
+  PinBuf<float4> pool_host;
   DevBuf<unsigned char> memb_a, memb_b;   // band-local membership maps of refine_cluster_kernel
 };
 
@@ -1357,16 +1369,13 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   int n_band_builds = 0, n_band_full = 0, n_cluster_fallbacks = 0, refine_evals = 0;
   double refine_phase_ns[6] = {0, 0, 0, 0, 0, 0};
   float4 *cand = rs.cand.ensure(kCandPerRound);
-  unsigned int *counts = rs.counts.ensure(kCandPerRound);
   double *acc = rs.acc.ensure(16);
-  int *d_nvalid = d_misc + 8, *d_uvbox = d_misc + 16, *d_nsel = d_misc + 24, *d_nb = d_misc + 28;
+  int *d_uvbox = d_misc + 16, *d_nsel = d_misc + 24, *d_nb = d_misc + 28;
 
   std::vector<FoundPlane> found;
   int m = n;                       // unassigned points
   double drawn = 0;
   unsigned long long round_seed = params.seed;
-  std::vector<unsigned int> h_counts(kStage2Cand);
-  std::vector<float4> h_cand(kStage2Cand);
   float4 best_pl = make_float4(0, 0, 0, 0);
   double best_est = 0;
   const int max_rounds = 4000;
@@ -1374,7 +1383,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   struct PoolEntry { double est; float4 pl; };
   constexpr int kPoolSize = 64;
   std::vector<PoolEntry> pool;
-  std::vector<float4> h_pool(kPoolSize), banned;
+  std::vector<float4> banned;
   for (int round = 0; round < max_rounds && m >= min_support && m >= 3; ++round) {
     int nlevels = 1;
     while ((8ll << nlevels) < m) ++nlevels;
@@ -1382,20 +1391,21 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     const int S = std::min(m, kSubsample), S1 = std::min(m, kStage1Points);
     float4 *sub = rs.sub.ensure((size_t) div_up(S, kScoreTile) * 2 * kScoreTile);
     float4 *sub1 = rs.sub1.ensure((size_t) div_up(S1, kScoreTile) * 2 * kScoreTile);
-    unsigned int *counts_sorted = rs.counts_sorted.ensure(kCandPerRound), *counts2 = rs.counts2.ensure(kStage2Cand);
-    int *cidx = rs.cidx.ensure(kCandPerRound), *cidx_sorted = rs.cidx_sorted.ensure(kCandPerRound);
-    float4 *cand_top = rs.cand_top.ensure(kStage2Cand);
-    PLADE_CUDA(cudaMemsetAsync(d_nvalid, 0, sizeof(int), s));
-    PLADE_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * kCandPerRound, s));
-    PLADE_CUDA(cudaMemsetAsync(counts2, 0, sizeof(unsigned int) * kStage2Cand, s));
+    unsigned int *rb = rs.round_buf.ensure(kRoundEnd);
+    unsigned int *counts = rb, *counts2 = rb + kRoundCounts2;
+    int *d_nvalid = reinterpret_cast<int *>(rb + kRoundNValid);
+    float4 *cand_top = reinterpret_cast<float4 *>(rb + kRoundTop);
+    int *cidx_sorted = rs.cidx_sorted.ensure(kStage2Cand);
+    unsigned int *h_round = rs.round_host.ensure(kRoundEnd - kRoundCounts2 + 64);
+    PLADE_CUDA(cudaMemsetAsync(rb, 0, sizeof(unsigned int) * kRoundTop, s));
     round_seed = mix64(round_seed + 1);
     gen_candidates_kernel<<<div_up(kCandPerRound, 128), 128, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, nlevels, nthresh, round_seed, cand, d_nvalid);
     if (!pool.empty()) {   // carried candidates occupy the first slots
-      for (size_t q = 0; q < pool.size(); ++q) h_pool[q] = pool[q].pl;
-      PLADE_CUDA(cudaMemcpyAsync(cand, h_pool.data(), sizeof(float4) * pool.size(), cudaMemcpyHostToDevice, s));
+      float4 *hp = rs.pool_host.ensure(kPoolSize);
+      for (size_t q = 0; q < pool.size(); ++q) hp[q] = pool[q].pl;
+      PLADE_CUDA(cudaMemcpyAsync(cand, hp, sizeof(float4) * pool.size(), cudaMemcpyHostToDevice, s));
     }
-    gather_sub_kernel<<<div_up(S1, 256), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S1, round_seed ^ 0x5bd1e995ull, sub1);
-    gather_sub_kernel<<<div_up(S, 256), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S, round_seed, sub);
+    gather_sub_kernel<<<div_up(S1 + S, 256), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S1, round_seed ^ 0x5bd1e995ull, sub1, S, round_seed, sub);
     {
       const int n_tiles = div_up(S1, kScoreTile);
       dim3 grid(n_tiles, kCandPerRound / kScoreThreads);
@@ -1403,7 +1413,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub1, S1, cand, nullptr, kCandPerRound, eps, nthresh, 1, counts);
       dev.clock.end(s);
     }
-    select_top_kernel<<<1, kSelThreads, 0, s>>>(counts, kCandPerRound, (int) pool.size(), cidx_sorted);
+    select_top_kernel<<<1, kSelThreads, 0, s>>>(counts, kCandPerRound, (int) pool.size(), cidx_sorted, cand, cand_top);
     {
       const int n_tiles = div_up(S, kScoreTile);
       const int tiles_per_block = std::max(1, n_tiles / 128);
@@ -1412,14 +1422,14 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub, S, cand, cidx_sorted, kStage2Cand, eps, nthresh, tiles_per_block, counts2);
       dev.clock.end(s);
     }
-    gather_planes_kernel<<<1, kStage2Cand, 0, s>>>(cand, cidx_sorted, kStage2Cand, cand_top);
     PLADE_LAUNCH_CHECK();
-    dev.launches.add(7);
-    int n_valid = 0;
-    PLADE_CUDA(cudaMemcpyAsync(h_counts.data(), counts2, sizeof(unsigned int) * kStage2Cand, cudaMemcpyDeviceToHost, s));
-    PLADE_CUDA(cudaMemcpyAsync(h_cand.data(), cand_top, sizeof(float4) * kStage2Cand, cudaMemcpyDeviceToHost, s));
-    PLADE_CUDA(cudaMemcpyAsync(&n_valid, d_nvalid, sizeof(int), cudaMemcpyDeviceToHost, s));
+    dev.launches.add(5);
+    // one copy into page-locked memory (a copy into pageable memory would block the host once per call)
+    PLADE_CUDA(cudaMemcpyAsync(h_round, counts2, sizeof(unsigned int) * (kRoundEnd - kRoundCounts2), cudaMemcpyDeviceToHost, s));
     PLADE_CUDA(cudaStreamSynchronize(s));
+    const unsigned int *h_counts = h_round;
+    const int n_valid = (int) h_round[kRoundNValid - kRoundCounts2];
+    const float4 *h_cand = reinterpret_cast<const float4 *>(h_round + (kRoundTop - kRoundCounts2));
     mark("ransac_score_round");
     drawn += n_valid;
     // Candidate pool (the reference keeps its candidate list across iterations, RansacShapeDetector.cpp:
@@ -1618,9 +1628,11 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       cfg.attrs = at; cfg.numAttrs = 1;
       PLADE_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel, ra));
       dev.launches.add();
-      RefineOut ro;
-      PLADE_CUDA(cudaMemcpyAsync(&ro, ra.out, sizeof(ro), cudaMemcpyDeviceToHost, s));
+      static_assert(sizeof(RefineOut) <= 64 * sizeof(unsigned int) && ((kRoundEnd - kRoundCounts2) * 4) % 8 == 0, "verdict slot of round_host");
+      RefineOut *h_ro = reinterpret_cast<RefineOut *>(rs.round_host.ensure(kRoundEnd - kRoundCounts2 + 64) + (kRoundEnd - kRoundCounts2));
+      PLADE_CUDA(cudaMemcpyAsync(h_ro, ra.out, sizeof(RefineOut), cudaMemcpyDeviceToHost, s));     // page-locked: no implicit host block
       PLADE_CUDA(cudaStreamSynchronize(s));
+      const RefineOut ro = *h_ro;
       for (int k = 0; k < 6; ++k) refine_phase_ns[k] += ro.phase_ns[k];
       refine_evals += ro.evals;
       if (ro.status == 0) {
