@@ -279,20 +279,16 @@ __global__ void cell_key_kernel(const float4 *__restrict__ p, int n, float minx,
   order[i] = i;
 }
 
+// points into cell order + per-cell point counts (the CSR table is the exclusive prefix sum of the counts)
 __global__ void gather_cells_kernel(const float4 *__restrict__ p, const int *__restrict__ order,
                                     const unsigned int *__restrict__ keys, int n, float4 *__restrict__ out,
-                                    int *__restrict__ cell_start, int ncells) {
+                                    int *__restrict__ cell_count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 v = p[order[i]];
   v.w = 0.f;
   out[i] = v;
-  unsigned int k = keys[i];
-  unsigned int prev = (i == 0) ? 0u : keys[i - 1] + 1u;   // first cell that starts at i
-  if (i == 0 || keys[i - 1] != k)
-    for (unsigned int c = prev; c <= k; ++c) cell_start[c] = i;
-  if (i == n - 1)
-    for (unsigned int c = k + 1; c <= (unsigned int) ncells; ++c) cell_start[c] = n;
+  atomicAdd(cell_count + keys[i], 1);
 }
 
 // raw occupancy bits over the grid extended by one empty cell on every side (bit xe = x + 1 of row (y + 1, z + 1))
@@ -398,9 +394,16 @@ void build_target_grid(Device &dev, const float4 *d_tgt, size_t n, float inlier_
   dev.launches.add(3);
   float4 *pts = grid.pts.ensure(n);
   int *cs = grid.cell_start.ensure((size_t) ncells + 1);
-  gather_cells_kernel<<<div_up((long long) n, 256), 256, 0, s>>>(d_tgt, ord2, keys2, (int) n, pts, cs, ncells);
+  // CSR table: zero, count the points of every cell, exclusive prefix sum in place (streams the table twice instead
+  // of having one thread per point fill the runs of empty cells in front of it)
+  PLADE_CUDA(cudaMemsetAsync(cs, 0, sizeof(int) * ((size_t) ncells + 1), s));
+  gather_cells_kernel<<<div_up((long long) n, 256), 256, 0, s>>>(d_tgt, ord2, keys2, (int) n, pts, cs);
   PLADE_LAUNCH_CHECK();
-  dev.launches.add();
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cs, cs, ncells + 1, s);
+  tmp = grid.cub_tmp.ensure(std::max(scan_bytes, tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(tmp, scan_bytes, cs, cs, ncells + 1, s);
+  dev.launches.add(3);
   // dilated occupancy bitmap
   const int gex = grid.nx + 2, gey = grid.ny + 2, gez = grid.nz + 2;
   grid.ey = gey;
