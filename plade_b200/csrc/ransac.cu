@@ -919,6 +919,49 @@ __device__ __forceinline__ double block_sum(double v, double *sh /* 32 */) {
   if (w == 0) for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   return v;      // valid in thread 0
 }
+// N sums at once: two block barriers in total instead of two per value; results valid in thread 0
+template <int N>
+__device__ __forceinline__ void block_sum_n(double (&v)[N], double *sh /* N * 32 */) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+  __syncthreads();
+  if (l == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) sh[k * 32 + w] = v[k];
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double x = l < nw ? sh[k * 32 + l] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      v[k] = x;
+    }
+  }
+}
+// (umin, vmin, umax, vmax) at once; results valid in thread 0
+__device__ __forceinline__ void block_box4(float (&v)[4], float *sh /* 4 * 32 */) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_down_sync(0xffffffffu, v[k], o); v[k] = k < 2 ? fminf(v[k], t) : fmaxf(v[k], t); }
+  __syncthreads();
+  if (l == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sh[k * 32 + w] = v[k];
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float x = l < nw ? sh[k * 32 + l] : (k < 2 ? 3.4e38f : -3.4e38f);
+      for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_down_sync(0xffffffffu, x, o); x = k < 2 ? fminf(x, t) : fmaxf(x, t); }
+      v[k] = x;
+    }
+  }
+}
 __device__ __forceinline__ float block_minmax(float v, bool is_min, float *sh /* 32 */) {
   for (int o = 16; o > 0; o >>= 1) { float t = __shfl_down_sync(0xffffffffu, v, o); v = is_min ? fminf(v, t) : fmaxf(v, t); }
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -937,8 +980,8 @@ __device__ __forceinline__ void cluster_barrier() {
 }
 
 __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const RefineArgs a) {
-  __shared__ double sh_d[32];
-  __shared__ float sh_f[32];
+  __shared__ double sh_d[6 * 32];
+  __shared__ float sh_f[4 * 32];
   __shared__ unsigned int sbits[kRefSmemPix / 32];     // per-CTA bit image of the bitmap (pass 2) / of the component mask (pass 4)
   const int rank = (int) cluster_rank(), nthr = (int) blockDim.x, nth = (int) cluster_size() * nthr;
   const int gt = rank * nthr + threadIdx.x;
@@ -986,7 +1029,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
     a.uvbox[0] = a.uvbox[1] = f2o(3.4e38f);
     a.uvbox[2] = a.uvbox[3] = f2o(-3.4e38f);
     for (int k = 0; k < 16; ++k) a.acc[k] = 0.0;
-    __threadfence();
+    // (made visible to the other CTAs by the release / acquire of the cluster barrier that follows)
   };
   // boss: top of the do-loop body -- refit the clone and, if the refit stays inside the band, evaluate it next
   auto try_next = [&]() -> bool {
@@ -1040,11 +1083,11 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
           }
         }
       }
-      float r0 = block_minmax(umin, true, sh_f), r1 = block_minmax(vmin, true, sh_f);
-      float r2 = block_minmax(umax, false, sh_f), r3 = block_minmax(vmax, false, sh_f);
+      float box4[4] = {umin, vmin, umax, vmax};
+      block_box4(box4, sh_f);
       if (threadIdx.x == 0) {
-        atomicMin(a.uvbox + 0, f2o(r0)); atomicMin(a.uvbox + 1, f2o(r1));
-        atomicMax(a.uvbox + 2, f2o(r2)); atomicMax(a.uvbox + 3, f2o(r3));
+        atomicMin(a.uvbox + 0, f2o(box4[0])); atomicMin(a.uvbox + 1, f2o(box4[1]));
+        atomicMax(a.uvbox + 2, f2o(box4[2])); atomicMax(a.uvbox + 3, f2o(box4[3]));
       }
     }
     cluster_barrier();
@@ -1139,9 +1182,10 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
           }
         }
       }
-      double r0 = block_sum(cnt, sh_d), r1 = block_sum(sx, sh_d), r2 = block_sum(sy, sh_d), r3 = block_sum(sz, sh_d), r4 = block_sum(sc, sh_d);
-      if (threadIdx.x == 0 && r0 > 0) {
-        atomicAdd(a.acc + 0, r0); atomicAdd(a.acc + 1, r1); atomicAdd(a.acc + 2, r2); atomicAdd(a.acc + 3, r3); atomicAdd(a.acc + 4, r4);
+      double r5[5] = {cnt, sx, sy, sz, sc};
+      block_sum_n<5>(r5, sh_d);
+      if (threadIdx.x == 0 && r5[0] > 0) {
+        atomicAdd(a.acc + 0, r5[0]); atomicAdd(a.acc + 1, r5[1]); atomicAdd(a.acc + 2, r5[2]); atomicAdd(a.acc + 3, r5[3]); atomicAdd(a.acc + 4, r5[4]);
       }
     }
     cluster_barrier();
@@ -1168,10 +1212,8 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
             c[0] += dx * dx; c[1] += dx * dy; c[2] += dx * dz; c[3] += dy * dy; c[4] += dy * dz; c[5] += dz * dz;
           }
         }
-        for (int k = 0; k < 6; ++k) {
-          double r = block_sum(c[k], sh_d);
-          if (threadIdx.x == 0 && r != 0) atomicAdd(a.acc + 8 + k, r);
-        }
+        block_sum_n<6>(c, sh_d);
+        if (threadIdx.x == 0) for (int k = 0; k < 6; ++k) if (c[k] != 0) atomicAdd(a.acc + 8 + k, c[k]);
       }
     }
     cluster_barrier();
@@ -1212,7 +1254,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
           if (B.newScore > B.oldScore && B.iter < 3) go = try_next();
         }
       }
-      if (!go) { a.ctl->go = 0; __threadfence(); }
+      if (!go) a.ctl->go = 0;
     }
     cluster_barrier();
     if (boss) lap(5);
