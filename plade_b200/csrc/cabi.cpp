@@ -191,9 +191,7 @@ int plade_register_clouds(plade_ctx *ctx, const float *tgt, size_t nt, const flo
   PLADE_TRY(ctx, 0, {
     ctx->err.clear();
     Registrar &r = *ctx->reg;
-    r.upload(tgt, nt, ctx->tmp_t);
-    r.upload(src, ns, ctx->tmp_s);
-    return r.register_clouds(ctx->tmp_t, ctx->tmp_s, out16) ? 1 : 0;
+    return r.register_host_clouds(tgt, nt, src, ns, ctx->tmp_t, ctx->tmp_s, out16) ? 1 : 0;
   })
 }
 
@@ -207,9 +205,7 @@ static int register_loaded(plade_ctx *ctx, const float *t, size_t nt, const floa
     if (announce) std::cout << "---->>> ATTENTION: target and source have been switched for efficiency <<<----" << std::endl;
   }
   Registrar &r = *ctx->reg;
-  r.upload(t, nt, ctx->tmp_t);
-  r.upload(s, ns, ctx->tmp_s);
-  if (!r.register_clouds(ctx->tmp_t, ctx->tmp_s, out16)) { std::cerr << "registration failed" << std::endl; return 0; }
+  if (!r.register_host_clouds(t, nt, s, ns, ctx->tmp_t, ctx->tmp_s, out16)) { std::cerr << "registration failed" << std::endl; return 0; }
   if (switched) {
     // the reference calls Matrix4f::inverse() (general 4x4 inverse); here the general inverse of the 3x3 block
     // via its adjugate in double (R need not be exactly orthonormal in float), equal up to rounding

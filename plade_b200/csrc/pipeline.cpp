@@ -142,13 +142,14 @@ Registrar::~Registrar() {
 // defined in split.cu
 void split_cloud(Device &dev, const float *d_xyzn, size_t n, float4 *pos, float4 *nrm);
 
-void Registrar::upload(const float *xyzn, size_t n, CloudDev &out) {
+void Registrar::upload(const float *xyzn, size_t n, CloudDev &out, int lane, bool wait) {
+  Device &d = lane == 0 ? dev : dev2;
   out.n = n;
   if (n == 0) return;
-  float *d_in = upload_stage.ensure(n * 6);
-  PLADE_CUDA(cudaMemcpyAsync(d_in, xyzn, sizeof(float) * n * 6, cudaMemcpyHostToDevice, dev.stream));
-  split_cloud(dev, d_in, n, out.pos.ensure(n), out.nrm.ensure(n));
-  PLADE_CUDA(cudaStreamSynchronize(dev.stream));
+  float *d_in = upload_stage[lane].ensure(n * 6);
+  PLADE_CUDA(cudaMemcpyAsync(d_in, xyzn, sizeof(float) * n * 6, cudaMemcpyHostToDevice, d.stream));
+  split_cloud(d, d_in, n, out.pos.ensure(n), out.nrm.ensure(n));
+  if (wait) PLADE_CUDA(cudaStreamSynchronize(d.stream));
 }
 
 // average_spacing (PLADE/util.cpp:1619-1648): k = 6, ~10000 strided samples
@@ -181,6 +182,16 @@ float Registrar::average_spacing(const CloudDev &c) {
   return static_cast<float>(total / total_count);
 }
 
+bool Registrar::register_host_clouds(const float *t, size_t nt, const float *s, size_t ns, CloudDev &dt, CloudDev &ds, float out16[16]) {
+  // each lane uploads its own cloud on its own stream and goes straight on to extract its planes: the two
+  // host-to-device copies share the link, and neither lane waits for the other's cloud
+  pending_host[0] = t; pending_n[0] = nt;
+  pending_host[1] = s; pending_n[1] = ns;
+  dt.n = nt; ds.n = ns;
+  struct Clear { Registrar &r; ~Clear() { r.pending_host[0] = r.pending_host[1] = nullptr; } } clear{*this};
+  return register_clouds(dt, ds, out16);
+}
+
 bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float out16[16]) {
   double t0 = now_s();
   dev.clock.reset();
@@ -194,10 +205,12 @@ bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float 
   std::thread helper([&] {
     try {
       PLADE_CUDA(cudaSetDevice(dev.id));
+      if (pending_host[1]) upload(pending_host[1], pending_n[1], const_cast<CloudDev &>(src), 1, false);
       sp = extract_planes_dev(src, params.init_min_support, group_s, 1);
     } catch (...) { helper_error = std::current_exception(); }
   });
   try {
+    if (pending_host[0]) upload(pending_host[0], pending_n[0], const_cast<CloudDev &>(tgt), 0, false);
     tp = extract_planes_dev(tgt, params.init_min_support, group_t, 0);
   } catch (...) { helper.join(); throw; }
   helper.join();

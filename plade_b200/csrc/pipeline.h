@@ -64,7 +64,10 @@ class Registrar {
   explicit Registrar(int device);
   ~Registrar();
 
-  void upload(const float *xyzn, size_t n, CloudDev &out);   // interleaved x y z nx ny nz (host)
+  // interleaved x y z nx ny nz (host) -> pos | nrm float4 streams, on the stream of `lane`
+  void upload(const float *xyzn, size_t n, CloudDev &out, int lane = 0, bool wait = true);
+  // registration(T, target, source) from host buffers: the uploads run inside the two plane-extraction lanes
+  bool register_host_clouds(const float *t, size_t nt, const float *s, size_t ns, CloudDev &dt, CloudDev &ds, float out16[16]);
 
   // registration(T, target, source) — PLADE/plade.cpp:638 (plane extraction + the body below)
   bool register_clouds(const CloudDev &tgt, const CloudDev &src, float out16[16]);
@@ -110,7 +113,9 @@ class Registrar {
   ObbScratch obb_sc;
   SvdScratch svd_sc;
   KnnScratch knn_sc;
-  DevBuf<float> upload_stage;                     // interleaved records of the cloud being uploaded
+  DevBuf<float> upload_stage[2];                  // interleaved records of the cloud being uploaded, per lane
+  const float *pending_host[2] = {nullptr, nullptr};   // host clouds register_clouds uploads inside its lanes
+  size_t pending_n[2] = {0, 0};
   DevBuf<int> stage_group;                        // plane membership of the stage API (extract_planes / detect_planes)
   void *ransac_scratch[2] = {nullptr, nullptr};   // opaque, owned (ransac.cu)
   DevBuf<int> group_t, group_s, qidx;
