@@ -82,6 +82,9 @@ int plade_register_min_support(plade_ctx *ctx, const float *tgt_xyzn, size_t nt,
  * Returns the number of successful pairs, or -1 when no device could be used. */
 int plade_register_batch(const int *devices, int n_devices, const char *const *target_files,
                          const char *const *source_files, int n_pairs, float *out16, int *ok);
+/* The worker contexts (streams, device scratch, page-locked PLY buffers) of plade_register_batch are kept for the
+ * next call; this frees them.  Optional: process exit releases everything. */
+void plade_batch_release(void);
 
 /* HBM-resident variants (inputs uploaded once; used for the device-resident throughput figure) */
 plade_cloud *plade_cloud_upload(plade_ctx *ctx, const float *xyzn, size_t n);

@@ -43,6 +43,7 @@ SIGNATURES = {
                                                   ctypes.c_int, ctypes.c_int, _c_float_p]),
     "plade_register_batch": (ctypes.c_int, [_c_int_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p),
                                             ctypes.c_int, _c_float_p, _c_int_p]),
+    "plade_batch_release": (None, []),
     "plade_cloud_upload": (ctypes.c_void_p, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t]),
     "plade_cloud_free": (None, [ctypes.c_void_p, ctypes.c_void_p]),
     "plade_cloud_size": (ctypes.c_size_t, [ctypes.c_void_p]),

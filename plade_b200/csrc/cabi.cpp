@@ -6,6 +6,7 @@
 #include "ply.h"
 #include "libm_flt32.h"
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <iostream>
@@ -249,29 +250,80 @@ int plade_register_files(plade_ctx *ctx, const char *target_ply, const char *sou
 // worker g (one host thread + one context on devices[g]) takes the next unclaimed pair from a shared counter;
 // each worker has a loader thread that parses the NEXT pair's PLY files into its second pair of pinned
 // buffers while the current pair is on the GPU.  No data-path collective; results are written by pair index.
+// Worker state of plade_register_batch, kept across calls: creating a context, growing its scratch (~100 device
+// allocations) and pinning the PLY buffers costs a few hundred milliseconds and synchronises the whole device, so a
+// worker takes an idle state of its device from this pool and returns it when the batch is done.
+namespace {
+struct BatchSlot {
+  PinBuf<float> t, s;
+  size_t nt = 0, ns = 0;
+  int pair = -1;          // -1: end of work
+  bool loaded = false;    // both files parsed
+  std::string why;
+};
+struct BatchWorkerState {
+  int device = 0;
+  plade_ctx *ctx = nullptr;
+  BatchSlot slots[2];
+};
+std::mutex g_batch_pool_mutex;
+std::vector<BatchWorkerState *> g_batch_pool;     // idle states (never destroyed implicitly: see plade_batch_release)
+BatchWorkerState *batch_state_acquire(int device) {
+  {
+    std::lock_guard<std::mutex> l(g_batch_pool_mutex);
+    for (size_t i = 0; i < g_batch_pool.size(); ++i)
+      if (g_batch_pool[i]->device == device) {
+        BatchWorkerState *st = g_batch_pool[i];
+        g_batch_pool.erase(g_batch_pool.begin() + i);
+        return st;
+      }
+  }
+  plade_ctx *ctx = plade_ctx_create(device);
+  if (!ctx) return nullptr;
+  BatchWorkerState *st = new BatchWorkerState;
+  st->device = device;
+  st->ctx = ctx;
+  return st;
+}
+void batch_state_release(BatchWorkerState *st) {
+  std::lock_guard<std::mutex> l(g_batch_pool_mutex);
+  g_batch_pool.push_back(st);
+}
+}  // namespace
+
+void plade_batch_release(void) {
+  std::vector<BatchWorkerState *> all;
+  { std::lock_guard<std::mutex> l(g_batch_pool_mutex); all.swap(g_batch_pool); }
+  for (BatchWorkerState *st : all) {
+    cudaSetDevice(st->device);
+    plade_ctx_destroy(st->ctx);
+    delete st;
+  }
+}
+
 int plade_register_batch(const int *devices, int n_devices, const char *const *target_files, const char *const *source_files,
                          int n_pairs, float *out16, int *ok) {
   if (n_pairs < 0 || n_devices < 1 || !target_files || !source_files || !out16 || !ok) return -1;
   for (int p = 0; p < n_pairs; ++p) { identity16(out16 + 16 * p); ok[p] = 0; }
-  struct Slot {
-    PinBuf<float> t, s;
-    size_t nt = 0, ns = 0;
-    int pair = -1;          // -1: end of work
-    bool loaded = false;    // both files parsed
-    std::string why;
-  };
+  typedef BatchSlot Slot;
   struct Pin {
     static float *alloc(size_t n, void *user) { return static_cast<PinBuf<float> *>(user)->ensure(std::max<size_t>(n, 1)); }
   };
   std::atomic<int> next(0), successes(0), workers_up(0);
   std::mutex io;     // one pair's messages at a time
+  const bool timing = getenv("PLADE_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   auto worker = [&](int g) {
+    const double t_begin = now();
+    double t_load = 0, t_reg = 0, t_wait = 0;
+    int n_done = 0;
     int device = devices ? devices[g] : g;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
-    plade_ctx *ctx = plade_ctx_create(device);
-    if (!ctx) return;
+    BatchWorkerState *state = batch_state_acquire(device);
+    if (!state) return;
+    plade_ctx *ctx = state->ctx;
     workers_up.fetch_add(1);
-    Slot slots[2];
+    Slot *slots = state->slots;
     std::mutex m;
     std::condition_variable cv;
     int ready[2] = {0, 0};    // 0 = free for the loader, 1 = filled for the worker
@@ -286,23 +338,29 @@ int plade_register_batch(const int *devices, int n_devices, const char *const *t
         if (sl.pair >= n_pairs) sl.pair = -1;
         else {
           const char *tf = target_files[sl.pair], *sf = source_files[sl.pair];
+          const double tl0 = now();
           try {
             if (file_extension(tf) != "ply" || file_extension(sf) != "ply") sl.why = "only PLY format is accepted";
             else if (!load_ply_xyzn_into(tf, &Pin::alloc, &sl.t, sl.nt)) sl.why = "loading target point cloud failed";
             else if (!load_ply_xyzn_into(sf, &Pin::alloc, &sl.s, sl.ns)) sl.why = "loading source point cloud failed";
             else sl.loaded = true;
           } catch (const std::exception &e) { sl.why = e.what(); }
+          t_load += now() - tl0;
         }
         { std::lock_guard<std::mutex> l(m); ready[k] = 1; }
         cv.notify_all();
         if (sl.pair < 0) break;
       }
     });
+    const double t_setup = now() - t_begin;
     for (int k = 0;; k ^= 1) {
+      const double tw0 = now();
       { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return ready[k] == 1; }); }
+      t_wait += now() - tw0;
       Slot &sl = slots[k];
       if (sl.pair < 0) break;
       int good = 0;
+      const double tr0 = now();
       if (!sl.loaded) {
         std::lock_guard<std::mutex> l(io);
         std::cerr << sl.why << " (pair " << sl.pair << ")" << std::endl;
@@ -317,13 +375,21 @@ int plade_register_batch(const int *devices, int n_devices, const char *const *t
           good = 0;
         }
       }
+      t_reg += now() - tr0;
+      ++n_done;
       ok[sl.pair] = good;
       if (good) successes.fetch_add(1);
       { std::lock_guard<std::mutex> l(m); ready[k] = 0; }
       cv.notify_all();
     }
     loader.join();
-    plade_ctx_destroy(ctx);
+    const double t_work = now() - t_begin;
+    batch_state_release(state);
+    if (timing) {
+      std::lock_guard<std::mutex> l(io);
+      fprintf(stderr, "[plade batch worker %d on device %d] %d pairs; ms: context %.1f, waiting for the loader %.1f, registering %.1f, loader busy %.1f, teardown %.1f\n",
+              g, device, n_done, 1e3 * t_setup, 1e3 * t_wait, 1e3 * t_reg, 1e3 * t_load, 1e3 * (now() - t_begin - t_work));
+    }
   };
   std::vector<std::thread> th;
   for (int g = 0; g < n_devices; ++g) th.emplace_back(worker, g);

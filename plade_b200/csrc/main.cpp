@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 // Eigen's default operator<< (IOFormat(): StreamPrecision, columns separated by one space, rows by
@@ -82,14 +83,21 @@ int main(int argc, char **argv) {
     if (file_pair.size() == 2) { tf.push_back(file_pair[0]); sf.push_back(file_pair[1]); }
   }
   int n_dev = plade_device_count();
-  if (const char *e = getenv("PLADE_DEVICES")) n_dev = std::max(1, std::min(n_dev, atoi(e)));
   if (n_dev < 1) { std::cerr << "no usable CUDA device (plade_b200 has no CPU fallback)" << std::endl; return EXIT_FAILURE; }
+  if (const char *e = getenv("PLADE_DEVICES")) n_dev = std::max(1, std::min(n_dev, atoi(e)));
+  // one registration cannot fill a B200 (it is a chain of small launches with host decisions in between), so every
+  // GPU gets several workers (PLADE_WORKERS_PER_GPU, default min(4, host cores / (2 x GPUs)): a worker keeps two host threads busy)
+  int per_gpu = std::max(1, std::min(4, (int) std::thread::hardware_concurrency() / (2 * n_dev)));
+  if (const char *e = getenv("PLADE_WORKERS_PER_GPU")) per_gpu = std::max(1, std::min(16, atoi(e)));
   const int n = (int) tf.size();
+  std::vector<int> devices;
+  for (int w = 0; w < per_gpu; ++w) for (int g = 0; g < n_dev; ++g) devices.push_back(g);
+  if ((int) devices.size() > std::max(n, 1)) devices.resize(std::max(n, 1));
   std::vector<const char *> tp(n), sp(n);
   for (int i = 0; i < n; ++i) { tp[i] = tf[i].c_str(); sp[i] = sf[i].c_str(); }
   std::vector<float> Ts(16 * (size_t) std::max(n, 1));
   std::vector<int> oks(std::max(n, 1), 0);
-  if (plade_register_batch(nullptr, std::min(n_dev, std::max(n, 1)), tp.data(), sp.data(), n, Ts.data(), oks.data()) < 0) return EXIT_FAILURE;
+  if (plade_register_batch(devices.data(), (int) devices.size(), tp.data(), sp.data(), n, Ts.data(), oks.data()) < 0) return EXIT_FAILURE;
   int count_success = 0, count_failure = 0;
   for (int i = 0; i < n; ++i) {
     output << "target: " << tf[i] << std::endl;

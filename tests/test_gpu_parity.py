@@ -542,6 +542,10 @@ def test_batch_mode_matches_single_registrations(ctx, poly_pair, tmp_path):
         assert np.array_equal(T[k], want[k][1]), k
     ok0, T0 = plade_b200.register_batch([], devices=[0])
     assert len(ok0) == 0 and T0.shape == (0, 4, 4)
+    # the worker contexts are pooled across calls: a second batch reuses them and gives the same answers; release frees them
+    ok2, T2 = plade_b200.register_batch(pairs, devices=[0, 0])
+    assert ok2.tolist() == ok.tolist() and np.array_equal(T2, T)
+    plade_b200.load_library().plade_batch_release()
 
 
 def test_cli_result_file_format(poly_pair, tmp_path):
