@@ -9,6 +9,8 @@
 #include <cstring>
 #include <iostream>
 #include <numeric>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <exception>
 
@@ -142,6 +144,25 @@ Registrar::~Registrar() {
 // defined in split.cu
 void split_cloud(Device &dev, const float *d_xyzn, size_t n, float4 *pos, float4 *nrm);
 
+void Registrar::prepare_side(int side, const CloudDev &C, const std::vector<PlaneParam> &P, const int *d_group, float leaf, SidePrep &out) {
+  Device &d = side == 0 ? dev : dev2;
+  VoxelScratch &vs = side == 0 ? vox : vox2;
+  DevBuf<float4> &ds_all = side == 0 ? ds_tgt : ds_src, &ds_pl = side == 0 ? ds_planes_t : ds_planes_s;
+  out.ready = false;
+  out.leaf = leaf;
+  out.n_ds = voxel_downsample(d, vs, C.pos.p, C.n, leaf, ds_all);
+  if (side == 0) mark("voxel_full");
+  out.n_plane_ds = voxel_downsample_groups(d, vs, C.pos.p, C.n, d_group, (int) P.size(), leaf, ds_pl, out.plane_ds_start);
+  if (side == 0) mark("voxel_planes");
+  // oriented bounding boxes of the cloud and of every plane: one batch
+  std::vector<ObbSeg> segs;
+  segs.push_back({ds_all.p, (int) out.n_ds, 0});
+  for (size_t i = 0; i < P.size(); ++i) segs.push_back({ds_pl.p + out.plane_ds_start[i], out.plane_ds_start[i + 1] - out.plane_ds_start[i], 0});
+  obb_segments(d, side == 0 ? obb_sc : obb_sc2, segs, out.obb);
+  if (side == 0) mark("obb");
+  out.ready = true;
+}
+
 void Registrar::upload(const float *xyzn, size_t n, CloudDev &out, int lane, bool wait) {
   Device &d = lane == 0 ? dev : dev2;
   out.n = n;
@@ -153,7 +174,8 @@ void Registrar::upload(const float *xyzn, size_t n, CloudDev &out, int lane, boo
 }
 
 // average_spacing (PLADE/util.cpp:1619-1648): k = 6, ~10000 strided samples
-float Registrar::average_spacing(const CloudDev &c) {
+float Registrar::average_spacing(const CloudDev &c, int lane) {
+  Device &dev = lane == 0 ? this->dev : this->dev2;      // shadows the member: everything below runs on the lane's stream
   const int k = 6, samples = 10000;
   size_t num = c.n;
   if (num == 0) return 0.f;
@@ -202,16 +224,38 @@ bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float 
   // host-side round trips of one lane hide behind the other's)
   std::vector<PlaneParam> tp, sp;
   std::exception_ptr helper_error;
+  std::mutex spacing_mutex;
+  std::condition_variable spacing_cv;
+  bool spacing_ready = false, helper_failed = false;
+  prep[0].ready = prep[1].ready = false;
+  lane_spacing = 0;
   std::thread helper([&] {
     try {
       PLADE_CUDA(cudaSetDevice(dev.id));
       if (pending_host[1]) upload(pending_host[1], pending_n[1], const_cast<CloudDev &>(src), 1, false);
+      // the leaf size of both voxel grids is 4 x the average spacing of the SOURCE cloud (PLADE/plade.cpp:41-45): this lane
+      // computes it first, so that each lane can down-sample its own cloud as soon as its planes are known
+      const float sp_avg = src.n ? average_spacing(src, 1) : 0.f;
+      { std::lock_guard<std::mutex> l(spacing_mutex); lane_spacing = sp_avg; spacing_ready = true; }
+      spacing_cv.notify_all();
       sp = extract_planes_dev(src, params.init_min_support, group_s, 1);
-    } catch (...) { helper_error = std::current_exception(); }
+      if ((int) sp.size() >= params.min_planes && sp_avg * 4 > 0) prepare_side(1, src, sp, group_s.p, sp_avg * 4, prep[1]);
+    } catch (...) {
+      helper_error = std::current_exception();
+      { std::lock_guard<std::mutex> l(spacing_mutex); helper_failed = true; }
+      spacing_cv.notify_all();
+    }
   });
   try {
     if (pending_host[0]) upload(pending_host[0], pending_n[0], const_cast<CloudDev &>(tgt), 0, false);
     tp = extract_planes_dev(tgt, params.init_min_support, group_t, 0);
+    float sp_avg = 0;
+    {
+      std::unique_lock<std::mutex> l(spacing_mutex);
+      spacing_cv.wait(l, [&] { return spacing_ready || helper_failed; });
+      sp_avg = lane_spacing;
+    }
+    if (!helper_failed && (int) tp.size() >= params.min_planes && sp_avg * 4 > 0) prepare_side(0, tgt, tp, group_t.p, sp_avg * 4, prep[0]);
   } catch (...) { helper.join(); throw; }
   helper.join();
   dev.launches.n += dev2.launches.n;
@@ -231,7 +275,10 @@ bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float 
     return false;
   }
   times.planes = now_s() - t0;
-  return register_core(tgt, src, tp, sp, group_t.p, group_s.p, out16);
+  const bool ok = register_core(tgt, src, tp, sp, group_t.p, group_s.p, out16);
+  prep[0].ready = prep[1].ready = false;      // valid for this call only
+  lane_spacing = 0;
+  return ok;
 }
 
 bool Registrar::register_min_support(const CloudDev &tgt, const CloudDev &src, int ms_t, int ms_s, float out16[16]) {
@@ -275,7 +322,7 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
 
   // ---- constants, PLADE/plade.cpp:41-56 -----------------------------------------------------------
   double t0 = now_s();
-  const float average_space = average_spacing(src);
+  const float average_space = lane_spacing > 0 ? lane_spacing : average_spacing(src);
   times.spacing = now_s() - t0;
   mark("spacing");
   float downSampleDistance = average_space * 4;
@@ -302,10 +349,15 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     Side &A = S[side];
     const CloudDev &C = *clouds[side];
     const std::vector<PlaneParam> &P = *planes_in[side];
-    A.n_ds = voxel_downsample(dev, vox, C.pos.p, C.n, downSampleDistance, *ds_dev[side]);
-    mark("voxel_full");
-    size_t nv = voxel_downsample_groups(dev, vox, C.pos.p, C.n, d_groups[side], (int) P.size(), downSampleDistance, *ds_pl[side], A.plane_ds_start);
-    mark("voxel_planes");
+    // done already inside the cloud's extraction lane (register_clouds), unless the planes came from the caller
+    if (!(prep[side].ready && prep[side].leaf == downSampleDistance)) {
+      if (side == 1) PLADE_CUDA(cudaStreamSynchronize(dev.stream));     // lane 1 reads nothing lane 0 still writes, but keep the order simple
+      prepare_side(side, C, P, d_groups[side], downSampleDistance, prep[side]);
+      if (side == 1) PLADE_CUDA(cudaStreamSynchronize(dev2.stream));
+    }
+    A.n_ds = prep[side].n_ds;
+    A.plane_ds_start = prep[side].plane_ds_start;
+    const size_t nv = prep[side].n_plane_ds;
     if (debug) {     // host copies are only needed for the stage dumps
       A.ds.resize(A.n_ds);
       A.plane_ds.resize(nv);
@@ -314,16 +366,9 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
       PLADE_CUDA(cudaStreamSynchronize(s));
     }
   }
-  // oriented bounding boxes of both clouds and of every plane: one batch
   {
-    std::vector<ObbSeg> segs;
-    for (int side = 0; side < 2; ++side) {
-      segs.push_back({ds_dev[side]->p, (int) S[side].n_ds, 0});
-      for (size_t i = 0; i < planes_in[side]->size(); ++i)
-        segs.push_back({ds_pl[side]->p + S[side].plane_ds_start[i], S[side].plane_ds_start[i + 1] - S[side].plane_ds_start[i], 0});
-    }
     std::vector<ObbResult> obb;
-    obb_segments(dev, obb_sc, segs, obb);
+    for (int side = 0; side < 2; ++side) obb.insert(obb.end(), prep[side].obb.begin(), prep[side].obb.end());
     size_t k = 0;
     for (int side = 0; side < 2; ++side) {
       Side &A = S[side];

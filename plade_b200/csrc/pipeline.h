@@ -49,6 +49,17 @@ struct StageTimes {
   double verify_kernel_ms = 0, verify_h = 0, verify_ns = 0, verify_nt = 0;
 };
 
+// Per-cloud set-up of the matching stage (PLADE/plade.cpp:74-122 / :287-335): down-sampled cloud, per-plane
+// down-sampled clouds, oriented bounding boxes.  Computed inside the cloud's plane-extraction lane when the leaf
+// size is already known, otherwise by register_core.
+struct SidePrep {
+  bool ready = false;
+  float leaf = 0;
+  size_t n_ds = 0, n_plane_ds = 0;
+  std::vector<int> plane_ds_start;      // P + 1
+  std::vector<ObbResult> obb;           // [0] = whole down-sampled cloud, [1 + i] = plane i
+};
+
 struct MatchedHyp {     // MatchedResult, PLADE/util.h:128-134
   M3 R;
   V3 T;
@@ -78,7 +89,7 @@ class Registrar {
                             const std::vector<PlaneRec> &sp, float out16[16]);
 
   // stage entry points (host buffers)
-  float average_spacing(const CloudDev &c);
+  float average_spacing(const CloudDev &c, int lane = 0);
   std::vector<PlaneRec> extract_planes(const CloudDev &c, int init_min_support);             // extract(), plade.cpp:602
   std::vector<PlaneRec> detect_planes(const CloudDev &c, int min_support);                   // PlaneExtraction::detect
   // device-resident variants used by the registration path: membership stays in HBM (group_out[n])
@@ -87,6 +98,10 @@ class Registrar {
   std::vector<PlaneRec> planes_to_host(const CloudDev &c, const std::vector<PlaneParam> &pp, const DevBuf<int> &group);
   bool register_core(const CloudDev &tgt, const CloudDev &src, const std::vector<PlaneParam> &tp, const std::vector<PlaneParam> &sp,
                      const int *d_group_t, const int *d_group_s, float out16[16]);
+  // side: 0 = target, 1 = source; runs on the stream of lane `side`
+  void prepare_side(int side, const CloudDev &c, const std::vector<PlaneParam> &planes, const int *d_group, float leaf, SidePrep &out);
+  SidePrep prep[2];
+  float lane_spacing = 0;               // average_spacing(source), computed by the source lane of register_clouds
 
   Device dev;
   Device dev2;      // helper stream: plane extraction of the source cloud runs concurrently with the target's
@@ -104,13 +119,13 @@ class Registrar {
   void *allreduce_user = nullptr;
 
   // scratch (grow-only, reused across calls)
-  VoxelScratch vox;
+  VoxelScratch vox, vox2;               // per lane
   TargetGrid grid;
   MatchScratch match_sc;
   HypScratch hyp_sc;
   DevBuf<float4> ds_tgt, ds_src, ds_planes_t, ds_planes_s;
   PenScratch pen_sc;
-  ObbScratch obb_sc;
+  ObbScratch obb_sc, obb_sc2;           // per lane
   SvdScratch svd_sc;
   KnnScratch knn_sc;
   DevBuf<float> upload_stage[2];                  // interleaved records of the cloud being uploaded, per lane
