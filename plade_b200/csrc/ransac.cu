@@ -42,7 +42,8 @@ constexpr int kStage1Points = 4096;    // stage 1: every candidate against a sma
 constexpr int kStage2Cand = 256;       // stage 2: the best stage-1 candidates ...
 constexpr int kSubsample = 65536;      // ... against the large subsample
 constexpr int kScoreTile = 512;       // points per TMA tile (pos + nrm = 16 KB)
-constexpr int kScoreThreads = 256;    // one candidate per thread
+constexpr int kScoreThreads = 256;    // threads per scoring block
+constexpr int kScoreC1 = 2;           // candidates per thread in stage 1 (16384 candidates x 4096 points)
 constexpr unsigned int kForcedKey = 2u * kStage1Points;   // stage-1 key of a carried candidate: above every real count
 constexpr int kStage1KeyBits = 14;    // bits of the stage-1 keys (counts <= 4096 < kForcedKey = 8192 < 2^14)
 static_assert(kForcedKey < (1u << kStage1KeyBits) && kStage1Points < (int) kForcedKey, "stage-1 sort key range");
@@ -201,14 +202,22 @@ __global__ void gather_sub_kernel(const float4 *__restrict__ pos, const float4 *
 }
 
 // K1a: every candidate of the round against the subsample.  grid = (tile groups, candidate groups).
+// C candidates per thread: the two shared-memory loads of a point (broadcast to the warp) are amortised over C
+// plane tests, and the C independent dependency chains keep the FP pipe busy with few warps per SM.
+template <int C>
 __global__ void __launch_bounds__(kScoreThreads)
 score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__restrict__ cand, const int *__restrict__ sel, int n_cand,
                         float eps, float nthresh, int tiles_per_block, unsigned int *__restrict__ counts) {
   __shared__ __align__(128) float4 buf[2][2 * kScoreTile];
   __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x;
-  const int c = blockIdx.y * kScoreThreads + tid;
-  const float4 pl = (c < n_cand) ? cand[sel ? sel[c] : c] : make_float4(0.f, 0.f, 0.f, 3.0e38f);
+  const int c0 = blockIdx.y * (kScoreThreads * C) + tid;          // this thread's candidates: c0 + k * kScoreThreads
+  float4 pl[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    const int c = c0 + k * kScoreThreads;
+    pl[k] = (c < n_cand) ? cand[sel ? sel[c] : c] : make_float4(0.f, 0.f, 0.f, 3.0e38f);
+  }
   const int n_tiles = (S + kScoreTile - 1) / kScoreTile;
   const int t0 = blockIdx.x * tiles_per_block, t1 = min(n_tiles, t0 + tiles_per_block);
   if (tid == 0) {
@@ -226,7 +235,9 @@ score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__r
   };
   uint32_t phase[2] = {0, 0};
   if (tid == 0 && t0 < t1) issue(t0, 0);
-  unsigned int cnt = 0;
+  unsigned int cnt[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) cnt[k] = 0;
   for (int t = t0; t < t1; ++t) {
     const int b = (t - t0) & 1;
     if (tid == 0 && t + 1 < t1) {
@@ -237,11 +248,50 @@ score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__r
     phase[b] ^= 1;
     const int np = min(kScoreTile, S - t * kScoreTile);
     const float4 *P = buf[b], *N = buf[b] + kScoreTile;
-#pragma unroll 4
-    for (int j = 0; j < np; ++j) cnt += compatible(pl, P[j], N[j], eps, nthresh) ? 1u : 0u;
+#pragma unroll 2
+    for (int j = 0; j < np; ++j) {
+      const float4 p = P[j], nr = N[j];
+#pragma unroll
+      for (int k = 0; k < C; ++k) cnt[k] += compatible(pl[k], p, nr, eps, nthresh) ? 1u : 0u;
+    }
     __syncthreads();   // everyone done with buf[b] before it is refilled two iterations later
   }
-  if (c < n_cand && cnt) atomicAdd(&counts[c], cnt);
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    const int c = c0 + k * kScoreThreads;
+    if (c < n_cand && cnt[k]) atomicAdd(&counts[c], cnt[k]);
+  }
+}
+
+// Stage 2 (kStage2Cand candidates x 65536 points) has too few candidates for one-candidate-per-thread to fill the
+// GPU, so the roles are swapped: one thread per subsample point (65536 threads), the candidate planes broadcast from
+// shared memory, and the per-candidate counts formed from warp ballots.  Same predicate, same integer counts.
+__global__ void __launch_bounds__(256)
+score_points_kernel(const float4 *__restrict__ sub, int S, const float4 *__restrict__ cand, const int *__restrict__ sel,
+                    float eps, float nthresh, unsigned int *__restrict__ counts) {
+  __shared__ float4 pl_s[kStage2Cand];
+  __shared__ unsigned int cnt_s[kStage2Cand];
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int c = tid; c < kStage2Cand; c += blockDim.x) { pl_s[c] = cand[sel[c]]; cnt_s[c] = 0u; }
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + tid;
+  const bool live = k < S;
+  const int kk = live ? k : S - 1;
+  const int tile = kk / kScoreTile, j = kk - tile * kScoreTile;
+  const float4 p = sub[(size_t) tile * 2 * kScoreTile + j], nr = sub[(size_t) tile * 2 * kScoreTile + kScoreTile + j];
+#pragma unroll 4
+  for (int c = 0; c < kStage2Cand; ++c) {
+    const float4 pl = pl_s[c];
+    const float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p.x), __fmul_rn(pl.y, p.y)), __fmul_rn(pl.z, p.z));
+    const bool near = live && fabsf(__fsub_rn(pl.w, dp)) < eps;
+    if (__any_sync(0xffffffffu, near)) {            // warp-uniform branch
+      const float dn = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, nr.x), __fmul_rn(pl.y, nr.y)), __fmul_rn(pl.z, nr.z));
+      const unsigned int m = __ballot_sync(0xffffffffu, near && fabsf(dn) >= nthresh);
+      if (lane == 0 && m) atomicAdd(&cnt_s[c], (unsigned int) __popc(m));
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < kStage2Cand; c += blockDim.x) if (cnt_s[c]) atomicAdd(&counts[c], cnt_s[c]);
 }
 
 // stage-1 keys: carried pool candidates are forced into stage 2; idx = iota
@@ -1450,20 +1500,15 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     gather_sub_kernel<<<div_up(S1 + S, 256), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S1, round_seed ^ 0x5bd1e995ull, sub1, S, round_seed, sub);
     {
       const int n_tiles = div_up(S1, kScoreTile);
-      dim3 grid(n_tiles, kCandPerRound / kScoreThreads);
+      dim3 grid(n_tiles, kCandPerRound / (kScoreThreads * kScoreC1));
       dev.clock.begin(KernelClock::kScoreCandidates, 28.0 * S1, s);     // 28 B per point per pass
-      score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub1, S1, cand, nullptr, kCandPerRound, eps, nthresh, 1, counts);
+      score_candidates_kernel<kScoreC1><<<grid, kScoreThreads, 0, s>>>(sub1, S1, cand, nullptr, kCandPerRound, eps, nthresh, 1, counts);
       dev.clock.end(s);
     }
     select_top_kernel<<<1, kSelThreads, 0, s>>>(counts, kCandPerRound, (int) pool.size(), cidx_sorted, cand, cand_top);
-    {
-      const int n_tiles = div_up(S, kScoreTile);
-      const int tiles_per_block = std::max(1, n_tiles / 128);
-      dim3 grid(div_up(n_tiles, tiles_per_block), kStage2Cand / kScoreThreads);
-      dev.clock.begin(KernelClock::kScoreCandidates, 28.0 * S, s);
-      score_candidates_kernel<<<grid, kScoreThreads, 0, s>>>(sub, S, cand, cidx_sorted, kStage2Cand, eps, nthresh, tiles_per_block, counts2);
-      dev.clock.end(s);
-    }
+    dev.clock.begin(KernelClock::kScoreCandidates, 28.0 * S, s);
+    score_points_kernel<<<div_up(S, 256), 256, 0, s>>>(sub, S, cand, cidx_sorted, eps, nthresh, counts2);
+    dev.clock.end(s);
     PLADE_LAUNCH_CHECK();
     dev.launches.add(5);
     // one copy into page-locked memory (a copy into pageable memory would block the host once per call)
