@@ -302,7 +302,7 @@ def run_ours(args):
                              "instruction issue; the HBM figure is the SURVEY.md 8(d) algorithmic-bytes convention"},
         # the kernels of the timed registration step itself, timed live with CUDA events around every launch (context 0, last step,
         # while the other contexts' kernels share the GPU)
-        "step_kernels": [kernel_line("score_candidates_kernel (K1a; ALU-bound: 16384 candidates x 4096 points, then 256 x 65536, per round)", k1, reg_ms),
+        "step_kernels": [kernel_line("score_candidates_kernel + score_points_kernel (K1a; ALU-bound: 16384 candidates x 4096 points, then 256 x 65536, per round)", k1, reg_ms),
                          kernel_line("verify_kernel (K5) inside the registration (H = %d surviving hypotheses)" % int(stage["verify_h"]), k5_in, reg_ms)],
         "verify_sharded": {"hypotheses": H, "src_ds_points": int(len(ds_s)), "tgt_ds_points": int(len(ds_t)), "ms": t_sh * 1e3,
                            "kernel_ms_max_rank": k_sh, "hyps_per_s": H / t_sh, "scaling": "strong", "collective": "ncclAllReduce(max, 1 x i64)" if world > 1 else "none",
