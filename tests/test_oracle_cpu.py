@@ -309,6 +309,29 @@ def test_no_gpu_means_loud_failure_not_fallback():
         plade_b200.Context()
 
 
+def test_no_gpu_cli_and_batch_fail_loudly(tmp_path):
+    """Without a device the CLI exits with failure (both usages) and plade_register_batch reports -1: no CPU path."""
+    import subprocess
+    import plade_b200
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cli = os.path.join(ROOT, "plade_b200", "plade_b200_cli")
+    assert os.path.exists(cli)
+    lib = plade_b200.load_library()
+    assert lib.plade_device_count() == 0
+    r = subprocess.run([cli, "a.ply", "b.ply", str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "no usable CUDA device" in r.stderr
+    lst = tmp_path / "pairs.txt"
+    lst.write_text("a.ply\nb.ply\n")
+    r = subprocess.run([cli, str(lst), str(tmp_path / "res.txt")], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "no usable CUDA device" in r.stderr
+    with pytest.raises(RuntimeError):
+        plade_b200.register_batch([("a.ply", "b.ply")], devices=[0])
+    r = subprocess.run([cli], capture_output=True, text=True, timeout=60)          # usage text, PLADE/main.cpp:46-72
+    assert r.returncode != 0 and "Usage 1" in r.stderr and "Usage 2" in r.stderr
+
+
 def test_product_never_touches_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may use oracle/."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "plade_b200")):
