@@ -49,33 +49,38 @@ struct PenArgs {
 
 __device__ __forceinline__ V3 ld3(const float *p) { return V3(p[0], p[1], p[2]); }
 
-// geometry part of AreTwoPlanesPenetrable (PLADE/util.cpp:1295-1373); returns 1 when the sampling passes are needed
-__device__ int segment_of_pair(const float plane1[4], const float plane2[4], const V3 c1[4], const V3 c2[4], V3 &start, V3 &direc,
-                               float &length) {
+// geometry part of AreTwoPlanesPenetrable (PLADE/util.cpp:1295-1373), eight lanes per (hypothesis, plane, plane)
+// triple: lane e of the group intersects the plane/plane line with rectangle edge e (0-3: first rectangle, 4-7:
+// second) -- the expensive part, a restated 9x9 SVD solve per edge -- then the leader lane finishes the scalar
+// logic exactly as the one-thread version did.  Returns 1 (in every lane) when the sampling passes are needed.
+__device__ int segment_of_pair8(const float plane1[4], const float plane2[4], const V3 c1[4], const V3 c2[4], int e, unsigned int gshift,
+                                V3 &start, V3 &direc, float &length) {
   V3 lineVec, linePoint;
-  if (0 != plane_intersection_line(plane1, plane2, lineVec, linePoint)) return 0;
-  V3 ip1[4], ip2[4];
-  int n1 = 0, n2 = 0;
-  for (int i = 1; i <= 4; ++i) {
-    V3 tl = c1[i % 4] - c1[(i - 1) % 4];
+  const int have_line = 0 == plane_intersection_line(plane1, plane2, lineVec, linePoint);   // same inputs in all 8 lanes
+  bool hit = false;
+  V3 ip;
+  if (have_line) {
+    const V3 *c = e < 4 ? c1 : c2;
+    const int i = (e & 3) + 1;                              // the reference's loop index, 1..4
+    V3 tl = c[i % 4] - c[(i - 1) % 4];
     normalize(tl);
-    V3 ip;
-    if (0 != line_line_point_cv(lineVec, linePoint, tl, c1[i - 1], ip)) continue;
-    if (dot(c1[(i - 1) % 4] - ip, c1[i % 4] - ip) > 0) continue;
-    ip1[n1++] = ip;
+    if (0 == line_line_point_cv(lineVec, linePoint, tl, c[i - 1], ip)) hit = !(dot(c[(i - 1) % 4] - ip, c[i % 4] - ip) > 0);
   }
-  for (int i = 1; i <= 4; ++i) {
-    V3 tl = c2[i % 4] - c2[(i - 1) % 4];
-    normalize(tl);
-    V3 ip;
-    if (0 != line_line_point_cv(lineVec, linePoint, tl, c2[i - 1], ip)) continue;
-    if (dot(c2[(i - 1) % 4] - ip, c2[i % 4] - ip) > 0) continue;
-    ip2[n2++] = ip;
+  const unsigned int all = __ballot_sync(0xffffffffu, hit);
+  const unsigned int m1 = (all >> gshift) & 0xFu, m2 = (all >> (gshift + 4)) & 0xFu;
+  // the two intersection points of each rectangle, in edge order (ip1[0], ip1[1], ip2[0], ip2[1] of the reference)
+  const int a0 = __ffs(m1) - 1, a1 = __ffs(m1 & (m1 - 1)) - 1, b0 = __ffs(m2) - 1, b1 = __ffs(m2 & (m2 - 1)) - 1;
+  const int src_lane[4] = {(int) gshift + max(a0, 0), (int) gshift + max(a1, 0), (int) gshift + 4 + max(b0, 0), (int) gshift + 4 + max(b1, 0)};
+  V3 inter[4];
+  for (int k = 0; k < 4; ++k) {
+    inter[k].x = __shfl_sync(0xffffffffu, ip.x, src_lane[k]);
+    inter[k].y = __shfl_sync(0xffffffffu, ip.y, src_lane[k]);
+    inter[k].z = __shfl_sync(0xffffffffu, ip.z, src_lane[k]);
   }
-  if (n1 != 2 || n2 != 2) return 0;      // empty -> not penetrable; any other count -> the reference returns -1
-  direc = ip1[1] - ip1[0];
+  if (!have_line) return 0;
+  if (__popc(m1) != 2 || __popc(m2) != 2) return 0;      // empty -> not penetrable; any other count -> the reference returns -1
+  direc = inter[1] - inter[0];
   normalize(direc);
-  V3 inter[4] = {ip1[0], ip1[1], ip2[0], ip2[1]};
   float len[4];
   int idx[4];
   for (int i = 0; i < 4; ++i) { len[i] = dot(inter[i] - inter[0], direc); idx[i] = i; }
@@ -94,29 +99,43 @@ __device__ int segment_of_pair(const float plane1[4], const float plane2[4], con
   return 1;
 }
 
-__global__ void pen_geometry_kernel(PenArgs a, Triple *__restrict__ out, int *__restrict__ n_out, int *__restrict__ overflow) {
-  long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long) a.H * a.Ps * a.Pt;
-  if (t >= total) return;
-  int j1 = (int) (t % a.Pt), i1 = (int) ((t / a.Pt) % a.Ps), h = (int) (t / ((long long) a.Pt * a.Ps));
-  if (a.off_s[i1 + 1] == a.off_s[i1] || a.off_t[j1 + 1] == a.off_t[j1]) return;   // no corner points -> returns -1
+__global__ void __launch_bounds__(128) pen_geometry_kernel(PenArgs a, Triple *__restrict__ out, int *__restrict__ n_out, int *__restrict__ overflow) {
+  const long long gtid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = gtid >> 3;                          // triple of this 8-lane group
+  const int e = (int) (gtid & 7);
+  const unsigned int gshift = (threadIdx.x & 31) & ~7u;
+  const long long total = (long long) a.H * a.Ps * a.Pt;
+  // (no early return before the warp-wide ballot / shuffles: out-of-range and gated-out groups stay in the warp, idle)
+  bool active = t < total;
+  int j1 = 0, i1 = 0, h = 0;
+  if (active) {
+    j1 = (int) (t % a.Pt); i1 = (int) ((t / a.Pt) % a.Ps); h = (int) (t / ((long long) a.Pt * a.Ps));
+    if (a.off_s[i1 + 1] == a.off_s[i1] || a.off_t[j1 + 1] == a.off_t[j1]) active = false;   // no corner points -> returns -1
+  }
   M3 R;
-  for (int k = 0; k < 9; ++k) R.m[k] = a.hyp[12 * h + k];
-  V3 T(a.hyp[12 * h + 9], a.hyp[12 * h + 10], a.hyp[12 * h + 11]);
-  float4 ps = a.planes_s[i1], pt = a.planes_t[j1];
-  V3 pn = mul(R, V3(ps.x, ps.y, ps.z));
-  float plane1[4] = {pn.x, pn.y, pn.z, -(-ps.w + dot(pn, T))};
-  float plane2[4] = {pt.x, pt.y, pt.z, pt.w};
-  V3 cc = mul(R, ld3(a.center_s + 3 * i1)) + T;
-  V3 plane_A(pt.x, pt.y, pt.z);
-  // PLADE/util.cpp:487-492 (note: the dot product is compared with the ANGLE threshold there)
-  double c2p = (fabsf(dot(plane_A, cc) + pt.w) + fabsf(dot(pn, ld3(a.center_t + 3 * j1)) + plane1[3])) / 2;
-  if (c2p < a.lengthThreshold && dot(pn, plane_A) > a.angleThreshold) return;
+  V3 T;
+  float plane1[4] = {0.f, 0.f, 1.f, 0.f}, plane2[4] = {0.f, 0.f, 1.f, 0.f};
   V3 c1[4], c2[4];
-  for (int k = 0; k < 4; ++k) { c1[k] = xform(R, T, ld3(a.corners_s + 12 * i1 + 3 * k)); c2[k] = ld3(a.corners_t + 12 * j1 + 3 * k); }
+  if (active) {
+    for (int k = 0; k < 9; ++k) R.m[k] = a.hyp[12 * h + k];
+    T = V3(a.hyp[12 * h + 9], a.hyp[12 * h + 10], a.hyp[12 * h + 11]);
+    float4 ps = a.planes_s[i1], pt = a.planes_t[j1];
+    V3 pn = mul(R, V3(ps.x, ps.y, ps.z));
+    plane1[0] = pn.x; plane1[1] = pn.y; plane1[2] = pn.z; plane1[3] = -(-ps.w + dot(pn, T));
+    plane2[0] = pt.x; plane2[1] = pt.y; plane2[2] = pt.z; plane2[3] = pt.w;
+    V3 cc = mul(R, ld3(a.center_s + 3 * i1)) + T;
+    V3 plane_A(pt.x, pt.y, pt.z);
+    // PLADE/util.cpp:487-492 (note: the dot product is compared with the ANGLE threshold there)
+    double c2p = (fabsf(dot(plane_A, cc) + pt.w) + fabsf(dot(pn, ld3(a.center_t + 3 * j1)) + plane1[3])) / 2;
+    if (c2p < a.lengthThreshold && dot(pn, plane_A) > a.angleThreshold) active = false;
+  }
+  if (active)
+    for (int k = 0; k < 4; ++k) { c1[k] = xform(R, T, ld3(a.corners_s + 12 * i1 + 3 * k)); c2[k] = ld3(a.corners_t + 12 * j1 + 3 * k); }
   V3 start, direc;
-  float length;
-  if (!segment_of_pair(plane1, plane2, c1, c2, start, direc, length)) return;
+  float length = 0.f;
+  // inactive groups run the edge step on a dummy pair of parallel planes (no intersection line: a cheap early out)
+  const int need = segment_of_pair8(plane1, plane2, c1, c2, e, gshift, start, direc, length);
+  if (!active || !need || e != 0) return;
   int nsteps = 0;
   while (nsteps < kMaxSteps && a.dist_table[nsteps] < length) ++nsteps;   // for (dist = 0; dist < length; dist += searchRadius)
   if (nsteps == 0) return;                // no sample: both counts stay 0 -> not penetrable
@@ -270,7 +289,7 @@ void penetration_filter(Device &dev, PenScratch &sc, const PenSide &src, const P
   int *d_flags = sc.flags.ensure((size_t) H + 8);
   PLADE_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * ((size_t) H + 8), s));
   int *d_n = d_flags + H, *d_ovf = d_flags + H + 1;
-  pen_geometry_kernel<<<div_up(total, 128), 128, 0, s>>>(a, d_tr, d_n, d_ovf);
+  pen_geometry_kernel<<<div_up(total * 8, 128), 128, 0, s>>>(a, d_tr, d_n, d_ovf);
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
   int h2[2];
