@@ -332,6 +332,25 @@ def test_no_gpu_cli_and_batch_fail_loudly(tmp_path):
     assert r.returncode != 0 and "Usage 1" in r.stderr and "Usage 2" in r.stderr
 
 
+def test_dropin_header_has_the_reference_overloads(tmp_path):
+    """include/plade.h compiles against Eigen + PCL types with the reference's four registration() signatures
+    (PLADE/plade.h:44-96); degenerate inputs (missing files, a 100-point line) return false and leave the identity."""
+    import subprocess
+    eigen = "/root/reference/code/3rd_party/eigen-3.4.0"
+    if not os.path.isdir(eigen):
+        pytest.skip("the reference's Eigen is not mounted here")
+    exe = str(tmp_path / "dropin_check")
+    cmd = ["g++", "-std=c++14", "-O1", "-DPLADE_WITH_PCL", "-I", os.path.join(ROOT, "include"), "-I", eigen,
+           "-I", os.path.join(ROOT, "oracle", "pcl_shim"), "-I", "/root/reference/code/3rd_party",
+           os.path.join(ROOT, "tests", "host", "dropin_check.cpp"), "-o", exe,
+           "-L", os.path.join(ROOT, "plade_b200"), "-lplade_b200", "-Wl,-rpath," + os.path.join(ROOT, "plade_b200")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "results=0 identity_after_failure=1" in r.stdout, (r.stdout, r.stderr[-500:])
+
+
 def test_product_never_touches_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may use oracle/."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "plade_b200")):
