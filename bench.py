@@ -189,6 +189,7 @@ def run_ours(args):
     ok = all(r[0] for r in last)
     stage = ctx.stage_times()        # context 0, last step
     k1 = ctx.kernel_times("score_candidates")
+    k1r, k1b = ctx.kernel_times("refine_cluster"), ctx.kernel_times("band_compact")
     k5_in = ctx.kernel_times("verify")
     t_step = max_over_ranks(ms / 1e3 / args.steps)
     value = world * B / t_step
@@ -301,8 +302,11 @@ def run_ours(args):
                      "note": "L2-resident working set (ds clouds + grid < 60 MB): DRAM traffic is ~0.1% of peak and the kernel is bound by "
                              "instruction issue; the HBM figure is the SURVEY.md 8(d) algorithmic-bytes convention"},
         # the kernels of the timed registration step itself, timed live with CUDA events around every launch (context 0, last step,
-        # while the other contexts' kernels share the GPU)
-        "step_kernels": [kernel_line("score_candidates_kernel + score_points_kernel (K1a; ALU-bound: 16384 candidates x 4096 points, then 256 x 65536, per round)", k1, reg_ms),
+        # while the other contexts' kernels share the GPU; times are summed over the two concurrent lanes of the registration,
+        # so the shares relate kernel time to wall time and can add up to more than 1)
+        "step_kernels": [kernel_line("refine_cluster_kernel (K1b-d; one 16-CTA cluster per candidate: latency-bound, 16 of 148 SMs)", k1r, reg_ms),
+                         kernel_line("band_compact_kernel (HBM streaming pass over all points, once per candidate)", k1b, reg_ms),
+                         kernel_line("score_candidates_kernel + score_points_kernel (K1a; ALU-bound: 16384 candidates x 4096 points, then 256 x 65536, per round)", k1, reg_ms),
                          kernel_line("verify_kernel (K5) inside the registration (H = %d surviving hypotheses)" % int(stage["verify_h"]), k5_in, reg_ms)],
         "verify_sharded": {"hypotheses": H, "src_ds_points": int(len(ds_s)), "tgt_ds_points": int(len(ds_t)), "ms": t_sh * 1e3,
                            "kernel_ms_max_rank": k_sh, "hyps_per_s": H / t_sh, "scaling": "strong", "collective": "ncclAllReduce(max, 1 x i64)" if world > 1 else "none",

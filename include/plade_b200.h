@@ -52,7 +52,8 @@ long long plade_launch_count(plade_ctx *ctx);     /* kernels launched by this co
 int plade_stage_times(plade_ctx *ctx, double *out, int n);
 /* Device time of one kernel family during the last plade_register_* call, measured with CUDA events recorded on
  * the launching stream around every launch: out = { total ms, launches, algorithmic bytes }.
- * kernel = "score_candidates" (K1a, 28 B per subsample point per pass) or "verify" (K5).  1 if known. */
+ * kernel = "score_candidates" (K1a, 28 B per subsample point per pass), "refine_cluster" (K1b-d, 28 B per band
+ * point per evaluation), "band_compact" (20 B per point) or "verify" (K5).  1 if known. */
 int plade_kernel_times(plade_ctx *ctx, const char *kernel, double out[3]);
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of this context is
  * launched on): start records an event, stop records a second one, waits for it and returns the

@@ -149,10 +149,12 @@ int plade_kernel_times(plade_ctx *ctx, const char *kernel, double out[3]) {
   out[0] = out[1] = out[2] = 0;
   const std::string k(kernel);
   const Registrar &r = *ctx->reg;
-  if (k == "score_candidates") {
-    out[0] = r.dev.clock.ms[KernelClock::kScoreCandidates];
-    out[1] = (double) r.dev.clock.launches[KernelClock::kScoreCandidates];
-    out[2] = r.dev.clock.bytes[KernelClock::kScoreCandidates];
+  const int kind = k == "score_candidates" ? KernelClock::kScoreCandidates : k == "refine_cluster" ? KernelClock::kRefineCluster
+                   : k == "band_compact" ? KernelClock::kBandCompact : -1;
+  if (kind >= 0) {
+    out[0] = r.dev.clock.ms[kind];
+    out[1] = (double) r.dev.clock.launches[kind];
+    out[2] = r.dev.clock.bytes[kind];
     return 1;
   }
   if (k == "verify") {

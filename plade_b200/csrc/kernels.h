@@ -11,7 +11,7 @@ namespace plade {
 // collect() is called once the stream is idle and adds the elapsed device times to the totals that bench.py
 // reads through plade_kernel_times (the roofline figure of the dominant kernel is measured live this way).
 struct KernelClock {
-  enum { kScoreCandidates = 0, kKinds = 1 };
+  enum { kScoreCandidates = 0, kRefineCluster = 1, kBandCompact = 2, kKinds = 3 };
   struct Span { cudaEvent_t a = nullptr, b = nullptr; int kind = 0; };
   std::vector<Span> spans;
   size_t used = 0;

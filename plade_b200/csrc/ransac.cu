@@ -938,7 +938,7 @@ struct RefineOut {
   int acc_sel;            // membership map that holds its members (0 = A, 1 = B)
   int status;             // 0 = done, 1 = bitmap larger than the device cap (host path), 2 = a refit left the band
   int evals;
-  int pad;
+  int n_band;             // points of the candidate's band (algorithmic bytes of the launch = 28 B x n_band x evals)
   unsigned int phase_ns[6];   // device time per phase summed over the evaluations (flags, raster, components, select, covariance, decision)
 };
 struct RefineArgs {
@@ -1313,7 +1313,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
     RefineOut o;
     o.acc_size = B.acc_size;
     for (int k = 0; k < 3; ++k) { o.acc_n[k] = B.acc_n[k]; o.acc_p[k] = B.acc_p[k]; }
-    o.acc_sel = B.acc_sel; o.status = B.status; o.evals = B.evals; o.pad = 0;
+    o.acc_sel = B.acc_sel; o.status = B.status; o.evals = B.evals; o.n_band = n;
     for (int k = 0; k < 6; ++k) o.phase_ns[k] = B.phase_ns[k];
     *a.out = o;
   }
@@ -1616,7 +1616,9 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     bool band_full = false;
     auto build_band = [&](const float4 &pl, bool full) {
       PLADE_CUDA(cudaMemsetAsync(d_nb, 0, sizeof(int), s));
+      dev.clock.begin(KernelClock::kBandCompact, 20.0 * n, s);       // assigned (4 B) + position (16 B) of every point, once
       band_compact_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, pl, full ? INFINITY : kBandMul * eps3, posB, nrmB, idxB, d_nb);
+      dev.clock.end(s);
       PLADE_LAUNCH_CHECK();
       dev.launches.add();
       band_pl = pl;
@@ -1713,13 +1715,16 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
+      dev.clock.begin(KernelClock::kRefineCluster, 0.0, s);
       PLADE_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel, ra));
+      dev.clock.end(s);
       dev.launches.add();
       static_assert(sizeof(RefineOut) <= 64 * sizeof(unsigned int) && ((kRoundEnd - kRoundCounts2) * 4) % 8 == 0, "verdict slot of round_host");
       RefineOut *h_ro = reinterpret_cast<RefineOut *>(rs.round_host.ensure(kRoundEnd - kRoundCounts2 + 64) + (kRoundEnd - kRoundCounts2));
       PLADE_CUDA(cudaMemcpyAsync(h_ro, ra.out, sizeof(RefineOut), cudaMemcpyDeviceToHost, s));     // page-locked: no implicit host block
       PLADE_CUDA(cudaStreamSynchronize(s));
       const RefineOut ro = *h_ro;
+      dev.clock.bytes[KernelClock::kRefineCluster] += 28.0 * ro.n_band * ro.evals;     // 28 B per point per pass
       for (int k = 0; k < 6; ++k) refine_phase_ns[k] += ro.phase_ns[k];
       refine_evals += ro.evals;
       if (ro.status == 0) {

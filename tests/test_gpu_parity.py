@@ -599,6 +599,9 @@ def test_kernel_times_and_cluster_path_parity(ctx):
     k1, k5 = ctx.kernel_times("score_candidates"), ctx.kernel_times("verify")
     assert k1["launches"] >= 2 and k1["ms"] > 0 and k1["algorithmic_bytes"] > 0
     assert k5["launches"] == 1 and k5["ms"] > 0
+    kr, kb = ctx.kernel_times("refine_cluster"), ctx.kernel_times("band_compact")
+    assert kr["launches"] >= 20 and kr["ms"] > 0 and kr["algorithmic_bytes"] > 0       # one cluster launch per evaluated candidate
+    assert kb["launches"] >= kr["launches"] and kb["algorithmic_bytes"] >= 20.0 * 150000 * kb["launches"] * 0.9
     with pytest.raises(KeyError):
         ctx.kernel_times("no_such_kernel")
     planes = ctx.extract_planes(tgt, 10000)
