@@ -227,8 +227,13 @@ bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float 
   std::mutex spacing_mutex;
   std::condition_variable spacing_cv;
   bool spacing_ready = false, helper_failed = false;
-  prep[0].ready = prep[1].ready = false;
-  lane_spacing = 0;
+  // the per-lane set-up is valid for this call only, whatever way it ends
+  struct PrepReset {
+    Registrar &r;
+    explicit PrepReset(Registrar &reg) : r(reg) { clear(); }
+    ~PrepReset() { clear(); }
+    void clear() { r.prep[0].ready = r.prep[1].ready = false; r.lane_spacing = 0; }
+  } prep_reset(*this);
   std::thread helper([&] {
     try {
       PLADE_CUDA(cudaSetDevice(dev.id));
@@ -275,14 +280,13 @@ bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float 
     return false;
   }
   times.planes = now_s() - t0;
-  const bool ok = register_core(tgt, src, tp, sp, group_t.p, group_s.p, out16);
-  prep[0].ready = prep[1].ready = false;      // valid for this call only
-  lane_spacing = 0;
-  return ok;
+  return register_core(tgt, src, tp, sp, group_t.p, group_s.p, out16);
 }
 
 bool Registrar::register_min_support(const CloudDev &tgt, const CloudDev &src, int ms_t, int ms_s, float out16[16]) {
   double t0 = now_s();
+  prep[0].ready = prep[1].ready = false;
+  lane_spacing = 0;
   std::vector<PlaneParam> tp = detect_planes_dev(tgt, ms_t, group_t);
   std::vector<PlaneParam> sp = detect_planes_dev(src, ms_s, group_s);
   times.planes = now_s() - t0;
@@ -309,6 +313,8 @@ bool Registrar::register_with_planes(const CloudDev &tgt, const CloudDev &src, c
     PLADE_CUDA(cudaStreamSynchronize(dev.stream));
   }
   times.planes = 0;
+  prep[0].ready = prep[1].ready = false;
+  lane_spacing = 0;
   return register_core(tgt, src, pp[0], pp[1], group_t.p, group_s.p, out16);
 }
 
