@@ -655,9 +655,9 @@ def test_largest_component_bit_exact(ctx):
         assert np.array_equal(got, want), (b.shape, int(got.sum()), int(want.sum()))
 
 
-@pytest.mark.xfail(strict=False, reason="round-1 gap: with the GPU RANSAC's plane set (10 + 13 planes) the room's 180-degree-symmetric "
-                   "hypothesis out-scores the true one (rot 179.85 deg, translation 2.2 %); the reference shows the same flip for 1 of 3 "
-                   "seeds at 16x and 2 of 3 at 12x decimation, and none at 8x")
+@pytest.mark.xfail(strict=False, reason="round-1 gap (DESIGN.md section 7): the GPU RANSAC finds exactly 10 planes on the 94 K scan at "
+                   "min_support 2500 and extract() stops there, the reference finds 9, halves the support and matches with 14-15 planes; "
+                   "with 10 planes the room's symmetric hypotheses (180 / 121 / 90 deg) out-score the true one for every seed tried")
 def test_room_pair_real_scan_swap_path(ctx, tmp_path):
     """BASELINE config 2 on real scanned data (tests/golden/room_decimated.npz: the reference's room pair, source decimated
     8x so that it can travel): the file overload swaps the clouds (source >= 1.2 x target, PLADE/plade.cpp:689-704) and
