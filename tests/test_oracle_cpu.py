@@ -351,6 +351,38 @@ def test_dropin_header_has_the_reference_overloads(tmp_path):
     assert "results=0 identity_after_failure=1" in r.stdout, (r.stdout, r.stderr[-500:])
 
 
+def test_room_pair_outcome_is_decided_by_the_plane_count(ref):
+    """Evidence for the open gap of DESIGN.md section 7 (BASELINE config 2): on the decimated room pair the REFERENCE's own
+    matching back end lands on a symmetric solution when it is given the ten planes of the 94 K scan that have >= 2500
+    points (the set the GPU RANSAC finds, where extract() stops), and on the true transform when it is given the 13-16
+    planes >= 1250 points (the set the reference's incomplete detection ends up with after one more halving)."""
+    from plade_b200.synth import transform_error
+    g = np.load(os.path.join(ROOT, "tests", "golden", "room_decimated.npz"))
+    small, big, gt = g["tgt"], g["src"], g["gt"]
+    diag = float(np.linalg.norm(np.ptp(small[:, :3], axis=0)))
+
+    def keep(planes, thr):
+        off, idx, par = planes
+        sel = [i for i in range(len(off) - 1) if off[i + 1] - off[i] >= thr]
+        no, ni = [0], []
+        for i in sel:
+            ni.extend(idx[off[i]:off[i + 1]].tolist())
+            no.append(len(ni))
+        return np.array(no, np.int32), np.array(ni, np.int32), np.asarray(par, np.float32)[sel]
+
+    ref.set_seed(1)
+    pb = ref.extract(big, 10000, "b_")
+    ps_all = ref.detect(small, 1250, "s_")
+    out = {}
+    for thr in (2500, 1250):
+        ps = keep(ps_all, thr)
+        ok, T = ref.registration_planes(big, small, pb, ps)          # swapped, as the file overload does
+        assert ok
+        out[thr] = (len(ps[0]) - 1,) + tuple(transform_error(np.linalg.inv(T.astype(np.float64)), gt, diag))
+    assert out[2500][0] == 10 and out[2500][1] > 90.0                 # ten planes: a symmetric solution
+    assert out[1250][0] >= 13 and out[1250][1] <= 2.0 and out[1250][2] <= 0.03
+
+
 def test_product_never_touches_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may use oracle/."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "plade_b200")):
