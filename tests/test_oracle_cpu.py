@@ -383,6 +383,62 @@ def test_room_pair_outcome_is_decided_by_the_plane_count(ref):
     assert out[1250][0] >= 13 and out[1250][1] <= 2.0 and out[1250][2] <= 0.03
 
 
+def test_ply_ingest_formats_and_errors(tmp_path):
+    """PLY ingest of the file overload (PLADE/ply_reader.cpp:46-148 -> util.cpp:1505-1546 in the reference; ply.cpp here):
+    the binary float fast path, reordered / extra / non-float properties, ASCII, and the failure cases."""
+    exe = str(tmp_path / "ply_check")
+    src = os.path.join(ROOT, "plade_b200", "csrc")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", src, os.path.join(ROOT, "tests", "host", "ply_check.cpp"),
+                        os.path.join(src, "ply.cpp"), "-o", exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+    def parse(path):
+        out = subprocess.run([exe, str(path)], capture_output=True, text=True, timeout=60).stdout.split("\n")
+        if out[0].startswith("fail"):
+            return None
+        n = int(out[0].split()[1])
+        return np.array([[float(x) for x in l.split()] for l in out[1:1 + n]], dtype=np.float32).reshape(n, 6)
+
+    rng = np.random.default_rng(4)
+    a = rng.normal(size=(257, 6)).astype(np.float32)
+    hdr6 = "property float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\n"
+    # 1. the layout of the reference's sample files: binary little-endian, six floats (straight fread)
+    p = tmp_path / "fast.ply"
+    p.write_bytes(("ply\nformat binary_little_endian 1.0\ncomment made by a test\nelement vertex %d\n%send_header\n" % (len(a), hdr6)).encode() + a.tobytes())
+    assert np.array_equal(parse(p), a)
+    # 2. reordered properties, an extra uchar colour and double coordinates, followed by a face element that is ignored
+    rec = np.zeros(len(a), dtype=[("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"), ("red", "u1"), ("x", "<f8"), ("y", "<f8"), ("z", "<f8")])
+    for k, nm in enumerate(["x", "y", "z", "nx", "ny", "nz"]):
+        rec[nm] = a[:, k]
+    rec["red"] = 7
+    hdr = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float nx\nproperty float ny\nproperty float nz\n"
+           "property uchar red\nproperty double x\nproperty double y\nproperty double z\nelement face 0\nproperty list uchar int vertex_indices\nend_header\n" % len(a))
+    p = tmp_path / "generic.ply"
+    p.write_bytes(hdr.encode() + rec.tobytes())
+    assert np.array_equal(parse(p), a)
+    # 3. ASCII
+    p = tmp_path / "ascii.ply"
+    p.write_text("ply\nformat ascii 1.0\nelement vertex %d\n%send_header\n" % (len(a), hdr6) + "\n".join(" ".join("%.9g" % v for v in row) for row in a) + "\n")
+    assert np.array_equal(parse(p), a)
+    # 4. failures: no normals, truncated payload, big-endian, not a PLY, missing file, zero vertices
+    p = tmp_path / "nonormals.ply"
+    p.write_bytes(("ply\nformat binary_little_endian 1.0\nelement vertex 2\nproperty float x\nproperty float y\nproperty float z\nend_header\n").encode() + a[:2, :3].tobytes())
+    assert parse(p) is None
+    p = tmp_path / "short.ply"
+    p.write_bytes(("ply\nformat binary_little_endian 1.0\nelement vertex %d\n%send_header\n" % (len(a), hdr6)).encode() + a.tobytes()[:-10])
+    assert parse(p) is None
+    p = tmp_path / "be.ply"
+    p.write_bytes(("ply\nformat binary_big_endian 1.0\nelement vertex %d\n%send_header\n" % (len(a), hdr6)).encode() + a.byteswap().tobytes())
+    assert parse(p) is None
+    p = tmp_path / "text.ply"
+    p.write_text("this is not a ply file\n")
+    assert parse(p) is None
+    assert parse(tmp_path / "missing.ply") is None
+    p = tmp_path / "empty.ply"
+    p.write_bytes(("ply\nformat binary_little_endian 1.0\nelement vertex 0\n%send_header\n" % hdr6).encode())
+    assert parse(p) is None
+
+
 def test_product_never_touches_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may use oracle/."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "plade_b200")):
