@@ -22,7 +22,13 @@ int type_size(const std::string &t) {
   if (t == "double" || t == "float64") return 8;
   return 0;
 }
-double decode(const unsigned char *p, const std::string &t) {
+double decode(const unsigned char *p, const std::string &t, bool swap_bytes = false) {
+  unsigned char tmp[8];
+  if (swap_bytes) {                       // binary_big_endian files (rply reads both byte orders)
+    const int n = type_size(t);
+    for (int i = 0; i < n; ++i) tmp[i] = p[n - 1 - i];
+    p = tmp;
+  }
   if (t == "float" || t == "float32") { float v; memcpy(&v, p, 4); return v; }
   if (t == "double" || t == "float64") { double v; memcpy(&v, p, 8); return v; }
   if (t == "char" || t == "int8") return (signed char) p[0];
@@ -86,7 +92,7 @@ bool load_ply_xyzn_into(const std::string &file_name, PlyAlloc alloc, void *user
       props.push_back(p);
     } else if (tok == "end_header") { header_ok = true; break; }
   }
-  if (!header_ok || binary_be || (!binary_le && !ascii) || !vertex_first) {
+  if (!header_ok || (!binary_le && !binary_be && !ascii) || !vertex_first) {
     fclose(f);
     std::cerr << "failed to read ply header" << std::endl;
     return false;
@@ -103,8 +109,8 @@ bool load_ply_xyzn_into(const std::string &file_name, PlyAlloc alloc, void *user
   float *out = alloc(n_vertex * 6, user);
   if (!out && n_vertex) { fclose(f); std::cerr << "failed to read ply file: " << file_name << std::endl; return false; }
   bool ok = true;
-  if (binary_le) {
-    bool fast = props.size() == 6;
+  if (binary_le || binary_be) {
+    bool fast = binary_le && props.size() == 6;
     for (int k = 0; k < 6 && fast; ++k) fast = ix[k] == k && (props[k].type == "float" || props[k].type == "float32");
     if (fast) {
       ok = fread(out, sizeof(float) * 6, n_vertex, f) == n_vertex;
@@ -118,7 +124,7 @@ bool load_ply_xyzn_into(const std::string &file_name, PlyAlloc alloc, void *user
         size_t chunk = std::min<size_t>(4096, n_vertex - done);
         ok = fread(buf.data(), rec, chunk, f) == chunk;
         for (size_t r = 0; r < chunk && ok; ++r)
-          for (int k = 0; k < 6; ++k) out[(done + r) * 6 + k] = (float) decode(buf.data() + r * rec + off[ix[k]], props[ix[k]].type);
+          for (int k = 0; k < 6; ++k) out[(done + r) * 6 + k] = (float) decode(buf.data() + r * rec + off[ix[k]], props[ix[k]].type, binary_be);
         done += chunk;
       }
     }

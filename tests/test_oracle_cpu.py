@@ -420,15 +420,19 @@ def test_ply_ingest_formats_and_errors(tmp_path):
     p = tmp_path / "ascii.ply"
     p.write_text("ply\nformat ascii 1.0\nelement vertex %d\n%send_header\n" % (len(a), hdr6) + "\n".join(" ".join("%.9g" % v for v in row) for row in a) + "\n")
     assert np.array_equal(parse(p), a)
-    # 4. failures: no normals, truncated payload, big-endian, not a PLY, missing file, zero vertices
+    # 4. big-endian payload (rply, which the reference reads through, accepts both byte orders)
+    p = tmp_path / "be.ply"
+    p.write_bytes(("ply\nformat binary_big_endian 1.0\nelement vertex %d\n%send_header\n" % (len(a), hdr6)).encode() + a.byteswap().tobytes())
+    assert np.array_equal(parse(p), a)
+    # 5. failures: no normals, truncated payload, unknown format, not a PLY, missing file, zero vertices
     p = tmp_path / "nonormals.ply"
     p.write_bytes(("ply\nformat binary_little_endian 1.0\nelement vertex 2\nproperty float x\nproperty float y\nproperty float z\nend_header\n").encode() + a[:2, :3].tobytes())
     assert parse(p) is None
     p = tmp_path / "short.ply"
     p.write_bytes(("ply\nformat binary_little_endian 1.0\nelement vertex %d\n%send_header\n" % (len(a), hdr6)).encode() + a.tobytes()[:-10])
     assert parse(p) is None
-    p = tmp_path / "be.ply"
-    p.write_bytes(("ply\nformat binary_big_endian 1.0\nelement vertex %d\n%send_header\n" % (len(a), hdr6)).encode() + a.byteswap().tobytes())
+    p = tmp_path / "fmt.ply"
+    p.write_bytes(("ply\nformat binary_middle_endian 1.0\nelement vertex %d\n%send_header\n" % (len(a), hdr6)).encode() + a.tobytes())
     assert parse(p) is None
     p = tmp_path / "text.ply"
     p.write_text("this is not a ply file\n")
