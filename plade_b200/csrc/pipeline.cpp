@@ -255,12 +255,14 @@ bool Registrar::register_clouds(const CloudDev &tgt, const CloudDev &src, float 
     if (pending_host[0]) upload(pending_host[0], pending_n[0], const_cast<CloudDev &>(tgt), 0, false);
     tp = extract_planes_dev(tgt, params.init_min_support, group_t, 0);
     float sp_avg = 0;
+    bool failed = false;
     {
       std::unique_lock<std::mutex> l(spacing_mutex);
       spacing_cv.wait(l, [&] { return spacing_ready || helper_failed; });
       sp_avg = lane_spacing;
+      failed = helper_failed;       // read under the lock: the helper thread may still be writing it
     }
-    if (!helper_failed && (int) tp.size() >= params.min_planes && sp_avg * 4 > 0) prepare_side(0, tgt, tp, group_t.p, sp_avg * 4, prep[0]);
+    if (!failed && (int) tp.size() >= params.min_planes && sp_avg * 4 > 0) prepare_side(0, tgt, tp, group_t.p, sp_avg * 4, prep[0]);
   } catch (...) { helper.join(); throw; }
   helper.join();
   dev.launches.n += dev2.launches.n;

@@ -35,6 +35,9 @@ struct Params {
   // RANSAC (PLADE/plade.cpp:591-595,607,627; PLADE/plane_extraction.cpp:93-98)
   float ransac_dist_thresh = 0.005f, ransac_bitmap_reso = 0.02f, ransac_normal_thresh = 0.8f, ransac_prob = 0.001f;
   int init_min_support = 10000, min_planes = 10, max_planes = 40, min_allowed_support = 200, max_trials = 10;
+  // extract(): planes count towards min_planes when their support is >= detect_margin x the pass's min_support (1 = the
+  // reference's literal rule; see extract_planes_dev)
+  double detect_margin = 1.25;
   // matching (PLADE/plade.cpp:46-56)
   int max_candidates = 200;
   float face_matches_weight = 0.2f;

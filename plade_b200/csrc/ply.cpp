@@ -3,6 +3,7 @@
 // PLADE/util.cpp:1505-1546).  Here: one header parse, then either a straight read of the binary
 // little-endian `float x y z nx ny nz` records (the layout of all sample_data files) or a generic
 // per-property decode (ascii / other scalar types / extra properties), into interleaved float[6].
+// Restriction (documented): `vertex` must be the first element of the file, as in every file the reference ships.
 #include "ply.h"
 #include <cstdio>
 #include <cstdlib>
@@ -89,6 +90,8 @@ bool load_ply_xyzn_into(const std::string &file_name, PlyAlloc alloc, void *user
       if (p.type == "list") { fclose(f); std::cerr << "failed to read ply header" << std::endl; return false; }
       ss >> p.name;
       p.size = type_size(p.type);
+      // an unknown scalar type (rply knows the eight above) would silently shift every later field offset
+      if (p.size == 0) { fclose(f); std::cerr << "failed to read ply header" << std::endl; return false; }
       props.push_back(p);
     } else if (tok == "end_header") { header_ok = true; break; }
   }
@@ -105,6 +108,18 @@ bool load_ply_xyzn_into(const std::string &file_name, PlyAlloc alloc, void *user
     fclose(f);
     std::cerr << "the number of points does not equal to the number of normals in the file" << std::endl;
     return false;
+  }
+  // the header's vertex count is untrusted: a binary file must actually hold n_vertex records (and an ascii one at
+  // least two characters per value) before anything of that size is allocated
+  {
+    size_t rec = 0;
+    for (const Prop &q : props) rec += (size_t) q.size;
+    const long here = ftell(f);
+    long end = here;
+    if (here >= 0 && fseek(f, 0, SEEK_END) == 0) { end = ftell(f); fseek(f, here, SEEK_SET); }
+    const unsigned long long remaining = end > here ? (unsigned long long) (end - here) : 0ull;
+    const unsigned long long need = (binary_le || binary_be) ? (unsigned long long) n_vertex * rec : (unsigned long long) n_vertex * props.size() * 2ull;
+    if (need > remaining + 1) { fclose(f); std::cerr << "failed to read ply file: " << file_name << std::endl; return false; }
   }
   float *out = alloc(n_vertex * 6, user);
   if (!out && n_vertex) { fclose(f); std::cerr << "failed to read ply file: " << file_name << std::endl; return false; }

@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstring>
 #include <iostream>
+#include <mutex>
 
 namespace plade {
 
@@ -1347,28 +1348,41 @@ int refine_block_threads() {
   static const int t = [] { const char *e = getenv("PLADE_REFINE_THREADS"); int v = e ? atoi(e) : kRefThreads; return (v == 256 || v == 512 || v == 1024) ? v : kRefThreads; }();
   return t;
 }
-int refine_cluster_size() {
-  static const int cached = [] {       // (thread-safe: the two lanes of a context ask concurrently)
+// Function attributes and occupancy are per device: plade_register_batch and the CLI run contexts on several GPUs in one
+// process, so the non-portable cluster opt-in and the occupancy query are made once per DEVICE (not once per process).
+int refine_cluster_size(int device) {
+  constexpr int kMaxDev = 64;
+  static std::mutex mu;
+  static int cached[kMaxDev];
+  static bool known[kMaxDev] = {};
+  std::lock_guard<std::mutex> lock(mu);       // (the two lanes of a context ask concurrently)
+  if (device < 0 || device >= kMaxDev) return 0;
+  if (known[device]) return cached[device];
   int size = 0;
-  if (getenv("PLADE_NO_CLUSTER_REFINE")) return size;
-  const char *e = getenv("PLADE_REFINE_CLUSTER");
-  const int first = e ? atoi(e) : 16;
-  for (int want : {first, 8}) {
-    if (want < 1 || want > 16) continue;
-    if (want > 8 && cudaFuncSetAttribute(refine_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(want); cfg.blockDim = dim3(refine_block_threads());
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int n_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&n_clusters, refine_cluster_kernel, &cfg) == cudaSuccess && n_clusters >= 1) { size = want; break; }
-    cudaGetLastError();
+  if (!getenv("PLADE_NO_CLUSTER_REFINE")) {
+    const char *e = getenv("PLADE_REFINE_CLUSTER");
+    const int first = e ? atoi(e) : 16;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != device) cudaSetDevice(device);
+    for (int want : {first, 8}) {
+      if (want < 1 || want > 16) continue;
+      if (want > 8 && cudaFuncSetAttribute(refine_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(want); cfg.blockDim = dim3(refine_block_threads());
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, refine_cluster_kernel, &cfg) == cudaSuccess && n_clusters >= 1) { size = want; break; }
+      cudaGetLastError();
+    }
+    if (cur != device && cur >= 0) cudaSetDevice(cur);
   }
+  cached[device] = size;
+  known[device] = true;
   return size;
-  }();
-  return cached;
 }
 
 struct FoundPlane { float n[3]; float pos[3]; long long size; };
@@ -1694,7 +1708,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     const unsigned char *band_member = nullptr;      // members of the accepted plane by band position (cluster path)
     build_band(fr.pl, false);
     // ---- the whole acceptance chain in one cluster kernel, one host round trip (refine_cluster_kernel) -----------
-    if (const int csize = refine_cluster_size()) {
+    if (const int csize = refine_cluster_size(dev.id)) {
       unsigned char *rm = reinterpret_cast<unsigned char *>(rs.refine_mem.ensure(64));
       RefineArgs ra;
       ra.posB = posB; ra.nrmB = nrmB; ra.idxB = idxB; ra.d_nb = d_nb;
@@ -1854,12 +1868,25 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   return result;
 }
 
-// extract(), PLADE/plade.cpp:602-635
+// extract(), PLADE/plade.cpp:602-635.
+// One documented, parameter-gated deviation: the reference stops halving the support as soon as
+// its detector RETURNS min_planes planes; its detector misses most planes whose support is below ~1.25 x min_support
+// (measured detection frequency over seeds: 0.2-0.35 below 1.2 x, ~1.0 from 1.6 x; tools/detection_curve.py), so its
+// loop effectively stops on planes comfortably above the threshold.  The detector here finds every plane >= min_support,
+// so counting all of them would stop one halving earlier than the reference does on scans that hold exactly min_planes
+// planes near the threshold (the reference's own room pair).  Planes count towards min_planes when their support is
+// >= detect_margin x the support of that pass; all planes >= min_support are still returned.  detect_margin = 1 is the
+// literal rule.
 std::vector<PlaneParam> Registrar::extract_planes_dev(const CloudDev &c, int init_min_support, DevBuf<int> &group_out, int lane) {
   Device &dev = lane == 0 ? this->dev : this->dev2;
   const int min_num = params.min_planes, max_num = params.max_planes, min_allowed_support = params.min_allowed_support;
+  auto counted = [&](const std::vector<PlaneParam> &pl, int support) {
+    int k = 0;
+    for (const PlaneParam &q : pl) if ((double) q.size >= params.detect_margin * support) ++k;
+    return k;
+  };
   std::vector<PlaneParam> planes = detect_planes_dev(c, init_min_support, group_out, lane);
-  if ((int) planes.size() >= min_num && (int) planes.size() <= max_num) return planes;
+  if (counted(planes, init_min_support) >= min_num && (int) planes.size() <= max_num) return planes;
   if ((int) planes.size() > max_num) {
     // the reference sorts with a (non-strict) `>=` comparator; a stable descending sort is the defined equivalent
     std::vector<int> ord(planes.size());
@@ -1879,8 +1906,10 @@ std::vector<PlaneParam> Registrar::extract_planes_dev(const CloudDev &c, int ini
   const int max_trials = params.max_trials;
   int min_support = init_min_support / 2;
   int trials = 1;
-  while ((int) planes.size() < min_num && trials < max_trials && min_support >= min_allowed_support) {
+  int used_support = init_min_support;
+  while (counted(planes, used_support) < min_num && trials < max_trials && min_support >= min_allowed_support) {
     planes = detect_planes_dev(c, min_support, group_out, lane);
+    used_support = min_support;
     min_support /= 2;
     ++trials;
   }

@@ -366,9 +366,13 @@ void build_target_grid(Device &dev, const float4 *d_tgt, size_t n, float inlier_
   double cell = (double) inlier_dist * (1.0 + 1.0 / 1024.0);
   if (!(cell > 0)) cell = 1e-6;
   double ex = (double) mx[0] - mn[0], ey = (double) mx[1] - mn[1], ez = (double) mx[2] - mn[2];
-  for (;;) {
+  // a non-finite coordinate (reachable from an untrusted PLY) would make the cell-growing loop below spin for ever
+  if (!(std::isfinite(ex) && std::isfinite(ey) && std::isfinite(ez) && ex >= 0 && ey >= 0 && ez >= 0))
+    throw std::runtime_error("build_target_grid: non-finite coordinates in the down-sampled target cloud");
+  for (int it = 0;; ++it) {
     double cells = (std::floor(ex / cell) + 1) * (std::floor(ey / cell) + 1) * (std::floor(ez / cell) + 1);
     if (cells <= 67108864.0) break;
+    if (it > 400) throw std::runtime_error("build_target_grid: grid extent out of range");
     cell *= 1.26;
   }
   grid.cell = (float) cell;
