@@ -142,6 +142,19 @@ class Ref:
         L.ref_transform_from_two_vecs.argtypes = [_fp, ctypes.c_int, _fp, _fp]
         L.ref_cluster_transformations.argtypes = [_fp, _fp, ctypes.c_int, ctypes.c_float, ctypes.c_float, _ip]
         L.ref_compute_overlap.argtypes = [_fp, ctypes.c_size_t, _fp, ctypes.c_size_t, _fp, _fp, _fp, ctypes.c_int, ctypes.c_float, ctypes.c_float, _fp, _ip]
+        # RANSAC building blocks and the PLY reader
+        L.ref_plane_parameters.restype = None
+        L.ref_plane_parameters.argtypes = [_fp, _fp, _fp, ctypes.c_size_t, _fp, _fp]
+        L.ref_connected_component.restype = ctypes.c_longlong
+        L.ref_connected_component.argtypes = [_fp, ctypes.c_size_t, _fp, _fp, _ip, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, _ip]
+        L.ref_plane_ls_fit.argtypes = [_fp, ctypes.c_size_t, _ip, ctypes.c_size_t, _fp, _fp]
+        L.ref_weighted_score.restype = ctypes.c_float
+        L.ref_weighted_score.argtypes = [_fp, ctypes.c_size_t, _fp, _fp, _ip, ctypes.c_size_t, ctypes.c_float, ctypes.c_float]
+        L.ref_refine_candidate.restype = ctypes.c_longlong
+        L.ref_refine_candidate.argtypes = [_fp, ctypes.c_size_t, _ip, _fp, _fp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_uint,
+                                           _fp, _fp, _ip, _ip]
+        L.ref_load_ply.restype = ctypes.c_longlong
+        L.ref_load_ply.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
 
     class _Quiet:
         def __init__(self, on):
@@ -309,6 +322,61 @@ class Ref:
         self.lib.ref_compute_overlap(_p(s, _fp), len(s), _p(t, _fp), len(t), _p(R9, _fp), _p(T3, _fp), _p(C3, _fp), len(R9),
                                      float(query_radius), float(inlier_distance), _p(ov, _fp), _p(cnt, _ip))
         return ov, cnt
+
+
+def _ref_methods():
+    def plane_parameters(self, normal, pos, xyz):
+        """PlanePrimitiveShape::Parameters: (uv[n,2], u[3], v[3])"""
+        nrm, p, a = _f32(normal), _f32(pos), _f32(xyz).reshape(-1, 3)
+        uv = np.zeros((len(a), 2), np.float32)
+        fr = np.zeros(6, np.float32)
+        self.lib.ref_plane_parameters(_p(nrm, _fp), _p(p, _fp), _p(a, _fp), len(a), _p(uv, _fp), _p(fr, _fp))
+        return uv, fr[:3].copy(), fr[3:].copy()
+
+    def connected_component(self, xyzn, normal, pos, idx, bitmap_eps, do_filtering=True):
+        """BitmapPrimitiveShape::ConnectedComponent on points idx: sorted member indices of the largest component"""
+        a, nrm, p, ix = _f32(xyzn).reshape(-1, 6), _f32(normal), _f32(pos), _i32(idx)
+        out = np.zeros(max(len(ix), 1), np.int32)
+        k = self.lib.ref_connected_component(_p(a, _fp), len(a), _p(nrm, _fp), _p(p, _fp), _p(ix, _ip), len(ix), float(bitmap_eps),
+                                             1 if do_filtering else 0, _p(out, _ip))
+        return out[:k].copy()
+
+    def plane_ls_fit(self, xyzn, idx):
+        a, ix = _f32(xyzn).reshape(-1, 6), _i32(idx)
+        n, p = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        ok = self.lib.ref_plane_ls_fit(_p(a, _fp), len(a), _p(ix, _ip), len(ix), _p(n, _fp), _p(p, _fp))
+        return bool(ok), n, p
+
+    def weighted_score(self, xyzn, normal, pos, idx, epsilon, normal_thresh=0.8):
+        a, nrm, p, ix = _f32(xyzn).reshape(-1, 6), _f32(normal), _f32(pos), _i32(idx)
+        return float(self.lib.ref_weighted_score(_p(a, _fp), len(a), _p(nrm, _fp), _p(p, _fp), _p(ix, _ip), len(ix), float(epsilon), float(normal_thresh)))
+
+    def refine_candidate(self, xyzn, normal, pos, epsilon, normal_thresh, bitmap_eps, min_support, assigned=None):
+        """acceptance chain of one candidate (Detect, R/RansacShapeDetector.cpp:613-655): (size, normal, pos, members, (accepted, tried))"""
+        a, nrm, p = _f32(xyzn).reshape(-1, 6), _f32(normal), _f32(pos)
+        asg = _i32(assigned) if assigned is not None else None
+        on, op = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        out = np.zeros(len(a), np.int32)
+        tr = np.zeros(2, np.int32)
+        with self.q():
+            k = self.lib.ref_refine_candidate(_p(a, _fp), len(a), _p(asg, _ip) if asg is not None else None, _p(nrm, _fp), _p(p, _fp),
+                                              float(epsilon), float(normal_thresh), float(bitmap_eps), int(min_support), _p(on, _fp), _p(op, _fp),
+                                              _p(out, _ip), _p(tr, _ip))
+        return int(k), on, op, out[:k].copy(), (int(tr[0]), int(tr[1]))
+
+    def load_ply_ref(self, path):
+        """load_ply_cloud (PLADE/util.cpp:1505-1546): (n, 6) float32 or None"""
+        with self.q():
+            k = self.lib.ref_load_ply(os.fsencode(path), b"ply")
+        if k < 0:
+            return None
+        return self.blob("ply", np.float32).reshape(-1, 6)
+
+    for f in (plane_parameters, connected_component, plane_ls_fit, weighted_score, refine_candidate, load_ply_ref):
+        setattr(Ref, f.__name__, f)
+
+
+_ref_methods()
 
 
 def load_ply(path):

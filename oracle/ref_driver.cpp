@@ -19,6 +19,12 @@
 #include "plane_extraction.h"
 #include <opencv2/imgproc/imgproc.hpp>
 #include <MiscLib/Random.h>
+#include <RansacShapeDetector.h>
+#include <PlanePrimitiveShape.h>
+#include <ScorePrimitiveShapeVisitor.h>
+#include <FlatNormalThreshPointCompatibilityFunc.h>
+#include <Candidate.h>
+#include <algorithm>
 
 #include <map>
 #include <string>
@@ -542,6 +548,155 @@ void ref_compute_overlap(const float *src_ds, size_t ns, const float *tgt_ds, si
       counts[i] = cnt;
     }
   }
+}
+
+// ==== RANSAC building blocks (rows a5-a8 of SURVEY.md 8a): the reference's own classes, one call each ==================
+// A RANSAC-library PointCloud as PlaneExtraction::detect builds it (PLADE/plane_extraction.cpp:186-197)
+static void make_ransac_cloud(const float *xyzn, size_t n, ::PointCloud &pc) {
+  pc.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    const float *p = xyzn + 6 * i;
+    pc[i] = Point(Vec3f(p[0], p[1], p[2]), Vec3f(p[3], p[4], p[5]));
+    pc[i].index = i;
+  }
+}
+static PlanePrimitiveShape *make_plane_shape(const float nrm[3], const float pos[3]) {
+  return new PlanePrimitiveShape(Plane(Vec3f(pos[0], pos[1], pos[2]), Vec3f(nrm[0], nrm[1], nrm[2])));   // R/Plane.cpp:13-23
+}
+
+// PlanePrimitiveShape::Parameters (R/PlanePrimitiveShape.h:97-109) with the in-plane frame of
+// HyperplaneCoordinateSystem::FromNormal (R/GfxTL/HyperplaneCoordinateSystem.h:81-93): uv[2n]; frame6 = u[3] v[3]
+void ref_plane_parameters(const float nrm[3], const float pos[3], const float *xyz, size_t n, float *uv, float *frame6) {
+  PlanePrimitiveShape *sh = make_plane_shape(nrm, pos);
+  for (size_t i = 0; i < n; ++i) {
+    std::pair<float, float> q;
+    sh->Parameters(Vec3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), &q);
+    uv[2 * i] = q.first; uv[2 * i + 1] = q.second;
+  }
+  Vec3f u = sh->getXDim(), v = sh->getYDim();
+  for (int k = 0; k < 3; ++k) { frame6[k] = u[k]; frame6[3 + k] = v[k]; }
+  sh->Release();
+}
+
+// BitmapPrimitiveShape::ConnectedComponent (R/BitmapPrimitiveShape.cpp:155-265; BuildBitmap R/BitmapPrimitiveShape.h:101-150,
+// BitmapExtent / InBitmap R/PlanePrimitiveShape.cpp:192-207, closing + Components R/Bitmap.cpp:154,459,633) on the points
+// idx[0..m) of the cloud: returns the size of the largest component and writes its members (ascending) to out_idx
+long long ref_connected_component(const float *xyzn, size_t n, const float nrm[3], const float pos[3], const int *idx, size_t m,
+                                  float bitmap_eps, int do_filtering, int *out_idx) {
+  ::PointCloud pc;
+  make_ransac_cloud(xyzn, n, pc);
+  PlanePrimitiveShape *sh = make_plane_shape(nrm, pos);
+  MiscLib::Vector<size_t> ind(m);
+  for (size_t i = 0; i < m; ++i) ind[i] = (size_t) idx[i];
+  size_t k = sh->ConnectedComponent(pc, bitmap_eps, &ind, do_filtering != 0);
+  std::vector<int> mem(k);
+  for (size_t i = 0; i < k; ++i) mem[i] = (int) ind[i];
+  std::sort(mem.begin(), mem.end());
+  for (size_t i = 0; i < k; ++i) out_idx[i] = mem[i];
+  sh->Release();
+  return (long long) k;
+}
+
+// Plane::LeastSquaresFit (R/Plane.h:66-74, R/Plane.cpp:169-176 -> GfxTL::Mean, CovarianceMatrix, Jacobi, R/GfxTL/Plane.h:58-95)
+int ref_plane_ls_fit(const float *xyzn, size_t n, const int *idx, size_t m, float out_nrm[3], float out_pos[3]) {
+  ::PointCloud pc;
+  make_ransac_cloud(xyzn, n, pc);
+  MiscLib::Vector<size_t> ind(m);
+  for (size_t i = 0; i < m; ++i) ind[i] = (size_t) idx[i];
+  Plane pl(Vec3f(0, 0, 0), Vec3f(0, 0, 1));
+  bool ok = pl.LeastSquaresFit(pc, ind.begin(), ind.end());
+  for (int k = 0; k < 3; ++k) { out_nrm[k] = pl.getNormal()[k]; out_pos[k] = pl.getPosition()[k]; }
+  return ok ? 1 : 0;
+}
+
+// Candidate::WeightedScore (R/Candidate.cpp:77-87, weigh() R/ScoreComputer.h:10-13) over idx[0..m)
+float ref_weighted_score(const float *xyzn, size_t n, const float nrm[3], const float pos[3], const int *idx, size_t m, float epsilon,
+                         float normal_thresh) {
+  ::PointCloud pc;
+  make_ransac_cloud(xyzn, n, pc);
+  PlanePrimitiveShape *sh = make_plane_shape(nrm, pos);
+  Candidate c(sh, 0);
+  c.Indices(new MiscLib::RefCounted<MiscLib::Vector<size_t> >);
+  c.Indices()->Release();
+  sh->Release();
+  for (size_t i = 0; i < m; ++i) c.Indices()->push_back((size_t) idx[i]);
+  return c.WeightedScore(pc, epsilon, normal_thresh);
+}
+
+// The acceptance chain of one candidate, RansacShapeDetector::Detect R/RansacShapeDetector.cpp:613-655, driven with the
+// reference's own Candidate / octree / visitor classes on a cloud whose points are all unassigned (assigned[i] != -1
+// marks points that already belong to a shape): GlobalScore at 3 eps (R/Candidate.h:284-292) -> ConnectedComponent at
+// bitmapEps -> up to three LS refits accepted while GlobalWeightedScore improves.  Detect's Fit() is private; it is
+// exactly initialShape.LSFit(...) for LS_FITTING (R/RansacShapeDetector.cpp:956-969), called here directly.
+// Returns the support of the accepted plane; out_nrm / out_pos = its Plane, out_idx = its members (ascending),
+// trace[0] = number of refits accepted, trace[1] = number of refits tried.
+long long ref_refine_candidate(const float *xyzn, size_t n, const int *assigned, const float nrm[3], const float pos[3], float epsilon,
+                               float normal_thresh, float bitmap_eps, unsigned int min_support, float out_nrm[3], float out_pos[3],
+                               int *out_idx, int *trace) {
+  ::PointCloud pc;
+  make_ransac_cloud(xyzn, n, pc);
+  GfxTL::AACube<GfxTL::Vector3Df> bcube;
+  bcube.Bound(pc.begin(), pc.end());
+  MiscLib::Vector<size_t> globalOctreeIndices(n);
+  for (size_t i = 0; i < n; ++i) globalOctreeIndices[i] = i;
+  IndexedOctreeType globalOctree;
+  globalOctree.MaxBucketSize() = 20;
+  globalOctree.MaxSubdivisionLevel() = 10;
+  globalOctree.IndexedData(globalOctreeIndices.begin(), globalOctreeIndices.end(), pc.begin());
+  globalOctree.Build(bcube);
+  ScorePrimitiveShapeVisitor<FlatNormalThreshPointCompatibilityFunc, IndexedOctreeType> globalScoreVisitor(3 * epsilon, normal_thresh);
+  MiscLib::Vector<int> shapeIndex(n, -1);
+  if (assigned) for (size_t i = 0; i < n; ++i) shapeIndex[i] = assigned[i];
+  globalScoreVisitor.SetShapeIndex(shapeIndex);
+
+  PlanePrimitiveShape *sh = make_plane_shape(nrm, pos);
+  Candidate cand(sh, 0);
+  cand.Indices(new MiscLib::RefCounted<MiscLib::Vector<size_t> >);
+  cand.Indices()->Release();
+  sh->Release();
+  cand.GlobalScore(globalScoreVisitor, globalOctree);
+  cand.ConnectedComponent(pc, bitmap_eps);
+  Candidate clone;
+  cand.Clone(&clone);
+  float oldScore, newScore;
+  newScore = clone.GlobalWeightedScore(globalScoreVisitor, globalOctree, pc, 3 * epsilon, normal_thresh, bitmap_eps);
+  size_t fittingIter = 0;
+  int accepted = 0, tried = 0;
+  do {
+    ++fittingIter;
+    oldScore = newScore;
+    std::pair<size_t, float> score;
+    PrimitiveShape *shape = clone.Shape()->LSFit(pc, epsilon, normal_thresh, clone.Indices()->begin(), clone.Indices()->end(), &score);
+    if (shape) {
+      ++tried;
+      clone.Shape(shape);
+      newScore = clone.GlobalWeightedScore(globalScoreVisitor, globalOctree, pc, 3 * epsilon, normal_thresh, bitmap_eps);
+      size_t newSize = clone.Size();
+      shape->Release();
+      if (newScore > oldScore && newSize > min_support) { clone.Clone(&cand); ++accepted; }
+    }
+  } while (newScore > oldScore && fittingIter < 3);
+  const Plane &pl = dynamic_cast<const PlanePrimitiveShape *>(cand.Shape())->Internal();
+  for (int k = 0; k < 3; ++k) { out_nrm[k] = pl.getNormal()[k]; out_pos[k] = pl.getPosition()[k]; }
+  std::vector<int> mem(cand.Indices()->size());
+  for (size_t i = 0; i < mem.size(); ++i) mem[i] = (int) (*cand.Indices())[i];
+  std::sort(mem.begin(), mem.end());
+  for (size_t i = 0; i < mem.size(); ++i) out_idx[i] = mem[i];
+  if (trace) { trace[0] = accepted; trace[1] = tried; }
+  return (long long) mem.size();
+}
+
+// load_ply_cloud (PLADE/util.cpp:1505-1546 over PlyReader, PLADE/ply_reader.cpp:46-148): blob `name` = interleaved x y z nx ny nz
+long long ref_load_ply(const char *path, const char *name) {
+  CloudPN::Ptr c(new CloudPN);
+  if (!load_ply_cloud(path, *c)) return -1;
+  std::vector<float> v(c->size() * 6);
+  for (size_t i = 0; i < c->size(); ++i) {
+    const pcl::PointNormal &p = c->at(i);
+    v[6 * i] = p.x; v[6 * i + 1] = p.y; v[6 * i + 2] = p.z; v[6 * i + 3] = p.normal_x; v[6 * i + 4] = p.normal_y; v[6 * i + 5] = p.normal_z;
+  }
+  put(name, v);
+  return (long long) c->size();
 }
 
 }  // extern "C"

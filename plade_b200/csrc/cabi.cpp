@@ -122,6 +122,7 @@ int plade_set_param(plade_ctx *ctx, const char *name, double v) {
   else if (n == "min_allowed_support") p.min_allowed_support = (int) v;
   else if (n == "max_trials") p.max_trials = (int) v;
   else if (n == "detect_margin") p.detect_margin = v;
+  else if (n == "ransac_batch") p.ransac_batch = (int) v;
   else if (n == "max_candidates") p.max_candidates = (int) v;
   else if (n == "descriptor_radius") p.descriptor_radius = v;
   else if (n == "seed") p.seed = (unsigned long long) v;

@@ -38,6 +38,8 @@ struct Params {
   // extract(): planes count towards min_planes when their support is >= detect_margin x the pass's min_support (1 = the
   // reference's literal rule; see extract_planes_dev)
   double detect_margin = 1.25;
+  // RANSAC: candidates refined speculatively per batch (1 = one at a time; results are the same, see resolve_kernel)
+  int ransac_batch = 8;
   // matching (PLADE/plade.cpp:46-56)
   int max_candidates = 200;
   float face_matches_weight = 0.2f;

@@ -27,6 +27,7 @@
 // counter-based generator with a fixed seed (the reference seeds rand() from time()), so detection is
 // reproducible; parity with the reference is at plane level (normal, offset, support), not bit level.
 #include "pipeline.h"
+#include "planefit.h"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
@@ -762,18 +763,6 @@ struct IsUnassigned {
 };
 
 // ---- host pieces ----------------------------------------------------------------------------------------
-// HyperplaneCoordinateSystem::FromNormal (R/GfxTL/HyperplaneCoordinateSystem.h:81-93), AutoCAD arbitrary axis
-__host__ __device__ void frame_from_normal(const float n[3], float u[3], float v[3]) {
-  V3 N(n[0], n[1], n[2]), a0;
-  if (fabsf(n[0]) < 0.015625f && fabsf(n[1]) < 0.015625f) a0 = cross(V3(0, 1, 0), N);
-  else a0 = cross(V3(0, 0, 1), N);
-  normalize(a0);
-  V3 a1 = cross(N, a0);
-  normalize(a1);
-  u[0] = a0.x; u[1] = a0.y; u[2] = a0.z;
-  v[0] = a1.x; v[1] = a1.y; v[2] = a1.z;
-}
-
 // cross closing (DilateCross then ErodeCross, no wrapping) + 8-connected labelling; returns the
 // per-pixel mask of the component with the most pixels (first one on ties), R/Bitmap.cpp:154,459,633.
 void largest_component(std::vector<unsigned char> &bmp, int ue, int ve, std::vector<unsigned char> &mask) {
@@ -823,53 +812,6 @@ void largest_component(std::vector<unsigned char> &bmp, int ue, int ve, std::vec
   for (size_t i = 0; i < lab.size(); ++i) mask[i] = lab[i] == best;
 }
 
-// Jacobi eigen-solver for symmetric 3x3 (float), the textbook cyclic algorithm started from V = I that
-// R/GfxTL/Jacobi.h implements; the eigenvector of smallest |eigenvalue| is the plane normal and its
-// sign is whatever the rotation sequence produces (it is never flipped afterwards).
-__host__ __device__ bool jacobi3f(float a[3][3], float d[3], float v[3][3]) {
-  float b[3], z[3];
-  for (int ip = 0; ip < 3; ++ip) { for (int iq = 0; iq < 3; ++iq) v[ip][iq] = 0.f; v[ip][ip] = 1.f; }
-  for (int ip = 0; ip < 3; ++ip) { b[ip] = d[ip] = a[ip][ip]; z[ip] = 0.f; }
-  for (int i = 1; i <= 200; ++i) {
-    float sm = 0.f;
-    for (int ip = 0; ip < 2; ++ip) for (int iq = ip + 1; iq < 3; ++iq) sm += fabsf(a[ip][iq]);
-    if (sm == 0.f) return true;
-    float tresh = i < 4 ? 0.2f * sm / 9.f : 0.f;
-    for (int ip = 0; ip < 2; ++ip)
-      for (int iq = ip + 1; iq < 3; ++iq) {
-        float g = 100.f * fabsf(a[ip][iq]);
-        volatile float t1 = fabsf(d[ip]) + g, t2 = fabsf(d[iq]) + g;
-        if (i > 4 && t1 == fabsf(d[ip]) && t2 == fabsf(d[iq])) a[ip][iq] = 0.f;
-        else if (fabsf(a[ip][iq]) > tresh) {
-          float h = d[iq] - d[ip], t;
-          volatile float t3 = fabsf(h) + g;
-          if (t3 == fabsf(h)) t = a[ip][iq] / h;
-          else {
-            float theta = 0.5f * h / a[ip][iq];
-            t = 1.f / (fabsf(theta) + sqrtf(1.f + theta * theta));
-            if (theta < 0.f) t = -t;
-          }
-          float c = 1.f / sqrtf(1.f + t * t), s = t * c, tau = s / (1.f + c);
-          h = t * a[ip][iq];
-          z[ip] -= h; z[iq] += h; d[ip] -= h; d[iq] += h;
-          a[ip][iq] = 0.f;
-#define PLADE_JROT(m, i1, j1, i2, j2) { float gg = m[i1][j1], hh = m[i2][j2]; m[i1][j1] = gg - s * (hh + gg * tau); m[i2][j2] = hh + s * (gg - hh * tau); }
-          for (int j = 0; j <= ip - 1; ++j) PLADE_JROT(a, j, ip, j, iq)
-          for (int j = ip + 1; j <= iq - 1; ++j) PLADE_JROT(a, ip, j, j, iq)
-          for (int j = iq + 1; j < 3; ++j) PLADE_JROT(a, ip, j, iq, j)
-          for (int j = 0; j < 3; ++j) PLADE_JROT(v, j, ip, j, iq)
-#undef PLADE_JROT
-        }
-      }
-    for (int ip = 0; ip < 3; ++ip) { b[ip] += z[ip]; d[ip] = b[ip]; z[ip] = 0.f; }
-  }
-  return false;
-}
-
-// result of one full evaluation of a plane: support of the largest connected component, gaussian-weighted score,
-// position sums of its members
-struct Eval { long long size; double score; double sum[3]; bool ok; };
-
 // PlanePrimitiveShape(normal, position): plane + in-plane frame
 __host__ __device__ PlaneFrame make_plane_frame(const float nrm3[3], const float pos3[3]) {
   PlaneFrame f;
@@ -881,20 +823,6 @@ __host__ __device__ PlaneFrame make_plane_frame(const float nrm3[3], const float
   f.u = make_float3(u[0], u[1], u[2]);
   f.v = make_float3(v[0], v[1], v[2]);
   return f;
-}
-
-// Plane::LeastSquaresFit (R/Plane.h:66-74) from the member sums: mean, covariance about float(mean), eigenvector
-// of the smallest |eigenvalue| (sign as the Jacobi rotations leave it)
-__host__ __device__ bool fit_plane_from_cov(const Eval &e, const double h[6], float nrm3[3], float pos3[3]) {
-  float a[3][3], d[3], v[3][3];
-  a[0][0] = (float) (h[0] / e.size); a[0][1] = a[1][0] = (float) (h[1] / e.size); a[0][2] = a[2][0] = (float) (h[2] / e.size);
-  a[1][1] = (float) (h[3] / e.size); a[1][2] = a[2][1] = (float) (h[4] / e.size); a[2][2] = (float) (h[5] / e.size);
-  if (!jacobi3f(a, d, v)) return false;
-  int k = 0;
-  for (int j = 1; j < 3; ++j) if (fabsf(d[j]) < fabsf(d[k])) k = j;
-  nrm3[0] = v[0][k]; nrm3[1] = v[1][k]; nrm3[2] = v[2][k];
-  pos3[0] = (float) (e.sum[0] / e.size); pos3[1] = (float) (e.sum[1] / e.size); pos3[2] = (float) (e.sum[2] / e.size);
-  return true;
 }
 
 // Can a point outside the band (|d_band(x)| < halfwidth) be within eps3 of plane `pl`?  d_pl(x) - d_band(x) is affine
@@ -950,6 +878,7 @@ struct RefineArgs {
   unsigned char *bmp, *btmp, *bmask;
   int *lab, *ccnt;
   unsigned char *member_a, *member_b;     // membership of the band points, by BAND position (two maps: candidate / clone)
+  unsigned char *touched;                 // band point was an inlier of ANY evaluation of this candidate (null: not recorded)
   int *uvbox;
   double *acc;
   RefineCtl *ctl;
@@ -958,6 +887,40 @@ struct RefineArgs {
   float eps3, nthresh, bmp_eps, band_halfwidth, ext;
   float mn[3], mx[3];
   int min_support, band_full;
+  int cap;                                // capacity of the band arrays (a band that does not fit is refined alone, status 4)
+};
+// Up to kMaxBatch candidates are refined by ONE launch, one cluster each (speculative: all against the same snapshot of
+// the unassigned points; resolve_kernel then replays the sequential accept order and stops at the first candidate
+// whose evaluation saw a point that an earlier candidate of the batch took).
+constexpr int kMaxBatch = 8;
+struct RefineBatch { RefineArgs a[kMaxBatch]; };
+struct BandBatch {
+  int k;
+  float band;                             // half-width (same for every candidate of a cloud)
+  float4 pl[kMaxBatch];
+  float4 *pos[kMaxBatch], *nrm[kMaxBatch];
+  int *idx[kMaxBatch], *nb[kMaxBatch];
+  int cap[kMaxBatch];
+};
+// state of the sequential accept loop while a batch is being resolved on the device
+struct BatchState {
+  long long m;                            // unassigned points
+  double drawn;                           // drawn candidates (rescaled after every accepted shape)
+  double prob;
+  int n_found, stop, nlevels, min_support;
+};
+enum { kVerdictSkipped = 0, kVerdictNotEligible = 1, kVerdictFallback = 2, kVerdictRejected = 3, kVerdictConflict = 4, kVerdictAccepted = 5 };
+struct Verdict { int kind, shape_id; long long size; float n[3], p[3]; int evals, n_band; };
+struct ResolveArgs {
+  const int *idxB, *d_nb;
+  const unsigned char *member_a, *member_b, *touched;
+  const RefineOut *out;
+  int *assigned;
+  BatchState *state;
+  Verdict *verdict;
+  int *conflict;                          // zeroed before the launch
+  double est;                             // the candidate's support estimate (pool order)
+  int slot, cap;
 };
 
 __device__ __forceinline__ double block_sum(double v, double *sh /* 32 */) {
@@ -1030,7 +993,8 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const RefineArgs a) {
+__global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __grid_constant__ RefineBatch batch) {
+  const RefineArgs &a = batch.a[blockIdx.x / cluster_size()];      // one cluster per candidate of the batch
   __shared__ double sh_d[6 * 32];
   __shared__ float sh_f[4 * 32];
   __shared__ unsigned int sbits[kRefSmemPix / 32];     // per-CTA bit image of the bitmap (pass 2) / of the component mask (pass 4)
@@ -1038,6 +1002,10 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
   const int gt = rank * nthr + threadIdx.x;
   const bool boss = gt == 0;
   const int n = *a.d_nb;
+  if (n > a.cap) {             // the band did not fit this slot (uniform over the cluster): the host refines this candidate alone
+    if (boss) { RefineOut o = {}; o.status = 4; o.n_band = n; *a.out = o; }
+    return;
+  }
   const float denom = 2.f / 9.f * a.eps3 * a.eps3;
   volatile RefineCtl *ctl = a.ctl;
 
@@ -1126,6 +1094,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
           if (i >= n) continue;
           const bool in = compatible(f.pl, p[u], nr[u], a.eps3, a.nthresh);
           a.flag[i] = in ? 1 : 0;
+          if (a.touched) { if (ev == 0) a.touched[i] = in ? 1 : 0; else if (in) a.touched[i] = 1; }
           if (in) {
             float px = __fsub_rn(p[u].x, f.pos.x), py = __fsub_rn(p[u].y, f.pos.y), pz = __fsub_rn(p[u].z, f.pos.z);
             float uu = __fadd_rn(__fadd_rn(__fmul_rn(px, f.u.x), __fmul_rn(py, f.u.y)), __fmul_rn(pz, f.u.z));
@@ -1320,10 +1289,134 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const Re
   }
 }
 
-double failure_probability(double size, double n, double drawn, double levels) {
-  // CandidateFailureProbability, R/RansacShapeDetector.h:61-67 (reqSamples = 3)
-  return std::min(std::pow(1.0 - size / (n * levels * 4.0), drawn), 1.0);
+// CandidateFailureProbability, R/RansacShapeDetector.h:61-67 (reqSamples = 3)
+__host__ __device__ inline double failure_probability_hd(double size, double n, double drawn, double levels) {
+  const double p = pow(1.0 - size / (n * levels * 4.0), drawn);
+  return p < 1.0 ? p : 1.0;
 }
+// drawn candidates that stay valid after a shape of `size` points left a cloud of m (RansacShapeDetector.cpp:673-674);
+// the cube is spelled out so that host and device round alike
+__host__ __device__ inline double rescale_drawn(double drawn, long long size, long long m) {
+  const float x = 1.f - ((float) size / (float) m);
+  return (double) ((x * x) * x) * drawn;
+}
+
+// Bands of up to kMaxBatch candidates in ONE pass over the cloud (20 B per point whatever the number of candidates):
+// the per-candidate work of band_compact_kernel, with the point loaded once and tested against every plane.
+__global__ void multi_band_compact_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const int *__restrict__ assigned, int n,
+                                          const __grid_constant__ BandBatch b) {
+  constexpr int kU = 4;
+  const unsigned lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (long long base = (long long) warp * (32 * kU); base < n; base += (long long) n_warps * (32 * kU)) {
+    int a[kU];
+    float4 p[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = base + u * 32 + lane;
+      a[u] = i < n ? __ldg(assigned + i) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = base + u * 32 + lane;
+      p[u] = (i < n && a[u] == -1) ? __ldg(pos + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int k = 0; k < b.k; ++k) {
+      const float4 pl = b.pl[k];
+      unsigned bal[kU];
+      bool in[kU];
+      int total = 0;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const long long i = base + u * 32 + lane;
+        const float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p[u].x), __fmul_rn(pl.y, p[u].y)), __fmul_rn(pl.z, p[u].z));
+        in[u] = i < n && a[u] == -1 && fabsf(__fsub_rn(pl.w, dp)) < b.band;
+        bal[u] = __ballot_sync(0xffffffffu, in[u]);
+        total += __popc(bal[u]);
+      }
+      if (!total) continue;
+      int start = 0;
+      if (lane == 0) start = atomicAdd(b.nb[k], total);
+      start = __shfl_sync(0xffffffffu, start, 0);
+      if (start + total > b.cap[k]) continue;          // overflow: the count keeps growing, the slot is refined alone later
+      float4 *posB = b.pos[k], *nrmB = b.nrm[k];
+      int *idxB = b.idx[k];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (in[u]) {
+          const int i = (int) (base + u * 32 + lane);
+          const int q = start + __popc(bal[u] & ((1u << lane) - 1));
+          posB[q] = p[u]; nrmB[q] = __ldg(nrm + i); idxB[q] = i;
+        }
+        start += __popc(bal[u]);
+      }
+    }
+  }
+}
+
+// Replays one step of the sequential accept loop (detect_planes_dev's pool walk) for slot r.slot of a batch, on the
+// device: launched once per slot, in pool order, on the same stream -- no host round trip in between.
+//   eligible?  (slots > 0: the candidate must still pass the failure-probability test with the state the earlier slots left)
+//   evaluated? (status != 0: the host has to refine it alone)      big enough? (else rejected, as FindBestCandidate would)
+//   conflict?  a band point that was an inlier of ANY of its evaluations has meanwhile been taken by an earlier slot:
+//              sequentially the candidate would have been evaluated without it -> stop, it is re-evaluated next batch
+//   accept:    members -> assigned, state advanced exactly as the host loop does.
+__global__ void __launch_bounds__(kRefThreads, 1) resolve_kernel(const ResolveArgs r) {
+  __shared__ int sh_conf;
+  const int rank = (int) cluster_rank(), nthr = (int) blockDim.x, nth = (int) cluster_size() * nthr;
+  const int gt = rank * nthr + threadIdx.x;
+  const bool boss = gt == 0;
+  volatile BatchState *st = r.state;
+  if (st->stop) {                          // (uniform: only written by a boss thread after the first cluster barrier)
+    if (boss) { Verdict v = {}; v.kind = kVerdictSkipped; *r.verdict = v; }
+    return;
+  }
+  const volatile RefineOut *o = r.out;
+  const int status = o->status;
+  const long long acc_size = o->acc_size;
+  const int n = *r.d_nb;
+  const bool scan = status == 0 && n <= r.cap && acc_size >= (long long) st->min_support;
+  if (threadIdx.x == 0) sh_conf = 0;
+  __syncthreads();
+  if (scan) {
+    int c = 0;
+    for (int i = gt; i < n; i += nth) c |= (r.touched[i] && __ldcg(r.assigned + r.idxB[i]) != -1) ? 1 : 0;
+    if (c) atomicOr(&sh_conf, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && sh_conf) atomicOr(r.conflict, 1);
+  }
+  cluster_barrier();
+  if (boss) {
+    Verdict v = {};
+    v.evals = o->evals; v.n_band = o->n_band;
+    const long long m = st->m;
+    const double drawn = st->drawn;
+    const bool eligible = r.slot == 0 || (r.est >= (double) st->min_support && failure_probability_hd(r.est, (double) m, drawn, (double) st->nlevels) <= st->prob);
+    if (!eligible) { v.kind = kVerdictNotEligible; st->stop = 1; }
+    else if (status != 0) { v.kind = kVerdictFallback; st->stop = 1; }
+    else if (acc_size < (long long) st->min_support) v.kind = kVerdictRejected;
+    else if (__ldcg(r.conflict)) { v.kind = kVerdictConflict; st->stop = 1; }
+    else {
+      v.kind = kVerdictAccepted;
+      v.shape_id = st->n_found;
+      v.size = acc_size;
+      for (int k = 0; k < 3; ++k) { v.n[k] = o->acc_n[k]; v.p[k] = o->acc_p[k]; }
+      st->n_found = v.shape_id + 1;
+      st->drawn = rescale_drawn(drawn, acc_size, m);
+      st->m = m - acc_size;
+      if (m - acc_size < (long long) st->min_support || m - acc_size < 3) st->stop = 1;
+    }
+    *r.verdict = v;
+  }
+  cluster_barrier();
+  const volatile Verdict *vv = r.verdict;
+  if (vv->kind != kVerdictAccepted) return;
+  const unsigned char *member = o->acc_sel ? r.member_b : r.member_a;
+  const int shape_id = vv->shape_id;
+  for (int i = gt; i < n; i += nth) if (member[i]) r.assigned[r.idxB[i]] = shape_id;
+}
+
+double failure_probability(double size, double n, double drawn, double levels) { return failure_probability_hd(size, n, drawn, levels); }
 
 struct RansacScratch {
   DevBuf<unsigned int> keys, keys_alt, counts, counts_sorted, counts2;
@@ -1341,7 +1434,22 @@ struct RansacScratch {
   PinBuf<unsigned int> round_host; // page-locked landing zone of the round's results and of the cluster kernel's verdict
   PinBuf<float4> pool_host;
   DevBuf<unsigned char> memb_a, memb_b;   // band-local membership maps of refine_cluster_kernel
+  // slots 1 .. kMaxBatch-1 of a speculative batch (slot 0 = the buffers above); band arrays of `cap` points each
+  struct Slot {
+    DevBuf<float4> band_pos, band_nrm;
+    DevBuf<int> band_idx, pix, cc_lab, cc_cnt;
+    DevBuf<unsigned char> flag, memb_a, memb_b, touched, bmp, btmp, bmask;
+    bool bmp_clean = false;
+  } slot[kMaxBatch];
+  DevBuf<unsigned char> touched0;         // slot 0
+  DevBuf<unsigned char> batch_mem;        // BatchState + per-slot control blocks (see kSlotStride)
+  PinBuf<unsigned char> batch_host;       // page-locked mirror: state upload and the verdicts' landing zone
 };
+// layout of RansacScratch::batch_mem: BatchState at 0, then one block per slot
+constexpr int kSlotBase = 256, kSlotStride = 1024;
+constexpr int kSlotCtl = 0, kSlotOut = 128, kSlotUvbox = 256, kSlotNb = 272, kSlotConflict = 276, kSlotVerdict = 320, kSlotAcc = 512;
+static_assert(sizeof(RefineCtl) <= 128 && sizeof(RefineOut) <= 128 && sizeof(Verdict) <= kSlotAcc - kSlotVerdict && kSlotAcc + 16 * 8 <= kSlotStride &&
+              sizeof(BatchState) <= kSlotBase, "batch_mem layout");
 
 // cluster size of refine_cluster_kernel on this device: 16 (non-portable) when the GPU can co-schedule it, else 8
 int refine_block_threads() {
@@ -1367,7 +1475,8 @@ int refine_cluster_size(int device) {
     if (cur != device) cudaSetDevice(device);
     for (int want : {first, 8}) {
       if (want < 1 || want > 16) continue;
-      if (want > 8 && cudaFuncSetAttribute(refine_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (want > 8 && (cudaFuncSetAttribute(refine_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                       cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) { cudaGetLastError(); continue; }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(want); cfg.blockDim = dim3(refine_block_threads());
       cudaLaunchAttribute at[1];
@@ -1472,7 +1581,8 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   float4 *posB = rs.band_pos.ensure(n), *nrmB = rs.band_nrm.ensure(n);
   int *idxB = rs.band_idx.ensure(n);
   const int blocks_b = std::min(blocks_n, dev.num_sms * 4);
-  int n_band_builds = 0, n_band_full = 0, n_cluster_fallbacks = 0, refine_evals = 0;
+  int n_band_builds = 0, n_band_full = 0, n_cluster_fallbacks = 0, refine_evals = 0, n_batches = 0, n_batch_cands = 0, n_batch_conflicts = 0;
+  bool force_single = false;
   double refine_phase_ns[6] = {0, 0, 0, 0, 0, 0};
   float4 *cand = rs.cand.ensure(kCandPerRound);
   double *acc = rs.acc.ensure(16);
@@ -1577,6 +1687,148 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     }
     fresh = false;
     dry_rounds = 0;
+    // ---- speculative batch: the next K eligible pool candidates refined by one launch, the accept order replayed on
+    // the device (multi_band_compact_kernel -> refine_cluster_kernel x K clusters -> resolve_kernel x K), ONE host round
+    // trip for all of them.  Falls through to the one-candidate path below when only one candidate is eligible, when
+    // the previous batch asked for it (a bitmap beyond the device cap, a refit that left its band, an overflowing band)
+    // or when the cluster kernel is not available.
+    {
+      const int csize = refine_cluster_size(dev.id);
+      int K = 0;
+      if (csize && !force_single && params.ransac_batch > 1) {
+        const int kmax = std::min<int>({kMaxBatch, params.ransac_batch, (int) pool.size()});
+        K = 1;
+        while (K < kmax && pool[K].est >= min_support && failure_probability(pool[K].est, m, drawn, nlevels) <= prob) ++K;
+      }
+      force_single = false;
+      if (K >= 2) {
+        unsigned char *bm = rs.batch_mem.ensure(kSlotBase + kMaxBatch * kSlotStride);
+        unsigned char *bh = rs.batch_host.ensure(2 * (kSlotBase + kMaxBatch * kSlotStride));
+        const size_t cap_other = std::max<size_t>((size_t) n / 2, 1024);
+        // state + clean control blocks, one upload from page-locked memory
+        memset(bh, 0, kSlotBase + kMaxBatch * kSlotStride);
+        BatchState st0;
+        st0.m = m; st0.drawn = drawn; st0.prob = prob; st0.n_found = (int) found.size(); st0.stop = 0; st0.nlevels = nlevels; st0.min_support = min_support;
+        memcpy(bh, &st0, sizeof(st0));
+        PLADE_CUDA(cudaMemcpyAsync(bm, bh, kSlotBase + K * kSlotStride, cudaMemcpyHostToDevice, s));
+        BandBatch bb;
+        RefineBatch rb;
+        ResolveArgs rv[kMaxBatch];
+        bb.k = K; bb.band = kBandMul * eps3;
+        for (int j = 0; j < K; ++j) {
+          unsigned char *blk = bm + kSlotBase + j * kSlotStride;
+          RansacScratch::Slot &sl = rs.slot[j];
+          const size_t cap = j == 0 ? (size_t) n : cap_other;
+          RefineArgs &ra = rb.a[j];
+          if (j == 0) {
+            ra.posB = posB; ra.nrmB = nrmB; ra.idxB = idxB; ra.flag = flag; ra.pix = pix;
+            ra.bmp = rs.bmp_dev.ensure(kBmpCap); ra.btmp = rs.bmp_tmp.ensure(kBmpCap); ra.bmask = rs.mask_dev.ensure(kBmpCap);
+            ra.lab = rs.cc_lab.ensure(kBmpCap); ra.ccnt = rs.cc_cnt.ensure(kBmpCap);
+            ra.member_a = rs.memb_a.ensure(n); ra.member_b = rs.memb_b.ensure(n); ra.touched = rs.touched0.ensure(n);
+            if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(ra.bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
+          } else {
+            ra.posB = sl.band_pos.ensure(cap); ra.nrmB = sl.band_nrm.ensure(cap); ra.idxB = sl.band_idx.ensure(cap);
+            ra.flag = sl.flag.ensure(cap); ra.pix = sl.pix.ensure(cap);
+            ra.bmp = sl.bmp.ensure(kBmpCap); ra.btmp = sl.btmp.ensure(kBmpCap); ra.bmask = sl.bmask.ensure(kBmpCap);
+            ra.lab = sl.cc_lab.ensure(kBmpCap); ra.ccnt = sl.cc_cnt.ensure(kBmpCap);
+            ra.member_a = sl.memb_a.ensure(cap); ra.member_b = sl.memb_b.ensure(cap); ra.touched = sl.touched.ensure(cap);
+            if (!sl.bmp_clean) { PLADE_CUDA(cudaMemsetAsync(ra.bmp, 0, kBmpCap, s)); sl.bmp_clean = true; }
+          }
+          ra.d_nb = reinterpret_cast<int *>(blk + kSlotNb);
+          ra.uvbox = reinterpret_cast<int *>(blk + kSlotUvbox);
+          ra.acc = reinterpret_cast<double *>(blk + kSlotAcc);
+          ra.ctl = reinterpret_cast<RefineCtl *>(blk + kSlotCtl);
+          ra.out = reinterpret_cast<RefineOut *>(blk + kSlotOut);
+          ra.cand_pl = pool[j].pl; ra.band_pl = pool[j].pl;
+          ra.eps3 = eps3; ra.nthresh = nthresh; ra.bmp_eps = bmp_eps; ra.band_halfwidth = kBandMul * eps3; ra.ext = ext;
+          for (int k = 0; k < 3; ++k) { ra.mn[k] = mn[k]; ra.mx[k] = mx[k]; }
+          ra.min_support = min_support; ra.band_full = 0; ra.cap = (int) cap;
+          bb.pl[j] = pool[j].pl;
+          bb.pos[j] = const_cast<float4 *>(ra.posB); bb.nrm[j] = const_cast<float4 *>(ra.nrmB); bb.idx[j] = const_cast<int *>(ra.idxB);
+          bb.nb[j] = const_cast<int *>(ra.d_nb); bb.cap[j] = (int) cap;
+          ResolveArgs &q = rv[j];
+          q.idxB = ra.idxB; q.d_nb = ra.d_nb; q.member_a = ra.member_a; q.member_b = ra.member_b; q.touched = ra.touched;
+          q.out = ra.out; q.assigned = assigned; q.state = reinterpret_cast<BatchState *>(bm);
+          q.verdict = reinterpret_cast<Verdict *>(blk + kSlotVerdict); q.conflict = reinterpret_cast<int *>(blk + kSlotConflict);
+          q.est = pool[j].est; q.slot = j; q.cap = (int) cap;
+        }
+        for (int j = K; j < kMaxBatch; ++j) rb.a[j] = rb.a[0];
+        dev.clock.begin(KernelClock::kBandCompact, 20.0 * n, s);       // one pass whatever K is
+        multi_band_compact_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, bb);
+        dev.clock.end(s);
+        PLADE_LAUNCH_CHECK();
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(refine_block_threads()); cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cfg.gridDim = dim3(csize * K);
+        dev.clock.begin(KernelClock::kRefineCluster, 0.0, s);
+        PLADE_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel, rb));
+        dev.clock.end(s);
+        cfg.gridDim = dim3(csize);
+        for (int j = 0; j < K; ++j) PLADE_CUDA(cudaLaunchKernelEx(&cfg, resolve_kernel, rv[j]));
+        dev.launches.add(2 + K);
+        n_band_builds += K;
+        unsigned char *back = bh + (kSlotBase + kMaxBatch * kSlotStride);
+        PLADE_CUDA(cudaMemcpyAsync(back, bm, kSlotBase + K * kSlotStride, cudaMemcpyDeviceToHost, s));
+        PLADE_CUDA(cudaStreamSynchronize(s));
+        BatchState st1;
+        memcpy(&st1, back, sizeof(st1));
+        const int m_before = m;
+        int n_acc = 0;
+        bool walk_on = true;
+        for (int j = 0; j < K && walk_on; ++j) {
+          Verdict v;
+          RefineOut ro;
+          memcpy(&v, back + kSlotBase + j * kSlotStride + kSlotVerdict, sizeof(v));
+          memcpy(&ro, back + kSlotBase + j * kSlotStride + kSlotOut, sizeof(ro));
+          if (v.kind != kVerdictSkipped && v.kind != kVerdictNotEligible && ro.status == 0) {
+            dev.clock.bytes[KernelClock::kRefineCluster] += 28.0 * ro.n_band * ro.evals;
+            for (int k = 0; k < 6; ++k) refine_phase_ns[k] += ro.phase_ns[k];
+            refine_evals += ro.evals;
+          }
+          switch (v.kind) {
+            case kVerdictAccepted: {
+              FoundPlane fp;
+              memcpy(fp.n, v.n, sizeof(fp.n)); memcpy(fp.pos, v.p, sizeof(fp.pos));
+              fp.size = v.size;
+              found.push_back(fp);
+              pool.erase(pool.begin());
+              ++n_acc;
+              break;
+            }
+            case kVerdictRejected:
+              banned.push_back(pool[0].pl);
+              pool.erase(pool.begin());
+              if (++rejects >= 256) { stop_all = true; walk_on = false; }
+              break;
+            case kVerdictFallback: force_single = true; ++n_cluster_fallbacks; walk_on = false; break;    // pool[0] is refined alone next
+            case kVerdictConflict: ++n_batch_conflicts; walk_on = false; break;                             // pool[0] gets a fresh band next
+            default: walk_on = false; break;                                                                // not eligible any more / skipped
+          }
+        }
+        ++n_batches;
+        n_batch_cands += K;
+        m = (int) st1.m;
+        drawn = st1.drawn;
+        if (n_acc) {
+          // compact the Morton list to the still-unassigned points, once per batch
+          IsUnassigned pr{assigned};
+          size_t tb3 = 0;
+          cub::DeviceSelect::If(nullptr, tb3, cur_order, alt_order, d_nsel, m_before, pr, s);
+          tmp = rs.cub_tmp.ensure(tb3);
+          cub::DeviceSelect::If(tmp, tb3, cur_order, alt_order, d_nsel, m_before, pr, s);
+          dev.launches.add(3);
+          std::swap(cur_order, alt_order);
+        }
+        mark("ransac_batch");
+        if (stop_all) break;
+        if (m < min_support || m < 3) break;
+        continue;
+      }
+    }
     // --- refine the best candidate on the full cloud -------------------------------------------------------
     PlaneFrame fr;
     auto make_frame = [&](const float nrm3[3], const float pos3[3]) { return make_plane_frame(nrm3, pos3); };
@@ -1722,6 +1974,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       ra.eps3 = eps3; ra.nthresh = nthresh; ra.bmp_eps = bmp_eps; ra.band_halfwidth = kBandMul * eps3; ra.ext = ext;
       for (int k = 0; k < 3; ++k) { ra.mn[k] = mn[k]; ra.mx[k] = mx[k]; }
       ra.min_support = min_support; ra.band_full = band_full ? 1 : 0;
+      ra.touched = nullptr; ra.cap = n;
       if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(ra.bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(csize); cfg.blockDim = dim3(refine_block_threads()); cfg.stream = s;
@@ -1730,7 +1983,9 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       dev.clock.begin(KernelClock::kRefineCluster, 0.0, s);
-      PLADE_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel, ra));
+      RefineBatch one;
+      for (int j = 0; j < kMaxBatch; ++j) one.a[j] = ra;
+      PLADE_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel, one));
       dev.clock.end(s);
       dev.launches.add();
       static_assert(sizeof(RefineOut) <= 64 * sizeof(unsigned int) && ((kRoundEnd - kRoundCounts2) * 4) % 8 == 0, "verdict slot of round_host");
@@ -1820,7 +2075,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     memcpy(fp.n, acc_n, sizeof(acc_n)); memcpy(fp.pos, acc_p, sizeof(acc_p));
     fp.size = acc_size;
     found.push_back(fp);
-    drawn = std::pow(1.f - (acc_size / float(m)), 3.f) * drawn;
+    drawn = rescale_drawn(drawn, acc_size, m);
     // compact the Morton list to the still-unassigned points
     IsUnassigned pr{assigned};
     size_t tb3 = 0;
@@ -1862,8 +2117,8 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   PLADE_CUDA(cudaStreamSynchronize(s));
   dev.clock.collect();
   mark("ransac_output");
-  if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade ransac lane %d] candidates evaluated on a band: %d, widened to all points: %d, cluster-kernel fallbacks: %d; cluster kernel: %d evaluations, us per phase: flags %.0f raster %.0f components %.0f select %.0f covariance %.0f decision %.0f\n",
-                                   lane, n_band_builds - n_band_full, n_band_full, n_cluster_fallbacks, refine_evals, refine_phase_ns[0] / 1e3, refine_phase_ns[1] / 1e3,
+  if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade ransac lane %d] planes %zu, rounds, batches %d (%d candidates, %d conflicts); candidates evaluated on a band: %d, widened to all points: %d, cluster-kernel fallbacks: %d; cluster kernel: %d evaluations, us per phase: flags %.0f raster %.0f components %.0f select %.0f covariance %.0f decision %.0f\n",
+                                   lane, found.size(), n_batches, n_batch_cands, n_batch_conflicts, n_band_builds - n_band_full, n_band_full, n_cluster_fallbacks, refine_evals, refine_phase_ns[0] / 1e3, refine_phase_ns[1] / 1e3,
                                    refine_phase_ns[2] / 1e3, refine_phase_ns[3] / 1e3, refine_phase_ns[4] / 1e3, refine_phase_ns[5] / 1e3);
   return result;
 }

@@ -52,13 +52,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--margins", default="1.25")
     ap.add_argument("--seeds", default="1,2,3,4,5,6,7,8")
+    ap.add_argument("--maxcand", default="200", help="comma list of max_candidates (the reference's budget is 200)")
     ap.add_argument("--cases", default="")
+    ap.add_argument("--batch", type=int, default=0, help="ransac_batch (0: library default)")
     ap.add_argument("--planes", action="store_true", help="also report the plane counts per cloud (runs extract() again)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "seed_sweep.json"))
     a = ap.parse_args()
     ref = json.load(open(os.path.join(GOLDEN, "seed_sweep_ref.json")))
     seeds = [int(s) for s in a.seeds.split(",")]
     ctx = plade_b200.Context(0)
+    if a.batch:
+        ctx.set_param("ransac_batch", a.batch)
     doc = {"seeds": seeds, "runs": {}}
     for name, (tgt, src, gt, swapped) in cases().items():
         if a.cases and name not in a.cases.split(","):
@@ -67,8 +71,9 @@ def main():
         bar = BARS.get(name, DEFAULT_BAR)
         refe = ref["cases"].get(name, {}).get("errors", [])
         ref_ok = sum(1 for e in refe if e[2] and e[0] <= bar[0] and e[1] <= bar[1])
-        for margin in [float(m) for m in a.margins.split(",")]:
+        for margin, maxcand in [(float(m), int(c)) for m in a.margins.split(",") for c in a.maxcand.split(",")]:
             ctx.set_param("detect_margin", margin)
+            ctx.set_param("max_candidates", maxcand)
             rows = []
             for seed in seeds:
                 ctx.set_param("seed", seed)
@@ -82,10 +87,10 @@ def main():
                 Tm = np.linalg.inv(T.astype(np.float64)) if (swapped and ok) else T
                 rot, tr = transform_error(Tm, gt, diag)
                 rows.append({"seed": seed, "ok": bool(ok), "rot_deg": float(rot), "trans_rel": float(tr), "planes_tgt": np_t, "planes_src": np_s, "s": dt})
-                print("%-15s margin %.2f seed %d: ok=%s rot %.3f deg trans %.5f  planes %d + %d  (%.2f s)" % (name, margin, seed, ok, rot, tr, np_t, np_s, dt), flush=True)
+                print("%-15s margin %.2f budget %d seed %d: ok=%s rot %.3f deg trans %.5f  planes %d + %d  (%.2f s)" % (name, margin, maxcand, seed, ok, rot, tr, np_t, np_s, dt), flush=True)
             n_ok = sum(1 for r in rows if r["ok"] and r["rot_deg"] <= bar[0] and r["trans_rel"] <= bar[1])
-            print("%-15s margin %.2f: GPU %d/%d within (%.1f deg, %.3f); reference %d/%d" % (name, margin, n_ok, len(rows), bar[0], bar[1], ref_ok, len(refe)), flush=True)
-            doc["runs"]["%s@%.2f" % (name, margin)] = {"rows": rows, "gpu_ok": n_ok, "ref_ok": ref_ok, "bar": bar}
+            print("%-15s margin %.2f budget %d: GPU %d/%d within (%.1f deg, %.3f); reference %d/%d" % (name, margin, maxcand, n_ok, len(rows), bar[0], bar[1], ref_ok, len(refe)), flush=True)
+            doc["runs"]["%s@%.2f@%d" % (name, margin, maxcand)] = {"rows": rows, "gpu_ok": n_ok, "ref_ok": ref_ok, "bar": bar}
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(doc, open(a.out, "w"), indent=1)
 
