@@ -10,6 +10,10 @@
  *
  * Threading: like the reference these functions are not re-entrant per context; each host thread gets
  * its own CUDA context object (thread_local).
+ *
+ * The wrappers are inline, so a translation unit that includes this header needs nothing but libplade_b200.so.  Code that only
+ * DECLARES the reference's prototypes (its own copy of PLADE/plade.h) and expects to link a `registration` symbol links
+ * plade_b200/libplade_dropin.so instead (plade_b200/csrc/dropin.cpp: the same functions out of line).
  */
 #ifndef PLADE_B200_DROPIN_H
 #define PLADE_B200_DROPIN_H
@@ -62,7 +66,7 @@ inline void planes_to_csr(const std::vector<PLANE> &p, std::vector<int> &off, st
 /* registration(T, target_file, source_file) — PLADE/plade.cpp:665-707 */
 inline bool registration(Eigen::Matrix<float, 4, 4> &transformation, const std::string &target_cloud_file,
                          const std::string &source_cloud_file) {
-    float m[16];
+    float m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   /* identity is what a failure leaves (PLADE/plade.cpp:696) */
     int ok = plade_register_files(plade_detail::ctx(), target_cloud_file.c_str(), source_cloud_file.c_str(), m);
     plade_detail::to_eigen(m, transformation);
     return ok != 0;
@@ -71,7 +75,7 @@ inline bool registration(Eigen::Matrix<float, 4, 4> &transformation, const std::
 /* PCL-free equivalent of registration(T, target_cloud, source_cloud): interleaved x y z nx ny nz records */
 inline bool registration_arrays(Eigen::Matrix<float, 4, 4> &transformation, const float *target_xyzn, size_t n_target,
                                 const float *source_xyzn, size_t n_source) {
-    float m[16];
+    float m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   /* identity is what a failure leaves (PLADE/plade.cpp:696) */
     int ok = plade_register_clouds(plade_detail::ctx(), target_xyzn, n_target, source_xyzn, n_source, m);
     plade_detail::to_eigen(m, transformation);
     return ok != 0;
@@ -106,7 +110,7 @@ inline bool registration(Eigen::Matrix<float, 4, 4> &transformation, pcl::PointC
     std::vector<float> tp, sp;
     plade_detail::planes_to_csr(target_planes, to, ti, tp);
     plade_detail::planes_to_csr(source_planes, so, si, sp);
-    float m[16];
+    float m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   /* identity is what a failure leaves (PLADE/plade.cpp:696) */
     int ok = plade_register_with_planes(plade_detail::ctx(), t.data(), t.size() / 6, s.data(), s.size() / 6, to.data(), ti.data(),
                                         tp.data(), (int) target_planes.size(), so.data(), si.data(), sp.data(),
                                         (int) source_planes.size(), m);
@@ -119,7 +123,7 @@ inline bool registration(Eigen::Matrix<float, 4, 4> &transformation, pcl::PointC
                          pcl::PointCloud<pcl::PointNormal>::Ptr source_cloud, int ransac_min_support_target,
                          int ransac_min_support_source) {
     std::vector<float> t = plade_detail::flatten(*target_cloud), s = plade_detail::flatten(*source_cloud);
-    float m[16];
+    float m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   /* identity is what a failure leaves (PLADE/plade.cpp:696) */
     int ok = plade_register_min_support(plade_detail::ctx(), t.data(), t.size() / 6, s.data(), s.size() / 6,
                                         ransac_min_support_target, ransac_min_support_source, m);
     plade_detail::to_eigen(m, transformation);

@@ -45,6 +45,21 @@ int plade_set_param(plade_ctx *ctx, const char *name, double value);
  * this context verifies hypotheses h with h % world == rank and `reduce` (may be NULL when world == 1)
  * must all-reduce(MAX) one u64 across the ranks (NCCL in bench.py). */
 void plade_set_shard(plade_ctx *ctx, int rank, int world, plade_allreduce_max_u64 reduce, void *user);
+/* The same sharding with the collective inside the library (PLADE/plade.cpp:547-564 is the loop that is split):
+ * every rank builds the same hypothesis list, rank r verifies h % world == r, the best (score bits << 32 | ~index) of each shard
+ * is formed on the device and ONE ncclAllReduce(ncclUint64, ncclMax) on the context's stream picks the winner -- no inlier count
+ * leaves the device.  A hash of the hypothesis list rides along: ranks that disagree on the list fail loudly.  libnccl.so.2 is
+ * opened at run time (no link-time dependency; inside a torch process it is the NCCL torch already loaded).
+ *   plade_nccl_unique_id     ncclGetUniqueId on rank 0; ship the 128 bytes to the other ranks out of band (MPI, torch, a file)
+ *   plade_shard_init_nccl    ncclCommInitRank on the context's device (one process per GPU)
+ *   plade_shard_init_nccl_all  one process, n contexts on n different GPUs: ncclCommInitAll, rank i = ctxs[i]; the n registrations
+ *                              must then run concurrently (one host thread per context), as any collective does
+ *   plade_shard_finalize     destroys the communicator and returns the context to unsharded operation
+ * All return 1 on success, 0 on failure (plade_last_error / plade_create_error). */
+int plade_nccl_unique_id(char out128[128]);
+int plade_shard_init_nccl(plade_ctx *ctx, const char id128[128], int rank, int world);
+int plade_shard_init_nccl_all(plade_ctx **ctxs, int n);
+void plade_shard_finalize(plade_ctx *ctx);
 long long plade_launch_count(plade_ctx *ctx);     /* kernels launched by this context so far */
 /* seconds of the last registration: upload, planes, spacing, downsample, lines, descriptors, match,
  * hypotheses, penetration, verify, total, then the verification kernel of that call as timed with
@@ -116,6 +131,23 @@ int plade_score_planes(plade_ctx *ctx, const float *xyzn, size_t n, const int *a
  * the ue x ve bitmap (row-major, ue fastest, non-zero = set), 8-connected labelling, mask (0/1) of the component
  * with the most pixels (first in raster order on ties).  ue * ve <= 2^20.  Returns 1, or 0 on error. */
 int plade_largest_component(plade_ctx *ctx, const unsigned char *bitmap, int ue, int ve, unsigned char *mask);
+/* The acceptance chain of ONE RANSAC candidate plane (RansacShapeDetector::Detect, 3rd_party/ransac/RansacShapeDetector.cpp:613-655:
+ * Candidate::GlobalScore at 3 eps -> ConnectedComponent at bitmapEps -> up to three least-squares refits accepted while
+ * Candidate::GlobalWeightedScore improves and the support stays above min_support), run on the device exactly as the detection
+ * runs it (band_compact_kernel + refine_cluster_kernel).  normal / position: the candidate (Plane(pos, normal), R/Plane.cpp:13-23);
+ * assigned may be NULL (all points free).  Out: the accepted plane, member_mask[n] (0/1), its support, the number of
+ * evaluations and its gaussian-weighted score (Candidate::WeightedScore, R/Candidate.cpp:77-87).  Returns 1, or 0 on error. */
+int plade_refine_candidate(plade_ctx *ctx, const float *xyzn, size_t n, const int *assigned, const float normal[3], const float position[3],
+                           int min_support, float out_normal[3], float out_position[3], unsigned char *member_mask, long long *size,
+                           int *evaluations, double *weighted_score);
+/* Host-side restatements shared with the kernels (plade_b200/csrc/planefit.h; no device needed):
+ * plade_plane_parameters  = HyperplaneCoordinateSystem::FromNormal (R/GfxTL/HyperplaneCoordinateSystem.h:81-93) + PlanePrimitiveShape::
+ *                           Parameters (R/PlanePrimitiveShape.h:97-109): uv[2n], frame6 = u[3] v[3];
+ * plade_plane_ls_fit      = Plane::LeastSquaresFit (R/Plane.h:66-74; member sums in double, see DESIGN.md deviations), xyz packed;
+ * plade_bitmap_layout     = BitmapExtent / InBitmap (R/PlanePrimitiveShape.cpp:192-207): extent2 = (uextent, vextent), pixels[n]. */
+void plade_plane_parameters(const float normal[3], const float position[3], const float *xyz, size_t n, float *uv, float frame6[6]);
+int plade_plane_ls_fit(const float *xyz, size_t n, float out_normal[3], float out_position[3]);
+void plade_bitmap_layout(float umin, float umax, float vmin, float vmax, float bitmap_eps, const float *uv, size_t n, long long extent2[2], int *pixels);
 /* average_spacing(cloud, 6) PLADE/util.cpp:1619-1648 */
 float plade_average_spacing(plade_ctx *ctx, const float *xyzn, size_t n);
 /* DownSamplePointCloud / pcl::VoxelGrid  PLADE/util.h:162-184; xyz has `stride` floats per point
@@ -162,6 +194,25 @@ int plade_verify_upload(plade_ctx *ctx, const float *src_ds_xyz, size_t ns, cons
                         float inlier_dist);
 int plade_verify_resident(plade_ctx *ctx, const float *R9, const float *T3, const float *centers3, int H,
                           float ball_radius, float inlier_dist, unsigned int *counts, float *kernel_ms);
+
+/* BASELINE config 4: H given hypotheses against the clouds made resident by plade_verify_upload (on every rank), sharded over the
+ * ranks of the context's NCCL communicator (world 1 without one): this rank verifies h % world == rank; best_index / best_count =
+ * the hypothesis with the most inliers over ALL ranks (ties: lowest index), agreed by ncclAllReduce(ncclUint64, ncclMax);
+ * device_ms = CUDA-event time of kernel + key + collective on the context stream.  Returns 1 or 0. */
+int plade_verify_sharded(plade_ctx *ctx, const float *R9, const float *T3, const float *centers3, int H, float ball_radius,
+                         float inlier_dist, int *best_index, unsigned int *best_count, float *device_ms);
+
+/* ---- result / CLI extras ----------------------------------------------------------------
+ * plade_last_report: JSON text describing the last registration of this context -- planes and supports per cloud, down-sampled
+ * sizes, hypotheses verified, the winner, its matched plane pairs, its inlier count / overlap ratio / score: the numbers the
+ * reference's ResultViewer lets a user judge by eye.  Valid until the next registration on the context.
+ * plade_dump_planes_vg: the reference's save_vg (PLADE/util.cpp:1553-1616) -- an ASCII .vg vertex-group file of a cloud and its planes
+ * (Mapple / Easy3D read it); group_parameters hold (nx, ny, nz, d) instead of the reference's zeros.  Host only.  1 on success. */
+/* plade_ply_read: the PLY reader of the file overload (load_ply_cloud, PLADE/util.cpp:1505-1546): interleaved x y z nx ny nz into
+ * out_xyzn (room for capacity_points records); out_xyzn == NULL only returns the number of points; -1 on failure.  Host only. */
+long long plade_ply_read(const char *path, float *out_xyzn, size_t capacity_points);
+const char *plade_last_report(plade_ctx *ctx);
+int plade_dump_planes_vg(const float *xyzn, size_t n, const int *offsets, const int *indices, const float *params4, int n_planes, const char *path);
 
 /* ---- debugging / parity dumps ------------------------------------------------------------------- */
 void plade_set_debug(plade_ctx *ctx, int on);     /* record named stage blobs during registration */

@@ -16,6 +16,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 RESTATE_PATH = os.path.join(_HERE, "libplade_oracle.so")
 REF_PATH = os.path.join(_HERE, "_ref", "libplade_ref.so")
+# the same sources at -O3 -march=x86-64-v3 (make -C oracle fast): the TIMING build of the CPU baseline, never used for parity
+REF_FAST_PATH = os.path.join(_HERE, "_ref_fast", "libplade_ref.so")
 
 _fp = ctypes.POINTER(ctypes.c_float)
 _ip = ctypes.POINTER(ctypes.c_int)
@@ -42,6 +44,10 @@ def build_restate():
 
 def have_ref():
     return os.path.exists(REF_PATH)
+
+
+def have_ref_fast():
+    return os.path.exists(REF_FAST_PATH)
 
 
 class Restate:
@@ -115,10 +121,11 @@ class Restate:
 class Ref:
     """The reference's own code (compiled from /root/reference by oracle/Makefile)."""
 
-    def __init__(self, quiet=True):
+    def __init__(self, quiet=True, fast=False):
         if not have_ref():
             raise RuntimeError("oracle/_ref/libplade_ref.so not built (needs /root/reference; `make -C oracle ref`)")
-        self.lib = ctypes.CDLL(REF_PATH)
+        self.fast = bool(fast and have_ref_fast())
+        self.lib = ctypes.CDLL(REF_FAST_PATH if self.fast else REF_PATH)
         self.quiet = quiet
         L = self.lib
         L.ref_set_seed.argtypes = [ctypes.c_long]

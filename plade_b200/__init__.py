@@ -29,6 +29,15 @@ SIGNATURES = {
     "plade_device_count": (ctypes.c_int, []),
     "plade_set_param": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]),
     "plade_set_shard": (None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ALLREDUCE_FN, ctypes.c_void_p]),
+    "plade_nccl_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
+    "plade_shard_init_nccl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
+    "plade_shard_init_nccl_all": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
+    "plade_shard_finalize": (None, [ctypes.c_void_p]),
+    "plade_verify_sharded": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                            _c_int_p, _c_uint_p, _c_float_p]),
+    "plade_ply_read": (ctypes.c_longlong, [ctypes.c_char_p, _c_float_p, ctypes.c_size_t]),
+    "plade_last_report": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "plade_dump_planes_vg": (ctypes.c_int, [_c_float_p, ctypes.c_size_t, _c_int_p, _c_int_p, _c_float_p, ctypes.c_int, ctypes.c_char_p]),
     "plade_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
     "plade_stage_times": (ctypes.c_int, [ctypes.c_void_p, _c_double_p, ctypes.c_int]),
     "plade_kernel_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, _c_double_p]),
@@ -58,6 +67,12 @@ SIGNATURES = {
     "plade_score_planes": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, _c_int_p, _c_float_p, ctypes.c_int,
                                           ctypes.c_float, ctypes.c_float, _c_uint_p, _c_ubyte_p]),
     "plade_largest_component": (ctypes.c_int, [ctypes.c_void_p, _c_ubyte_p, ctypes.c_int, ctypes.c_int, _c_ubyte_p]),
+    "plade_refine_candidate": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, _c_int_p, _c_float_p, _c_float_p, ctypes.c_int,
+                                              _c_float_p, _c_float_p, _c_ubyte_p, ctypes.POINTER(ctypes.c_longlong), _c_int_p, _c_double_p]),
+    "plade_plane_parameters": (None, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_size_t, _c_float_p, _c_float_p]),
+    "plade_plane_ls_fit": (ctypes.c_int, [_c_float_p, ctypes.c_size_t, _c_float_p, _c_float_p]),
+    "plade_bitmap_layout": (None, [ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_float_p, ctypes.c_size_t,
+                                   ctypes.POINTER(ctypes.c_longlong), _c_int_p]),
     "plade_average_spacing": (ctypes.c_float, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t]),
     "plade_voxel_downsample": (ctypes.c_longlong, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, _c_float_p]),
     "plade_bounding_box": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, ctypes.c_size_t, _c_float_p, _c_double_p, _c_float_p]),
@@ -113,6 +128,78 @@ STAGE_NAMES = ["upload", "planes", "spacing", "downsample", "lines", "descriptor
                "penetration", "verify", "total", "verify_kernel_ms", "verify_h", "verify_ns", "verify_nt"]
 
 
+def dump_planes_vg(xyzn, planes, path):
+    """the reference's save_vg: ASCII vertex-group file of a cloud and its planes"""
+    lib = load_library()
+    a = _f32(xyzn).reshape(-1, 6)
+    if not lib.plade_dump_planes_vg(_p(a, _c_float_p), len(a), _p(planes.offsets, _c_int_p), _p(planes.indices, _c_int_p), _p(planes.params, _c_float_p),
+                                    len(planes), os.fsencode(path)):
+        raise RuntimeError("plade_dump_planes_vg failed: %s" % path)
+
+
+def ply_read(path):
+    """the library's PLY reader: (n, 6) float32, or None when the reference would report a load failure"""
+    lib = load_library()
+    n = lib.plade_ply_read(os.fsencode(path), None, 0)
+    if n < 0:
+        return None
+    out = np.zeros((n, 6), np.float32)
+    if lib.plade_ply_read(os.fsencode(path), _p(out, _c_float_p), n) != n:
+        return None
+    return out
+
+
+def device_count():
+    """visible CUDA devices (0 when there is none)"""
+    return int(load_library().plade_device_count())
+
+
+def nccl_unique_id():
+    """ncclGetUniqueId through the library (rank 0 calls it and ships the 128 bytes to the other ranks)"""
+    lib = load_library()
+    buf = ctypes.create_string_buffer(128)
+    if not lib.plade_nccl_unique_id(buf):
+        raise RuntimeError("plade_nccl_unique_id: %s" % lib.plade_create_error().decode())
+    return buf.raw
+
+
+def shard_init_nccl_all(contexts):
+    """one process, one context per GPU: ncclCommInitAll over the contexts' devices (rank i = contexts[i])"""
+    lib = load_library()
+    arr = (ctypes.c_void_p * len(contexts))(*[c.h for c in contexts])
+    if not lib.plade_shard_init_nccl_all(arr, len(contexts)):
+        raise RuntimeError("plade_shard_init_nccl_all: %s" % lib.plade_create_error().decode())
+
+
+def plane_parameters(normal, position, xyz):
+    """host-side restatement shared with the kernels (planefit.h): (uv[n,2], u[3], v[3]); needs no device"""
+    lib = load_library()
+    nrm, pos, a = _f32(normal), _f32(position), _f32(xyz).reshape(-1, 3)
+    uv, fr = np.zeros((len(a), 2), np.float32), np.zeros(6, np.float32)
+    lib.plade_plane_parameters(_p(nrm, _c_float_p), _p(pos, _c_float_p), _p(a, _c_float_p), len(a), _p(uv, _c_float_p), _p(fr, _c_float_p))
+    return uv, fr[:3].copy(), fr[3:].copy()
+
+
+def plane_ls_fit(xyz):
+    """host-side restatement of Plane::LeastSquaresFit as the kernels evaluate it: (ok, normal, position)"""
+    lib = load_library()
+    a = _f32(xyz).reshape(-1, 3)
+    n, p = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    ok = lib.plade_plane_ls_fit(_p(a, _c_float_p), len(a), _p(n, _c_float_p), _p(p, _c_float_p))
+    return bool(ok), n, p
+
+
+def bitmap_layout(uv, bitmap_eps):
+    """BitmapExtent / InBitmap as the kernels evaluate them: ((uextent, vextent), pixel index per point)"""
+    lib = load_library()
+    a = _f32(uv).reshape(-1, 2)
+    ext = (ctypes.c_longlong * 2)()
+    pix = np.zeros(len(a), np.int32)
+    lib.plade_bitmap_layout(float(a[:, 0].min()), float(a[:, 0].max()), float(a[:, 1].min()), float(a[:, 1].max()), float(bitmap_eps),
+                            _p(a, _c_float_p), len(a), ext, _p(pix, _c_int_p))
+    return (int(ext[0]), int(ext[1])), pix
+
+
 class Planes:
     """CSR plane set: offsets[np+1], indices, params[np,4] = (nx, ny, nz, d)."""
 
@@ -153,6 +240,31 @@ class Context:
     def set_param(self, name, value):
         if not self.lib.plade_set_param(self.h, name.encode(), float(value)):
             raise KeyError(name)
+
+    # ---- NCCL-sharded verification: the collective lives in the C++ library
+    def shard_init_nccl(self, unique_id, rank, world):
+        """join the NCCL communicator identified by `unique_id` (128 bytes from nccl_unique_id() on rank 0, sent out of band)"""
+        if not self.lib.plade_shard_init_nccl(self.h, bytes(unique_id), int(rank), int(world)):
+            raise RuntimeError(self.last_error())
+
+    def shard_finalize(self):
+        self.lib.plade_shard_finalize(self.h)
+
+    def verify_sharded(self, R, T, centers, ball_radius, inlier_dist):
+        """config 4: all H hypotheses given on every rank, this rank verifies h % world == rank, one ncclAllReduce(u64, max)
+        agrees on the winner: (best index, best inlier count, device ms incl. the collective)"""
+        R9, T3, C3 = _f32(R).reshape(-1, 9), _f32(T).reshape(-1, 3), _f32(centers).reshape(-1, 3)
+        bi, bc, ms = ctypes.c_int(-1), ctypes.c_uint(0), ctypes.c_float(0)
+        if not self.lib.plade_verify_sharded(self.h, _p(R9, _c_float_p), _p(T3, _c_float_p), _p(C3, _c_float_p), len(R9), float(ball_radius),
+                                             float(inlier_dist), ctypes.byref(bi), ctypes.byref(bc), ctypes.byref(ms)):
+            raise RuntimeError(self.last_error())
+        return bi.value, bc.value, ms.value
+
+    def last_report(self):
+        """dict describing the last registration (planes, hypotheses, winner, inliers, overlap ratio, score)"""
+        import json
+        t = self.lib.plade_last_report(self.h).decode()
+        return json.loads(t) if t else {}
 
     def set_debug(self, on=True):
         self.lib.plade_set_debug(self.h, 1 if on else 0)
@@ -277,6 +389,20 @@ class Context:
         if not self.lib.plade_largest_component(self.h, _p(b, _c_ubyte_p), b.shape[1], b.shape[0], _p(mask, _c_ubyte_p)):
             raise RuntimeError(self.last_error())
         return mask
+
+    def refine_candidate(self, xyzn, normal, position, min_support, assigned=None):
+        """acceptance chain of one candidate plane on the device: (size, normal, position, member mask, evaluations, weighted score)"""
+        a = _f32(xyzn).reshape(-1, 6)
+        nrm, pos = _f32(normal), _f32(position)
+        asg = _i32(assigned) if assigned is not None else None
+        on, op = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        mask = np.zeros(len(a), np.uint8)
+        size, ev, sc = ctypes.c_longlong(0), ctypes.c_int(0), ctypes.c_double(0)
+        if not self.lib.plade_refine_candidate(self.h, _p(a, _c_float_p), len(a), _p(asg, _c_int_p) if asg is not None else None, _p(nrm, _c_float_p),
+                                               _p(pos, _c_float_p), int(min_support), _p(on, _c_float_p), _p(op, _c_float_p), _p(mask, _c_ubyte_p),
+                                               ctypes.byref(size), ctypes.byref(ev), ctypes.byref(sc)):
+            raise RuntimeError(self.last_error())
+        return size.value, on, op, mask, ev.value, sc.value
 
     def score_planes(self, xyzn, planes4, eps, normal_thresh, assigned=None, want_mask=False):
         a = _f32(xyzn).reshape(-1, 6)

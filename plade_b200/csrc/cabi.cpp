@@ -3,6 +3,8 @@
 // nothing throws or aborts across the ABI.
 #include "../../include/plade_b200.h"
 #include "pipeline.h"
+#include "nccl_shard.h"
+#include "planefit.h"
 #include "ply.h"
 #include "libm_flt32.h"
 #include <atomic>
@@ -76,7 +78,7 @@ static void upload_xyz(Registrar &r, const float *pts, size_t n, int stride, Dev
   for (size_t i = 0; i < n; ++i) h[i] = make_float4(pts[i * stride], pts[i * stride + 1], pts[i * stride + 2], 0.f);
   float4 *d = out.ensure(std::max<size_t>(n, 1));
   if (n) PLADE_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, r.dev.stream));
-  PLADE_CUDA(cudaStreamSynchronize(r.dev.stream));
+  stream_sync(r.dev.stream);
 }
 
 extern "C" {
@@ -123,6 +125,9 @@ int plade_set_param(plade_ctx *ctx, const char *name, double v) {
   else if (n == "max_trials") p.max_trials = (int) v;
   else if (n == "detect_margin") p.detect_margin = v;
   else if (n == "ransac_batch") p.ransac_batch = (int) v;
+  else if (n == "detect_resume") p.detect_resume = (int) v;
+  else if (n == "blocking_sync") set_blocking_sync(v != 0);       // process-wide, see stream_sync
+  else if (n == "kernel_clock") { ctx->reg->dev.clock.enabled = ctx->reg->dev2.clock.enabled = v != 0; }
   else if (n == "max_candidates") p.max_candidates = (int) v;
   else if (n == "descriptor_radius") p.descriptor_radius = v;
   else if (n == "seed") p.seed = (unsigned long long) v;
@@ -132,10 +137,141 @@ int plade_set_param(plade_ctx *ctx, const char *name, double v) {
 
 void plade_set_shard(plade_ctx *ctx, int rank, int world, plade_allreduce_max_u64 reduce, void *user) {
   if (!ctx) return;
+  if (world > 1 && !reduce && !ctx->reg->nccl) {
+    // a shard without a reducer would silently return the best of the local shard only
+    ctx->err = "plade_set_shard: world > 1 needs a reducer (or plade_shard_init_nccl)";
+    std::cerr << "plade_b200: " << ctx->err << std::endl;
+    world = 1; rank = 0;
+  }
   ctx->reg->shard_rank = rank;
   ctx->reg->shard_world = world < 1 ? 1 : world;
   ctx->reg->allreduce = reduce;
   ctx->reg->allreduce_user = user;
+}
+
+static void fill_hyp(std::vector<HypParams> &hp, const float *R9, const float *T3, const float *c3, int H);
+
+// PLY ingest of the file overload as a stage entry (ply.cpp; PLADE/util.cpp:1505-1546): out_xyzn == NULL -> only the point count
+long long plade_ply_read(const char *path, float *out_xyzn, size_t capacity_points) {
+  if (!path) return -1;
+  std::vector<float> v;
+  if (!load_ply_xyzn(path, v)) return -1;
+  const size_t n = v.size() / 6;
+  if (out_xyzn) {
+    if (n > capacity_points) return -1;
+    memcpy(out_xyzn, v.data(), v.size() * sizeof(float));
+  }
+  return (long long) n;
+}
+
+const char *plade_last_report(plade_ctx *ctx) { return ctx ? ctx->reg->report.c_str() : ""; }
+
+// save_vg of the reference (PLADE/util.cpp:1553-1616), same text layout; group_parameters carry the plane (nx, ny, nz, d) where the
+// reference writes zeros, and the colours are a fixed function of the plane index instead of rand()
+int plade_dump_planes_vg(const float *xyzn, size_t n, const int *offsets, const int *indices, const float *params4, int n_planes, const char *path) {
+  if (!path || (n && !xyzn) || n_planes < 0) return 0;
+  FILE *f = fopen(path, "w");
+  if (!f) { std::cerr << "could not open file: " << path << std::endl; return 0; }
+  fprintf(f, "num_points: %zu\n", n);
+  for (size_t i = 0; i < n; ++i) fprintf(f, "%.9g %.9g %.9g ", xyzn[6 * i], xyzn[6 * i + 1], xyzn[6 * i + 2]);
+  fprintf(f, "\nnum_colors: 0\nnum_normals: %zu\n", n);
+  for (size_t i = 0; i < n; ++i) fprintf(f, "%.9g %.9g %.9g ", xyzn[6 * i + 3], xyzn[6 * i + 4], xyzn[6 * i + 5]);
+  fprintf(f, "\nnum_groups: %d\n", n_planes);
+  for (int k = 0; k < n_planes; ++k) {
+    fprintf(f, "group_type: 0\nnum_group_parameters: 4\ngroup_parameters: %.9g %.9g %.9g %.9g \ngroup_label: unknown\n", params4[4 * k], params4[4 * k + 1],
+            params4[4 * k + 2], params4[4 * k + 3]);
+    const unsigned h = 2654435761u * (unsigned) (k + 1);
+    fprintf(f, "group_color: %.3f %.3f %.3f\n", 0.3 + 0.7 * ((h >> 8) & 255) / 255.0, 0.3 + 0.7 * ((h >> 16) & 255) / 255.0, 0.3 + 0.7 * ((h >> 24) & 255) / 255.0);
+    fprintf(f, "group_num_point: %d\n", offsets[k + 1] - offsets[k]);
+    for (int i = offsets[k]; i < offsets[k + 1]; ++i) fprintf(f, "%d ", indices[i]);
+    fprintf(f, "\nnum_children: 0\n");
+  }
+  const bool ok = !ferror(f);
+  fclose(f);
+  return ok ? 1 : 0;
+}
+
+int plade_nccl_unique_id(char out128[128]) {
+  try { nccl_unique_id(out128); return 1; } catch (const std::exception &e) { g_create_error = e.what(); std::cerr << "plade_b200: " << e.what() << std::endl; return 0; }
+}
+int plade_shard_init_nccl(plade_ctx *ctx, const char id128[128], int rank, int world) {
+  PLADE_TRY(ctx, 0, {
+    Registrar &r = *ctx->reg;
+    if (r.nccl) { nccl_comm_destroy(r.nccl); r.nccl = nullptr; }
+    if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("plade_shard_init_nccl: bad rank / world");
+    r.nccl = nccl_comm_init_rank(id128, rank, world);
+    r.shard_rank = rank; r.shard_world = world;
+    r.allreduce = nullptr; r.allreduce_user = nullptr;
+    return 1;
+  })
+}
+int plade_shard_init_nccl_all(plade_ctx **ctxs, int n) {
+  if (!ctxs || n < 1) return 0;
+  try {
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; ++i) { if (!ctxs[i]) return 0; devs[i] = ctxs[i]->reg->dev.id; }
+    std::vector<ShardComm *> comms(n, nullptr);
+    nccl_comm_init_all(comms.data(), devs.data(), n);
+    for (int i = 0; i < n; ++i) {
+      Registrar &r = *ctxs[i]->reg;
+      if (r.nccl) nccl_comm_destroy(r.nccl);
+      r.nccl = comms[i];
+      r.shard_rank = i; r.shard_world = n;
+      r.allreduce = nullptr; r.allreduce_user = nullptr;
+    }
+    return 1;
+  } catch (const std::exception &e) {
+    g_create_error = e.what();
+    std::cerr << "plade_b200: " << e.what() << std::endl;
+    return 0;
+  }
+}
+void plade_shard_finalize(plade_ctx *ctx) {
+  if (!ctx) return;
+  Registrar &r = *ctx->reg;
+  if (r.nccl) { cudaSetDevice(r.dev.id); nccl_comm_destroy(r.nccl); r.nccl = nullptr; }
+  r.shard_rank = 0; r.shard_world = 1; r.allreduce = nullptr; r.allreduce_user = nullptr;
+}
+
+// Config 4: H given hypotheses against the resident down-sampled clouds (plade_verify_upload on every rank),
+// sharded over the ranks of the context's NCCL communicator: this rank verifies h % world == rank, the winner (highest
+// inlier count, ties -> lowest index) is agreed with one ncclAllReduce(ncclUint64, ncclMax).  No count leaves the device.
+int plade_verify_sharded(plade_ctx *ctx, const float *R9, const float *T3, const float *centers3, int H, float ball_radius, float inlier_dist,
+                         int *best_index, unsigned int *best_count, float *device_ms) {
+  PLADE_TRY(ctx, 0, {
+    Registrar &r = *ctx->reg;
+    cudaStream_t s = r.dev.stream;
+    const int world = r.shard_world, rank = r.shard_rank;
+    if (world > 1 && !r.nccl) throw std::runtime_error("plade_verify_sharded: no NCCL communicator (plade_shard_init_nccl)");
+    std::vector<HypParams> hp;
+    fill_hyp(hp, R9, T3, centers3, H);
+    std::vector<HypParams> mine;
+    for (int h = rank; h < H; h += world) mine.push_back(hp[h]);
+    const int nm = (int) mine.size();
+    HypParams *d_h = ctx->v_hyp.ensure(std::max(nm, 1));
+    unsigned int *d_c = ctx->v_counts.ensure(std::max(nm, 1));
+    unsigned long long *d_key = r.d_shard_key.ensure(4), *h_key = r.h_shard_key.ensure(4);
+    if (nm) PLADE_CUDA(cudaMemcpyAsync(d_h, mine.data(), sizeof(HypParams) * nm, cudaMemcpyHostToDevice, s));
+    PLADE_CUDA(cudaEventRecord(r.ev_user0, s));
+    verify_hypotheses(r.dev, ctx->v_src.p, ctx->v_ns, ctx->v_grid, d_h, nm, ball_radius, inlier_dist, d_c);
+    shard_best_key(r.dev, d_c, d_h, nm, rank, world, 1.0, 1.0, 1, d_key);
+    if (world > 1) nccl_allreduce_max_u64(r.nccl, d_key, 1, s);
+    PLADE_CUDA(cudaEventRecord(r.ev_user1, s));
+    PLADE_CUDA(cudaMemcpyAsync(h_key, d_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    stream_sync(s);
+    float ms = 0;
+    PLADE_CUDA(cudaEventElapsedTime(&ms, r.ev_user0, r.ev_user1));
+    if (device_ms) *device_ms = ms;
+    const unsigned long long key = h_key[0];
+    if (key == 0 && H > 0) {      // every count is zero: the lowest index wins
+      if (best_index) *best_index = 0;
+      if (best_count) *best_count = 0;
+      return 1;
+    }
+    if (best_index) *best_index = H > 0 ? (int) (0xFFFFFFFFu - (unsigned int) (key & 0xFFFFFFFFull)) : -1;
+    if (best_count) *best_count = (unsigned int) (key >> 32);
+    return 1;
+  })
 }
 long long plade_launch_count(plade_ctx *ctx) { return ctx ? ctx->reg->dev.launches.n : 0; }
 int plade_stage_times(plade_ctx *ctx, double *out, int n) {
@@ -506,6 +642,53 @@ int plade_largest_component(plade_ctx *ctx, const unsigned char *bitmap, int ue,
   })
 }
 
+int plade_refine_candidate(plade_ctx *ctx, const float *xyzn, size_t n, const int *assigned, const float normal[3], const float position[3],
+                           int min_support, float out_normal[3], float out_position[3], unsigned char *member_mask, long long *size,
+                           int *evaluations, double *weighted_score) {
+  PLADE_TRY(ctx, 0, {
+    Registrar &r = *ctx->reg;
+    r.upload(xyzn, n, ctx->tmp_t);
+    long long sz = 0;
+    int ev = 0;
+    double sc = 0;
+    if (!r.refine_candidate_stage(ctx->tmp_t, assigned, normal, position, min_support, out_normal, out_position, member_mask, &sz, &ev, &sc)) {
+      ctx->err = r.last_error;
+      return 0;
+    }
+    if (size) *size = sz;
+    if (evaluations) *evaluations = ev;
+    if (weighted_score) *weighted_score = sc;
+    return 1;
+  })
+}
+
+// ---- host-side plane arithmetic (planefit.h, the same inline functions the kernels call) ------------------------------
+void plade_plane_parameters(const float normal[3], const float position[3], const float *xyz, size_t n, float *uv, float frame6[6]) {
+  float u[3], v[3];
+  frame_from_normal(normal, u, v);
+  for (int k = 0; k < 3; ++k) { frame6[k] = u[k]; frame6[3 + k] = v[k]; }
+  for (size_t i = 0; i < n; ++i) plane_uv(xyz + 3 * i, position, u, v, uv[2 * i], uv[2 * i + 1]);
+}
+int plade_plane_ls_fit(const float *xyz, size_t n, float out_normal[3], float out_position[3]) {
+  if (n < 1) return 0;
+  // member sums in double, mean rounded to float, covariance about float(mean) -- as refine_candidate_dev forms them
+  Eval e{(long long) n, 0, {0, 0, 0}, true};
+  for (size_t i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) e.sum[k] += (double) xyz[3 * i + k];
+  const float mx = (float) (e.sum[0] / e.size), my = (float) (e.sum[1] / e.size), mz = (float) (e.sum[2] / e.size);
+  double c[6] = {0, 0, 0, 0, 0, 0};
+  for (size_t i = 0; i < n; ++i) {
+    const double dx = (double) (xyz[3 * i] - mx), dy = (double) (xyz[3 * i + 1] - my), dz = (double) (xyz[3 * i + 2] - mz);
+    c[0] += dx * dx; c[1] += dx * dy; c[2] += dx * dz; c[3] += dy * dy; c[4] += dy * dz; c[5] += dz * dz;
+  }
+  return fit_plane_from_cov(e, c, out_normal, out_position) ? 1 : 0;
+}
+void plade_bitmap_layout(float umin, float umax, float vmin, float vmax, float bitmap_eps, const float *uv, size_t n, long long extent2[2], int *pixels) {
+  extent2[0] = bitmap_extent(umin, umax, bitmap_eps);
+  extent2[1] = bitmap_extent(vmin, vmax, bitmap_eps);
+  for (size_t i = 0; i < n; ++i)
+    pixels[i] = bitmap_pixel(uv[2 * i], umin, bitmap_eps, (int) extent2[0]) + bitmap_pixel(uv[2 * i + 1], vmin, bitmap_eps, (int) extent2[1]) * (int) extent2[0];
+}
+
 int plade_score_planes(plade_ctx *ctx, const float *xyzn, size_t n, const int *assigned, const float *planes4, int n_planes,
                        float eps, float normal_thresh, unsigned int *counts, unsigned char *inlier_mask) {
   PLADE_TRY(ctx, 0, {
@@ -524,7 +707,7 @@ int plade_score_planes(plade_ctx *ctx, const float *xyzn, size_t n, const int *a
     score_planes_full(r.dev, ctx->tmp_t.pos.p, ctx->tmp_t.nrm.p, d_as, n, d_pl, n_planes, eps, normal_thresh, d_c, d_m);
     PLADE_CUDA(cudaMemcpyAsync(counts, d_c, sizeof(unsigned int) * n_planes, cudaMemcpyDeviceToHost, s));
     if (inlier_mask && n) PLADE_CUDA(cudaMemcpyAsync(inlier_mask, d_m, n, cudaMemcpyDeviceToHost, s));
-    PLADE_CUDA(cudaStreamSynchronize(s));
+    stream_sync(s);
     return 1;
   })
 }
@@ -544,7 +727,7 @@ long long plade_voxel_downsample(plade_ctx *ctx, const float *pts, size_t n, int
     size_t nv = voxel_downsample(r.dev, r.vox, ctx->stage_a.p, n, leaf, ctx->stage_b);
     std::vector<float4> h(nv);
     if (nv) PLADE_CUDA(cudaMemcpyAsync(h.data(), ctx->stage_b.p, sizeof(float4) * nv, cudaMemcpyDeviceToHost, r.dev.stream));
-    PLADE_CUDA(cudaStreamSynchronize(r.dev.stream));
+    stream_sync(r.dev.stream);
     for (size_t i = 0; i < nv; ++i) { out_xyz[3 * i] = h[i].x; out_xyz[3 * i + 1] = h[i].y; out_xyz[3 * i + 2] = h[i].z; }
     return (long long) nv;
   })
@@ -691,7 +874,7 @@ int plade_verify_upload(plade_ctx *ctx, const float *src_ds_xyz, size_t ns, cons
     upload_xyz(r, tgt_ds_xyz, nt, 3, ctx->v_tgt);
     ctx->v_ns = ns; ctx->v_nt = nt;
     build_target_grid(r.dev, ctx->v_tgt.p, nt, inlier_dist, ctx->v_grid);
-    PLADE_CUDA(cudaStreamSynchronize(r.dev.stream));
+    stream_sync(r.dev.stream);
     return 1;
   })
 }
@@ -713,7 +896,7 @@ int plade_verify_resident(plade_ctx *ctx, const float *R9, const float *T3, cons
     verify_hypotheses(r.dev, ctx->v_src.p, ctx->v_ns, ctx->v_grid, d_h, H, ball_radius, inlier_dist, d_c);
     PLADE_CUDA(cudaEventRecord(e1, s));
     if (H) PLADE_CUDA(cudaMemcpyAsync(counts, d_c, sizeof(unsigned int) * H, cudaMemcpyDeviceToHost, s));
-    PLADE_CUDA(cudaStreamSynchronize(s));
+    stream_sync(s);
     float ms = 0;
     PLADE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);

@@ -152,7 +152,7 @@ void transforms_from_matches(Device &dev, HypScratch &sc, const MatchPairIn *h_i
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
   PLADE_CUDA(cudaMemcpyAsync(out.data(), d_out, sizeof(RigidOut) * m, cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
 }
 
 void cluster_transforms(Device &dev, HypScratch &sc, const std::vector<RigidOut> &rt, float dist_thresh, float ang_thresh,
@@ -185,7 +185,7 @@ void cluster_transforms(Device &dev, HypScratch &sc, const std::vector<RigidOut>
   PLADE_LAUNCH_CHECK();
   dev.launches.add(12);
   PLADE_CUDA(cudaMemcpyAsync(label.data(), d_label, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
 }
 
 }  // namespace plade

@@ -17,7 +17,11 @@ struct KernelClock {
   size_t used = 0;
   double ms[kKinds] = {0}, bytes[kKinds] = {0};
   long long launches[kKinds] = {0};
+  // off by default: two event records per timed launch are two more driver calls on a path that is bound by the
+  // number of driver calls (plade_set_param("kernel_clock", 1) turns the clock on for the calls that want the figures)
+  bool enabled = false;
   void begin(int kind, double algorithmic_bytes, cudaStream_t s) {
+    if (!enabled) return;
     if (used == spans.size()) {
       Span sp;
       PLADE_CUDA(cudaEventCreate(&sp.a));
@@ -28,7 +32,7 @@ struct KernelClock {
     bytes[kind] += algorithmic_bytes;
     PLADE_CUDA(cudaEventRecord(spans[used].a, s));
   }
-  void end(cudaStream_t s) { PLADE_CUDA(cudaEventRecord(spans[used].b, s)); ++used; }
+  void end(cudaStream_t s) { if (!enabled) return; PLADE_CUDA(cudaEventRecord(spans[used].b, s)); ++used; }
   void collect() {          // the stream must be idle
     for (size_t i = 0; i < used; ++i) {
       float t = 0;
@@ -80,6 +84,10 @@ void build_target_grid(Device &dev, const float4 *d_tgt, size_t n, float inlier_
 void verify_hypotheses(Device &dev, const float4 *d_src, size_t ns, const TargetGrid &grid,
                        const HypParams *d_hyp, int H, float ball_radius, float inlier_dist,
                        unsigned int *d_counts);
+
+// best hypothesis of a shard as a packed u64 key in d_key[0] (see shard_key_kernel, verify.cu); entry i = hypothesis rank + i * world
+void shard_best_key(Device &dev, const unsigned int *d_counts, const HypParams *d_hyp, int n_mine, int rank, int world, double denom,
+                    double n_src_planes, int mode, unsigned long long *d_key);
 
 // ------------------------------------------------------------------------------------------------
 // K2b — voxel-grid down-sampling (pcl VoxelGrid::applyFilter, filters/impl/voxel_grid.hpp:214-437)

@@ -32,11 +32,66 @@ static void write_matrix(std::ostream &o, const float m[16]) {
   }
 }
 
-int main(int argc, char **argv) {
+// --dump-planes: the planes extract() finds in a cloud as an ASCII .vg file (the reference's save_vg, PLADE/util.cpp:1553-1616)
+static void dump_planes(plade_ctx *ctx, const char *ply, const std::string &out) {
+  const long long n = plade_ply_read(ply, nullptr, 0);
+  if (n <= 0) { std::cerr << "--dump-planes: cannot read " << ply << std::endl; return; }
+  std::vector<float> cloud((size_t) n * 6);
+  if (plade_ply_read(ply, cloud.data(), (size_t) n) != n) return;
+  if (plade_extract_planes(ctx, cloud.data(), (size_t) n, 10000) < 0) { std::cerr << "--dump-planes: " << plade_last_error(ctx) << std::endl; return; }
+  int np = 0;
+  long long ni = 0;
+  plade_planes_size(ctx, &np, &ni);
+  std::vector<int> off(np + 1), idx((size_t) std::max<long long>(ni, 1));
+  std::vector<float> par((size_t) std::max(np, 1) * 4);
+  plade_planes_get(ctx, off.data(), idx.data(), par.data());
+  if (plade_dump_planes_vg(cloud.data(), (size_t) n, off.data(), idx.data(), par.data(), np, out.c_str()))
+    std::cout << np << " planes of " << ply << " written into file: " << out << std::endl;
+}
+
+// --shard-verify: ONE pair on all visible GPUs (PLADE_DEVICES=n limits how many): every GPU extracts the planes and builds the
+// hypotheses (replicas), the verification loop (PLADE/plade.cpp:547-564) is split over the GPUs by hypothesis and the winner
+// agreed with one ncclAllReduce(ncclUint64, ncclMax) inside the library (plade_shard_init_nccl_all)
+static int register_sharded(const char *tgt, const char *src, float T[16], std::string *report) {
+  int n_dev = plade_device_count();
+  if (const char *e = getenv("PLADE_DEVICES")) n_dev = std::max(1, std::min(n_dev, atoi(e)));
+  if (n_dev < 1) { std::cerr << "no usable CUDA device" << std::endl; return 0; }
+  std::vector<plade_ctx *> ctxs(n_dev, nullptr);
+  for (int d = 0; d < n_dev; ++d) if (!(ctxs[d] = plade_ctx_create(d))) { std::cerr << "no usable CUDA device: " << plade_create_error() << std::endl; return 0; }
+  if (n_dev > 1 && !plade_shard_init_nccl_all(ctxs.data(), n_dev)) { std::cerr << "NCCL: " << plade_create_error() << std::endl; return 0; }
+  std::vector<int> oks(n_dev, 0);
+  std::vector<float> Ts((size_t) n_dev * 16);
+  std::vector<std::thread> th;
+  for (int d = 0; d < n_dev; ++d) th.emplace_back([&, d] { oks[d] = plade_register_files(ctxs[d], tgt, src, &Ts[(size_t) d * 16]); });
+  for (auto &t : th) t.join();
+  for (int i = 0; i < 16; ++i) T[i] = Ts[i];
+  if (report) *report = plade_last_report(ctxs[0]);
+  const int ok = oks[0];
+  for (int d = 0; d < n_dev; ++d) { plade_shard_finalize(ctxs[d]); plade_ctx_destroy(ctxs[d]); }
+  return ok;
+}
+
+int main(int argc0, char **argv0) {
+  // options (anywhere on the command line); what remains are the reference's positional arguments
+  std::string report_file, dump_prefix;
+  bool shard_verify = false;
+  std::vector<char *> pos;
+  for (int i = 0; i < argc0; ++i) {
+    const std::string a = argv0[i];
+    if (a == "--report" && i + 1 < argc0) report_file = argv0[++i];
+    else if (a == "--dump-planes" && i + 1 < argc0) dump_prefix = argv0[++i];
+    else if (a == "--shard-verify") shard_verify = true;
+    else pos.push_back(argv0[i]);
+  }
+  const int argc = (int) pos.size();
+  char **argv = pos.data();
   if (argc != 3 && argc != 4) {
     std::cerr << "PLADE (B200) registers two point clouds dominated by planar structures.\n"
               << "Usage 1:  plade_b200_cli  target.ply  source.ply  result.txt\n"
-              << "Usage 2:  plade_b200_cli  file_pairs.txt  results.txt   (two lines per pair: target, source)\n";
+              << "Usage 2:  plade_b200_cli  file_pairs.txt  results.txt   (two lines per pair: target, source)\n"
+              << "Options (usage 1):  --report file.json   planes, hypotheses, winner, inlier count / overlap ratio of the registration\n"
+              << "                    --dump-planes prefix  the extracted planes as prefix_target.vg / prefix_source.vg\n"
+              << "                    --shard-verify        verify the hypotheses on all visible GPUs (NCCL max-allreduce)\n";
     return EXIT_FAILURE;
   }
   float T[16];
@@ -45,7 +100,11 @@ int main(int argc, char **argv) {
     if (!ctx) { std::cerr << "no usable CUDA device: " << plade_create_error() << std::endl; return EXIT_FAILURE; }
     std::ofstream output(argv[3]);
     if (!output.is_open()) { std::cerr << "failed opening the result file: " << argv[3] << std::endl; return EXIT_FAILURE; }
-    int ok = plade_register_files(ctx, argv[1], argv[2], T);
+    std::string report;
+    int ok = shard_verify ? register_sharded(argv[1], argv[2], T, &report) : plade_register_files(ctx, argv[1], argv[2], T);
+    if (!shard_verify) report = plade_last_report(ctx);
+    if (!report_file.empty() && ok) { std::ofstream rf(report_file); rf << report << std::endl; }
+    if (!dump_prefix.empty()) { dump_planes(ctx, argv[1], dump_prefix + "_target.vg"); dump_planes(ctx, argv[2], dump_prefix + "_source.vg"); }
     if (ok) {
       output << "target: " << argv[1] << "\nsource: " << argv[2] << "\ntransformation:\n";
       write_matrix(output, T);

@@ -99,7 +99,7 @@ size_t match_descriptors(Device &dev, MatchScratch &sc, const float *h_db, int n
     PLADE_LAUNCH_CHECK();
     dev.launches.add();
     PLADE_CUDA(cudaMemcpyAsync(&m, d_counter, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
-    PLADE_CUDA(cudaStreamSynchronize(s));
+    stream_sync(s);
     if (m <= capacity) break;
     capacity = (size_t) m + 1024;   // exact size known now: rerun once
   }
@@ -122,7 +122,7 @@ size_t match_descriptors(Device &dev, MatchScratch &sc, const float *h_db, int n
   PLADE_CUDA(cudaMemcpyAsync(h_qi.data(), qi2, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost, s));
   PLADE_CUDA(cudaMemcpyAsync(h_di.data(), di2, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost, s));
   PLADE_CUDA(cudaMemcpyAsync(offsets.data(), d_off, sizeof(int) * ((size_t) nq + 1), cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
   idx.resize(m);
   dist2.resize(m);
   for (unsigned int i = 0; i < m; ++i) {

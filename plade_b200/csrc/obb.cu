@@ -113,7 +113,7 @@ void obb_segments(Device &dev, ObbScratch &sc, const std::vector<ObbSeg> &segs, 
   PLADE_LAUNCH_CHECK();
   std::vector<double> acc((size_t) 16 * S);
   PLADE_CUDA(cudaMemcpyAsync(acc.data(), d_acc, sizeof(double) * 16 * S, cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
   // host: eigen frames (same statements as the tail of ComputeBoundingBox)
   std::vector<float> frames((size_t) 12 * S, 0.f);
   std::vector<M3> Es(S);
@@ -148,7 +148,7 @@ void obb_segments(Device &dev, ObbScratch &sc, const std::vector<ObbSeg> &segs, 
   dev.launches.add(3);
   std::vector<int> mm((size_t) 6 * S);
   PLADE_CUDA(cudaMemcpyAsync(mm.data(), d_mm, sizeof(int) * 6 * S, cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
   for (int i = 0; i < S; ++i) {
     if (segs[i].n <= 0) continue;
     ObbResult &o = out[i];

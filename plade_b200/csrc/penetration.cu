@@ -294,7 +294,7 @@ void penetration_filter(Device &dev, PenScratch &sc, const PenSide &src, const P
   dev.launches.add();
   int h2[2];
   PLADE_CUDA(cudaMemcpyAsync(h2, d_n, sizeof(h2), cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
   if (h2[1]) throw std::runtime_error("penetration filter: segment longer than 4096 search radii");
   if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade penetration] hypotheses %d, planes %d x %d, (hypothesis, plane, plane) triples to sample: %d\n", H, Ps, Pt, h2[0]);
   if (h2[0] > 0) {
@@ -305,7 +305,7 @@ void penetration_filter(Device &dev, PenScratch &sc, const PenSide &src, const P
   }
   std::vector<int> flags(H);
   PLADE_CUDA(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * H, cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
   for (int h = 0; h < H; ++h) pen_out[h] = flags[h] != 0;
 }
 

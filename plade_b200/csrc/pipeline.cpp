@@ -4,6 +4,8 @@
 // comparators, the candidate budget) follows the reference statement by statement because it
 // decides WHICH hypothesis wins; file:line citations are relative to /root/reference/code/.
 #include "pipeline.h"
+#include <atomic>
+#include "nccl_shard.h"
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -11,6 +13,7 @@
 #include <numeric>
 #include <condition_variable>
 #include <mutex>
+#include <sstream>
 #include <thread>
 #include <exception>
 
@@ -97,6 +100,21 @@ void pair_descriptor(const V3 &l1, const V3 &l2, const V3 &l1sp1, const V3 &l1sp
 
 }  // namespace
 
+namespace {
+std::atomic<int> g_blocking_sync{[] { const char *e = getenv("PLADE_BLOCKING_SYNC"); return (e && atoi(e) != 0) ? 1 : 0; }()};
+}
+void set_blocking_sync(bool on) { g_blocking_sync.store(on ? 1 : 0); }
+void stream_sync(cudaStream_t s) {
+  if (!g_blocking_sync.load(std::memory_order_relaxed)) { PLADE_CUDA(cudaStreamSynchronize(s)); return; }
+  thread_local cudaEvent_t ev[64] = {};
+  int d = 0;
+  PLADE_CUDA(cudaGetDevice(&d));
+  if (d < 0 || d >= 64) { PLADE_CUDA(cudaStreamSynchronize(s)); return; }
+  if (!ev[d]) PLADE_CUDA(cudaEventCreateWithFlags(&ev[d], cudaEventBlockingSync | cudaEventDisableTiming));
+  PLADE_CUDA(cudaEventRecord(ev[d], s));
+  PLADE_CUDA(cudaEventSynchronize(ev[d]));
+}
+
 Registrar::Registrar(int device) {
   if (device >= 0) PLADE_CUDA(cudaSetDevice(device));
   PLADE_CUDA(cudaGetDevice(&dev.id));
@@ -133,6 +151,7 @@ void Registrar::print_marks() {
 }
 
 Registrar::~Registrar() {
+  if (nccl) { nccl_comm_destroy(nccl); nccl = nullptr; }
   free_ransac_scratch(*this);
   for (cudaEvent_t e : {ev0, ev1, ev_user0, ev_user1}) if (e) cudaEventDestroy(e);
   dev.clock.destroy();
@@ -170,7 +189,7 @@ void Registrar::upload(const float *xyzn, size_t n, CloudDev &out, int lane, boo
   float *d_in = upload_stage[lane].ensure(n * 6);
   PLADE_CUDA(cudaMemcpyAsync(d_in, xyzn, sizeof(float) * n * 6, cudaMemcpyHostToDevice, d.stream));
   split_cloud(d, d_in, n, out.pos.ensure(n), out.nrm.ensure(n));
-  if (wait) PLADE_CUDA(cudaStreamSynchronize(d.stream));
+  if (wait) stream_sync(d.stream);
 }
 
 // average_spacing (PLADE/util.cpp:1619-1648): k = 6, ~10000 strided samples
@@ -190,7 +209,7 @@ float Registrar::average_spacing(const CloudDev &c, int lane) {
   knn_sqdist(dev, knn_sc, c.pos.p, num, d_q, (int) q.size(), kk, d_o);
   std::vector<float> h(q.size() * kk);
   PLADE_CUDA(cudaMemcpyAsync(h.data(), d_o, sizeof(float) * h.size(), cudaMemcpyDeviceToHost, dev.stream));
-  PLADE_CUDA(cudaStreamSynchronize(dev.stream));
+  stream_sync(dev.stream);
   double total = 0.0;
   size_t total_count = 0;
   for (size_t s = 0; s < q.size(); ++s) {
@@ -312,7 +331,7 @@ bool Registrar::register_with_planes(const CloudDev &tgt, const CloudDev &src, c
     }
     int *d = gbuf[side]->ensure(std::max<size_t>(n, 1));
     if (n) PLADE_CUDA(cudaMemcpyAsync(d, grp.data(), sizeof(int) * n, cudaMemcpyHostToDevice, dev.stream));
-    PLADE_CUDA(cudaStreamSynchronize(dev.stream));
+    stream_sync(dev.stream);
   }
   times.planes = 0;
   prep[0].ready = prep[1].ready = false;
@@ -359,9 +378,9 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     const std::vector<PlaneParam> &P = *planes_in[side];
     // done already inside the cloud's extraction lane (register_clouds), unless the planes came from the caller
     if (!(prep[side].ready && prep[side].leaf == downSampleDistance)) {
-      if (side == 1) PLADE_CUDA(cudaStreamSynchronize(dev.stream));     // lane 1 reads nothing lane 0 still writes, but keep the order simple
+      if (side == 1) stream_sync(dev.stream);     // lane 1 reads nothing lane 0 still writes, but keep the order simple
       prepare_side(side, C, P, d_groups[side], downSampleDistance, prep[side]);
-      if (side == 1) PLADE_CUDA(cudaStreamSynchronize(dev2.stream));
+      if (side == 1) stream_sync(dev2.stream);
     }
     A.n_ds = prep[side].n_ds;
     A.plane_ds_start = prep[side].plane_ds_start;
@@ -371,7 +390,7 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
       A.plane_ds.resize(nv);
       if (A.n_ds) PLADE_CUDA(cudaMemcpyAsync(A.ds.data(), ds_dev[side]->p, sizeof(float4) * A.n_ds, cudaMemcpyDeviceToHost, s));
       if (nv) PLADE_CUDA(cudaMemcpyAsync(A.plane_ds.data(), ds_pl[side]->p, sizeof(float4) * nv, cudaMemcpyDeviceToHost, s));
-      PLADE_CUDA(cudaStreamSynchronize(s));
+      stream_sync(s);
     }
   }
   {
@@ -728,9 +747,33 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     hp[i].c[0] = cc.x; hp[i].c[1] = cc.y; hp[i].c[2] = cc.z;
     hp[i].pad = 0;
   }
+  const bool nccl_path = shard_world > 1 && nccl != nullptr;
+  for (int i = 0; i < H; ++i) { const int np = (int) results[i].planes.size(); memcpy(&hp[i].pad, &np, sizeof(int)); }   // rides along for shard_key_kernel
+  bool list_is_local = true;
+  if (nccl_path) {
+    // Every rank ran its own plane extraction and matching; their hypothesis lists agree unless a float sum went the other
+    // way somewhere.  Rank 0's list is THE list: its length, then its records, are broadcast (two small ncclBroadcasts).
+    unsigned long long *d_key = d_shard_key.ensure(4), *h_key = h_shard_key.ensure(4);
+    h_key[0] = (unsigned long long) H;
+    PLADE_CUDA(cudaMemcpyAsync(d_key, h_key, sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    nccl_broadcast_bytes(nccl, d_key, sizeof(unsigned long long), 0, s);
+    PLADE_CUDA(cudaMemcpyAsync(h_key, d_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    stream_sync(s);
+    const int H0 = (int) h_key[0];
+    if (H0 <= 0) { last_error = "sharded verification: rank 0 has no hypothesis"; return false; }
+    HypParams *d_all = d_hyp_all.ensure((size_t) H0);
+    if (shard_rank == 0) PLADE_CUDA(cudaMemcpyAsync(d_all, hp.data(), sizeof(HypParams) * H0, cudaMemcpyHostToDevice, s));
+    nccl_broadcast_bytes(nccl, d_all, sizeof(HypParams) * (size_t) H0, 0, s);
+    std::vector<HypParams> hp0((size_t) H0);
+    PLADE_CUDA(cudaMemcpyAsync(hp0.data(), d_all, sizeof(HypParams) * H0, cudaMemcpyDeviceToHost, s));
+    stream_sync(s);
+    list_is_local = H0 == H && memcmp(hp0.data(), hp.data(), sizeof(HypParams) * (size_t) H0) == 0;
+    hp.swap(hp0);
+  }
+  const int H_all = (int) hp.size();
   // hypothesis shard of this rank (all ranks hold replicas of the clouds)
   std::vector<int> mine;
-  for (int i = 0; i < H; ++i) if (i % shard_world == shard_rank) mine.push_back(i);
+  for (int i = 0; i < H_all; ++i) if (i % shard_world == shard_rank) mine.push_back(i);
   std::vector<HypParams> hp_mine(mine.size());
   for (size_t i = 0; i < mine.size(); ++i) hp_mine[i] = hp[mine[i]];
   build_target_grid(dev, ds_tgt.p, M.n_ds, downSampleDistance, grid);
@@ -741,8 +784,29 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
   verify_hypotheses(dev, ds_src.p, Cu.n_ds, grid, d_h, (int) hp_mine.size(), (float) Cu.radius, downSampleDistance, d_c);
   PLADE_CUDA(cudaEventRecord(ev1, s));
   std::vector<unsigned int> counts_mine(hp_mine.size());
-  if (!hp_mine.empty()) PLADE_CUDA(cudaMemcpyAsync(counts_mine.data(), d_c, sizeof(unsigned int) * hp_mine.size(), cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  // Every rank runs its own RANSAC and matching: the shards are only comparable if all ranks hold the SAME hypothesis
+  // list.  A hash of the list travels with the key (MAX of h and of ~h: both equal the local values iff all ranks agree).
+  unsigned long long list_hash = 1469598103934665603ull;
+  if (shard_world > 1) {
+    auto mix = [&](const void *p, size_t nbytes) { const unsigned char *b = static_cast<const unsigned char *>(p); for (size_t k = 0; k < nbytes; ++k) { list_hash ^= b[k]; list_hash *= 1099511628211ull; } };
+    mix(&H_all, sizeof(H_all));
+    for (int i = 0; i < H_all; ++i) mix(hp[i].R, sizeof(float) * 16);
+  }
+  unsigned long long reduced[3] = {0, 0, 0};
+  if (nccl_path) {
+    // device-side argmax of the shard + ONE ncclAllReduce(ncclUint64, ncclMax) on this stream; no count leaves the device
+    unsigned long long *d_key = d_shard_key.ensure(4), *h_key = h_shard_key.ensure(4);
+    shard_best_key(dev, d_c, d_h, (int) hp_mine.size(), shard_rank, shard_world, (double) std::min(Cu.n_ds, M.n_ds), (double) currentPlanesNum, 0, d_key);
+    h_key[1] = list_hash; h_key[2] = ~list_hash;
+    PLADE_CUDA(cudaMemcpyAsync(d_key + 1, h_key + 1, sizeof(unsigned long long) * 2, cudaMemcpyHostToDevice, s));
+    nccl_allreduce_max_u64(nccl, d_key, 3, s);
+    PLADE_CUDA(cudaMemcpyAsync(h_key, d_key, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost, s));
+    stream_sync(s);
+    for (int k = 0; k < 3; ++k) reduced[k] = h_key[k];
+  } else {
+    if (!hp_mine.empty()) PLADE_CUDA(cudaMemcpyAsync(counts_mine.data(), d_c, sizeof(unsigned int) * hp_mine.size(), cudaMemcpyDeviceToHost, s));
+    stream_sync(s);
+  }
   {
     float ms = 0;
     PLADE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -770,21 +834,53 @@ bool Registrar::register_core(const CloudDev &tgt, const CloudDev &src, const st
     best = ov[0].index;
   } else {
     // packed key {score bits, ~index}: max picks the highest score, ties -> lowest index
-    unsigned long long key = 0;
-    for (size_t i = 0; i < mine.size(); ++i) {
-      float sc = score_of(mine[i], counts_mine[i]);
-      unsigned int bits;
-      memcpy(&bits, &sc, 4);
-      unsigned long long k = ((unsigned long long) bits << 32) | (0xFFFFFFFFu - (unsigned int) mine[i]);
-      key = std::max(key, k);
+    if (!nccl_path) {
+      if (!allreduce) { last_error = "sharded verification without a reducer (plade_shard_init_nccl or plade_set_shard with a callback)"; return false; }
+      unsigned long long key = 0;
+      for (size_t i = 0; i < mine.size(); ++i) {
+        float sc = score_of(mine[i], counts_mine[i]);
+        unsigned int bits;
+        memcpy(&bits, &sc, 4);
+        unsigned long long k = ((unsigned long long) bits << 32) | (0xFFFFFFFFu - (unsigned int) mine[i]);
+        key = std::max(key, k);
+      }
+      reduced[0] = key; reduced[1] = list_hash; reduced[2] = ~list_hash;
+      for (int k = 0; k < 3; ++k) allreduce(&reduced[k], allreduce_user);
     }
-    if (allreduce) allreduce(&key, allreduce_user);
-    best = (int) (0xFFFFFFFFu - (unsigned int) (key & 0xFFFFFFFFu));
-    if (best < 0 || best >= H) { last_error = "sharded verification failed"; return false; }
+    if (reduced[1] != list_hash || reduced[2] != ~list_hash) {
+      std::cerr << "sharded verification: the ranks built different hypothesis lists" << std::endl;
+      last_error = "sharded verification: the ranks built different hypothesis lists";
+      return false;
+    }
+    if (reduced[0] == 0) { last_error = "sharded verification failed: no hypothesis was verified"; return false; }
+    best = (int) (0xFFFFFFFFu - (unsigned int) (reduced[0] & 0xFFFFFFFFu));
+    if (best < 0 || best >= H_all) { last_error = "sharded verification failed"; return false; }
   }
   times.verify = now_s() - t0;
 
-  const MatchedHyp &W = results[best];
+  MatchedHyp W;
+  if (list_is_local) W = results[best];
+  else { memcpy(W.R.m, hp[best].R, sizeof(float) * 9); W.T = V3(hp[best].T[0], hp[best].T[1], hp[best].T[2]); }     // rank 0's record
+  {
+    // headless stand-in for the reference's ResultViewer: what the winner rests on (plade_last_report, CLI --report)
+    std::ostringstream js;
+    js.precision(9);
+    js << "{\"target_points\": " << tgt.n << ", \"source_points\": " << src.n << ", \"target_planes\": " << M.planes.size() << ", \"source_planes\": "
+       << Cu.planes.size() << ", \"average_spacing\": " << average_space << ", \"target_ds_points\": " << M.n_ds << ", \"source_ds_points\": " << Cu.n_ds
+       << ", \"hypotheses_verified\": " << H << ", \"shard_world\": " << shard_world << ", \"winner\": " << best << ", \"winner_matched_planes\": [";
+    for (size_t k = 0; k < W.planes.size(); ++k) js << (k ? ", " : "") << "[" << W.planes[k].first << ", " << W.planes[k].second << "]";
+    js << "]";
+    if (shard_world == 1) {
+      const double ov = double(counts_mine[best]) / double(denom);
+      js << ", \"winner_inliers\": " << counts_mine[best] << ", \"overlap_ratio\": " << ov << ", \"score\": " << score_of(best, counts_mine[best]);
+    }
+    js << ", \"target_plane_supports\": [";
+    for (size_t k = 0; k < tplanes.size(); ++k) js << (k ? ", " : "") << tplanes[k].size;
+    js << "], \"source_plane_supports\": [";
+    for (size_t k = 0; k < splanes.size(); ++k) js << (k ? ", " : "") << splanes[k].size;
+    js << "]}";
+    report = js.str();
+  }
   for (int r = 0; r < 3; ++r) {
     for (int c = 0; c < 3; ++c) out16[4 * r + c] = W.R(r, c);
     out16[4 * r + 3] = W.T[r];

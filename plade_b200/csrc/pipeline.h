@@ -38,8 +38,11 @@ struct Params {
   // extract(): planes count towards min_planes when their support is >= detect_margin x the pass's min_support (1 = the
   // reference's literal rule; see extract_planes_dev)
   double detect_margin = 1.25;
-  // RANSAC: candidates refined speculatively per batch (1 = one at a time; results are the same, see resolve_kernel)
-  int ransac_batch = 8;
+  // extract(): a pass with halved support continues the previous pass (its planes, its unassigned points, its drawn
+  // candidates) instead of starting over; 0 = every pass starts from scratch, as the reference's does
+  int detect_resume = 1;
+  // RANSAC: pool entries one accept_loop_kernel launch may walk (1 = host-driven, one candidate per round trip; same planes)
+  int ransac_batch = 64;
   // matching (PLADE/plade.cpp:46-56)
   int max_candidates = 200;
   float face_matches_weight = 0.2f;
@@ -97,8 +100,10 @@ class Registrar {
   float average_spacing(const CloudDev &c, int lane = 0);
   std::vector<PlaneRec> extract_planes(const CloudDev &c, int init_min_support);             // extract(), plade.cpp:602
   std::vector<PlaneRec> detect_planes(const CloudDev &c, int min_support);                   // PlaneExtraction::detect
+  bool refine_candidate_stage(const CloudDev &c, const int *h_assigned, const float nrm3[3], const float pos3[3], int min_support,
+                              float out_n[3], float out_p[3], unsigned char *h_member, long long *out_size, int *out_evals, double *out_score);
   // device-resident variants used by the registration path: membership stays in HBM (group_out[n])
-  std::vector<PlaneParam> detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out, int lane = 0);
+  std::vector<PlaneParam> detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out, int lane = 0, bool resume = false);
   std::vector<PlaneParam> extract_planes_dev(const CloudDev &c, int init_min_support, DevBuf<int> &group_out, int lane = 0);
   std::vector<PlaneRec> planes_to_host(const CloudDev &c, const std::vector<PlaneParam> &pp, const DevBuf<int> &group);
   bool register_core(const CloudDev &tgt, const CloudDev &src, const std::vector<PlaneParam> &tp, const std::vector<PlaneParam> &sp,
@@ -115,13 +120,19 @@ class Registrar {
   bool debug = false;
   std::map<std::string, std::vector<char>> blobs;
   std::string last_error;
+  std::string report;                   // JSON summary of the last registration (plade_last_report)
   // fine-grained wall-clock marks, printed to stderr at the end of a registration when PLADE_TIMING is set
   std::vector<std::pair<std::string, double>> marks;
   void mark(const char *name);
   void print_marks();
+  // hypothesis sharding of the verification: either an NCCL communicator (plade_shard_init_nccl: device-side key +
+  // ncclAllReduce on the context stream) or a caller-supplied reducer (plade_set_shard)
   int shard_rank = 0, shard_world = 1;
   AllreduceMaxU64 allreduce = nullptr;
   void *allreduce_user = nullptr;
+  struct ShardComm *nccl = nullptr;
+  DevBuf<unsigned long long> d_shard_key;
+  PinBuf<unsigned long long> h_shard_key;
 
   // scratch (grow-only, reused across calls)
   VoxelScratch vox, vox2;               // per lane
@@ -140,7 +151,7 @@ class Registrar {
   void *ransac_scratch[2] = {nullptr, nullptr};   // opaque, owned (ransac.cu)
   DevBuf<int> group_t, group_s, qidx;
   DevBuf<float> knn_out;
-  DevBuf<HypParams> d_hyp;
+  DevBuf<HypParams> d_hyp, d_hyp_all;
   DevBuf<unsigned int> d_counts;
   PinBuf<float> pin_in;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_user0 = nullptr, ev_user1 = nullptr;

@@ -9,13 +9,21 @@
 namespace plade {
 
 // HyperplaneCoordinateSystem::FromNormal (R/GfxTL/HyperplaneCoordinateSystem.h:81-93), AutoCAD arbitrary axis
+// GfxTL's Normalize (R/GfxTL/MatrixXX.h:80-91): the squared length is summed left to right (linalg.h's normalize() follows Eigen)
+PLADE_HD void gfxtl_normalize(V3 &a) {
+  float s = 0.f;
+  s += a.x * a.x; s += a.y * a.y; s += a.z * a.z;
+  if (s == 0.f) return;
+  s = sqrtf(s);
+  a.x /= s; a.y /= s; a.z /= s;
+}
 PLADE_HD void frame_from_normal(const float n[3], float u[3], float v[3]) {
   V3 N(n[0], n[1], n[2]), a0;
   if (fabsf(n[0]) < 0.015625f && fabsf(n[1]) < 0.015625f) a0 = cross(V3(0, 1, 0), N);
   else a0 = cross(V3(0, 0, 1), N);
-  normalize(a0);
+  gfxtl_normalize(a0);
   V3 a1 = cross(N, a0);
-  normalize(a1);
+  gfxtl_normalize(a1);
   u[0] = a0.x; u[1] = a0.y; u[2] = a0.z;
   v[0] = a1.x; v[1] = a1.y; v[2] = a1.z;
 }

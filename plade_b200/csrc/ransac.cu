@@ -43,6 +43,7 @@ constexpr int kCandPerRound = 16384;   // candidates drawn per round
 constexpr int kStage1Points = 4096;    // stage 1: every candidate against a small stratified subsample
 constexpr int kStage2Cand = 256;       // stage 2: the best stage-1 candidates ...
 constexpr int kSubsample = 65536;      // ... against the large subsample
+constexpr int kBandBlock = 4096;      // points per band block (see RefineArgs)
 constexpr int kScoreTile = 512;       // points per TMA tile (pos + nrm = 16 KB)
 constexpr int kScoreThreads = 256;    // threads per scoring block
 constexpr int kScoreC1 = 2;           // candidates per thread in stage 1 (16384 candidates x 4096 points)
@@ -457,10 +458,12 @@ __global__ void flag_uv_kernel(const float4 *__restrict__ pos, const float4 *__r
 // evaluation that no point outside the band can be an inlier of the plane being evaluated (see band_covers).
 __global__ void band_compact_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const int *__restrict__ assigned, int n,
                                     float4 pl, float band, float4 *__restrict__ posB, float4 *__restrict__ nrmB, int *__restrict__ idxB,
-                                    int *__restrict__ d_nb) {
+                                    int *__restrict__ d_nb /* [segs] */, int seg_cap, int segs) {
   // HBM streaming pass (20 B per point: assigned + pos): four independent loads in flight per thread, the warp's
-  // survivors are appended with one atomic per 4 x 32 points
+  // survivors are appended with one atomic per 4 x 32 points.  Output layout: see RefineArgs (block b of kBandBlock
+  // points -> segment b % segs; a warp's 128 points never straddle a block).
   constexpr int kU = 4;
+  static_assert(kBandBlock % (32 * kU) == 0, "a warp chunk stays inside one band block");
   const unsigned lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (long long base = (long long) warp * (32 * kU); base < n; base += (long long) n_warps * (32 * kU)) {
@@ -488,9 +491,10 @@ __global__ void band_compact_kernel(const float4 *__restrict__ pos, const float4
       total += __popc(bal[u]);
     }
     if (!total) continue;
+    const int seg = (int) ((base / kBandBlock) % segs);
     int start = 0;
-    if (lane == 0) start = atomicAdd(d_nb, total);
-    start = __shfl_sync(0xffffffffu, start, 0);
+    if (lane == 0) start = atomicAdd(d_nb + seg, total);
+    start = __shfl_sync(0xffffffffu, start, 0) + seg * seg_cap;
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       if (in[u]) {
@@ -696,12 +700,14 @@ __global__ void band_finish_kernel(const int *__restrict__ idx, const int *__res
   }
 }
 
-// accept after refine_cluster_kernel: its membership map is indexed by band position
-__global__ void band_assign_kernel(const int *__restrict__ idx, const int *__restrict__ d_count, const unsigned char *__restrict__ member_band,
-                                   int shape_id, int *__restrict__ assigned) {
-  const int n = *d_count;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    if (member_band[i]) assigned[idx[i]] = shape_id;
+// accept after refine_cluster_kernel: its membership map is indexed by band position (segmented layout, see RefineArgs)
+__global__ void band_assign_kernel(const int *__restrict__ idx, const int *__restrict__ d_nb, int seg_cap, int segs,
+                                   const unsigned char *__restrict__ member_band, int shape_id, int *__restrict__ assigned) {
+  for (int sg = 0; sg < segs; ++sg) {
+    const int n = d_nb[sg], sb = sg * seg_cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      if (member_band[sb + i]) assigned[idx[sb + i]] = shape_id;
+  }
 }
 
 // pass E: members of the largest component; count, sum of positions, gaussian-weighted score
@@ -869,58 +875,54 @@ struct RefineOut {
   int evals;
   int n_band;             // points of the candidate's band (algorithmic bytes of the launch = 28 B x n_band x evals)
   unsigned int phase_ns[6];   // device time per phase summed over the evaluations (flags, raster, components, select, covariance, decision)
+  double acc_score;           // gaussian-weighted score (Candidate::WeightedScore) of the accepted plane
 };
 struct RefineArgs {
-  const float4 *posB, *nrmB;
-  const int *idxB, *d_nb;
+  // The band of a candidate is stored in `segs` segments of seg_cap points each (one per CTA of the refinement cluster):
+  // points [4096 b, 4096 (b + 1)) of the cloud go to segment b % segs, so a segment never holds more than seg_cap points
+  // and every CTA refines the part of the band it (or band_compact_kernel on its behalf) wrote -- band data never
+  // crosses CTAs, only the reductions do.  d_nb[s] = points in segment s.
+  float4 *posB, *nrmB;
+  int *idxB, *d_nb;
+  int seg_cap, segs;
   unsigned char *flag;
   int *pix;
   unsigned char *bmp, *btmp, *bmask;
   int *lab, *ccnt;
   unsigned char *member_a, *member_b;     // membership of the band points, by BAND position (two maps: candidate / clone)
-  unsigned char *touched;                 // band point was an inlier of ANY evaluation of this candidate (null: not recorded)
   int *uvbox;
   double *acc;
   RefineCtl *ctl;
   RefineOut *out;
   float4 cand_pl, band_pl;
+  float cand_pos[3];                      // a point on the candidate plane (the frame origin of its first evaluation)
   float eps3, nthresh, bmp_eps, band_halfwidth, ext;
   float mn[3], mx[3];
   int min_support, band_full;
-  int cap;                                // capacity of the band arrays (a band that does not fit is refined alone, status 4)
 };
-// Up to kMaxBatch candidates are refined by ONE launch, one cluster each (speculative: all against the same snapshot of
-// the unassigned points; resolve_kernel then replays the sequential accept order and stops at the first candidate
-// whose evaluation saw a point that an earlier candidate of the batch took).
-constexpr int kMaxBatch = 8;
-struct RefineBatch { RefineArgs a[kMaxBatch]; };
-struct BandBatch {
-  int k;
-  float band;                             // half-width (same for every candidate of a cloud)
-  float4 pl[kMaxBatch];
-  float4 *pos[kMaxBatch], *nrm[kMaxBatch];
-  int *idx[kMaxBatch], *nb[kMaxBatch];
-  int cap[kMaxBatch];
-};
-// state of the sequential accept loop while a batch is being resolved on the device
+__host__ __device__ inline int band_seg_cap(long long n, int segs) { return (int) ((n / kBandBlock / segs + 1) * kBandBlock); }
+
+// state of the accept loop (detect_planes_dev's pool walk) while accept_loop_kernel runs it on the device
 struct BatchState {
   long long m;                            // unassigned points
   double drawn;                           // drawn candidates (rescaled after every accepted shape)
   double prob;
   int n_found, stop, nlevels, min_support;
 };
-enum { kVerdictSkipped = 0, kVerdictNotEligible = 1, kVerdictFallback = 2, kVerdictRejected = 3, kVerdictConflict = 4, kVerdictAccepted = 5 };
-struct Verdict { int kind, shape_id; long long size; float n[3], p[3]; int evals, n_band; };
-struct ResolveArgs {
-  const int *idxB, *d_nb;
-  const unsigned char *member_a, *member_b, *touched;
-  const RefineOut *out;
+enum { kVerdictSkipped = 0, kVerdictNotEligible = 1, kVerdictFallback = 2, kVerdictRejected = 3, kVerdictAccepted = 5 };
+struct Verdict { int kind, shape_id; long long size; float n[3], p[3]; int evals, n_band; unsigned int phase_ns[6]; unsigned int band_ns, pad; };
+struct PoolCand { float4 pl; double est; double pad; };
+struct AcceptCtl { int go, accept, shape_id, pad; };      // boss -> cluster, per candidate
+struct AcceptArgs {
+  RefineArgs r;                           // buffers and thresholds; the candidate plane is filled in per pool entry
+  const float4 *pos, *nrm;
   int *assigned;
+  int n, k;
+  const PoolCand *pool;
   BatchState *state;
   Verdict *verdict;
-  int *conflict;                          // zeroed before the launch
-  double est;                             // the candidate's support estimate (pool order)
-  int slot, cap;
+  AcceptCtl *actl;
+  float band;
 };
 
 __device__ __forceinline__ double block_sum(double v, double *sh /* 32 */) {
@@ -993,19 +995,18 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __grid_constant__ RefineBatch batch) {
-  const RefineArgs &a = batch.a[blockIdx.x / cluster_size()];      // one cluster per candidate of the batch
+// The acceptance chain of ONE candidate on its (segmented) band, executed by every thread of a cluster; the verdict lands
+// in *a.out.  cand_pl / cand_pos: the candidate (a.cand_pl for the host-driven launch, a pool entry in accept_loop_kernel).
+__device__ void refine_candidate_dev(const RefineArgs &a, const float4 cand_pl, const float cand_pos0, const float cand_pos1, const float cand_pos2,
+                                     const float4 band_pl) {
   __shared__ double sh_d[6 * 32];
   __shared__ float sh_f[4 * 32];
   __shared__ unsigned int sbits[kRefSmemPix / 32];     // per-CTA bit image of the bitmap (pass 2) / of the component mask (pass 4)
-  const int rank = (int) cluster_rank(), nthr = (int) blockDim.x, nth = (int) cluster_size() * nthr;
-  const int gt = rank * nthr + threadIdx.x;
-  const bool boss = gt == 0;
-  const int n = *a.d_nb;
-  if (n > a.cap) {             // the band did not fit this slot (uniform over the cluster): the host refines this candidate alone
-    if (boss) { RefineOut o = {}; o.status = 4; o.n_band = n; *a.out = o; }
-    return;
-  }
+  const int rank = (int) cluster_rank(), nthr = (int) blockDim.x;
+  const int tid = (int) threadIdx.x;
+  const bool boss = rank == 0 && tid == 0;
+  const int n = __ldcg(a.d_nb + rank);      // points of this CTA's band segment
+  const int sb = rank * a.seg_cap;          // ... which starts here
   const float denom = 2.f / 9.f * a.eps3 * a.eps3;
   volatile RefineCtl *ctl = a.ctl;
 
@@ -1016,6 +1017,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
     double cov_clone[6], newScore, oldScore;
     float acc_n[3], acc_p[3], fn[3], fp[3];
     long long acc_size;
+    double acc_score;
     int acc_sel, work_sel, iter, status, evals;
     unsigned long long t_prev;
     unsigned int phase_ns[6];
@@ -1031,11 +1033,12 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
     B.clone = Eval{0, 0, {0, 0, 0}, false};
     for (int k = 0; k < 6; ++k) B.cov_clone[k] = 0;
     B.newScore = B.oldScore = 0;
-    B.acc_n[0] = a.cand_pl.x; B.acc_n[1] = a.cand_pl.y; B.acc_n[2] = a.cand_pl.z;
-    // position of the 3-point plane: any point on it (the reference keeps the first sample); n * dist lies on the plane
-    B.acc_p[0] = a.cand_pl.x * a.cand_pl.w; B.acc_p[1] = a.cand_pl.y * a.cand_pl.w; B.acc_p[2] = a.cand_pl.z * a.cand_pl.w;
+    B.acc_n[0] = cand_pl.x; B.acc_n[1] = cand_pl.y; B.acc_n[2] = cand_pl.z;
+    // position of the 3-point plane: any point on it (the reference keeps the first sample)
+    B.acc_p[0] = cand_pos0; B.acc_p[1] = cand_pos1; B.acc_p[2] = cand_pos2;
     for (int k = 0; k < 3; ++k) B.fn[k] = B.fp[k] = 0;
     B.acc_size = 0;
+    B.acc_score = 0;
     B.acc_sel = 0; B.work_sel = 1; B.iter = 0; B.status = 0; B.evals = 0;
     for (int k = 0; k < 6; ++k) B.phase_ns[k] = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(B.t_prev));
@@ -1056,13 +1059,13 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
     B.oldScore = B.newScore;
     if (!fit_plane_from_cov(B.clone, B.cov_clone, B.fn, B.fp)) return false;
     PlaneFrame f2 = make_plane_frame(B.fn, B.fp);
-    if (!a.band_full && !band_covers_plane(a.band_pl, a.band_halfwidth, f2.pl, a.mn, a.mx, a.ext, a.eps3)) { B.status = 2; return false; }
+    if (!a.band_full && !band_covers_plane(band_pl, a.band_halfwidth, f2.pl, a.mn, a.mx, a.ext, a.eps3)) { B.status = 2; return false; }
     publish(f2, B.work_sel, 1);
     return true;
   };
   if (boss) {
     PlaneFrame f0 = make_plane_frame(B.acc_n, B.acc_p);
-    f0.pl.w = a.cand_pl.w;
+    f0.pl.w = cand_pl.w;
     publish(f0, B.acc_sel, 1);
   }
   cluster_barrier();
@@ -1081,20 +1084,19 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
     // pass 1: inlier flags at eps3 + (u, v) box (flag_uv_kernel)
     {
       float umin = 3.4e38f, vmin = 3.4e38f, umax = -3.4e38f, vmax = -3.4e38f;
-      for (int base = gt; base < n; base += kRefUnroll1 * nth) {
+      for (int base = tid; base < n; base += kRefUnroll1 * nthr) {
         float4 p[kRefUnroll1], nr[kRefUnroll1];
 #pragma unroll
         for (int u = 0; u < kRefUnroll1; ++u) {
-          const int ic = min(base + u * nth, n - 1);          // clamped: the loads are unconditional (no partially
-          p[u] = __ldg(a.posB + ic); nr[u] = __ldg(a.nrmB + ic);   // defined arrays, which would live in local memory)
+          const int ic = sb + min(base + u * nthr, n - 1);    // clamped: the loads are unconditional (no partially
+          p[u] = a.posB[ic]; nr[u] = a.nrmB[ic];              // defined arrays, which would live in local memory)
         }
 #pragma unroll
         for (int u = 0; u < kRefUnroll1; ++u) {
-          const int i = base + u * nth;
+          const int i = base + u * nthr;
           if (i >= n) continue;
           const bool in = compatible(f.pl, p[u], nr[u], a.eps3, a.nthresh);
-          a.flag[i] = in ? 1 : 0;
-          if (a.touched) { if (ev == 0) a.touched[i] = in ? 1 : 0; else if (in) a.touched[i] = 1; }
+          a.flag[sb + i] = in ? 1 : 0;
           if (in) {
             float px = __fsub_rn(p[u].x, f.pos.x), py = __fsub_rn(p[u].y, f.pos.y), pz = __fsub_rn(p[u].z, f.pos.z);
             float uu = __fadd_rn(__fadd_rn(__fmul_rn(px, f.u.x), __fmul_rn(py, f.u.y)), __fmul_rn(pz, f.u.z));
@@ -1123,18 +1125,18 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
         for (int w = threadIdx.x; w < (P + 31) / 32; w += nthr) sbits[w] = 0u;
         __syncthreads();
       }
-      for (int base = gt; base < n; base += kRefUnroll * nth) {
+      for (int base = tid; base < n; base += kRefUnroll * nthr) {
         float4 p[kRefUnroll];
         unsigned int fl[kRefUnroll];
 #pragma unroll
         for (int u = 0; u < kRefUnroll; ++u) {
-          const int i = base + u * nth, ic = min(i, n - 1);
-          fl[u] = a.flag[ic]; p[u] = __ldg(a.posB + ic);
+          const int i = base + u * nthr, ic = sb + min(i, n - 1);
+          fl[u] = a.flag[ic]; p[u] = a.posB[ic];
           if (i >= n) fl[u] = 0;
         }
 #pragma unroll
         for (int u = 0; u < kRefUnroll; ++u) {
-          const int i = base + u * nth;
+          const int i = base + u * nthr;
           if (!fl[u]) continue;
           float px = __fsub_rn(p[u].x, f.pos.x), py = __fsub_rn(p[u].y, f.pos.y), pz = __fsub_rn(p[u].z, f.pos.z);
           float uu = __fadd_rn(__fadd_rn(__fmul_rn(px, f.u.x), __fmul_rn(py, f.u.y)), __fmul_rn(pz, f.u.z));
@@ -1144,7 +1146,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
           bu = min(max(bu, 0), I.ue - 1);
           bv = min(max(bv, 0), I.ve - 1);
           const int id = bu + bv * I.ue;
-          a.pix[i] = id;
+          a.pix[sb + i] = id;
           if (small) atomicOr(&sbits[id >> 5], 1u << (id & 31));
           else a.bmp[id] = 1;
         }
@@ -1173,15 +1175,15 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
         __syncthreads();
       }
       double cnt = 0, sx = 0, sy = 0, sz = 0, sc = 0;
-      for (int base = gt; base < n; base += kRefUnroll * nth) {
+      for (int base = tid; base < n; base += kRefUnroll * nthr) {
         float4 p[kRefUnroll];
         int px[kRefUnroll];
         unsigned int fl[kRefUnroll], mk[kRefUnroll];
 #pragma unroll
         for (int u = 0; u < kRefUnroll; ++u) {
-          const int i = base + u * nth, ic = min(i, n - 1);
+          const int i = base + u * nthr, ic = sb + min(i, n - 1);
           fl[u] = a.flag[ic]; px[u] = a.pix[ic];
-          p[u] = __ldg(a.posB + ic);
+          p[u] = a.posB[ic];
           if (i >= n || !I.ok) fl[u] = 0;
         }
 #pragma unroll
@@ -1189,11 +1191,11 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
           mk[u] = !fl[u] ? 0u : small ? ((sbits[px[u] >> 5] >> (px[u] & 31)) & 1u) : (unsigned int) __ldcg(a.bmask + px[u]);
 #pragma unroll
         for (int u = 0; u < kRefUnroll; ++u) {
-          const int i = base + u * nth;
+          const int i = base + u * nthr;
           if (i >= n) continue;
           const bool mem = fl[u] && mk[u];
-          member[i] = mem ? 1 : 0;
-          a.flag[i] = (unsigned char) ((fl[u] & 1) | (mem ? 2 : 0));
+          member[sb + i] = mem ? 1 : 0;
+          a.flag[sb + i] = (unsigned char) ((fl[u] & 1) | (mem ? 2 : 0));
           if (mem) {
             float dp = __fadd_rn(__fadd_rn(__fmul_rn(f.pl.x, p[u].x), __fmul_rn(f.pl.y, p[u].y)), __fmul_rn(f.pl.z, p[u].z));
             float d = fabsf(__fsub_rn(f.pl.w, dp));
@@ -1216,13 +1218,13 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
       if (cnt > 0) {
         const float mx = (float) (__ldcg(a.acc + 1) / cnt), my = (float) (__ldcg(a.acc + 2) / cnt), mz = (float) (__ldcg(a.acc + 3) / cnt);
         double c[6] = {0, 0, 0, 0, 0, 0};
-        for (int base = gt; base < n; base += kRefUnroll * nth) {
+        for (int base = tid; base < n; base += kRefUnroll * nthr) {
           float4 p[kRefUnroll];
           unsigned int fl[kRefUnroll];
 #pragma unroll
           for (int u = 0; u < kRefUnroll; ++u) {
-            const int i = base + u * nth, ic = min(i, n - 1);
-            fl[u] = a.flag[ic]; p[u] = __ldg(a.posB + ic);
+            const int i = base + u * nthr, ic = sb + min(i, n - 1);
+            fl[u] = a.flag[ic]; p[u] = a.posB[ic];
             if (i >= n) fl[u] = 0;
           }
 #pragma unroll
@@ -1253,6 +1255,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
         if (I.overflow) B.status = 1;
         else {
           B.acc_size = e.ok ? e.size : 0;
+          B.acc_score = e.ok ? e.score : 0;
           if (e.ok) {
             B.clone = e;
             for (int k = 0; k < 6; ++k) B.cov_clone[k] = cov[k];
@@ -1269,6 +1272,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
           if (B.newScore > B.oldScore && e.size > a.min_support) {
             for (int k = 0; k < 3; ++k) { B.acc_n[k] = B.fn[k]; B.acc_p[k] = B.fp[k]; }
             B.acc_size = e.size;
+            B.acc_score = e.score;
             const int t = B.acc_sel; B.acc_sel = B.work_sel; B.work_sel = t;      // the B.clone becomes the candidate
           }
           if (B.newScore > B.oldScore && B.iter < 3) go = try_next();
@@ -1283,10 +1287,17 @@ __global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __
     RefineOut o;
     o.acc_size = B.acc_size;
     for (int k = 0; k < 3; ++k) { o.acc_n[k] = B.acc_n[k]; o.acc_p[k] = B.acc_p[k]; }
-    o.acc_sel = B.acc_sel; o.status = B.status; o.evals = B.evals; o.n_band = n;
+    o.acc_sel = B.acc_sel; o.status = B.status; o.evals = B.evals; o.acc_score = B.acc_score;
+    o.n_band = 0;
+    for (int q = 0; q < a.segs; ++q) o.n_band += __ldcg(a.d_nb + q);
     for (int k = 0; k < 6; ++k) o.phase_ns[k] = B.phase_ns[k];
     *a.out = o;
   }
+}
+
+// host-driven launch: one candidate whose band band_compact_kernel has already built
+__global__ void __launch_bounds__(kRefThreads, 1) refine_cluster_kernel(const __grid_constant__ RefineArgs a) {
+  refine_candidate_dev(a, a.cand_pl, a.cand_pos[0], a.cand_pos[1], a.cand_pos[2], a.band_pl);
 }
 
 // CandidateFailureProbability, R/RansacShapeDetector.h:61-67 (reqSamples = 3)
@@ -1301,122 +1312,110 @@ __host__ __device__ inline double rescale_drawn(double drawn, long long size, lo
   return (double) ((x * x) * x) * drawn;
 }
 
-// Bands of up to kMaxBatch candidates in ONE pass over the cloud (20 B per point whatever the number of candidates):
-// the per-candidate work of band_compact_kernel, with the point loaded once and tested against every plane.
-__global__ void multi_band_compact_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const int *__restrict__ assigned, int n,
-                                          const __grid_constant__ BandBatch b) {
-  constexpr int kU = 4;
-  const unsigned lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (long long base = (long long) warp * (32 * kU); base < n; base += (long long) n_warps * (32 * kU)) {
-    int a[kU];
-    float4 p[kU];
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const long long i = base + u * 32 + lane;
-      a[u] = i < n ? __ldg(assigned + i) : 0;
+// The accept loop of one scoring round (detect_planes_dev's pool walk, RansacShapeDetector.cpp:583-675) on the device:
+// ONE cluster walks the pool in order -- eligibility test, band of the candidate (a streaming pass of the cluster over
+// the cloud), acceptance chain (refine_candidate_dev), accept / reject decision, removal of the accepted points -- with
+// exactly the sequential semantics of the host loop and no host round trip between candidates.  It stops at the first
+// candidate that is no longer eligible, or that needs the host (bitmap beyond the device cap, refit leaving its band).
+__global__ void __launch_bounds__(kRefThreads, 1) accept_loop_kernel(const __grid_constant__ AcceptArgs A) {
+  __shared__ int s_nb;
+  const RefineArgs &a = A.r;
+  const int rank = (int) cluster_rank(), segs = (int) cluster_size(), nthr = (int) blockDim.x, tid = (int) threadIdx.x;
+  const bool boss = rank == 0 && tid == 0;
+  const unsigned lane = tid & 31;
+  volatile BatchState *st = A.state;
+  volatile AcceptCtl *ac = A.actl;
+  const int sb = rank * a.seg_cap;
+  const long long n_blocks = ((long long) A.n + kBandBlock - 1) / kBandBlock;
+  for (int j = 0; j < A.k; ++j) {
+    const float4 pl = A.pool[j].pl;
+    unsigned long long t0 = 0;
+    // ---- eligible?  (entry 0 was tested by the host with the same state)
+    if (boss) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      const long long m = st->m;
+      const double est = A.pool[j].est;
+      const bool ok = !st->stop && (j == 0 || (est >= (double) st->min_support && failure_probability_hd(est, (double) m, st->drawn, (double) st->nlevels) <= st->prob));
+      if (!ok && !st->stop) { Verdict v = {}; v.kind = kVerdictNotEligible; A.verdict[j] = v; st->stop = 1; }
+      ac->go = ok ? 1 : 0;
     }
+    if (tid == 0) s_nb = 0;
+    cluster_barrier();
+    if (!ac->go) break;                        // uniform over the cluster
+    // ---- band: the unassigned points within A.band of the candidate plane, block b of the cloud -> segment b % segs
+    for (long long b = rank; b < n_blocks; b += segs) {
+      constexpr int kU = kBandBlock / kRefThreads;      // 4 loads in flight per thread
+      int as[kU];
+      float4 p[kU];
+      const long long base = b * kBandBlock + tid;
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const long long i = base + u * 32 + lane;
-      p[u] = (i < n && a[u] == -1) ? __ldg(pos + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int k = 0; k < b.k; ++k) {
-      const float4 pl = b.pl[k];
-      unsigned bal[kU];
-      bool in[kU];
-      int total = 0;
+      for (int u = 0; u < kU; ++u) { const long long i = base + u * kRefThreads; as[u] = i < A.n ? __ldcg(A.assigned + i) : 0; }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) { const long long i = base + u * kRefThreads; p[u] = (i < A.n && as[u] == -1) ? __ldg(A.pos + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const long long i = base + u * 32 + lane;
+        const long long i = base + u * kRefThreads;
         const float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p[u].x), __fmul_rn(pl.y, p[u].y)), __fmul_rn(pl.z, p[u].z));
-        in[u] = i < n && a[u] == -1 && fabsf(__fsub_rn(pl.w, dp)) < b.band;
-        bal[u] = __ballot_sync(0xffffffffu, in[u]);
-        total += __popc(bal[u]);
-      }
-      if (!total) continue;
-      int start = 0;
-      if (lane == 0) start = atomicAdd(b.nb[k], total);
-      start = __shfl_sync(0xffffffffu, start, 0);
-      if (start + total > b.cap[k]) continue;          // overflow: the count keeps growing, the slot is refined alone later
-      float4 *posB = b.pos[k], *nrmB = b.nrm[k];
-      int *idxB = b.idx[k];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        if (in[u]) {
-          const int i = (int) (base + u * 32 + lane);
-          const int q = start + __popc(bal[u] & ((1u << lane) - 1));
-          posB[q] = p[u]; nrmB[q] = __ldg(nrm + i); idxB[q] = i;
+        const bool in = i < A.n && as[u] == -1 && fabsf(__fsub_rn(pl.w, dp)) < A.band;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (!bal) continue;
+        int start = 0;
+        if (lane == 0) start = atomicAdd(&s_nb, __popc(bal));
+        start = __shfl_sync(0xffffffffu, start, 0);
+        if (in) {
+          const int q = sb + start + __popc(bal & ((1u << lane) - 1));
+          a.posB[q] = p[u]; a.nrmB[q] = __ldg(A.nrm + i); a.idxB[q] = (int) i;
         }
-        start += __popc(bal[u]);
       }
     }
-  }
-}
-
-// Replays one step of the sequential accept loop (detect_planes_dev's pool walk) for slot r.slot of a batch, on the
-// device: launched once per slot, in pool order, on the same stream -- no host round trip in between.
-//   eligible?  (slots > 0: the candidate must still pass the failure-probability test with the state the earlier slots left)
-//   evaluated? (status != 0: the host has to refine it alone)      big enough? (else rejected, as FindBestCandidate would)
-//   conflict?  a band point that was an inlier of ANY of its evaluations has meanwhile been taken by an earlier slot:
-//              sequentially the candidate would have been evaluated without it -> stop, it is re-evaluated next batch
-//   accept:    members -> assigned, state advanced exactly as the host loop does.
-__global__ void __launch_bounds__(kRefThreads, 1) resolve_kernel(const ResolveArgs r) {
-  __shared__ int sh_conf;
-  const int rank = (int) cluster_rank(), nthr = (int) blockDim.x, nth = (int) cluster_size() * nthr;
-  const int gt = rank * nthr + threadIdx.x;
-  const bool boss = gt == 0;
-  volatile BatchState *st = r.state;
-  if (st->stop) {                          // (uniform: only written by a boss thread after the first cluster barrier)
-    if (boss) { Verdict v = {}; v.kind = kVerdictSkipped; *r.verdict = v; }
-    return;
-  }
-  const volatile RefineOut *o = r.out;
-  const int status = o->status;
-  const long long acc_size = o->acc_size;
-  const int n = *r.d_nb;
-  const bool scan = status == 0 && n <= r.cap && acc_size >= (long long) st->min_support;
-  if (threadIdx.x == 0) sh_conf = 0;
-  __syncthreads();
-  if (scan) {
-    int c = 0;
-    for (int i = gt; i < n; i += nth) c |= (r.touched[i] && __ldcg(r.assigned + r.idxB[i]) != -1) ? 1 : 0;
-    if (c) atomicOr(&sh_conf, 1);
     __syncthreads();
-    if (threadIdx.x == 0 && sh_conf) atomicOr(r.conflict, 1);
-  }
-  cluster_barrier();
-  if (boss) {
-    Verdict v = {};
-    v.evals = o->evals; v.n_band = o->n_band;
-    const long long m = st->m;
-    const double drawn = st->drawn;
-    const bool eligible = r.slot == 0 || (r.est >= (double) st->min_support && failure_probability_hd(r.est, (double) m, drawn, (double) st->nlevels) <= st->prob);
-    if (!eligible) { v.kind = kVerdictNotEligible; st->stop = 1; }
-    else if (status != 0) { v.kind = kVerdictFallback; st->stop = 1; }
-    else if (acc_size < (long long) st->min_support) v.kind = kVerdictRejected;
-    else if (__ldcg(r.conflict)) { v.kind = kVerdictConflict; st->stop = 1; }
-    else {
-      v.kind = kVerdictAccepted;
-      v.shape_id = st->n_found;
-      v.size = acc_size;
-      for (int k = 0; k < 3; ++k) { v.n[k] = o->acc_n[k]; v.p[k] = o->acc_p[k]; }
-      st->n_found = v.shape_id + 1;
-      st->drawn = rescale_drawn(drawn, acc_size, m);
-      st->m = m - acc_size;
-      if (m - acc_size < (long long) st->min_support || m - acc_size < 3) st->stop = 1;
+    const int n_seg = s_nb;                    // (read before thread 0 can reset it for the next candidate)
+    if (tid == 0) a.d_nb[rank] = n_seg;
+    cluster_barrier();
+    unsigned int band_ns = 0;
+    if (boss) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); band_ns = (unsigned int) (t1 - t0); }
+    // ---- acceptance chain; n * dist is a point on the 3-point plane
+    refine_candidate_dev(a, pl, pl.x * pl.w, pl.y * pl.w, pl.z * pl.w, pl);
+    // ---- decision (RansacShapeDetector.cpp:297,423-430,659-675)
+    if (boss) {
+      const volatile RefineOut *o = a.out;
+      Verdict v = {};
+      v.evals = o->evals; v.n_band = o->n_band; v.band_ns = band_ns;
+      for (int k = 0; k < 6; ++k) v.phase_ns[k] = o->phase_ns[k];
+      const long long m = st->m, acc_size = o->acc_size;
+      int accept = 0;
+      if (o->status != 0) { v.kind = kVerdictFallback; st->stop = 1; }
+      else if (acc_size < (long long) st->min_support) v.kind = kVerdictRejected;
+      else {
+        v.kind = kVerdictAccepted;
+        v.shape_id = st->n_found;
+        v.size = acc_size;
+        for (int k = 0; k < 3; ++k) { v.n[k] = o->acc_n[k]; v.p[k] = o->acc_p[k]; }
+        st->n_found = v.shape_id + 1;
+        st->drawn = rescale_drawn(st->drawn, acc_size, m);
+        st->m = m - acc_size;
+        if (m - acc_size < (long long) st->min_support || m - acc_size < 3) st->stop = 1;
+        accept = 1;
+      }
+      A.verdict[j] = v;
+      ac->accept = accept; ac->shape_id = v.shape_id;
+      ac->pad = o->acc_sel;
     }
-    *r.verdict = v;
+    cluster_barrier();
+    // ---- accept: the members leave the cloud
+    if (ac->accept) {
+      const unsigned char *member = ac->pad ? a.member_b : a.member_a;
+      const int shape_id = ac->shape_id;
+      for (int i = tid; i < n_seg; i += nthr) if (member[sb + i]) A.assigned[a.idxB[sb + i]] = shape_id;
+    }
+    // (the barrier at the top of the next iteration orders these writes before the next band pass reads `assigned`)
   }
-  cluster_barrier();
-  const volatile Verdict *vv = r.verdict;
-  if (vv->kind != kVerdictAccepted) return;
-  const unsigned char *member = o->acc_sel ? r.member_b : r.member_a;
-  const int shape_id = vv->shape_id;
-  for (int i = gt; i < n; i += nth) if (member[i]) r.assigned[r.idxB[i]] = shape_id;
+  // entries the loop never reached keep kind == kVerdictSkipped (the host zeroes the verdicts before the launch)
 }
 
 double failure_probability(double size, double n, double drawn, double levels) { return failure_probability_hd(size, n, drawn, levels); }
+
+struct FoundPlane { float n[3]; float pos[3]; long long size; };
 
 struct RansacScratch {
   DevBuf<unsigned int> keys, keys_alt, counts, counts_sorted, counts2;
@@ -1434,22 +1433,24 @@ struct RansacScratch {
   PinBuf<unsigned int> round_host; // page-locked landing zone of the round's results and of the cluster kernel's verdict
   PinBuf<float4> pool_host;
   DevBuf<unsigned char> memb_a, memb_b;   // band-local membership maps of refine_cluster_kernel
-  // slots 1 .. kMaxBatch-1 of a speculative batch (slot 0 = the buffers above); band arrays of `cap` points each
-  struct Slot {
-    DevBuf<float4> band_pos, band_nrm;
-    DevBuf<int> band_idx, pix, cc_lab, cc_cnt;
-    DevBuf<unsigned char> flag, memb_a, memb_b, touched, bmp, btmp, bmask;
-    bool bmp_clean = false;
-  } slot[kMaxBatch];
-  DevBuf<unsigned char> touched0;         // slot 0
-  DevBuf<unsigned char> batch_mem;        // BatchState + per-slot control blocks (see kSlotStride)
-  PinBuf<unsigned char> batch_host;       // page-locked mirror: state upload and the verdicts' landing zone
+  // state of the last detection on this lane, so that extract() can CONTINUE it with a halved min_support instead of
+  // starting over (the planes found so far are exactly the ones a fresh run would find first)
+  struct Resume {
+    bool valid = false;
+    const void *cloud = nullptr;
+    int n = 0, m = 0, cur_is_order2 = 1;
+    double drawn = 0;
+    unsigned long long round_seed = 0;
+    float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+    std::vector<FoundPlane> found;
+  } resume;
+  DevBuf<unsigned char> batch_mem;        // accept_loop_kernel: BatchState | AcceptCtl | pool entries | verdicts (see kAcc* offsets)
+  PinBuf<unsigned char> batch_host;       // page-locked mirror: upload source and the verdicts' landing zone
 };
-// layout of RansacScratch::batch_mem: BatchState at 0, then one block per slot
-constexpr int kSlotBase = 256, kSlotStride = 1024;
-constexpr int kSlotCtl = 0, kSlotOut = 128, kSlotUvbox = 256, kSlotNb = 272, kSlotConflict = 276, kSlotVerdict = 320, kSlotAcc = 512;
-static_assert(sizeof(RefineCtl) <= 128 && sizeof(RefineOut) <= 128 && sizeof(Verdict) <= kSlotAcc - kSlotVerdict && kSlotAcc + 16 * 8 <= kSlotStride &&
-              sizeof(BatchState) <= kSlotBase, "batch_mem layout");
+constexpr int kAcceptMax = 64;            // pool entries one accept_loop_kernel launch can walk (= the pool size)
+constexpr int kAccState = 0, kAccCtl = 64, kAccPool = 128, kAccVerdict = kAccPool + kAcceptMax * (int) sizeof(PoolCand),
+              kAccBytes = kAccVerdict + kAcceptMax * (int) sizeof(Verdict);
+static_assert(sizeof(BatchState) <= 64 && sizeof(AcceptCtl) <= 64 && sizeof(PoolCand) == 32 && sizeof(Verdict) % 8 == 0, "batch_mem layout");
 
 // cluster size of refine_cluster_kernel on this device: 16 (non-portable) when the GPU can co-schedule it, else 8
 int refine_block_threads() {
@@ -1476,7 +1477,7 @@ int refine_cluster_size(int device) {
     for (int want : {first, 8}) {
       if (want < 1 || want > 16) continue;
       if (want > 8 && (cudaFuncSetAttribute(refine_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-                       cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) { cudaGetLastError(); continue; }
+                       cudaFuncSetAttribute(accept_loop_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) { cudaGetLastError(); continue; }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(want); cfg.blockDim = dim3(refine_block_threads());
       cudaLaunchAttribute at[1];
@@ -1493,8 +1494,6 @@ int refine_cluster_size(int device) {
   known[device] = true;
   return size;
 }
-
-struct FoundPlane { float n[3]; float pos[3]; long long size; };
 
 }  // namespace
 
@@ -1516,7 +1515,7 @@ __global__ void remap_group_kernel(const int *__restrict__ assigned, int n, cons
   group[i] = (a >= 0 && a < n_remap) ? remap[a] : -1;
 }
 
-std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out, int lane) {
+std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_support, DevBuf<int> &group_out, int lane, bool resume) {
   std::vector<PlaneParam> result;
   Device &dev = lane == 0 ? this->dev : this->dev2;          // shadows the member: everything below runs on the lane's stream
   auto mark = [&](const char *name) { if (lane == 0) this->mark(name); };
@@ -1528,8 +1527,12 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   const int blocks_n = std::min(div_up(n, 256), dev.num_sms * 8);
 
   // bounding box -> scale (bug-compatible: z ignored)
-  int *d_misc = rs.misc.ensure(64);
-  {
+  int *d_misc = rs.misc.ensure(128);
+  RansacScratch::Resume &rz = rs.resume;
+  const bool cont = resume && rz.valid && rz.cloud == (const void *) c.pos.p && rz.n == n;      // continue the previous detection of this cloud
+  float mn[3], mx[3];
+  if (cont) { for (int k = 0; k < 3; ++k) { mn[k] = rz.mn[k]; mx[k] = rz.mx[k]; } }
+  else {
     int init[6];
     float big = 3.4e38f, nbig = -3.4e38f;
     int bi, nbi;
@@ -1537,18 +1540,18 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     nbi ^= 0x7fffffff;
     init[0] = init[1] = init[2] = bi; init[3] = init[4] = init[5] = nbi;
     PLADE_CUDA(cudaMemcpyAsync(d_misc, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    bbox_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, n, d_misc);
+    PLADE_LAUNCH_CHECK();
+    int h6[6];
+    PLADE_CUDA(cudaMemcpyAsync(h6, d_misc, sizeof(h6), cudaMemcpyDeviceToHost, s));
+    stream_sync(s);
+    for (int k = 0; k < 3; ++k) {
+      int a = h6[k], b = h6[3 + k];
+      a = a >= 0 ? a : a ^ 0x7fffffff; b = b >= 0 ? b : b ^ 0x7fffffff;
+      memcpy(&mn[k], &a, 4); memcpy(&mx[k], &b, 4);
+    }
   }
-  bbox_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, n, d_misc);
-  PLADE_LAUNCH_CHECK();
-  int h6[6];
-  PLADE_CUDA(cudaMemcpyAsync(h6, d_misc, sizeof(h6), cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
-  float mn[3], mx[3];
-  for (int k = 0; k < 3; ++k) {
-    int a = h6[k], b = h6[3 + k];
-    a = a >= 0 ? a : a ^ 0x7fffffff; b = b >= 0 ? b : b ^ 0x7fffffff;
-    memcpy(&mn[k], &a, 4); memcpy(&mx[k], &b, 4);
-  }
+  rz.valid = false;
   const float scale = std::max(mx[0] - mn[0], mx[1] - mn[1]);
   const float eps = params.ransac_dist_thresh * scale;
   const float bmp_eps = params.ransac_bitmap_reso * scale;
@@ -1560,38 +1563,49 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   unsigned int *keys = rs.keys.ensure(n), *keys2 = rs.keys_alt.ensure(n);
   int *order = rs.order.ensure(n), *order2 = rs.order_alt.ensure(n);
   float ext = std::max(std::max(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
-  morton_kernel<<<div_up(n, 256), 256, 0, s>>>(c.pos.p, n, make_float3(mn[0], mn[1], mn[2]), ext > 0 ? 1.f / ext : 0.f, keys, order);
-  PLADE_LAUNCH_CHECK();
-  size_t tb = 0, tb2 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, order, order2, n, 0, 30, s);
-  IsUnassigned pred{nullptr};
-  cub::DeviceSelect::If(nullptr, tb2, order, order2, d_misc, n, pred, s);
-  unsigned char *tmp = rs.cub_tmp.ensure(std::max(tb, tb2));
-  cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, order, order2, n, 0, 30, s);
-  dev.launches.add(8);
+  unsigned char *tmp = nullptr;
+  int *assigned = rs.assigned.ensure(n);
   int *cur_order = order2, *alt_order = order;
+  if (cont) {
+    if (!rz.cur_is_order2) std::swap(cur_order, alt_order);
+  } else {
+    morton_kernel<<<div_up(n, 256), 256, 0, s>>>(c.pos.p, n, make_float3(mn[0], mn[1], mn[2]), ext > 0 ? 1.f / ext : 0.f, keys, order);
+    PLADE_LAUNCH_CHECK();
+    size_t tb = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, order, order2, n, 0, 30, s);
+    IsUnassigned pred{nullptr};
+    cub::DeviceSelect::If(nullptr, tb2, order, order2, d_misc, n, pred, s);
+    tmp = rs.cub_tmp.ensure(std::max(tb, tb2));
+    cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, order, order2, n, 0, 30, s);
+    dev.launches.add(8);
+    PLADE_CUDA(cudaMemsetAsync(assigned, 0xff, sizeof(int) * n, s));
+  }
   mark("ransac_morton");
 
-  int *assigned = rs.assigned.ensure(n);
-  PLADE_CUDA(cudaMemsetAsync(assigned, 0xff, sizeof(int) * n, s));
-  unsigned char *flag = rs.flag.ensure(n), *member_a = rs.member.ensure(n), *member_b = rs.member2.ensure(n);
+  // band-indexed scratch: a segmented band (RefineArgs) spans up to seg_cap x 16 >= n positions
+  const size_t band_cap_max = std::max<size_t>((size_t) n, (size_t) band_seg_cap(n, 16) * 16);
+  unsigned char *flag = rs.flag.ensure(band_cap_max), *member_a = rs.member.ensure(n), *member_b = rs.member2.ensure(n);
   PLADE_CUDA(cudaMemsetAsync(member_a, 0, n, s));       // membership maps over all points; all-zero between candidates
   PLADE_CUDA(cudaMemsetAsync(member_b, 0, n, s));
-  int *pix = rs.pix.ensure(n);
-  float4 *posB = rs.band_pos.ensure(n), *nrmB = rs.band_nrm.ensure(n);
-  int *idxB = rs.band_idx.ensure(n);
+  int *pix = rs.pix.ensure(band_cap_max);
+  float4 *posB = rs.band_pos.ensure(band_cap_max), *nrmB = rs.band_nrm.ensure(band_cap_max);
+  int *idxB = rs.band_idx.ensure(band_cap_max);
+  rs.memb_a.ensure(band_cap_max); rs.memb_b.ensure(band_cap_max);
   const int blocks_b = std::min(blocks_n, dev.num_sms * 4);
-  int n_band_builds = 0, n_band_full = 0, n_cluster_fallbacks = 0, refine_evals = 0, n_batches = 0, n_batch_cands = 0, n_batch_conflicts = 0;
+  int n_band_builds = 0, n_band_full = 0, n_cluster_fallbacks = 0, refine_evals = 0, n_batches = 0, n_batch_cands = 0;
+  double band_phase_ns = 0;
   bool force_single = false;
   double refine_phase_ns[6] = {0, 0, 0, 0, 0, 0};
   float4 *cand = rs.cand.ensure(kCandPerRound);
   double *acc = rs.acc.ensure(16);
-  int *d_uvbox = d_misc + 16, *d_nsel = d_misc + 24, *d_nb = d_misc + 28;
+  int *d_uvbox = d_misc + 16, *d_nsel = d_misc + 24, *d_nb = d_misc + 64;      // d_nb: one count per band segment (<= 16)
 
   std::vector<FoundPlane> found;
   int m = n;                       // unassigned points
   double drawn = 0;
   unsigned long long round_seed = params.seed;
+  // (the drawn-candidate count starts again: the candidates of the previous pass were only kept when they promised >= its min_support)
+  if (cont) { found = rz.found; m = rz.m; round_seed = rz.round_seed; }
   float4 best_pl = make_float4(0, 0, 0, 0);
   double best_est = 0;
   const int max_rounds = 4000;
@@ -1637,7 +1651,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     dev.launches.add(5);
     // one copy into page-locked memory (a copy into pageable memory would block the host once per call)
     PLADE_CUDA(cudaMemcpyAsync(h_round, counts2, sizeof(unsigned int) * (kRoundEnd - kRoundCounts2), cudaMemcpyDeviceToHost, s));
-    PLADE_CUDA(cudaStreamSynchronize(s));
+    stream_sync(s);
     const unsigned int *h_counts = h_round;
     const int n_valid = (int) h_round[kRoundNValid - kRoundCounts2];
     const float4 *h_cand = reinterpret_cast<const float4 *>(h_round + (kRoundTop - kRoundCounts2));
@@ -1687,107 +1701,79 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     }
     fresh = false;
     dry_rounds = 0;
-    // ---- speculative batch: the next K eligible pool candidates refined by one launch, the accept order replayed on
-    // the device (multi_band_compact_kernel -> refine_cluster_kernel x K clusters -> resolve_kernel x K), ONE host round
-    // trip for all of them.  Falls through to the one-candidate path below when only one candidate is eligible, when
-    // the previous batch asked for it (a bitmap beyond the device cap, a refit that left its band, an overflowing band)
-    // or when the cluster kernel is not available.
+    // ---- the pool walk on the device: accept_loop_kernel takes the eligible pool entries in order (band, acceptance chain,
+    // decision, removal of the accepted points), ONE launch and one host round trip for all of them.  The one-candidate
+    // path below remains for the candidate the kernel hands back (bitmap beyond the device cap, refit that left its
+    // band), for ransac_batch = 1 and for devices without the cluster kernel.
     {
       const int csize = refine_cluster_size(dev.id);
       int K = 0;
       if (csize && !force_single && params.ransac_batch > 1) {
-        const int kmax = std::min<int>({kMaxBatch, params.ransac_batch, (int) pool.size()});
-        K = 1;
-        while (K < kmax && pool[K].est >= min_support && failure_probability(pool[K].est, m, drawn, nlevels) <= prob) ++K;
+        const int kmax = std::min<int>({kAcceptMax, params.ransac_batch, (int) pool.size()});
+        K = 1;       // entry 0 is eligible (best_ok); the kernel re-tests the others with the state it has by then
+        while (K < kmax && pool[K].est >= min_support) ++K;
       }
       force_single = false;
-      if (K >= 2) {
-        unsigned char *bm = rs.batch_mem.ensure(kSlotBase + kMaxBatch * kSlotStride);
-        unsigned char *bh = rs.batch_host.ensure(2 * (kSlotBase + kMaxBatch * kSlotStride));
-        const size_t cap_other = std::max<size_t>((size_t) n / 2, 1024);
-        // state + clean control blocks, one upload from page-locked memory
-        memset(bh, 0, kSlotBase + kMaxBatch * kSlotStride);
+      if (K >= 1) {
+        unsigned char *bm = rs.batch_mem.ensure(kAccBytes);
+        unsigned char *bh = rs.batch_host.ensure(2 * kAccBytes);
+        memset(bh, 0, kAccBytes);
         BatchState st0;
         st0.m = m; st0.drawn = drawn; st0.prob = prob; st0.n_found = (int) found.size(); st0.stop = 0; st0.nlevels = nlevels; st0.min_support = min_support;
-        memcpy(bh, &st0, sizeof(st0));
-        PLADE_CUDA(cudaMemcpyAsync(bm, bh, kSlotBase + K * kSlotStride, cudaMemcpyHostToDevice, s));
-        BandBatch bb;
-        RefineBatch rb;
-        ResolveArgs rv[kMaxBatch];
-        bb.k = K; bb.band = kBandMul * eps3;
-        for (int j = 0; j < K; ++j) {
-          unsigned char *blk = bm + kSlotBase + j * kSlotStride;
-          RansacScratch::Slot &sl = rs.slot[j];
-          const size_t cap = j == 0 ? (size_t) n : cap_other;
-          RefineArgs &ra = rb.a[j];
-          if (j == 0) {
-            ra.posB = posB; ra.nrmB = nrmB; ra.idxB = idxB; ra.flag = flag; ra.pix = pix;
-            ra.bmp = rs.bmp_dev.ensure(kBmpCap); ra.btmp = rs.bmp_tmp.ensure(kBmpCap); ra.bmask = rs.mask_dev.ensure(kBmpCap);
-            ra.lab = rs.cc_lab.ensure(kBmpCap); ra.ccnt = rs.cc_cnt.ensure(kBmpCap);
-            ra.member_a = rs.memb_a.ensure(n); ra.member_b = rs.memb_b.ensure(n); ra.touched = rs.touched0.ensure(n);
-            if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(ra.bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
-          } else {
-            ra.posB = sl.band_pos.ensure(cap); ra.nrmB = sl.band_nrm.ensure(cap); ra.idxB = sl.band_idx.ensure(cap);
-            ra.flag = sl.flag.ensure(cap); ra.pix = sl.pix.ensure(cap);
-            ra.bmp = sl.bmp.ensure(kBmpCap); ra.btmp = sl.btmp.ensure(kBmpCap); ra.bmask = sl.bmask.ensure(kBmpCap);
-            ra.lab = sl.cc_lab.ensure(kBmpCap); ra.ccnt = sl.cc_cnt.ensure(kBmpCap);
-            ra.member_a = sl.memb_a.ensure(cap); ra.member_b = sl.memb_b.ensure(cap); ra.touched = sl.touched.ensure(cap);
-            if (!sl.bmp_clean) { PLADE_CUDA(cudaMemsetAsync(ra.bmp, 0, kBmpCap, s)); sl.bmp_clean = true; }
-          }
-          ra.d_nb = reinterpret_cast<int *>(blk + kSlotNb);
-          ra.uvbox = reinterpret_cast<int *>(blk + kSlotUvbox);
-          ra.acc = reinterpret_cast<double *>(blk + kSlotAcc);
-          ra.ctl = reinterpret_cast<RefineCtl *>(blk + kSlotCtl);
-          ra.out = reinterpret_cast<RefineOut *>(blk + kSlotOut);
-          ra.cand_pl = pool[j].pl; ra.band_pl = pool[j].pl;
-          ra.eps3 = eps3; ra.nthresh = nthresh; ra.bmp_eps = bmp_eps; ra.band_halfwidth = kBandMul * eps3; ra.ext = ext;
-          for (int k = 0; k < 3; ++k) { ra.mn[k] = mn[k]; ra.mx[k] = mx[k]; }
-          ra.min_support = min_support; ra.band_full = 0; ra.cap = (int) cap;
-          bb.pl[j] = pool[j].pl;
-          bb.pos[j] = const_cast<float4 *>(ra.posB); bb.nrm[j] = const_cast<float4 *>(ra.nrmB); bb.idx[j] = const_cast<int *>(ra.idxB);
-          bb.nb[j] = const_cast<int *>(ra.d_nb); bb.cap[j] = (int) cap;
-          ResolveArgs &q = rv[j];
-          q.idxB = ra.idxB; q.d_nb = ra.d_nb; q.member_a = ra.member_a; q.member_b = ra.member_b; q.touched = ra.touched;
-          q.out = ra.out; q.assigned = assigned; q.state = reinterpret_cast<BatchState *>(bm);
-          q.verdict = reinterpret_cast<Verdict *>(blk + kSlotVerdict); q.conflict = reinterpret_cast<int *>(blk + kSlotConflict);
-          q.est = pool[j].est; q.slot = j; q.cap = (int) cap;
-        }
-        for (int j = K; j < kMaxBatch; ++j) rb.a[j] = rb.a[0];
-        dev.clock.begin(KernelClock::kBandCompact, 20.0 * n, s);       // one pass whatever K is
-        multi_band_compact_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, bb);
-        dev.clock.end(s);
-        PLADE_LAUNCH_CHECK();
+        memcpy(bh + kAccState, &st0, sizeof(st0));
+        for (int j = 0; j < K; ++j) { PoolCand pc; pc.pl = pool[j].pl; pc.est = pool[j].est; pc.pad = 0; memcpy(bh + kAccPool + j * sizeof(PoolCand), &pc, sizeof(pc)); }
+        PLADE_CUDA(cudaMemcpyAsync(bm, bh, kAccBytes, cudaMemcpyHostToDevice, s));
+        AcceptArgs aa;
+        RefineArgs &ra = aa.r;
+        ra.seg_cap = band_seg_cap(n, csize); ra.segs = csize;
+        ra.posB = posB; ra.nrmB = nrmB; ra.idxB = idxB; ra.d_nb = d_nb;
+        ra.flag = flag; ra.pix = pix;
+        ra.bmp = rs.bmp_dev.ensure(kBmpCap); ra.btmp = rs.bmp_tmp.ensure(kBmpCap); ra.bmask = rs.mask_dev.ensure(kBmpCap);
+        ra.lab = rs.cc_lab.ensure(kBmpCap); ra.ccnt = rs.cc_cnt.ensure(kBmpCap);
+        ra.member_a = rs.memb_a.ensure(band_cap_max); ra.member_b = rs.memb_b.ensure(band_cap_max);
+        ra.uvbox = d_uvbox; ra.acc = acc;
+        unsigned char *rm = reinterpret_cast<unsigned char *>(rs.refine_mem.ensure(64));
+        ra.ctl = reinterpret_cast<RefineCtl *>(rm); ra.out = reinterpret_cast<RefineOut *>(rm + 128);
+        ra.cand_pl = pool[0].pl; ra.band_pl = pool[0].pl;
+        for (int k = 0; k < 3; ++k) ra.cand_pos[k] = 0.f;
+        ra.eps3 = eps3; ra.nthresh = nthresh; ra.bmp_eps = bmp_eps; ra.band_halfwidth = kBandMul * eps3; ra.ext = ext;
+        for (int k = 0; k < 3; ++k) { ra.mn[k] = mn[k]; ra.mx[k] = mx[k]; }
+        ra.min_support = min_support; ra.band_full = 0;
+        if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(ra.bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
+        aa.pos = c.pos.p; aa.nrm = c.nrm.p; aa.assigned = assigned; aa.n = n; aa.k = K;
+        aa.pool = reinterpret_cast<const PoolCand *>(bm + kAccPool);
+        aa.state = reinterpret_cast<BatchState *>(bm + kAccState);
+        aa.verdict = reinterpret_cast<Verdict *>(bm + kAccVerdict);
+        aa.actl = reinterpret_cast<AcceptCtl *>(bm + kAccCtl);
+        aa.band = kBandMul * eps3;
         cudaLaunchConfig_t cfg = {};
-        cfg.blockDim = dim3(refine_block_threads()); cfg.stream = s;
+        cfg.gridDim = dim3(csize); cfg.blockDim = dim3(kRefThreads); cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cfg.gridDim = dim3(csize * K);
         dev.clock.begin(KernelClock::kRefineCluster, 0.0, s);
-        PLADE_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel, rb));
+        PLADE_CUDA(cudaLaunchKernelEx(&cfg, accept_loop_kernel, aa));
         dev.clock.end(s);
-        cfg.gridDim = dim3(csize);
-        for (int j = 0; j < K; ++j) PLADE_CUDA(cudaLaunchKernelEx(&cfg, resolve_kernel, rv[j]));
-        dev.launches.add(2 + K);
-        n_band_builds += K;
-        unsigned char *back = bh + (kSlotBase + kMaxBatch * kSlotStride);
-        PLADE_CUDA(cudaMemcpyAsync(back, bm, kSlotBase + K * kSlotStride, cudaMemcpyDeviceToHost, s));
-        PLADE_CUDA(cudaStreamSynchronize(s));
+        dev.launches.add();
+        unsigned char *back = bh + kAccBytes;
+        PLADE_CUDA(cudaMemcpyAsync(back, bm, kAccBytes, cudaMemcpyDeviceToHost, s));
+        stream_sync(s);
         BatchState st1;
-        memcpy(&st1, back, sizeof(st1));
+        memcpy(&st1, back + kAccState, sizeof(st1));
         const int m_before = m;
         int n_acc = 0;
         bool walk_on = true;
         for (int j = 0; j < K && walk_on; ++j) {
           Verdict v;
-          RefineOut ro;
-          memcpy(&v, back + kSlotBase + j * kSlotStride + kSlotVerdict, sizeof(v));
-          memcpy(&ro, back + kSlotBase + j * kSlotStride + kSlotOut, sizeof(ro));
-          if (v.kind != kVerdictSkipped && v.kind != kVerdictNotEligible && ro.status == 0) {
-            dev.clock.bytes[KernelClock::kRefineCluster] += 28.0 * ro.n_band * ro.evals;
-            for (int k = 0; k < 6; ++k) refine_phase_ns[k] += ro.phase_ns[k];
-            refine_evals += ro.evals;
+          memcpy(&v, back + kAccVerdict + j * sizeof(Verdict), sizeof(v));
+          if (v.kind == kVerdictAccepted || v.kind == kVerdictRejected || v.kind == kVerdictFallback) {
+            // algorithmic bytes: 20 B per point for the band pass + 28 B per band point per evaluation
+            if (dev.clock.enabled) dev.clock.bytes[KernelClock::kRefineCluster] += 20.0 * n + 28.0 * v.n_band * v.evals;
+            for (int k = 0; k < 6; ++k) refine_phase_ns[k] += v.phase_ns[k];
+            band_phase_ns += v.band_ns;
+            refine_evals += v.evals;
+            ++n_band_builds;
           }
           switch (v.kind) {
             case kVerdictAccepted: {
@@ -1800,13 +1786,13 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
               break;
             }
             case kVerdictRejected:
+              // its score can only shrink from here on: never look at this plane (or a duplicate of it) again
               banned.push_back(pool[0].pl);
               pool.erase(pool.begin());
               if (++rejects >= 256) { stop_all = true; walk_on = false; }
               break;
-            case kVerdictFallback: force_single = true; ++n_cluster_fallbacks; walk_on = false; break;    // pool[0] is refined alone next
-            case kVerdictConflict: ++n_batch_conflicts; walk_on = false; break;                             // pool[0] gets a fresh band next
-            default: walk_on = false; break;                                                                // not eligible any more / skipped
+            case kVerdictFallback: force_single = true; ++n_cluster_fallbacks; walk_on = false; break;    // pool[0] goes through the host-driven path
+            default: walk_on = false; break;                                                                // not eligible any more / not reached
           }
         }
         ++n_batches;
@@ -1814,7 +1800,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
         m = (int) st1.m;
         drawn = st1.drawn;
         if (n_acc) {
-          // compact the Morton list to the still-unassigned points, once per batch
+          // compact the Morton list to the still-unassigned points, once per launch
           IsUnassigned pr{assigned};
           size_t tb3 = 0;
           cub::DeviceSelect::If(nullptr, tb3, cur_order, alt_order, d_nsel, m_before, pr, s);
@@ -1823,7 +1809,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
           dev.launches.add(3);
           std::swap(cur_order, alt_order);
         }
-        mark("ransac_batch");
+        mark("ransac_accept_loop");
         if (stop_all) break;
         if (m < min_support || m < 3) break;
         continue;
@@ -1842,7 +1828,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       dev.launches.add();
       int hb[4];
       PLADE_CUDA(cudaMemcpyAsync(hb, d_uvbox, sizeof(hb), cudaMemcpyDeviceToHost, s));
-      PLADE_CUDA(cudaStreamSynchronize(s));
+      stream_sync(s);
       float uv[4];
       for (int k = 0; k < 4; ++k) { int a = hb[k]; a = a >= 0 ? a : a ^ 0x7fffffff; memcpy(&uv[k], &a, 4); }
       if (uv[0] > uv[2]) return e;     // no inliers
@@ -1857,7 +1843,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       PLADE_LAUNCH_CHECK();
       std::vector<unsigned char> hbmp(ue * ve), hmask;
       PLADE_CUDA(cudaMemcpyAsync(hbmp.data(), bitmap, ue * ve, cudaMemcpyDeviceToHost, s));
-      PLADE_CUDA(cudaStreamSynchronize(s));
+      stream_sync(s);
       largest_component(hbmp, (int) ue, (int) ve, hmask);
       PLADE_CUDA(cudaMemcpyAsync(mask, hmask.data(), ue * ve, cudaMemcpyHostToDevice, s));
       PLADE_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 16, s));
@@ -1866,7 +1852,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       dev.launches.add(2);
       double h[5];
       PLADE_CUDA(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, s));
-      PLADE_CUDA(cudaStreamSynchronize(s));
+      stream_sync(s);
       e.size = (long long) h[0]; e.sum[0] = h[1]; e.sum[1] = h[2]; e.sum[2] = h[3]; e.score = h[4]; e.ok = e.size > 0;
       return e;
     };
@@ -1880,10 +1866,13 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     // ---- band of this candidate (see band_compact_kernel) -------------------------------------------------------
     float4 band_pl = make_float4(0, 0, 0, 0);
     bool band_full = false;
-    auto build_band = [&](const float4 &pl, bool full) {
-      PLADE_CUDA(cudaMemsetAsync(d_nb, 0, sizeof(int), s));
+    int band_segs = 1, band_cap_seg = n;
+    auto build_band = [&](const float4 &pl, bool full, int segs = 1) {      // segs > 1: the layout of the cluster kernel (RefineArgs)
+      band_segs = segs; band_cap_seg = segs > 1 ? band_seg_cap(n, segs) : n;
+      posB = rs.band_pos.ensure((size_t) band_cap_seg * segs); nrmB = rs.band_nrm.ensure((size_t) band_cap_seg * segs); idxB = rs.band_idx.ensure((size_t) band_cap_seg * segs);
+      PLADE_CUDA(cudaMemsetAsync(d_nb, 0, sizeof(int) * 16, s));
       dev.clock.begin(KernelClock::kBandCompact, 20.0 * n, s);       // assigned (4 B) + position (16 B) of every point, once
-      band_compact_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, pl, full ? INFINITY : kBandMul * eps3, posB, nrmB, idxB, d_nb);
+      band_compact_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, pl, full ? INFINITY : kBandMul * eps3, posB, nrmB, idxB, d_nb, band_cap_seg, segs);
       dev.clock.end(s);
       PLADE_LAUNCH_CHECK();
       dev.launches.add();
@@ -1920,7 +1909,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       BmpInfo hi;
       PLADE_CUDA(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, s));
       PLADE_CUDA(cudaMemcpyAsync(&hi, info, sizeof(hi), cudaMemcpyDeviceToHost, s));
-      PLADE_CUDA(cudaStreamSynchronize(s));
+      stream_sync(s);
       overflow = hi.overflow != 0;
       e.size = (long long) h[0]; e.sum[0] = h[1]; e.sum[1] = h[2]; e.sum[2] = h[3]; e.score = h[4]; e.ok = e.size > 0;
       for (int k = 0; k < 6; ++k) cov6[k] = h[8 + k];
@@ -1936,7 +1925,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       dev.launches.add();
       double h[6];
       PLADE_CUDA(cudaMemcpyAsync(h, acc + 8, sizeof(h), cudaMemcpyDeviceToHost, s));
-      PLADE_CUDA(cudaStreamSynchronize(s));
+      stream_sync(s);
       float a[3][3], d[3], v[3][3];
       a[0][0] = (float) (h[0] / e.size); a[0][1] = a[1][0] = (float) (h[1] / e.size); a[0][2] = a[2][0] = (float) (h[2] / e.size);
       a[1][1] = (float) (h[3] / e.size); a[1][2] = a[2][1] = (float) (h[4] / e.size); a[2][2] = (float) (h[5] / e.size);
@@ -1958,23 +1947,25 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     long long acc_size = 0;
     bool host_path = false, refined = false;
     const unsigned char *band_member = nullptr;      // members of the accepted plane by band position (cluster path)
-    build_band(fr.pl, false);
+    const int csize = refine_cluster_size(dev.id);
+    build_band(fr.pl, false, csize ? csize : 1);
     // ---- the whole acceptance chain in one cluster kernel, one host round trip (refine_cluster_kernel) -----------
-    if (const int csize = refine_cluster_size(dev.id)) {
+    if (csize) {
       unsigned char *rm = reinterpret_cast<unsigned char *>(rs.refine_mem.ensure(64));
       RefineArgs ra;
       ra.posB = posB; ra.nrmB = nrmB; ra.idxB = idxB; ra.d_nb = d_nb;
+      ra.seg_cap = band_cap_seg; ra.segs = csize;
+      for (int k = 0; k < 3; ++k) ra.cand_pos[k] = cp[k];
       ra.flag = flag; ra.pix = pix;
       ra.bmp = rs.bmp_dev.ensure(kBmpCap); ra.btmp = rs.bmp_tmp.ensure(kBmpCap); ra.bmask = rs.mask_dev.ensure(kBmpCap);
       ra.lab = rs.cc_lab.ensure(kBmpCap); ra.ccnt = rs.cc_cnt.ensure(kBmpCap);
-      ra.member_a = rs.memb_a.ensure(n); ra.member_b = rs.memb_b.ensure(n);
+      ra.member_a = rs.memb_a.ensure(band_cap_max); ra.member_b = rs.memb_b.ensure(band_cap_max);
       ra.uvbox = d_uvbox; ra.acc = acc;
       ra.ctl = reinterpret_cast<RefineCtl *>(rm); ra.out = reinterpret_cast<RefineOut *>(rm + 128);
       ra.cand_pl = best_pl; ra.band_pl = band_pl;
       ra.eps3 = eps3; ra.nthresh = nthresh; ra.bmp_eps = bmp_eps; ra.band_halfwidth = kBandMul * eps3; ra.ext = ext;
       for (int k = 0; k < 3; ++k) { ra.mn[k] = mn[k]; ra.mx[k] = mx[k]; }
       ra.min_support = min_support; ra.band_full = band_full ? 1 : 0;
-      ra.touched = nullptr; ra.cap = n;
       if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(ra.bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(csize); cfg.blockDim = dim3(refine_block_threads()); cfg.stream = s;
@@ -1983,17 +1974,15 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       dev.clock.begin(KernelClock::kRefineCluster, 0.0, s);
-      RefineBatch one;
-      for (int j = 0; j < kMaxBatch; ++j) one.a[j] = ra;
-      PLADE_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel, one));
+      PLADE_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel, ra));
       dev.clock.end(s);
       dev.launches.add();
       static_assert(sizeof(RefineOut) <= 64 * sizeof(unsigned int) && ((kRoundEnd - kRoundCounts2) * 4) % 8 == 0, "verdict slot of round_host");
       RefineOut *h_ro = reinterpret_cast<RefineOut *>(rs.round_host.ensure(kRoundEnd - kRoundCounts2 + 64) + (kRoundEnd - kRoundCounts2));
       PLADE_CUDA(cudaMemcpyAsync(h_ro, ra.out, sizeof(RefineOut), cudaMemcpyDeviceToHost, s));     // page-locked: no implicit host block
-      PLADE_CUDA(cudaStreamSynchronize(s));
+      stream_sync(s);
       const RefineOut ro = *h_ro;
-      dev.clock.bytes[KernelClock::kRefineCluster] += 28.0 * ro.n_band * ro.evals;     // 28 B per point per pass
+      if (dev.clock.enabled) dev.clock.bytes[KernelClock::kRefineCluster] += 28.0 * ro.n_band * ro.evals;     // 28 B per point per pass
       for (int k = 0; k < 6; ++k) refine_phase_ns[k] += ro.phase_ns[k];
       refine_evals += ro.evals;
       if (ro.status == 0) {
@@ -2067,7 +2056,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       PLADE_CUDA(cudaMemsetAsync(member_a, 0, n, s));
       PLADE_CUDA(cudaMemsetAsync(member_b, 0, n, s));
     } else if (refined) {
-      band_assign_kernel<<<blocks_b, 256, 0, s>>>(idxB, d_nb, band_member, (int) found.size(), assigned);
+      band_assign_kernel<<<blocks_b, 256, 0, s>>>(idxB, d_nb, band_cap_seg, band_segs, band_member, (int) found.size(), assigned);
       PLADE_LAUNCH_CHECK();
       dev.launches.add();
     } else band_finish((int) found.size(), member);
@@ -2093,6 +2082,12 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     if (stop_all) break;
   }
 
+  // what extract() needs to continue this detection with a lower min_support
+  rz.cloud = (const void *) c.pos.p; rz.n = n; rz.m = m; rz.drawn = drawn; rz.round_seed = round_seed;
+  rz.cur_is_order2 = cur_order == order2 ? 1 : 0;
+  for (int k = 0; k < 3; ++k) { rz.mn[k] = mn[k]; rz.mx[k] = mx[k]; }
+  rz.found = found;
+  rz.valid = true;
   // ---- output (PLADE/plane_extraction.cpp:115-160): drop shapes below min_support, unit normal, d = -n.p --------
   // membership stays on the device: group_out[i] = index of the returned plane of point i, or -1
   std::vector<int> remap(std::max<size_t>(found.size(), 1), -1);
@@ -2114,11 +2109,11 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
   remap_group_kernel<<<div_up(n, 256), 256, 0, s>>>(assigned, n, d_remap, (int) found.size(), g);
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
   dev.clock.collect();
   mark("ransac_output");
-  if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade ransac lane %d] planes %zu, rounds, batches %d (%d candidates, %d conflicts); candidates evaluated on a band: %d, widened to all points: %d, cluster-kernel fallbacks: %d; cluster kernel: %d evaluations, us per phase: flags %.0f raster %.0f components %.0f select %.0f covariance %.0f decision %.0f\n",
-                                   lane, found.size(), n_batches, n_batch_cands, n_batch_conflicts, n_band_builds - n_band_full, n_band_full, n_cluster_fallbacks, refine_evals, refine_phase_ns[0] / 1e3, refine_phase_ns[1] / 1e3,
+  if (getenv("PLADE_TIMING")) fprintf(stderr, "[plade ransac lane %d] planes %zu, accept-loop launches %d (%d pool entries offered), band pass %.0f us; candidates evaluated on a band: %d, widened to all points: %d, cluster-kernel fallbacks: %d; cluster kernel: %d evaluations, us per phase: flags %.0f raster %.0f components %.0f select %.0f covariance %.0f decision %.0f\n",
+                                   lane, found.size(), n_batches, n_batch_cands, band_phase_ns / 1e3, n_band_builds - n_band_full, n_band_full, n_cluster_fallbacks, refine_evals, refine_phase_ns[0] / 1e3, refine_phase_ns[1] / 1e3,
                                    refine_phase_ns[2] / 1e3, refine_phase_ns[3] / 1e3, refine_phase_ns[4] / 1e3, refine_phase_ns[5] / 1e3);
   return result;
 }
@@ -2154,7 +2149,7 @@ std::vector<PlaneParam> Registrar::extract_planes_dev(const CloudDev &c, int ini
     PLADE_CUDA(cudaMemcpyAsync(dr, remap.data(), sizeof(int) * remap.size(), cudaMemcpyHostToDevice, dev.stream));
     remap_group_kernel<<<div_up((long long) c.n, 256), 256, 0, dev.stream>>>(group_out.p, (int) c.n, dr, (int) remap.size(), group_out.p);
     PLADE_LAUNCH_CHECK();
-    PLADE_CUDA(cudaStreamSynchronize(dev.stream));
+    stream_sync(dev.stream);
     std::cout << kept.size() << " of the " << planes.size() << " extracted planes will be used for registration" << std::endl;
     return kept;
   }
@@ -2163,7 +2158,7 @@ std::vector<PlaneParam> Registrar::extract_planes_dev(const CloudDev &c, int ini
   int trials = 1;
   int used_support = init_min_support;
   while (counted(planes, used_support) < min_num && trials < max_trials && min_support >= min_allowed_support) {
-    planes = detect_planes_dev(c, min_support, group_out, lane);
+    planes = detect_planes_dev(c, min_support, group_out, lane, params.detect_resume != 0);
     used_support = min_support;
     min_support /= 2;
     ++trials;
@@ -2177,7 +2172,7 @@ std::vector<PlaneParam> Registrar::extract_planes_dev(const CloudDev &c, int ini
 std::vector<PlaneRec> Registrar::planes_to_host(const CloudDev &c, const std::vector<PlaneParam> &pp, const DevBuf<int> &group) {
   std::vector<int> h(c.n);
   if (c.n) PLADE_CUDA(cudaMemcpyAsync(h.data(), group.p, sizeof(int) * c.n, cudaMemcpyDeviceToHost, dev.stream));
-  PLADE_CUDA(cudaStreamSynchronize(dev.stream));
+  stream_sync(dev.stream);
   std::vector<PlaneRec> out(pp.size());
   for (size_t k = 0; k < pp.size(); ++k) {
     out[k].idx.reserve((size_t) pp[k].size);
@@ -2200,6 +2195,96 @@ std::vector<PlaneRec> Registrar::extract_planes(const CloudDev &c, int init_min_
   return planes_to_host(c, pp, g);
 }
 
+// stage API: the acceptance chain of ONE candidate plane (RansacShapeDetector.cpp:613-655) on the device -- band_compact_kernel
+// + refine_cluster_kernel exactly as the detection runs them -- for the parity test against the reference's own Candidate /
+// BitmapPrimitiveShape / Plane classes.  assigned (may be null): points with assigned[i] != -1 are not available.
+bool Registrar::refine_candidate_stage(const CloudDev &c, const int *h_assigned, const float nrm3[3], const float pos3[3], int min_support,
+                                       float out_n[3], float out_p[3], unsigned char *h_member, long long *out_size, int *out_evals, double *out_score) {
+  const int n = (int) c.n;
+  cudaStream_t s = dev.stream;
+  RansacScratch &rs = scratch_of(*this, 0);
+  const int csize = refine_cluster_size(dev.id);
+  if (!csize) throw std::runtime_error("refine_candidate_stage: the cluster kernel is not available on this device");
+  if (n < 3) return false;
+  const int blocks_n = std::min(div_up(n, 256), dev.num_sms * 8);
+  int *d_misc = rs.misc.ensure(128);
+  {
+    int init[6];
+    float big = 3.4e38f, nbig = -3.4e38f;
+    int bi, nbi;
+    memcpy(&bi, &big, 4); memcpy(&nbi, &nbig, 4);
+    nbi ^= 0x7fffffff;
+    init[0] = init[1] = init[2] = bi; init[3] = init[4] = init[5] = nbi;
+    PLADE_CUDA(cudaMemcpyAsync(d_misc, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  }
+  bbox_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, n, d_misc);
+  PLADE_LAUNCH_CHECK();
+  int h6[6];
+  PLADE_CUDA(cudaMemcpyAsync(h6, d_misc, sizeof(h6), cudaMemcpyDeviceToHost, s));
+  stream_sync(s);
+  float mn[3], mx[3];
+  for (int k = 0; k < 3; ++k) {
+    int a = h6[k], b = h6[3 + k];
+    a = a >= 0 ? a : a ^ 0x7fffffff; b = b >= 0 ? b : b ^ 0x7fffffff;
+    memcpy(&mn[k], &a, 4); memcpy(&mx[k], &b, 4);
+  }
+  const float scale = std::max(mx[0] - mn[0], mx[1] - mn[1]);       // (bug-compatible: z ignored)
+  const float eps3 = 3 * params.ransac_dist_thresh * scale, bmp_eps = params.ransac_bitmap_reso * scale;
+  const float ext = std::max(std::max(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
+  int *assigned = rs.assigned.ensure(n);
+  if (h_assigned) PLADE_CUDA(cudaMemcpyAsync(assigned, h_assigned, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  else PLADE_CUDA(cudaMemsetAsync(assigned, 0xff, sizeof(int) * n, s));
+  const int seg_cap = band_seg_cap(n, csize);
+  const size_t cap = (size_t) seg_cap * csize;
+  RefineArgs ra;
+  ra.posB = rs.band_pos.ensure(cap); ra.nrmB = rs.band_nrm.ensure(cap); ra.idxB = rs.band_idx.ensure(cap);
+  ra.d_nb = d_misc + 64; ra.seg_cap = seg_cap; ra.segs = csize;
+  ra.flag = rs.flag.ensure(cap); ra.pix = rs.pix.ensure(cap);
+  ra.bmp = rs.bmp_dev.ensure(kBmpCap); ra.btmp = rs.bmp_tmp.ensure(kBmpCap); ra.bmask = rs.mask_dev.ensure(kBmpCap);
+  ra.lab = rs.cc_lab.ensure(kBmpCap); ra.ccnt = rs.cc_cnt.ensure(kBmpCap);
+  ra.member_a = rs.memb_a.ensure(cap); ra.member_b = rs.memb_b.ensure(cap);
+  ra.uvbox = d_misc + 16; ra.acc = rs.acc.ensure(16);
+  unsigned char *rm = reinterpret_cast<unsigned char *>(rs.refine_mem.ensure(64));
+  ra.ctl = reinterpret_cast<RefineCtl *>(rm); ra.out = reinterpret_cast<RefineOut *>(rm + 128);
+  const float dist = (pos3[0] * nrm3[0] + pos3[1] * nrm3[1]) + pos3[2] * nrm3[2];       // m_pos.dot(m_normal), R/Plane.cpp:13-23
+  ra.cand_pl = make_float4(nrm3[0], nrm3[1], nrm3[2], dist); ra.band_pl = ra.cand_pl;
+  for (int k = 0; k < 3; ++k) { ra.cand_pos[k] = pos3[k]; ra.mn[k] = mn[k]; ra.mx[k] = mx[k]; }
+  ra.eps3 = eps3; ra.nthresh = params.ransac_normal_thresh; ra.bmp_eps = bmp_eps; ra.band_halfwidth = kBandMul * eps3; ra.ext = ext;
+  ra.min_support = min_support; ra.band_full = 0;
+  if (!rs.bmp_dev_clean) { PLADE_CUDA(cudaMemsetAsync(ra.bmp, 0, kBmpCap, s)); rs.bmp_dev_clean = true; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize); cfg.blockDim = dim3(refine_block_threads()); cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  RefineOut ro;
+  for (int attempt = 0; attempt < 2; ++attempt) {      // a refit that leaves the band is redone on all unassigned points, as the detection does
+    ra.band_full = attempt;
+    PLADE_CUDA(cudaMemsetAsync(ra.d_nb, 0, sizeof(int) * 16, s));
+    band_compact_kernel<<<blocks_n, 256, 0, s>>>(c.pos.p, c.nrm.p, assigned, n, ra.cand_pl, attempt ? INFINITY : kBandMul * eps3, ra.posB, ra.nrmB, ra.idxB, ra.d_nb, seg_cap, csize);
+    PLADE_LAUNCH_CHECK();
+    PLADE_CUDA(cudaLaunchKernelEx(&cfg, refine_cluster_kernel, ra));
+    dev.launches.add(3);
+    PLADE_CUDA(cudaMemcpyAsync(&ro, ra.out, sizeof(ro), cudaMemcpyDeviceToHost, s));
+    stream_sync(s);
+    if (ro.status != 2) break;
+  }
+  if (ro.status != 0) { last_error = "refine_candidate_stage: candidate needs the host path (status " + std::to_string(ro.status) + ")"; return false; }
+  // members: band-local map -> per-point mask (through a scratch shape index)
+  int *mark = rs.order_alt.ensure(n);
+  PLADE_CUDA(cudaMemsetAsync(mark, 0, sizeof(int) * n, s));
+  band_assign_kernel<<<std::min(blocks_n, dev.num_sms * 4), 256, 0, s>>>(ra.idxB, ra.d_nb, seg_cap, csize, ro.acc_sel ? ra.member_b : ra.member_a, 1, mark);
+  PLADE_LAUNCH_CHECK();
+  std::vector<int> hm(n);
+  PLADE_CUDA(cudaMemcpyAsync(hm.data(), mark, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  stream_sync(s);
+  for (int i = 0; i < n; ++i) h_member[i] = hm[i] ? 1 : 0;
+  memcpy(out_n, ro.acc_n, sizeof(float) * 3); memcpy(out_p, ro.acc_p, sizeof(float) * 3);
+  *out_size = ro.acc_size; *out_evals = ro.evals; *out_score = ro.acc_score;
+  return true;
+}
+
 // stage API: closing + largest 8-connected component of a ue x ve bitmap on the device (cc_kernel), as the RANSAC
 // acceptance test runs it (BitmapPrimitiveShape::ConnectedComponent, R/BitmapPrimitiveShape.cpp:155-205)
 void largest_component_device(Device &dev, const unsigned char *h_bitmap, int ue, int ve, unsigned char *h_mask) {
@@ -2218,7 +2303,7 @@ void largest_component_device(Device &dev, const unsigned char *h_bitmap, int ue
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
   PLADE_CUDA(cudaMemcpyAsync(h_mask, d_mask, P, cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
 }
 
 // stage API: plane consensus counts over the whole cloud (K1a/K1b predicate)

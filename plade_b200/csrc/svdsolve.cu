@@ -36,7 +36,7 @@ void nearest_points_batch(Device &dev, SvdScratch &sc, const float *h_in12, int 
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
   PLADE_CUDA(cudaMemcpyAsync(h_out6, d_out, sizeof(float) * 6 * (size_t) n, cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
 }
 
 }  // namespace plade

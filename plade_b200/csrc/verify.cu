@@ -357,7 +357,7 @@ void build_target_grid(Device &dev, const float4 *d_tgt, size_t n, float inlier_
   dev.launches.add();
   int h6[6];
   PLADE_CUDA(cudaMemcpyAsync(h6, d6, sizeof(h6), cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
   float mn[3], mx[3];
   for (int k = 0; k < 3; ++k) { mn[k] = ordered_int_to_float(h6[k]); mx[k] = ordered_int_to_float(h6[3 + k]); }
 
@@ -442,6 +442,41 @@ void verify_hypotheses(Device &dev, const float4 *d_src, size_t ns, const Target
   }
   int blocks = (int) std::min<long long>(n_work, (long long) dev.num_sms * per_sm);
   verify_kernel<<<blocks, kThreads, 0, s>>>(d_src, (int) ns, g, d_hyp, H, rball2, rin2, d_counts, n_tiles, n_chunks);
+  PLADE_LAUNCH_CHECK();
+  dev.launches.add();
+}
+
+// ---- sharded verification: the best hypothesis of this rank's shard as one packed u64 ---------------------------
+// key = (float bits of the score) << 32 | (0xFFFFFFFF - global hypothesis index): a MAX over keys -- here over the shard,
+// then over the ranks by ncclAllReduce -- picks the highest score, ties -> the lowest index.  Entry i of the shard is the
+// hypothesis rank + i * world.  mode 0: the registration score of PLADE/plade.cpp:558-562 with ComputeOverlap's ratio
+// (PLADE/util.h:644), the same float / double mix as the host path (matched planes ride in HypParams::pad as an int);
+// mode 1: the inlier count itself.
+__global__ void shard_key_kernel(const unsigned int *__restrict__ counts, const HypParams *__restrict__ hyp, int n_mine, int rank, int world,
+                                 double denom, double n_src_planes, int mode, unsigned long long *__restrict__ key) {
+  unsigned long long best = 0ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_mine; i += gridDim.x * blockDim.x) {
+    const unsigned int cnt = counts[i];
+    unsigned int bits;
+    if (mode == 0) {
+      const float overlap = (float) ((double) cnt / denom);
+      const double planes = (double) __float_as_int(hyp[i].pad);
+      const float score = (float) (0.2 * (planes / n_src_planes) + 0.8 * overlap);
+      bits = __float_as_uint(score);
+    } else bits = cnt;
+    const unsigned int h = (unsigned int) rank + (unsigned int) i * (unsigned int) world;
+    const unsigned long long k = ((unsigned long long) bits << 32) | (unsigned long long) (0xFFFFFFFFu - h);
+    best = k > best ? k : best;
+  }
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_down_sync(0xffffffffu, best, o); best = t > best ? t : best; }
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(key, best);
+}
+
+void shard_best_key(Device &dev, const unsigned int *d_counts, const HypParams *d_hyp, int n_mine, int rank, int world, double denom,
+                    double n_src_planes, int mode, unsigned long long *d_key) {
+  PLADE_CUDA(cudaMemsetAsync(d_key, 0, sizeof(unsigned long long), dev.stream));
+  if (n_mine <= 0) return;
+  shard_key_kernel<<<std::min(div_up(n_mine, 256), dev.num_sms), 256, 0, dev.stream>>>(d_counts, d_hyp, n_mine, rank, world, denom, n_src_planes, mode, d_key);
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
 }

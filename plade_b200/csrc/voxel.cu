@@ -159,7 +159,7 @@ size_t voxel_impl(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n, 
   PLADE_LAUNCH_CHECK();
   dev.launches.add();
   PLADE_CUDA(cudaMemcpyAsync(h_bbox.data(), d_bbox, sizeof(int) * h_bbox.size(), cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
 
   // 2. per-group grid parameters, exactly as voxel_grid.hpp:237-262
   std::vector<GroupParams> gp(ngroups);
@@ -216,7 +216,7 @@ size_t voxel_impl(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n, 
   dev.launches.add(d_group ? 9 : 5);
   int m = 0;
   PLADE_CUDA(cudaMemcpyAsync(&m, d_counter, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
   if (m == 0) return 0;
 
   // 5. voxel ids
@@ -230,7 +230,7 @@ size_t voxel_impl(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n, 
   dev.launches.add(3);
   int nvox = 0;
   PLADE_CUDA(cudaMemcpyAsync(&nvox, flags + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
   int *seg = sc.seg_start.ensure((size_t) nvox + 1);
   seg_start_kernel<<<div_up(m, 256), 256, 0, s>>>(keys2, flags, m, vbits, seg, d_group_first);
   PLADE_LAUNCH_CHECK();
@@ -242,7 +242,7 @@ size_t voxel_impl(Device &dev, VoxelScratch &sc, const float4 *d_pts, size_t n, 
   if (group_start) {
     std::vector<int> first(kMaxGroups);
     PLADE_CUDA(cudaMemcpyAsync(first.data(), d_group_first, sizeof(int) * kMaxGroups, cudaMemcpyDeviceToHost, s));
-    PLADE_CUDA(cudaStreamSynchronize(s));
+    stream_sync(s);
     (*group_start)[ngroups] = nvox;
     for (int g = ngroups - 1; g >= 0; --g) (*group_start)[g] = first[g] >= 0 ? first[g] : (*group_start)[g + 1];
   }
@@ -419,7 +419,7 @@ void knn_sqdist(Device &dev, KnnScratch &ks, const float4 *d_pts, size_t n, cons
   single_bbox_kernel<<<std::min(div_up((long long) n, 256), dev.num_sms * 8), 256, 0, s>>>(d_pts, (int) n, d_bbox);
   PLADE_LAUNCH_CHECK();
   PLADE_CUDA(cudaMemcpyAsync(h_bbox, d_bbox, sizeof(h_bbox), cudaMemcpyDeviceToHost, s));
-  PLADE_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
   float mn[3], mx[3];
   for (int a = 0; a < 3; ++a) { mn[a] = o2f(h_bbox[a]); mx[a] = o2f(h_bbox[3 + a]); }
   double ex = (double) mx[0] - mn[0], ey = (double) mx[1] - mn[1], ez = (double) mx[2] - mn[2];

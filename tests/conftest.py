@@ -48,3 +48,14 @@ def poly_stages():
 @pytest.fixture(scope="session")
 def synth_stages():
     return dict(np.load(os.path.join(GOLDEN, "synth_small_stages.npz")))
+
+
+_SYNTH_SMALL = {}
+
+
+def synth_small_tgt():
+    """the target cloud of tests/golden/synth_small_stages.npz (tests/golden/make_golden.py: make_pair(200000, 20, seed 11))"""
+    if "tgt" not in _SYNTH_SMALL:
+        from plade_b200.synth import make_pair
+        _SYNTH_SMALL["tgt"] = make_pair(n_points=200000, n_planes=20, seed=11)[0]
+    return _SYNTH_SMALL["tgt"]

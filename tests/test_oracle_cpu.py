@@ -10,6 +10,8 @@ import sys
 import numpy as np
 import pytest
 
+from tests.conftest import synth_small_tgt
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -351,6 +353,23 @@ def test_dropin_header_has_the_reference_overloads(tmp_path):
     assert "results=0 identity_after_failure=1" in r.stdout, (r.stdout, r.stderr[-500:])
 
 
+def test_dropin_library_links_against_the_reference_prototype(tmp_path):
+    """plade_b200/libplade_dropin.so exports `registration` with the reference's exact signature (PLADE/plade.h:44-47): a
+    translation unit that only declares the prototype links against it; without a usable file pair the call returns false
+    and leaves the identity, as the reference does (PLADE/plade.cpp:696)."""
+    eigen = "/root/reference/code/3rd_party/eigen-3.4.0"
+    lib = os.path.join(ROOT, "plade_b200", "libplade_dropin.so")
+    if not os.path.isdir(eigen) or not os.path.exists(lib):
+        pytest.skip("needs Eigen's headers (the reference tree) and the built libplade_dropin.so")
+    exe = str(tmp_path / "dropin_link_check")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-I" + eigen, os.path.join(ROOT, "tests", "host", "dropin_link_check.cpp"), "-o", exe,
+                        "-L" + os.path.join(ROOT, "plade_b200"), "-lplade_dropin", "-lplade_b200", "-Wl,-rpath," + os.path.join(ROOT, "plade_b200")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.split()
+    assert out[0] == "0" and [float(x) for x in out[1:]] == [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]
+
+
 def test_room_pair_outcome_is_decided_by_the_plane_count(ref):
     """Evidence for the open gap of DESIGN.md section 7 (BASELINE config 2): on the decimated room pair the REFERENCE's own
     matching back end lands on a symmetric solution when it is given the ten planes of the 94 K scan that have >= 2500
@@ -392,12 +411,23 @@ def test_ply_ingest_formats_and_errors(tmp_path):
                         os.path.join(src, "ply.cpp"), "-o", exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
 
+    from oracle import ref as _r
+    reference = _r.Ref() if _r.have_ref() else None
+
     def parse(path):
         out = subprocess.run([exe, str(path)], capture_output=True, text=True, timeout=60).stdout.split("\n")
-        if out[0].startswith("fail"):
-            return None
-        n = int(out[0].split()[1])
-        return np.array([[float(x) for x in l.split()] for l in out[1:1 + n]], dtype=np.float32).reshape(n, 6)
+        got = None
+        if not out[0].startswith("fail"):
+            n = int(out[0].split()[1])
+            got = np.array([[float(x) for x in l.split()] for l in out[1:1 + n]], dtype=np.float32).reshape(n, 6)
+        # f1 pin: the reference's own reader (load_ply_cloud, PLADE/util.cpp:1505-1546 over rply) on the same file
+        if reference is not None and os.path.exists(str(path)):
+            want = reference.load_ply_ref(str(path))
+            if got is None:
+                assert want is None or len(want) == 0, "the reference reads a file the product rejects: %s" % path
+            else:
+                assert want is not None and np.array_equal(got, want), "PLY contents differ from the reference's reader: %s" % path
+        return got
 
     rng = np.random.default_rng(4)
     a = rng.normal(size=(257, 6)).astype(np.float32)
@@ -441,6 +471,71 @@ def test_ply_ingest_formats_and_errors(tmp_path):
     p = tmp_path / "empty.ply"
     p.write_bytes(("ply\nformat binary_little_endian 1.0\nelement vertex 0\n%send_header\n" % hdr6).encode())
     assert parse(p) is None
+
+
+def test_plane_frame_and_parameters_bit_exact_vs_reference(ref, poly_pair, poly_stages):
+    """Row a6: planefit.h (frame_from_normal, plane_uv -- the inline functions refine_candidate_dev calls on the device,
+    here through their host build in the product library) against the reference's HyperplaneCoordinateSystem::FromNormal
+    (R/GfxTL/HyperplaneCoordinateSystem.h:81-93) and PlanePrimitiveShape::Parameters (R/PlanePrimitiveShape.h:97-109):
+    frame axes and (u, v) bit for bit, on the reference's planes, on random planes and on the near-z branch."""
+    import plade_b200
+    rng = np.random.default_rng(1)
+    cloud = poly_pair["tgt"]
+    off, idx, par = poly_stages["t_off"], poly_stages["t_idx"], poly_stages["t_par"].reshape(-1, 4)
+    for k in range(len(off) - 1):
+        n0 = par[k, :3].astype(np.float32)
+        pos0 = (-par[k, 3] * n0).astype(np.float32)
+        pts = cloud[idx[off[k]:off[k + 1]], :3]
+        a, b = ref.plane_parameters(n0, pos0, pts), plade_b200.plane_parameters(n0, pos0, pts)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    for t in range(1500):
+        n0 = rng.normal(size=3).astype(np.float32)
+        n0 /= np.linalg.norm(n0)
+        if t % 10 == 0:                       # |nx|, |ny| < 1/64: the other branch of the arbitrary-axis rule
+            n0[:2] *= np.float32(0.005)
+            n0 /= np.linalg.norm(n0)
+        pos0 = rng.normal(size=3).astype(np.float32)
+        pts = rng.normal(size=(4, 3)).astype(np.float32)
+        a, b = ref.plane_parameters(n0, pos0, pts), plade_b200.plane_parameters(n0, pos0, pts)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_plane_ls_fit_vs_reference(ref, poly_pair, poly_stages, synth_stages):
+    """Row a8: the least-squares refit as the kernels evaluate it (member sums in double, float mean, float Jacobi:
+    planefit.h fit_plane_from_cov) against Plane::LeastSquaresFit (R/Plane.h:66-74 -> GfxTL Mean / CovarianceMatrix /
+    Jacobi / Plane::Fit).  The reference sums sequentially in float, so the bar is 0.05 deg / 1e-5 on the position --
+    and the SIGN of the normal, which PLADE never corrects afterwards, must be the same."""
+    import plade_b200
+    rng = np.random.default_rng(2)
+    n_checked = 0
+    for cloud, g in ((poly_pair["tgt"], poly_stages), (synth_small_tgt(), synth_stages)):
+        off, idx = g["t_off"], g["t_idx"]
+        for k in range(len(off) - 1):
+            mem = idx[off[k]:off[k + 1]]
+            for sub in (mem, rng.choice(mem, max(50, len(mem) // 3), replace=False)):
+                ok_r, n_r, p_r = ref.plane_ls_fit(cloud, sub)
+                ok_g, n_g, p_g = plade_b200.plane_ls_fit(cloud[sub, :3])
+                assert ok_r and ok_g
+                dn = float(np.dot(n_r, n_g))
+                assert dn > 0, "normal sign differs"
+                assert np.degrees(np.arccos(min(1.0, dn))) <= 0.05
+                assert np.abs(p_r - p_g).max() <= 1e-5
+                n_checked += 1
+    assert n_checked >= 30
+
+
+def test_reference_detection_curve_is_what_detect_margin_assumes():
+    """Params::detect_margin = 1.25 rests on a measurement of the reference's detector (tests/golden/make_golden_seed_sweep.py,
+    eight seeds per cloud and min_support): planes whose support is below 1.25 x min_support are found in a minority of the
+    runs, planes above 1.6 x practically always.  The committed curve must say so."""
+    import json
+    doc = json.load(open(os.path.join(ROOT, "tests", "golden", "seed_sweep_ref.json")))
+    rows = doc["detection_curve"]
+    ratio = np.array([r["support"] / r["min_support"] for r in rows])
+    freq = np.array([r["found"] / r["runs"] for r in rows])
+    assert len(rows) >= 60
+    assert freq[ratio < 1.25].mean() <= 0.5
+    assert freq[ratio >= 1.6].mean() >= 0.9
 
 
 def test_product_never_touches_the_oracle():
