@@ -29,6 +29,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "registration pairs/sec (2M-pt clouds)"
+REF_BUILD = "g++ -O3 -march=x86-64-v3 (oracle/_ref_fast: the timing build of the reference's own sources)"
+REF_BUILD_PARITY = "g++ -O2 -ffp-contract=off (oracle/_ref: the parity build; the timing build is missing)"
 SEED = 20240611
 
 
@@ -109,11 +111,19 @@ def pinned_copy(a):
     return t, v
 
 
+def shared_config(n_points, nt, ns):
+    """the `config` object: identical in both arms (the driver compares them)"""
+    return {"workload": workload_name(n_points, nt, ns), "points_per_cloud": int(n_points), "planes": 20, "scene_seed": SEED}
+
+
+PAIRS_PER_GPU = 4      # pairs registered concurrently per GPU and step: the same at every N
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import plade_b200
-    from plade_b200.synth import transform_error, perturbed_hypotheses
+    from plade_b200.synth import make_pair, transform_error, perturbed_hypotheses
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -136,16 +146,29 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     tgt, src, gt = workload(args.points)
     diag = float(np.linalg.norm(np.ptp(tgt[:, :3], axis=0)))
-    # Pairs are independent, and one registration is a chain of small launches with host decisions in between
-    # (the RANSAC accept loop), so ONE pair cannot fill 148 SMs: a step registers B pairs per GPU concurrently,
-    # one context (own streams + scratch) and one host thread per pair — the batch mode of the reference CLI
-    # (PLADE/main.cpp:97-159, plade_register_batch).  B is fixed per run and reported in `config`.
+    # Pairs are independent, and one registration is a chain of dependent launches (the RANSAC rounds), so ONE pair cannot
+    # fill 148 SMs: a step registers B pairs per GPU concurrently, one context (own streams + scratch) and one host thread
+    # per pair -- the batch mode of the reference CLI (PLADE/main.cpp:97-159, plade_register_batch).  B is the same at
+    # every N; when the box has fewer cores than waiting host threads the waits block instead of spinning.
     cores = os.cpu_count() or 1
-    B = args.pairs_per_gpu if args.pairs_per_gpu > 0 else max(1, min(4, cores // (2 * world)))
+    B = args.pairs_per_gpu if args.pairs_per_gpu > 0 else PAIRS_PER_GPU
+    host_threads = 3 * B * world          # per pair: the calling thread + the two plane-extraction lanes
+    blocking = host_threads > cores
     ctxs = [plade_b200.Context(local) for _ in range(B)]
+    for kv in args.param:
+        for c in ctxs:
+            c.set_param(kv.split("=")[0], float(kv.split("=")[1]))
     ctx = ctxs[0]
+    if blocking:
+        ctx.set_param("blocking_sync", 1)          # process-wide
     quiet = open(os.devnull, "w")
     saved = os.dup(1)
 
@@ -153,15 +176,21 @@ def run_ours(args):
         sys.stdout.flush()
         os.dup2(quiet.fileno() if on else saved, 1)
 
+    step_no = [0]
+
     def run_concurrent(fn, reps, timed):
-        """every context runs fn(k) `reps` times on its own host thread; returns (max device ms over contexts, wall ms, last results)"""
-        dev_ms, last = [0.0] * B, [None] * B
+        """every context runs fn(k) `reps` times on its own host thread, each registration with its own RANSAC seed;
+        returns (max device ms over contexts, wall ms, every result)"""
+        dev_ms, res = [0.0] * B, [[] for _ in range(B)]
+        base = step_no[0]
+        step_no[0] += reps
 
         def work(k):
             if timed:
                 ctxs[k].timer_start()
-            for _ in range(reps):
-                last[k] = fn(k)
+            for r in range(reps):
+                ctxs[k].set_param("seed", SEED + 1000 * rank + 100 * k + base + r)
+                res[k].append(fn(k))
             if timed:
                 dev_ms[k] = ctxs[k].timer_stop_ms()
         th = [threading.Thread(target=work, args=(k,)) for k in range(B)]
@@ -170,7 +199,13 @@ def run_ours(args):
             t.start()
         for t in th:
             t.join()
-        return max(dev_ms), (time.perf_counter() - t0) * 1e3, last
+        return max(dev_ms), (time.perf_counter() - t0) * 1e3, [r for rr in res for r in rr]
+
+    def judge(results):
+        errs = [transform_error(T, gt, diag) for ok, T in results if ok]
+        landed = sum(1 for (r, t) in errs if r <= 0.5 and t <= 5e-3)
+        return {"registrations": len(results), "ok": sum(1 for ok, _ in results if ok), "within_0.5deg_5e-3": landed,
+                "max_rot_err_deg": max([e[0] for e in errs], default=None), "max_trans_err_rel_diag": max([e[1] for e in errs], default=None)}
 
     # ---- device-resident throughput ("value") ---------------------------------------------------------
     resident = [(c.upload(tgt), c.upload(src)) for c in ctxs]
@@ -179,25 +214,25 @@ def run_ours(args):
     hush(False)
     barrier()
     l0 = sum(c.launch_count() for c in ctxs)
+    ctx.set_param("kernel_clock", 1)      # context 0 also times its own kernels with CUDA events on their streams (the live roofline figures)
     with ClockSampler(local) as clocks:
         hush(True)
-        ms, wall_ms, last = run_concurrent(lambda k: ctxs[k].register_resident(*resident[k]), args.steps, True)
+        ms, wall_ms, results = run_concurrent(lambda k: ctxs[k].register_resident(*resident[k]), args.steps, True)
         hush(False)
     barrier()
+    ctx.set_param("kernel_clock", 0)
     launches = sum(c.launch_count() for c in ctxs) - l0
-    ok, T = last[0]
-    ok = all(r[0] for r in last)
     stage = ctx.stage_times()        # context 0, last step
     k1 = ctx.kernel_times("score_candidates")
     k1r, k1b = ctx.kernel_times("refine_cluster"), ctx.kernel_times("band_compact")
     k5_in = ctx.kernel_times("verify")
     t_step = max_over_ranks(ms / 1e3 / args.steps)
     value = world * B / t_step
-    rot, tr = max(transform_error(r[1], gt, diag) for r in last)
+    verdict = judge(results)
     if args.profile:     # short run under ncu: never a bench value
         if rank == 0:
-            emit({"profile_run": True, "ms_per_step": t_step * 1e3, "pairs_per_step": B, "gpu_launches": int(launches), "ok": bool(ok),
-                  "rot_err_deg": rot, "stage_ms": {k: 1e3 * v for k, v in stage.items() if not k.startswith("verify_")}})
+            emit({"profile_run": True, "ms_per_step": t_step * 1e3, "pairs_per_step": B, "gpu_launches": int(launches), "result": verdict,
+                  "stage_ms": {k: 1e3 * v for k, v in stage.items() if not k.startswith("verify_")}})
         return
 
     # ---- end to end through the C ABI with host buffers ("e2e") -------------------------------------------
@@ -208,116 +243,122 @@ def run_ours(args):
     hush(False)
     barrier()
     hush(True)
-    ms_e, wall_e, last_e = run_concurrent(lambda k: ctxs[k].register_clouds(ptgt, psrc), args.steps, True)
+    ms_e, wall_e, results_e = run_concurrent(lambda k: ctxs[k].register_clouds(ptgt, psrc), args.steps, True)
     hush(False)
     barrier()
     t_e2e = max_over_ranks(ms_e / 1e3 / args.steps)
-    rot_e, tr_e = max(transform_error(r[1], gt, diag) for r in last_e)
+    verdict_e = judge(results_e)
     for k in range(1, B):        # the remaining legs use context 0 only
         ctxs[k].free_cloud(resident[k][0]); ctxs[k].free_cloud(resident[k][1])
         ctxs[k].close()
     ht, hs = resident[0]
+    ctx.free_cloud(ht)
+    ctx.free_cloud(hs)
+    ctx.set_param("seed", SEED)
 
-    # ---- hypothesis-sharded verification + NCCL max-allreduce (BASELINE config 4 shape) -----------------------
-    spacing = ctx.average_spacing(src)
-    leaf = 4 * spacing
-    ds_t, ds_s = ctx.voxel_downsample(tgt[:, :3], leaf), ctx.voxel_downsample(src[:, :3], leaf)
-    H = args.hypotheses
-    Rh, Th, true_idx = perturbed_hypotheses(gt, H, seed=7)
-    rc, c_src, whd, _ = ctx.bounding_box(ds_s)
-    cen = (np.einsum("hij,j->hi", Rh, c_src) + Th).astype(np.float32)
-    ball = float(max(whd) / 2)
-    mine = np.arange(rank, H, world)
-    ctx.verify_upload(ds_s, ds_t, leaf)
-    key_t = torch.zeros(1, dtype=torch.int64, device="cuda")
-
-    def sharded_once():
-        counts, kms = ctx.verify_resident(Rh[mine], Th[mine], cen[mine], ball, leaf)
-        b = int(np.argmax(counts)) if len(counts) else 0
-        # packed key {count, ~index}: max picks the best count, ties -> lowest hypothesis index
-        key = (int(counts[b]) << 32) | (0xFFFFFFFF - int(mine[b])) if len(counts) else 0
-        key_t.fill_(key)
+    # ---- BASELINE config 4: 10 K hypotheses on the 5 M-point scene, sharded over the ranks; the collective is the library's own
+    # ncclAllReduce(ncclUint64, ncclMax) (plade_shard_init_nccl + plade_verify_sharded): torch only carries the unique id ------------
+    c4 = None
+    if not args.skip_config4:
+        t4, s4, gt4 = make_pair(n_points=args.config4_points, n_planes=24, seed=SEED)
+        spacing = ctx.average_spacing(s4)
+        leaf = 4 * spacing
+        ds_t, ds_s = ctx.voxel_downsample(t4[:, :3], leaf), ctx.voxel_downsample(s4[:, :3], leaf)
+        H = args.hypotheses
+        Rh, Th, true_idx = perturbed_hypotheses(gt4, H, seed=7)
+        rc, c_src, whd, _ = ctx.bounding_box(ds_s)
+        cen = (np.einsum("hij,j->hi", Rh, c_src) + Th).astype(np.float32)
+        ball = float(max(whd) / 2)
+        ctx.verify_upload(ds_s, ds_t, leaf)
         if world > 1:
-            dist.all_reduce(key_t, op=dist.ReduceOp.MAX)
-        k = int(key_t.item())
-        return 0xFFFFFFFF - (k & 0xFFFFFFFF), k >> 32, kms
-
-    for _ in range(2):
-        sharded_once()
-    barrier()
-    t0 = time.perf_counter()
-    vk = []
-    for _ in range(3):
-        best_idx, best_cnt, kms = sharded_once()
-        vk.append(kms)
-    torch.cuda.synchronize()
-    t_sh = max_over_ranks((time.perf_counter() - t0) / 3)
-    k_sh = max_over_ranks(float(np.mean(vk)))
+            uid = [plade_b200.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.shard_init_nccl(uid[0], rank, world)
+        for _ in range(2):
+            ctx.verify_sharded(Rh, Th, cen, ball, leaf)
+        barrier()
+        dms = []
+        t0 = time.perf_counter()
+        for _ in range(3):
+            best_idx, best_cnt, d_ms = ctx.verify_sharded(Rh, Th, cen, ball, leaf)
+            dms.append(d_ms)
+        t_sh = max_over_ranks((time.perf_counter() - t0) / 3)
+        k_sh = max_over_ranks(float(np.mean(dms)))
+        if world > 1:
+            ctx.shard_finalize()
+        nsk, ntk = int(len(ds_s)), int(len(ds_t))
+        c4 = {"scene": "synthetic %d-pt scene, 24 planes (make_pair seed %d): %d-pt target vs %d-pt source" % (args.config4_points, SEED, len(t4), len(s4)),
+              "hypotheses": H, "src_ds_points": nsk, "tgt_ds_points": ntk, "ms": t_sh * 1e3, "device_ms_max_rank": k_sh, "hyps_per_s": H / t_sh,
+              "scaling": "strong", "collective": "ncclAllReduce(1 x ncclUint64, ncclMax) inside libplade_b200 (plade_verify_sharded)" if world > 1 else "none (1 rank)",
+              "best_index": int(best_idx), "best_count": int(best_cnt), "best_is_true_transform": bool(best_idx == true_idx),
+              "algorithmic_bytes_per_rank": (H // world) * 16.0 * nsk + 16.0 * ntk,
+              "achieved_gbs_per_gpu": ((H / world) * 16.0 * nsk + 16.0 * ntk) / (k_sh / 1e3) / 1e9 if k_sh > 0 else None}
 
     peak, peak_src = measured_peak()
-    # roofline of the kernel BASELINE.json names for the ncu capture (K5, hypothesis verification), at the config-4
-    # shape: the launches of the sharded leg above, each timed with CUDA events on the context's stream
-    nsk, ntk = int(len(ds_s)), int(len(ds_t))
-    Hk = int(len(mine))
-    alg_bytes = Hk * 16.0 * nsk + 16.0 * ntk
-    k5_ms = float(np.mean(vk))
-    achieved = alg_bytes / (k5_ms / 1e3) / 1e9 if k5_ms > 0 else 0.0
-    traffic, traffic_shape = None, None        # dram bytes of one K5 launch from the committed ncu --set full capture
-    tp = os.path.join(ROOT, "profiles", "k5_traffic.json")
-    if os.path.exists(tp):
-        try:
-            tj = json.load(open(tp))
-            traffic, traffic_shape = tj.get("dram_bytes_per_launch"), tj.get("shape")
-        except Exception:
-            traffic = None
 
     def kernel_line(name, kt, share_of_ms):
         per = kt["ms"] / kt["launches"] if kt["launches"] else 0.0
         gbs = kt["algorithmic_bytes"] / (kt["ms"] / 1e3) / 1e9 if kt["ms"] > 0 else 0.0
-        return {"kernel": name, "launches_per_registration": kt["launches"], "ms_per_registration": kt["ms"], "avg_launch_ms": per,
-                "algorithmic_bytes_per_registration": kt["algorithmic_bytes"], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak if peak else None,
+        return {"kernel": name, "launches": kt["launches"], "ms": kt["ms"], "avg_launch_ms": per,
+                "algorithmic_bytes": kt["algorithmic_bytes"], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak if peak else None,
                 "share_of_registration": kt["ms"] / share_of_ms if share_of_ms > 0 else None}
-    reg_ms = 1e3 * (stage["planes"] + stage["total"])
+    # kernels of context 0 in the LAST timed step (CUDA events around every launch, on the launching stream, while the other
+    # contexts share the GPU); the two plane-extraction lanes of a registration run concurrently, so shares can add up to > 1
+    reg_ms_total = ms / args.steps
+    lines = [kernel_line("accept_loop_kernel (K1b-d: per pool entry a band pass of the 16-CTA cluster over the cloud + the acceptance chain "
+                         "(flags, raster, components, select, covariance) + accept; one launch per scoring round)", k1r, reg_ms_total),
+             kernel_line("score_candidates_kernel + score_points_kernel (K1a: 16384 candidates x 4096 points, then 256 x 65536, per round)", k1, reg_ms_total),
+             kernel_line("band_compact_kernel (host-driven fallback path only)", k1b, reg_ms_total),
+             kernel_line("verify_kernel (K5) inside the registration (H = %d surviving hypotheses)" % int(stage["verify_h"]), k5_in, reg_ms_total)]
+    dom = max(lines[:2], key=lambda l: l["ms"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if tj.get("kernel", "") in dom["kernel"]:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": dom["kernel"], "bound": "hbm",
+                "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["achieved_gbs"] / peak if peak else None, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"] / dom["launches"] if dom["launches"] else None,
+                "launch_ms": dom["avg_launch_ms"], "share_of_step": dom["share_of_registration"],
+                "note": "the dominant kernel of the timed step by device time (context 0, last timed step, live CUDA events); algorithmic bytes per "
+                        "SURVEY.md 8(d): 20 B per cloud point for every band pass + 28 B per band point per evaluation (accept loop), 28 B per "
+                        "subsample point per pass (K1a).  Both are latency / issue bound on a working set that lives in L2 -- see DESIGN.md section 4"}
     out = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.points, len(tgt), len(src)), "pairs_per_step_per_gpu": B,
-                   "concurrency": "%d contexts (one host thread + CUDA streams each) per GPU register %d pairs concurrently per step" % (B, B),
-                   "parallelism": "pairs sharded over GPUs, no data-path collective" if world > 1 else "single GPU",
-                   "host_cores": cores,
-                   "l2": "per-step working set (%d pairs x 2 clouds x 2 float4 streams = %d MB + sort scratch) exceeds the 126 MB L2" % (B, B * (len(tgt) + len(src)) * 32 // 2**20)},
+        "config": shared_config(args.points, len(tgt), len(src)),
+        "run": {"pairs_per_step_per_gpu": B,
+                "concurrency": "%d contexts (one host thread + two plane-extraction lanes each) per GPU register %d pairs concurrently per step; "
+                               "every registration has its own RANSAC seed" % (B, B),
+                "parallelism": "pairs sharded over GPUs, no data-path collective" if world > 1 else "single GPU",
+                "host_cores": cores, "host_threads": host_threads, "blocking_sync": bool(blocking),
+                "l2": "per-step working set (%d pairs x 2 clouds x 2 float4 streams = %d MB + sort scratch) exceeds the 126 MB L2" % (B, B * (len(tgt) + len(src)) * 32 // 2**20)},
         "e2e": {"value": world * B / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(B * (len(tgt) + len(src)) * 24), "d2h_bytes_per_step": 64 * B,
-                "ms_per_step": t_e2e * 1e3, "wall_ms_per_step": wall_e / args.steps, "rot_err_deg": rot_e, "trans_err_rel": tr_e},
+                "ms_per_step": t_e2e * 1e3, "wall_ms_per_step": wall_e / args.steps, "result": verdict_e},
         "wall_ms_per_step": wall_ms / args.steps,
         "latency_ms_per_pair": ms / args.steps,
-        "gpu_launches": int(launches),
+        "gpu_launches": int(sum_over_ranks(float(launches))),
         "clocks": clocks.summary(),
-        "result": {"ok": bool(ok), "rot_err_deg": rot, "trans_err_rel_diag": tr},
+        "result": verdict,
         "stage_ms": {k: 1e3 * v for k, v in stage.items() if not k.startswith("verify_")},
-        "roofline": {"kernel": "verify_kernel (K5 hypothesis verification) at the 10K-hypothesis shape of BASELINE config 4", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "traffic_shape": traffic_shape, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k5_ms,
-                     "shape": {"hypotheses": Hk, "src_ds_points": nsk, "tgt_ds_points": ntk},
-                     "note": "L2-resident working set (ds clouds + grid < 60 MB): DRAM traffic is ~0.1% of peak and the kernel is bound by "
-                             "instruction issue; the HBM figure is the SURVEY.md 8(d) algorithmic-bytes convention"},
-        # the kernels of the timed registration step itself, timed live with CUDA events around every launch (context 0, last step,
-        # while the other contexts' kernels share the GPU; times are summed over the two concurrent lanes of the registration,
-        # so the shares relate kernel time to wall time and can add up to more than 1)
-        "step_kernels": [kernel_line("refine_cluster_kernel (K1b-d; one 16-CTA cluster per candidate: latency-bound, 16 of 148 SMs)", k1r, reg_ms),
-                         kernel_line("band_compact_kernel (HBM streaming pass over all points, once per candidate)", k1b, reg_ms),
-                         kernel_line("score_candidates_kernel + score_points_kernel (K1a; ALU-bound: 16384 candidates x 4096 points, then 256 x 65536, per round)", k1, reg_ms),
-                         kernel_line("verify_kernel (K5) inside the registration (H = %d surviving hypotheses)" % int(stage["verify_h"]), k5_in, reg_ms)],
-        "verify_sharded": {"hypotheses": H, "src_ds_points": int(len(ds_s)), "tgt_ds_points": int(len(ds_t)), "ms": t_sh * 1e3,
-                           "kernel_ms_max_rank": k_sh, "hyps_per_s": H / t_sh, "scaling": "strong", "collective": "ncclAllReduce(max, 1 x i64)" if world > 1 else "none",
-                           "best_index": int(best_idx), "best_count": int(best_cnt), "best_is_true_transform": bool(best_idx == true_idx),
-                           "achieved_gbs": (H * 16.0 * len(ds_s) / world + 16.0 * len(ds_t)) / (k_sh / 1e3) / 1e9 if k_sh > 0 else None},
+        "roofline": roofline,
+        "step_kernels": lines,
     }
+    if c4 is not None:
+        out["config4_verify_sharded"] = c4
+        out["roofline_k5_config4"] = {"kernel": "verify_kernel (K5) at BASELINE config 4: %d hypotheses per rank on the 5 M-point scene" % (c4["hypotheses"] // world),
+                                      "bound": "hbm", "achieved": c4["achieved_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
+                                      "frac": c4["achieved_gbs_per_gpu"] / peak if (peak and c4["achieved_gbs_per_gpu"]) else None,
+                                      "note": "kernel + device-side key + collective, CUDA events on the context stream; L2-resident working set: issue-bound, "
+                                              "the HBM figure is the SURVEY.md 8(d) algorithmic-bytes convention (16 B per hypothesis and source point)"}
     # ---- CPU baseline: the reference's own code on the same pair, rank 0 at N = 1 only --------------------------
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_once(tgt, src, gt, diag)
-    ctx.free_cloud(ht)
-    ctx.free_cloud(hs)
     ctx.close()
     if rank == 0:
         emit(out)
@@ -330,14 +371,14 @@ def cpu_baseline_once(tgt, src, gt, diag):
     from plade_b200.synth import transform_error
     if not oref.have_ref():
         return {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/libplade_ref.so not present on this box"}
-    r = oref.Ref(quiet=True)
+    r = oref.Ref(quiet=True, fast=True)
     r.set_seed(1)
     t0 = time.perf_counter()
     ok, T = r.registration_clouds(tgt, src)
     dt = time.perf_counter() - t0
     rot, tr = transform_error(T, gt, diag)
-    return {"value": 1.0 / dt, "unit": "pairs/s", "cores": 1, "kind": "reference",
-            "sample": "1 full registration(T, target, source) of the same pair by the reference's own sources (oracle/_ref), "
+    return {"value": 1.0 / dt, "unit": "pairs/s", "cores": 1, "kind": "reference", "build": REF_BUILD if r.fast else REF_BUILD_PARITY,
+            "sample": "1 full registration(T, target, source) of the same pair by the reference's own sources (oracle/_ref_fast), "
                       "single thread (the reference has no parallelism); %.1f s" % dt,
             "seconds_per_pair": dt, "ok": bool(ok), "rot_err_deg": rot, "trans_err_rel_diag": tr,
             "host": {"nproc": os.cpu_count()}}
@@ -347,7 +388,7 @@ def _ref_worker(args):
     path, seed = args
     from oracle import ref as oref
     d = np.load(path)
-    r = oref.Ref(quiet=True)
+    r = oref.Ref(quiet=True, fast=True)
     r.set_seed(seed)
     t0 = time.perf_counter()
     ok, T = r.registration_clouds(d["tgt"], d["src"])
@@ -390,8 +431,9 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.points, len(tgt), len(src)), "pairs_per_step": workers},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": workers, "kind": "reference",
+        "config": shared_config(args.points, len(tgt), len(src)),
+        "run": {"pairs_per_step": workers, "host_cores": os.cpu_count()},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": workers, "kind": "reference", "build": REF_BUILD if oref.have_ref_fast() else REF_BUILD_PARITY,
                          "sample": "each step = %d concurrent single-threaded registration() calls of the reference's own sources "
                                    "(oracle/_ref) on the same pair, one per host core used" % workers,
                          "seconds_per_pair_single_thread": float(np.mean([r[2] for r in res])), "host": {"nproc": os.cpu_count()}},
@@ -425,8 +467,11 @@ def main():
     ap.add_argument("--hypotheses", type=int, default=10000)
     ap.add_argument("--ref-workers", type=int, default=0, help="concurrent single-threaded reference processes (0 = every host core, at most 64)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--pairs-per-gpu", type=int, default=0, help="pairs registered concurrently per GPU and step (0 = min(4, cores / (2 x GPUs)))")
+    ap.add_argument("--pairs-per-gpu", type=int, default=0, help="pairs registered concurrently per GPU and step (0 = 4, the same at every N)")
+    ap.add_argument("--skip-config4", action="store_true", help="skip the sharded verification of BASELINE config 4")
+    ap.add_argument("--config4-points", type=int, default=5_000_000)
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up, no e2e / sharded / cpu arms")
+    ap.add_argument("--param", action="append", default=[], help="name=value passed to plade_set_param on every context (diagnostic runs)")
     args = ap.parse_args()
     if args.impl == "ours" and not args.profile:
         args.warmup = max(args.warmup, 3)

@@ -8,7 +8,8 @@ from plade_b200.synth import make_pair, perturbed_hypotheses
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-tgt, src, gt = make_pair(n_points=n, n_planes=20, seed=20240611)
+planes = int(sys.argv[4]) if len(sys.argv) > 4 else 20
+tgt, src, gt = make_pair(n_points=n, n_planes=planes, seed=20240611)
 ctx = plade_b200.Context()
 leaf = 4 * ctx.average_spacing(src)
 ds_t, ds_s = ctx.voxel_downsample(tgt[:, :3], leaf), ctx.voxel_downsample(src[:, :3], leaf)

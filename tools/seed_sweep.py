@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--maxcand", default="200", help="comma list of max_candidates (the reference's budget is 200)")
     ap.add_argument("--cases", default="")
     ap.add_argument("--batch", type=int, default=0, help="ransac_batch (0: library default)")
+    ap.add_argument("--resume", type=int, default=-1, help="detect_resume (-1: library default)")
     ap.add_argument("--planes", action="store_true", help="also report the plane counts per cloud (runs extract() again)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "seed_sweep.json"))
     a = ap.parse_args()
@@ -63,6 +64,8 @@ def main():
     ctx = plade_b200.Context(0)
     if a.batch:
         ctx.set_param("ransac_batch", a.batch)
+    if a.resume >= 0:
+        ctx.set_param("detect_resume", a.resume)
     doc = {"seeds": seeds, "runs": {}}
     for name, (tgt, src, gt, swapped) in cases().items():
         if a.cases and name not in a.cases.split(","):
