@@ -16,6 +16,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from plyio import write_ply
 
 
+def _make_one(job):
+    k, points, d = job
+    t, s, gt = make_pair(n_points=points, n_planes=20, seed=1000 + k)
+    tp, sp = os.path.join(d, "t%d.ply" % k), os.path.join(d, "s%d.ply" % k)
+    write_ply(tp, t); write_ply(sp, s)
+    return tp, sp, gt, float(np.linalg.norm(np.ptp(t[:, :3], axis=0)))
+
+
 def parse_results(path, n):
     """[(ok, 4x4)] in list order (PLADE/main.cpp:136-147 text format)"""
     out, lines = [], open(path).read().split("\n")
@@ -58,12 +66,12 @@ def main():
     d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     gts, names = [], []
     t0 = time.perf_counter()
-    for k in range(a.pairs):
-        t, s, gt = make_pair(n_points=a.points, n_planes=20, seed=1000 + k)
-        tp, sp = os.path.join(d, "t%d.ply" % k), os.path.join(d, "s%d.ply" % k)
-        write_ply(tp, t); write_ply(sp, s)
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 16)) as pool:
+        made = pool.map(_make_one, [(k, a.points, d) for k in range(a.pairs)])
+    for tp, sp, gt, diag in made:
         names += [tp, sp]
-        gts.append((gt, float(np.linalg.norm(np.ptp(t[:, :3], axis=0)))))
+        gts.append((gt, diag))
     pairs_file = os.path.join(d, "file_pairs.txt")
     open(pairs_file, "w").write("\n".join(names) + "\n")
     print("wrote %d pairs (%.1f GB of PLY) in %.0f s" % (a.pairs, sum(os.path.getsize(n) for n in names) / 1e9, time.perf_counter() - t0), flush=True)
