@@ -39,7 +39,7 @@ namespace plade {
 
 namespace {
 
-constexpr int kCandPerRound = 65536;   // raw 3-point draws per round; ~12 % of them are verified planes (compacted before they are scored)
+constexpr int kCandPerRound = 16384;   // candidates drawn per round
 constexpr int kGenTries = 1;           // draws per candidate slot (see gen_candidates_kernel: more tries were measured and rejected)
 constexpr int kStage1Points = 4096;    // stage 1: every candidate against a small stratified subsample
 constexpr int kStage2Cand = 256;       // stage 2: the best stage-1 candidates ...
@@ -219,12 +219,10 @@ __global__ void gather_sub_kernel(const float4 *__restrict__ pos, const float4 *
 template <int C>
 __global__ void __launch_bounds__(kScoreThreads)
 score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__restrict__ cand, const int *__restrict__ sel, int n_cand,
-                        const int *__restrict__ d_n_cand, float eps, float nthresh, int tiles_per_block, unsigned int *__restrict__ counts) {
+                        float eps, float nthresh, int tiles_per_block, unsigned int *__restrict__ counts) {
   __shared__ __align__(128) float4 buf[2][2 * kScoreTile];
   __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x;
-  if (d_n_cand) n_cand = min(n_cand, *d_n_cand);                  // the compacted list of verified candidates (sel) is this long
-  if (blockIdx.y * (kScoreThreads * C) >= n_cand) return;         // (uniform over the block)
   const int c0 = blockIdx.y * (kScoreThreads * C) + tid;          // this thread's candidates: c0 + k * kScoreThreads
   float4 pl[C];
 #pragma unroll
@@ -326,10 +324,8 @@ constexpr int kRoundCounts2 = kCandPerRound, kRoundNValid = kRoundCounts2 + kSta
               kRoundEnd = kRoundTop + 4 * kStage2Cand;
 static_assert((kRoundTop * 4) % 16 == 0, "selected planes must be float4-aligned");
 __global__ void __launch_bounds__(kSelThreads)
-select_top_kernel(const unsigned int *__restrict__ counts, int n, const int *__restrict__ d_n, const int *__restrict__ sel, int n_forced,
-                  int *__restrict__ out /* kStage2Cand candidate slots */, const float4 *__restrict__ cand,
-                  float4 *__restrict__ cand_top /* the selected planes, in order */) {
-  if (d_n) n = min(n, *d_n);              // counts[] is indexed by position in the compacted list sel[0 .. n)
+select_top_kernel(const unsigned int *__restrict__ counts, int n, int n_forced, int *__restrict__ out /* kStage2Cand */,
+                  const float4 *__restrict__ cand, float4 *__restrict__ cand_top /* the selected planes, in order */) {
   constexpr int K = kStage2Cand, kBins = kStage1Points + 1, kPerThread = (kBins + kSelThreads - 1) / kSelThreads;
   __shared__ unsigned int hist[kSelThreads * kPerThread];
   __shared__ unsigned long long keys[K];
@@ -400,10 +396,9 @@ select_top_kernel(const unsigned int *__restrict__ counts, int n, const int *__r
   // unfilled slots (fewer than K candidates) keep key 0 -> index 0xFFFFFFFF: point them at candidate 0 as the sort did not exist for them
   if (tid < K) {
     const unsigned long long kx = keys[tid];
-    const int pick = kx ? (int) (0xFFFFFFFFu - (unsigned int) (kx & 0xFFFFFFFFull)) : 0;
-    const int slot = (sel && n > 0) ? sel[min(pick, n - 1)] : pick;
-    out[tid] = slot;
-    cand_top[tid] = cand[slot];
+    const int sel = kx ? (int) (0xFFFFFFFFu - (unsigned int) (kx & 0xFFFFFFFFull)) : 0;
+    out[tid] = sel;
+    cand_top[tid] = cand[sel];
   }
 }
 
@@ -776,14 +771,6 @@ __global__ void mark_kernel(const unsigned char *__restrict__ member, int n, int
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && member[i]) assigned[i] = shape_id;
 }
-
-// a candidate slot holds a verified plane (gen_candidates_kernel leaves dist = 3e38 otherwise); the carried pool entries
-// in the first slots always count
-struct IsValidCandidate {
-  const float4 *cand;
-  int n_forced;
-  __device__ bool operator()(const int &c) const { return c < n_forced || cand[c].w < 1.0e38f; }
-};
 
 struct IsUnassigned {
   const int *assigned;
@@ -1340,16 +1327,7 @@ __host__ __device__ inline double rescale_drawn(double drawn, long long size, lo
 // exactly the sequential semantics of the host loop and no host round trip between candidates.  It stops at the first
 // candidate that is no longer eligible, or that needs the host (bitmap beyond the device cap, refit leaving its band).
 __global__ void __launch_bounds__(kRefThreads, 1) accept_loop_kernel(const __grid_constant__ AcceptArgs A) {
-  extern __shared__ __align__(128) float4 band_tile[];      // two stages of kBandBlock positions (kAcceptSmemBytes)
-  __shared__ __align__(8) uint64_t band_bar[2];
   __shared__ int s_nb;
-  unsigned int band_phase[2] = {0u, 0u};
-  if (threadIdx.x == 0) {
-    mbar_init(&band_bar[0], 1);
-    mbar_init(&band_bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
   const RefineArgs &a = A.r;
   const int rank = (int) cluster_rank(), segs = (int) cluster_size(), nthr = (int) blockDim.x, tid = (int) threadIdx.x;
   const bool boss = rank == 0 && tid == 0;
@@ -1373,54 +1351,30 @@ __global__ void __launch_bounds__(kRefThreads, 1) accept_loop_kernel(const __gri
     if (tid == 0) s_nb = 0;
     cluster_barrier();
     if (!ac->go) break;                        // uniform over the cluster
-    // ---- band: the unassigned points within A.band of the candidate plane, block b of the cloud -> segment b % segs.
-    // The positions of a block (4096 x 16 B = 64 KB) arrive by ONE 1-D TMA bulk copy into shared memory, issued a block
-    // ahead (two stages): 128 KB in flight per SM instead of the 64 KB that 1024 threads x 4 register loads can hold, and
-    // no address arithmetic or long-scoreboard stalls in the streaming loop.  `assigned` changes inside this kernel, so it
-    // is read by the threads themselves with L2-coherent loads (4 B per point).
-    {
-      constexpr int kU = kBandBlock / kRefThreads;      // 4 points per thread and block
-      auto issue = [&](long long b, int stage) {        // thread 0
-        const long long first = b * kBandBlock;
-        const unsigned int cnt = (unsigned int) min((long long) kBandBlock, (long long) A.n - first);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the stage's previous readers are done (block barrier)
-        mbar_expect_tx(&band_bar[stage], cnt * 16u);
-        tma_load_1d(band_tile + (size_t) stage * kBandBlock, A.pos + first, cnt * 16u, &band_bar[stage]);
-      };
-      if (tid == 0 && rank < n_blocks) issue(rank, 0);
-      int it = 0;
-      int as_next[kU];      // `assigned` of the NEXT block, requested while the current one is processed
+    // ---- band: the unassigned points within A.band of the candidate plane, block b of the cloud -> segment b % segs
+    for (long long b = rank; b < n_blocks; b += segs) {
+      constexpr int kU = kBandBlock / kRefThreads;      // 4 loads in flight per thread
+      int as[kU];
+      float4 p[kU];
+      const long long base = b * kBandBlock + tid;
 #pragma unroll
-      for (int u = 0; u < kU; ++u) { const long long i = (long long) rank * kBandBlock + tid + u * kRefThreads; as_next[u] = (rank < n_blocks && i < A.n) ? __ldcg(A.assigned + i) : 0; }
-      for (long long b = rank; b < n_blocks; b += segs, ++it) {
-        const int stage = it & 1;
-        if (tid == 0 && b + segs < n_blocks) issue(b + segs, stage ^ 1);
-        int as[kU];
-        const long long base = b * kBandBlock + tid;
+      for (int u = 0; u < kU; ++u) { const long long i = base + u * kRefThreads; as[u] = i < A.n ? __ldcg(A.assigned + i) : 0; }
 #pragma unroll
-        for (int u = 0; u < kU; ++u) as[u] = as_next[u];
+      for (int u = 0; u < kU; ++u) { const long long i = base + u * kRefThreads; p[u] = (i < A.n && as[u] == -1) ? __ldg(A.pos + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
-        for (int u = 0; u < kU; ++u) { const long long i = base + (long long) segs * kBandBlock + u * kRefThreads; as_next[u] = (b + segs < n_blocks && i < A.n) ? __ldcg(A.assigned + i) : 0; }
-        mbar_wait(&band_bar[stage], band_phase[stage]);
-        band_phase[stage] ^= 1u;
-        const float4 *tile = band_tile + (size_t) stage * kBandBlock;
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          const long long i = base + u * kRefThreads;
-          const float4 pt = tile[tid + u * kRefThreads];
-          const float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, pt.x), __fmul_rn(pl.y, pt.y)), __fmul_rn(pl.z, pt.z));
-          const bool in = i < A.n && as[u] == -1 && fabsf(__fsub_rn(pl.w, dp)) < A.band;
-          const unsigned bal = __ballot_sync(0xffffffffu, in);
-          if (!bal) continue;
-          int start = 0;
-          if (lane == 0) start = atomicAdd(&s_nb, __popc(bal));
-          start = __shfl_sync(0xffffffffu, start, 0);
-          if (in) {
-            const int q = sb + start + __popc(bal & ((1u << lane) - 1));
-            a.posB[q] = pt; a.nrmB[q] = __ldg(A.nrm + i); a.idxB[q] = (int) i;
-          }
+      for (int u = 0; u < kU; ++u) {
+        const long long i = base + u * kRefThreads;
+        const float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p[u].x), __fmul_rn(pl.y, p[u].y)), __fmul_rn(pl.z, p[u].z));
+        const bool in = i < A.n && as[u] == -1 && fabsf(__fsub_rn(pl.w, dp)) < A.band;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (!bal) continue;
+        int start = 0;
+        if (lane == 0) start = atomicAdd(&s_nb, __popc(bal));
+        start = __shfl_sync(0xffffffffu, start, 0);
+        if (in) {
+          const int q = sb + start + __popc(bal & ((1u << lane) - 1));
+          a.posB[q] = p[u]; a.nrmB[q] = __ldg(A.nrm + i); a.idxB[q] = (int) i;
         }
-        __syncthreads();      // everyone is done with this stage before it is refilled
       }
     }
     __syncthreads();
@@ -1478,7 +1432,7 @@ struct RansacScratch {
   DevBuf<float4> cand, sub, sub1, cand_top, band_pos, band_nrm;
   DevBuf<int> band_idx;
   DevBuf<int> cidx, cidx_sorted;
-  DevBuf<unsigned char> flag, member, member2, bitmap, mask, cub_tmp, cub_tmp2, bmp_dev, bmp_tmp, mask_dev;
+  DevBuf<unsigned char> flag, member, member2, bitmap, mask, cub_tmp, bmp_dev, bmp_tmp, mask_dev;
   DevBuf<int> cc_lab, cc_cnt, remap;
   DevBuf<float> mean3;
   bool bmp_dev_clean = false;
@@ -1502,7 +1456,6 @@ struct RansacScratch {
   DevBuf<unsigned char> batch_mem;        // accept_loop_kernel: BatchState | AcceptCtl | pool entries | verdicts (see kAcc* offsets)
   PinBuf<unsigned char> batch_host;       // page-locked mirror: upload source and the verdicts' landing zone
 };
-constexpr int kAcceptSmemBytes = 2 * kBandBlock * 16;      // dynamic shared memory of accept_loop_kernel (two TMA stages of positions)
 constexpr int kAcceptMax = 64;            // pool entries one accept_loop_kernel launch can walk (= the pool size)
 constexpr int kAccState = 0, kAccCtl = 64, kAccPool = 128, kAccVerdict = kAccPool + kAcceptMax * (int) sizeof(PoolCand),
               kAccBytes = kAccVerdict + kAcceptMax * (int) sizeof(Verdict);
@@ -1544,8 +1497,6 @@ int refine_cluster_size(int device) {
       if (cudaOccupancyMaxActiveClusters(&n_clusters, refine_cluster_kernel, &cfg) == cudaSuccess && n_clusters >= 1) { size = want; break; }
       cudaGetLastError();
     }
-    // (the dynamic shared memory of the accept loop -- two 64 KB TMA stages -- is a per-device opt-in as well)
-    if (size && cudaFuncSetAttribute(accept_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAcceptSmemBytes) != cudaSuccess) { cudaGetLastError(); size = 0; }
     if (cur != device && cur >= 0) cudaSetDevice(cur);
   }
   cached[device] = size;
@@ -1694,27 +1645,14 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       PLADE_CUDA(cudaMemcpyAsync(cand, hp, sizeof(float4) * pool.size(), cudaMemcpyHostToDevice, s));
     }
     gather_sub_kernel<<<div_up(S1 + S, 256), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S1, round_seed ^ 0x5bd1e995ull, sub1, S, round_seed, sub);
-    // only the verified planes are scored: their slots are compacted (in slot order: deterministic) into sel[0 .. n_sel)
-    int *sel = rs.cidx.ensure(kCandPerRound);
-    int *d_nselc = d_misc + 26;
-    {
-      IsValidCandidate vp{cand, (int) pool.size()};
-      cub::CountingInputIterator<int> iota(0);
-      size_t tbc = 0;
-      cub::DeviceSelect::If(nullptr, tbc, iota, sel, d_nselc, kCandPerRound, vp, s);
-      unsigned char *tmpc = rs.cub_tmp2.ensure(tbc);
-      cub::DeviceSelect::If(tmpc, tbc, iota, sel, d_nselc, kCandPerRound, vp, s);
-      dev.launches.add(2);
-    }
     {
       const int n_tiles = div_up(S1, kScoreTile);
-      // grid for the worst case (a quarter of the draws verified); blocks beyond the compacted list exit at once
-      dim3 grid(n_tiles, kCandPerRound / 4 / (kScoreThreads * kScoreC1));
+      dim3 grid(n_tiles, kCandPerRound / (kScoreThreads * kScoreC1));
       dev.clock.begin(KernelClock::kScoreCandidates, 28.0 * S1, s);     // 28 B per point per pass
-      score_candidates_kernel<kScoreC1><<<grid, kScoreThreads, 0, s>>>(sub1, S1, cand, sel, kCandPerRound / 4, d_nselc, eps, nthresh, 1, counts);
+      score_candidates_kernel<kScoreC1><<<grid, kScoreThreads, 0, s>>>(sub1, S1, cand, nullptr, kCandPerRound, eps, nthresh, 1, counts);
       dev.clock.end(s);
     }
-    select_top_kernel<<<1, kSelThreads, 0, s>>>(counts, kCandPerRound / 4, d_nselc, sel, (int) pool.size(), cidx_sorted, cand, cand_top);
+    select_top_kernel<<<1, kSelThreads, 0, s>>>(counts, kCandPerRound, (int) pool.size(), cidx_sorted, cand, cand_top);
     dev.clock.begin(KernelClock::kScoreCandidates, 28.0 * S, s);
     score_points_kernel<<<div_up(S, 256), 256, 0, s>>>(sub, S, cand, cidx_sorted, eps, nthresh, counts2);
     dev.clock.end(s);
@@ -1724,7 +1662,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     PLADE_CUDA(cudaMemcpyAsync(h_round, counts2, sizeof(unsigned int) * (kRoundEnd - kRoundCounts2), cudaMemcpyDeviceToHost, s));
     stream_sync(s);
     const unsigned int *h_counts = h_round;
-    const int n_valid = std::min((int) h_round[kRoundNValid - kRoundCounts2], kCandPerRound / 4);      // verified planes that were scored this round
+    const int n_valid = (int) h_round[kRoundNValid - kRoundCounts2];
     const float4 *h_cand = reinterpret_cast<const float4 *>(h_round + (kRoundTop - kRoundCounts2));
     mark("ransac_score_round");
     drawn += n_valid;
@@ -1819,7 +1757,6 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
         aa.band = kBandMul * eps3;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(csize); cfg.blockDim = dim3(kRefThreads); cfg.stream = s;
-        cfg.dynamicSmemBytes = kAcceptSmemBytes;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

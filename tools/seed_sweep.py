@@ -50,9 +50,9 @@ class Quiet:
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--margins", default="1.25")
+    ap.add_argument("--margins", default="2.0", help="comma list of detect_margin values (library default 2.0; 1.0 = the reference's literal rule)")
     ap.add_argument("--seeds", default="1,2,3,4,5,6,7,8")
-    ap.add_argument("--maxcand", default="200", help="comma list of max_candidates (the reference's budget is 200)")
+    ap.add_argument("--maxcand", default="1000", help="comma list of max_candidates (library default 1000; the reference's budget is 200)")
     ap.add_argument("--cases", default="")
     ap.add_argument("--batch", type=int, default=0, help="ransac_batch (0: library default)")
     ap.add_argument("--resume", type=int, default=-1, help="detect_resume (-1: library default)")
