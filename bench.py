@@ -50,12 +50,14 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, enabled=True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:      # one sampler per box is enough: NVML queries from 8 ranks at once stall each other's launches
+            return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -133,6 +135,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.pin_cores and world > 1 and hasattr(os, "sched_setaffinity"):
+        # every rank keeps to its own share of the host cores (no migration between the ranks' threads)
+        allc = sorted(os.sched_getaffinity(0))
+        per = max(1, len(allc) // world)
+        os.sched_setaffinity(0, set(allc[local * per:(local + 1) * per]))
 
     def barrier():
         torch.cuda.synchronize()
@@ -158,17 +165,17 @@ def run_ours(args):
     # fill 148 SMs: a step registers B pairs per GPU concurrently, one context (own streams + scratch) and one host thread
     # per pair -- the batch mode of the reference CLI (PLADE/main.cpp:97-159, plade_register_batch).  B is the same at
     # every N; when the box has fewer cores than waiting host threads the waits block instead of spinning.
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)      # cores this process may use
     B = args.pairs_per_gpu if args.pairs_per_gpu > 0 else PAIRS_PER_GPU
     host_threads = 3 * B * world          # per pair: the calling thread + the two plane-extraction lanes
-    blocking = host_threads > cores
+    blocking = (1 if host_threads > cores else 0) if args.blocking_sync < 0 else int(args.blocking_sync)      # 0 spin, 1 blocking event, 2 poll + yield
     ctxs = [plade_b200.Context(local) for _ in range(B)]
     for kv in args.param:
         for c in ctxs:
             c.set_param(kv.split("=")[0], float(kv.split("=")[1]))
     ctx = ctxs[0]
     if blocking:
-        ctx.set_param("blocking_sync", 1)          # process-wide
+        ctx.set_param("blocking_sync", blocking)          # process-wide
     quiet = open(os.devnull, "w")
     saved = os.dup(1)
 
@@ -215,7 +222,7 @@ def run_ours(args):
     barrier()
     l0 = sum(c.launch_count() for c in ctxs)
     ctx.set_param("kernel_clock", 1)      # context 0 also times its own kernels with CUDA events on their streams (the live roofline figures)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=(rank == 0)) as clocks:
         hush(True)
         ms, wall_ms, results = run_concurrent(lambda k: ctxs[k].register_resident(*resident[k]), args.steps, True)
         hush(False)
@@ -336,7 +343,7 @@ def run_ours(args):
                 "concurrency": "%d contexts (one host thread + two plane-extraction lanes each) per GPU register %d pairs concurrently per step; "
                                "every registration has its own RANSAC seed" % (B, B),
                 "parallelism": "pairs sharded over GPUs, no data-path collective" if world > 1 else "single GPU",
-                "host_cores": cores, "host_threads": host_threads, "blocking_sync": bool(blocking),
+                "host_cores": cores, "host_threads": host_threads, "wait_mode": ["spin", "blocking event", "poll + yield"][blocking], "blocking_sync": bool(blocking),
                 "l2": "per-step working set (%d pairs x 2 clouds x 2 float4 streams = %d MB + sort scratch) exceeds the 126 MB L2" % (B, B * (len(tgt) + len(src)) * 32 // 2**20)},
         "e2e": {"value": world * B / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(B * (len(tgt) + len(src)) * 24), "d2h_bytes_per_step": 64 * B,
                 "ms_per_step": t_e2e * 1e3, "wall_ms_per_step": wall_e / args.steps, "result": verdict_e},
@@ -469,6 +476,8 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--pairs-per-gpu", type=int, default=0, help="pairs registered concurrently per GPU and step (0 = 4, the same at every N)")
     ap.add_argument("--skip-config4", action="store_true", help="skip the sharded verification of BASELINE config 4")
+    ap.add_argument("--pin-cores", type=int, default=0, help="1: with N > 1 ranks, every rank keeps to its own 1/N of the host cores")
+    ap.add_argument("--blocking-sync", type=int, default=-1, help="-1: block instead of spinning when host threads > cores; 0 / 1: force")
     ap.add_argument("--config4-points", type=int, default=5_000_000)
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up, no e2e / sharded / cpu arms")
     ap.add_argument("--param", action="append", default=[], help="name=value passed to plade_set_param on every context (diagnostic runs)")

@@ -126,7 +126,7 @@ int plade_set_param(plade_ctx *ctx, const char *name, double v) {
   else if (n == "detect_margin") p.detect_margin = v;
   else if (n == "ransac_batch") p.ransac_batch = (int) v;
   else if (n == "detect_resume") p.detect_resume = (int) v;
-  else if (n == "blocking_sync") set_blocking_sync(v != 0);       // process-wide, see stream_sync
+  else if (n == "blocking_sync") set_blocking_sync((int) v);       // process-wide, see stream_sync
   else if (n == "kernel_clock") { ctx->reg->dev.clock.enabled = ctx->reg->dev2.clock.enabled = v != 0; }
   else if (n == "max_candidates") p.max_candidates = (int) v;
   else if (n == "descriptor_radius") p.descriptor_radius = v;

@@ -69,10 +69,10 @@ struct PinBuf {
 
 // Wait for a stream.  Spinning (cudaStreamSynchronize) has the lowest wake-up latency and is the default; with more host
 // threads than cores (several pairs in flight per GPU x several GPUs per box) the waiting threads must yield instead:
-// plade_set_param(ctx, "blocking_sync", 1) or PLADE_BLOCKING_SYNC=1 switches every wait of the process to a blocking
-// event (cudaEventBlockingSync).  Defined in pipeline.cpp.
+// plade_set_param(ctx, "blocking_sync", 1 | 2) or PLADE_BLOCKING_SYNC switches every wait of the process to a blocking
+// event (1: cudaEventBlockingSync) or to polling with sched_yield between the polls (2).  Defined in pipeline.cpp.
 void stream_sync(cudaStream_t s);
-void set_blocking_sync(bool on);
+void set_blocking_sync(int mode);      // 0 = spin (cudaStreamSynchronize), 1 = blocking event, 2 = poll + sched_yield
 
 inline int div_up(long long a, long long b) { return (int) ((a + b - 1) / b); }
 

@@ -10,6 +10,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <sys/types.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 // Eigen's default operator<< (IOFormat(): StreamPrecision, columns separated by one space, rows by
 // newline, every coefficient right-aligned to the widest one) as PLADE/main.cpp:86 prints the 4x4.
@@ -141,7 +144,17 @@ int main(int argc0, char **argv0) {
     }
     if (file_pair.size() == 2) { tf.push_back(file_pair[0]); sf.push_back(file_pair[1]); }
   }
-  int n_dev = plade_device_count();
+  // The parent process never touches CUDA: with several GPUs the pairs are split over ONE CHILD PROCESS PER GPU (pair p ->
+  // GPU p mod n), because creating the CUDA contexts of 8 GPUs inside one process is serialised by the driver and costs more
+  // than registering 64 pairs does; separate processes bring their GPUs up in parallel (PLADE_CLI_FORK=0: one process).
+  // The device count comes from a short-lived probe child for the same reason (fork after CUDA initialisation is not allowed).
+  int n_dev = 0;
+  {
+    const pid_t probe = fork();
+    if (probe == 0) _exit(std::min(plade_device_count(), 255));
+    int status = 0;
+    if (probe > 0 && waitpid(probe, &status, 0) == probe && WIFEXITED(status)) n_dev = WEXITSTATUS(status);
+  }
   if (n_dev < 1) { std::cerr << "no usable CUDA device (plade_b200 has no CPU fallback)" << std::endl; return EXIT_FAILURE; }
   if (const char *e = getenv("PLADE_DEVICES")) n_dev = std::max(1, std::min(n_dev, atoi(e)));
   // one registration cannot fill a B200 (it is a chain of small launches with host decisions in between), so every
@@ -149,14 +162,67 @@ int main(int argc0, char **argv0) {
   int per_gpu = std::max(1, std::min(4, (int) std::thread::hardware_concurrency() / (2 * n_dev)));
   if (const char *e = getenv("PLADE_WORKERS_PER_GPU")) per_gpu = std::max(1, std::min(16, atoi(e)));
   const int n = (int) tf.size();
-  std::vector<int> devices;
-  for (int w = 0; w < per_gpu; ++w) for (int g = 0; g < n_dev; ++g) devices.push_back(g);
-  if ((int) devices.size() > std::max(n, 1)) devices.resize(std::max(n, 1));
   std::vector<const char *> tp(n), sp(n);
   for (int i = 0; i < n; ++i) { tp[i] = tf[i].c_str(); sp[i] = sf[i].c_str(); }
   std::vector<float> Ts(16 * (size_t) std::max(n, 1));
   std::vector<int> oks(std::max(n, 1), 0);
-  if (plade_register_batch(devices.data(), (int) devices.size(), tp.data(), sp.data(), n, Ts.data(), oks.data()) < 0) return EXIT_FAILURE;
+  const char *fk = getenv("PLADE_CLI_FORK");
+  const bool use_fork = n_dev > 1 && n > 1 && !(fk && atoi(fk) == 0);
+  if (!use_fork) {
+    std::vector<int> devices;
+    for (int w = 0; w < per_gpu; ++w) for (int g = 0; g < n_dev; ++g) devices.push_back(g);
+    if ((int) devices.size() > std::max(n, 1)) devices.resize(std::max(n, 1));
+    if (plade_register_batch(devices.data(), (int) devices.size(), tp.data(), sp.data(), n, Ts.data(), oks.data()) < 0) return EXIT_FAILURE;
+  } else {
+    for (int i = 0; i < n; ++i) for (int k = 0; k < 16; ++k) Ts[16 * (size_t) i + k] = (k % 5 == 0) ? 1.f : 0.f;
+    struct Child { pid_t pid; int fd; std::vector<int> mine; };
+    std::vector<Child> kids;
+    for (int g = 0; g < n_dev; ++g) {
+      Child c;
+      for (int i = g; i < n; i += n_dev) c.mine.push_back(i);
+      if (c.mine.empty()) continue;
+      int fds[2];
+      if (pipe(fds) != 0) { std::cerr << "pipe() failed" << std::endl; return EXIT_FAILURE; }
+      c.pid = fork();
+      if (c.pid == 0) {      // child: its share of the list on its GPU, results back through the pipe
+        close(fds[0]);
+        const int m = (int) c.mine.size();
+        std::vector<const char *> ct(m), cs(m);
+        for (int j = 0; j < m; ++j) { ct[j] = tp[c.mine[j]]; cs[j] = sp[c.mine[j]]; }
+        std::vector<int> devices(std::min(per_gpu, m), g);
+        std::vector<float> cT(16 * (size_t) m);
+        std::vector<int> cok(m, 0);
+        const int rc = plade_register_batch(devices.data(), (int) devices.size(), ct.data(), cs.data(), m, cT.data(), cok.data());
+        bool sent = write(fds[1], cok.data(), sizeof(int) * m) == (ssize_t) (sizeof(int) * m) &&
+                    write(fds[1], cT.data(), sizeof(float) * 16 * m) == (ssize_t) (sizeof(float) * 16 * m);
+        close(fds[1]);
+        _exit(rc < 0 || !sent ? 1 : 0);
+      }
+      close(fds[1]);
+      c.fd = fds[0];
+      if (c.pid < 0) { std::cerr << "fork() failed" << std::endl; return EXIT_FAILURE; }
+      kids.push_back(c);
+    }
+    auto read_all = [](int fd, void *buf, size_t nbytes) {
+      char *p = static_cast<char *>(buf);
+      while (nbytes) { const ssize_t r = read(fd, p, nbytes); if (r <= 0) return false; p += r; nbytes -= (size_t) r; }
+      return true;
+    };
+    for (Child &c : kids) {
+      const int m = (int) c.mine.size();
+      std::vector<int> cok(m, 0);
+      std::vector<float> cT(16 * (size_t) m);
+      const bool got = read_all(c.fd, cok.data(), sizeof(int) * m) && read_all(c.fd, cT.data(), sizeof(float) * 16 * m);
+      close(c.fd);
+      int status = 0;
+      waitpid(c.pid, &status, 0);
+      if (!got) { std::cerr << "a GPU worker process ended without results (" << m << " pairs recorded as failed)" << std::endl; continue; }
+      for (int j = 0; j < m; ++j) {
+        oks[c.mine[j]] = cok[j];
+        for (int k = 0; k < 16; ++k) Ts[16 * (size_t) c.mine[j] + k] = cT[16 * (size_t) j + k];
+      }
+    }
+  }
   int count_success = 0, count_failure = 0;
   for (int i = 0; i < n; ++i) {
     output << "target: " << tf[i] << std::endl;

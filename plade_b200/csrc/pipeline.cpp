@@ -5,6 +5,7 @@
 // decides WHICH hypothesis wins; file:line citations are relative to /root/reference/code/.
 #include "pipeline.h"
 #include <atomic>
+#include <sched.h>
 #include "nccl_shard.h"
 #include <chrono>
 #include <cmath>
@@ -101,11 +102,22 @@ void pair_descriptor(const V3 &l1, const V3 &l2, const V3 &l1sp1, const V3 &l1sp
 }  // namespace
 
 namespace {
-std::atomic<int> g_blocking_sync{[] { const char *e = getenv("PLADE_BLOCKING_SYNC"); return (e && atoi(e) != 0) ? 1 : 0; }()};
+std::atomic<int> g_blocking_sync{[] { const char *e = getenv("PLADE_BLOCKING_SYNC"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : v > 2 ? 2 : v; }()};
 }
-void set_blocking_sync(bool on) { g_blocking_sync.store(on ? 1 : 0); }
+void set_blocking_sync(int mode) { g_blocking_sync.store(mode < 0 ? 0 : mode > 2 ? 2 : mode); }
 void stream_sync(cudaStream_t s) {
-  if (!g_blocking_sync.load(std::memory_order_relaxed)) { PLADE_CUDA(cudaStreamSynchronize(s)); return; }
+  const int mode = g_blocking_sync.load(std::memory_order_relaxed);
+  if (mode == 0) { PLADE_CUDA(cudaStreamSynchronize(s)); return; }
+  if (mode == 2) {
+    // poll and yield: the waiting thread gives its core to any other runnable thread between two polls (the waits of this
+    // pipeline are 0.1-0.5 ms: too short for a sleeping wait to be cheap, too many for a spinning wait to be fair)
+    for (;;) {
+      const cudaError_t q = cudaStreamQuery(s);
+      if (q == cudaSuccess) return;
+      if (q != cudaErrorNotReady) PLADE_CUDA(q);
+      sched_yield();
+    }
+  }
   thread_local cudaEvent_t ev[64] = {};
   int d = 0;
   PLADE_CUDA(cudaGetDevice(&d));

@@ -26,6 +26,8 @@ def _make_one(job):
 
 def parse_results(path, n):
     """[(ok, 4x4)] in list order (PLADE/main.cpp:136-147 text format)"""
+    if not os.path.exists(path):
+        return []
     out, lines = [], open(path).read().split("\n")
     i = 0
     while i < len(lines) and len(out) < n:
@@ -83,15 +85,43 @@ def main():
     cli = os.path.join(ROOT, "plade_b200", "plade_b200_cli")
     doc = {"config": "BASELINE config 5: %d synthetic %d-pt pairs (seeds 1000..%d) from PLY files, whole box" % (a.pairs, a.points, 999 + a.pairs),
            "host_cores": os.cpu_count()}
-    for label in ("cold", "timed"):          # the first run also pays context creation and scratch allocation
-        out_file = os.path.join(d, "results_gpu.txt")
+    # (a) the CLI as a user runs it: ONE process, start to finish -- includes creating a CUDA context on every GPU, loading the
+    #     kernels there and allocating / page-locking the scratch of every worker, which for 64 pairs outweighs the work
+    out_file = os.path.join(d, "results_gpu.txt")
+    for label, extra in (("gpu_cli_one_shot", {}), ("gpu_cli_one_shot_single_process", {"PLADE_CLI_FORK": "0"})):
+        e2 = dict(env, PLADE_TIMING="1", **extra)
         t0 = time.perf_counter()
-        r = subprocess.run([cli, pairs_file, out_file], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        r = subprocess.run([cli, pairs_file, out_file], env=e2, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
         dt = time.perf_counter() - t0
         res = parse_results(out_file, a.pairs)
-        doc["gpu_" + label] = {"seconds": dt, "pairs_per_s": a.pairs / dt, "exit_code": r.returncode, **judge(res, gts),
-                               "command": "plade_b200_cli file_pairs.txt results.txt", "gpus": a.gpus or "all visible"}
-        print(label, json.dumps(doc["gpu_" + label]), flush=True)
+        workers = [l for l in r.stderr.split("\n") if l.startswith("[plade batch worker")]
+        doc[label] = {"seconds": dt, "pairs_per_s": a.pairs / dt, "exit_code": r.returncode, **judge(res, gts),
+                      "command": "plade_b200_cli file_pairs.txt results.txt" + ("  (PLADE_CLI_FORK=0: all GPUs in one process)" if extra else "  (one child process per GPU)"),
+                      "gpus": a.gpus or "all visible", "worker_lines": workers[:4],
+                      "note": "includes process start-up (CUDA contexts, scratch allocation, page-locking)"}
+        print(label, json.dumps({k: v for k, v in doc[label].items() if k != "worker_lines"}), flush=True)
+        for w in workers[:2]:
+            print("   ", w[:300], flush=True)
+    # (b) the same call the CLI makes (plade_register_batch, PLY reading included) in a process that is already warm: the
+    #     steady-state whole-box throughput of a service that keeps its contexts
+    import plade_b200
+    n_dev = a.gpus or plade_b200.device_count()
+    per_gpu = a.workers_per_gpu or max(1, min(4, (os.cpu_count() or 1) // (2 * n_dev)))
+    devs = [g for _ in range(per_gpu) for g in range(n_dev)]
+    pairs = [(names[2 * k], names[2 * k + 1]) for k in range(a.pairs)]
+    fd, dn = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+    os.dup2(dn, 1)
+    try:
+        plade_b200.register_batch(pairs[:len(devs)], devices=devs)          # warm-up: contexts, scratch, page-locked buffers
+        t0 = time.perf_counter()
+        ok, T = plade_b200.register_batch(pairs, devices=devs)
+        dt = time.perf_counter() - t0
+    finally:
+        os.dup2(fd, 1)
+    res = [(bool(ok[k]), np.asarray(T[k], dtype=np.float64)) for k in range(a.pairs)]
+    doc["gpu_steady_state"] = {"seconds": dt, "pairs_per_s": a.pairs / dt, **judge(res, gts), "call": "plade_register_batch (what the CLI calls), warm process",
+                               "gpus": n_dev, "workers_per_gpu": per_gpu}
+    print("steady", json.dumps(doc["gpu_steady_state"]), flush=True)
     ref_bin = os.path.join(ROOT, "oracle", "_ref_fast", "plade_ref")
     if not os.path.exists(ref_bin):
         ref_bin = os.path.join(ROOT, "oracle", "_ref", "plade_ref")
