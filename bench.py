@@ -168,7 +168,7 @@ def run_ours(args):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)      # cores this process may use
     B = args.pairs_per_gpu if args.pairs_per_gpu > 0 else PAIRS_PER_GPU
     host_threads = 3 * B * world          # per pair: the calling thread + the two plane-extraction lanes
-    blocking = (1 if host_threads > cores else 0) if args.blocking_sync < 0 else int(args.blocking_sync)      # 0 spin, 1 blocking event, 2 poll + yield
+    blocking = (2 if host_threads > cores else 0) if args.blocking_sync < 0 else int(args.blocking_sync)      # 0 spin, 1 blocking event, 2 poll + yield
     ctxs = [plade_b200.Context(local) for _ in range(B)]
     for kv in args.param:
         for c in ctxs:
@@ -477,7 +477,7 @@ def main():
     ap.add_argument("--pairs-per-gpu", type=int, default=0, help="pairs registered concurrently per GPU and step (0 = 4, the same at every N)")
     ap.add_argument("--skip-config4", action="store_true", help="skip the sharded verification of BASELINE config 4")
     ap.add_argument("--pin-cores", type=int, default=0, help="1: with N > 1 ranks, every rank keeps to its own 1/N of the host cores")
-    ap.add_argument("--blocking-sync", type=int, default=-1, help="-1: block instead of spinning when host threads > cores; 0 / 1: force")
+    ap.add_argument("--blocking-sync", type=int, default=-1, help="-1: poll + yield instead of spinning when host threads > cores; 0 spin / 1 blocking event / 2 poll + yield: force")
     ap.add_argument("--config4-points", type=int, default=5_000_000)
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up, no e2e / sharded / cpu arms")
     ap.add_argument("--param", action="append", default=[], help="name=value passed to plade_set_param on every context (diagnostic runs)")

@@ -148,12 +148,28 @@ int main(int argc0, char **argv0) {
   // GPU p mod n), because creating the CUDA contexts of 8 GPUs inside one process is serialised by the driver and costs more
   // than registering 64 pairs does; separate processes bring their GPUs up in parallel (PLADE_CLI_FORK=0: one process).
   // The device count comes from a short-lived probe child for the same reason (fork after CUDA initialisation is not allowed).
-  int n_dev = 0;
-  {
+  // The GPUs this process may use, WITHOUT initialising CUDA here (on an 8-GPU box cuInit alone takes ~10 s per process when
+  // all GPUs are visible): the entries of CUDA_VISIBLE_DEVICES if it is set, else the /dev/nvidia<N> device nodes; only when
+  // neither says anything, a short-lived probe child asks the runtime.
+  std::vector<std::string> visible;
+  if (const char *cvd = getenv("CUDA_VISIBLE_DEVICES")) {
+    std::stringstream ss(cvd);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) if (!tok.empty()) visible.push_back(tok);
+  } else {
+    for (int k = 0; k < 64; ++k) {
+      std::ifstream node("/dev/nvidia" + std::to_string(k));
+      if (!node.good()) break;
+      visible.push_back(std::to_string(k));
+    }
+  }
+  int n_dev = (int) visible.size();
+  if (n_dev == 0) {
     const pid_t probe = fork();
     if (probe == 0) _exit(std::min(plade_device_count(), 255));
     int status = 0;
     if (probe > 0 && waitpid(probe, &status, 0) == probe && WIFEXITED(status)) n_dev = WEXITSTATUS(status);
+    for (int k = 0; k < n_dev; ++k) visible.push_back(std::to_string(k));
   }
   if (n_dev < 1) { std::cerr << "no usable CUDA device (plade_b200 has no CPU fallback)" << std::endl; return EXIT_FAILURE; }
   if (const char *e = getenv("PLADE_DEVICES")) n_dev = std::max(1, std::min(n_dev, atoi(e)));
@@ -184,12 +200,13 @@ int main(int argc0, char **argv0) {
       int fds[2];
       if (pipe(fds) != 0) { std::cerr << "pipe() failed" << std::endl; return EXIT_FAILURE; }
       c.pid = fork();
-      if (c.pid == 0) {      // child: its share of the list on its GPU, results back through the pipe
+      if (c.pid == 0) {      // child: its share of the list on its GPU (the only one it sees), results back through the pipe
         close(fds[0]);
+        setenv("CUDA_VISIBLE_DEVICES", visible[g].c_str(), 1);
         const int m = (int) c.mine.size();
         std::vector<const char *> ct(m), cs(m);
         for (int j = 0; j < m; ++j) { ct[j] = tp[c.mine[j]]; cs[j] = sp[c.mine[j]]; }
-        std::vector<int> devices(std::min(per_gpu, m), g);
+        std::vector<int> devices(std::min(per_gpu, m), 0);
         std::vector<float> cT(16 * (size_t) m);
         std::vector<int> cok(m, 0);
         const int rc = plade_register_batch(devices.data(), (int) devices.size(), ct.data(), cs.data(), m, cT.data(), cok.data());

@@ -658,6 +658,17 @@ def test_cli_result_file_format(poly_pair, tmp_path):
     diag = float(np.linalg.norm(np.ptp(st[:, :3], axis=0)))
     rot, tr = transform_error(M, gt, diag)
     assert rot <= 0.5 and tr <= 5e-3
+    # options on top of usage 1: the headless report and the .vg plane dumps
+    import json
+    rep, pre = str(tmp_path / "report.json"), str(tmp_path / "planes")
+    r = subprocess.run([cli, "--report", rep, "--dump-planes", pre, t, s, res], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    doc = json.load(open(rep))
+    assert doc["target_points"] == len(st) and doc["source_points"] == len(ss) and doc["target_planes"] >= 10 and doc["source_planes"] >= 10
+    assert 0 < doc["overlap_ratio"] <= 1 and doc["winner_inliers"] > 0 and len(doc["winner_matched_planes"]) >= 2
+    for side, cloud in (("target", st), ("source", ss)):
+        vg = open(pre + "_%s.vg" % side).read().split("\n")
+        assert vg[0] == "num_points: %d" % len(cloud) and vg[5].startswith("num_groups: ")
     # usage 2: pair list -> blocks separated by a blank line; a name that cannot be opened is skipped with a message
     # and the pairing continues with the next existing name (main.cpp:117-134); a failed registration records the
     # identity; exit code is failure only when every pair failed (main.cpp:150-158)

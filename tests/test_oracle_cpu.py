@@ -538,6 +538,31 @@ def test_reference_detection_curve_is_what_detect_margin_assumes():
     assert freq[ratio >= 1.6].mean() >= 0.9
 
 
+def test_vg_dump_and_ply_read_are_host_only(tmp_path, poly_pair, poly_stages):
+    """f4 / f1 stage entries need no device: plade_ply_read returns the PLY records, plade_dump_planes_vg writes the reference's
+    save_vg layout (PLADE/util.cpp:1553-1616: num_points / num_colors / num_normals / num_groups, one group block per plane)."""
+    import plade_b200
+    from tests.plyio import write_ply
+    cloud = poly_pair["tgt"][:5000]
+    f = str(tmp_path / "c.ply")
+    write_ply(f, cloud)
+    assert np.array_equal(plade_b200.ply_read(f), cloud)
+    assert plade_b200.ply_read(str(tmp_path / "missing.ply")) is None
+    off, idx, par = poly_stages["t_off"], poly_stages["t_idx"], poly_stages["t_par"].reshape(-1, 4)
+    keep = [k for k in range(len(off) - 1)][:3]
+    sub_idx = [np.array([i for i in idx[off[k]:off[k + 1]] if i < len(cloud)], np.int32) for k in keep]
+    planes = plade_b200.Planes(np.concatenate([[0], np.cumsum([len(x) for x in sub_idx])]), np.concatenate(sub_idx), par[keep])
+    out = str(tmp_path / "planes.vg")
+    plade_b200.dump_planes_vg(cloud, planes, out)
+    lines = open(out).read().split("\n")
+    assert lines[0] == "num_points: 5000" and lines[2] == "num_colors: 0" and lines[3] == "num_normals: 5000"
+    assert lines[5] == "num_groups: 3" and lines[6] == "group_type: 0" and lines[7] == "num_group_parameters: 4"
+    assert [float(x) for x in lines[8].split(":")[1].split()] == pytest.approx(par[keep[0]].tolist(), rel=1e-6)
+    assert lines[11] == "group_num_point: %d" % len(sub_idx[0])
+    assert [int(x) for x in lines[12].split()] == sub_idx[0].tolist()
+    assert sum(1 for l in lines if l == "num_children: 0") == 3
+
+
 def test_product_never_touches_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may use oracle/."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "plade_b200")):
