@@ -157,11 +157,10 @@ int main(int argc0, char **argv0) {
     std::string tok;
     while (std::getline(ss, tok, ',')) if (!tok.empty()) visible.push_back(tok);
   } else {
-    for (int k = 0; k < 64; ++k) {
-      std::ifstream node("/dev/nvidia" + std::to_string(k));
-      if (!node.good()) break;
-      visible.push_back(std::to_string(k));
-    }
+    // (the minor numbers of the nodes need not start at 0 in a container; CUDA numbers the devices it can see from 0)
+    int nodes = 0;
+    for (int k = 0; k < 256; ++k) if (access(("/dev/nvidia" + std::to_string(k)).c_str(), F_OK) == 0) ++nodes;
+    for (int k = 0; k < nodes; ++k) visible.push_back(std::to_string(k));
   }
   int n_dev = (int) visible.size();
   if (n_dev == 0) {

@@ -630,6 +630,9 @@ def test_batch_mode_matches_single_registrations(ctx, poly_pair, tmp_path):
     want.insert(1, (False, np.eye(4, dtype=np.float32)))
     # two workers on the same device: exercises the per-thread contexts and the loader threads
     ok, T = plade_b200.register_batch(pairs, devices=[0, 0])
+    if plade_b200.device_count() >= 2:       # workers on different GPUs of one process (the per-device kernel attributes)
+        okm, Tm = plade_b200.register_batch(pairs, devices=[0, 1])
+        assert okm.tolist() == ok.tolist() and np.array_equal(Tm, T)
     assert ok.tolist() == [bool(w[0]) for w in want]
     for k in range(len(pairs)):
         assert np.array_equal(T[k], want[k][1]), k
