@@ -144,10 +144,11 @@ int main(int argc0, char **argv0) {
     }
     if (file_pair.size() == 2) { tf.push_back(file_pair[0]); sf.push_back(file_pair[1]); }
   }
-  // The parent process never touches CUDA: with several GPUs the pairs are split over ONE CHILD PROCESS PER GPU (pair p ->
-  // GPU p mod n), because creating the CUDA contexts of 8 GPUs inside one process is serialised by the driver and costs more
-  // than registering 64 pairs does; separate processes bring their GPUs up in parallel (PLADE_CLI_FORK=0: one process).
-  // The device count comes from a short-lived probe child for the same reason (fork after CUDA initialisation is not allowed).
+  // Default: all GPUs from this one process (plade_register_batch: worker threads + contexts per GPU).  PLADE_CLI_FORK=1 splits
+  // the pairs over ONE CHILD PROCESS PER GPU instead (pair p -> GPU p mod n, each child sees only its GPU); the parent then
+  // never touches CUDA (fork after CUDA initialisation is not allowed).  Measured on an 8-GPU box: the first CUDA call of a
+  // process costs 7-11 s there whatever it can see, so the children do not start faster than the single process does
+  // (64 pairs: 14.7 s forked, 11.4 s in one process, 0.6 s in a warm process) -- the option is for isolation, not speed.
   // The GPUs this process may use, WITHOUT initialising CUDA here (on an 8-GPU box cuInit alone takes ~10 s per process when
   // all GPUs are visible): the entries of CUDA_VISIBLE_DEVICES if it is set, else the /dev/nvidia<N> device nodes; only when
   // neither says anything, a short-lived probe child asks the runtime.
@@ -182,7 +183,7 @@ int main(int argc0, char **argv0) {
   std::vector<float> Ts(16 * (size_t) std::max(n, 1));
   std::vector<int> oks(std::max(n, 1), 0);
   const char *fk = getenv("PLADE_CLI_FORK");
-  const bool use_fork = n_dev > 1 && n > 1 && !(fk && atoi(fk) == 0);
+  const bool use_fork = n_dev > 1 && n > 1 && fk && atoi(fk) != 0;
   if (!use_fork) {
     std::vector<int> devices;
     for (int w = 0; w < per_gpu; ++w) for (int g = 0; g < n_dev; ++g) devices.push_back(g);

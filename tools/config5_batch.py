@@ -88,7 +88,7 @@ def main():
     # (a) the CLI as a user runs it: ONE process, start to finish -- includes creating a CUDA context on every GPU, loading the
     #     kernels there and allocating / page-locking the scratch of every worker, which for 64 pairs outweighs the work
     out_file = os.path.join(d, "results_gpu.txt")
-    for label, extra in (("gpu_cli_one_shot", {}), ("gpu_cli_one_shot_single_process", {"PLADE_CLI_FORK": "0"})):
+    for label, extra in (("gpu_cli_one_shot", {}), ("gpu_cli_one_shot_process_per_gpu", {"PLADE_CLI_FORK": "1"})):
         e2 = dict(env, PLADE_TIMING="1", **extra)
         t0 = time.perf_counter()
         r = subprocess.run([cli, pairs_file, out_file], env=e2, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
@@ -96,7 +96,7 @@ def main():
         res = parse_results(out_file, a.pairs)
         workers = [l for l in r.stderr.split("\n") if l.startswith("[plade batch worker")]
         doc[label] = {"seconds": dt, "pairs_per_s": a.pairs / dt, "exit_code": r.returncode, **judge(res, gts),
-                      "command": "plade_b200_cli file_pairs.txt results.txt" + ("  (PLADE_CLI_FORK=0: all GPUs in one process)" if extra else "  (one child process per GPU)"),
+                      "command": "plade_b200_cli file_pairs.txt results.txt" + ("  (PLADE_CLI_FORK=1: one child process per GPU)" if extra else "  (all GPUs from one process)"),
                       "gpus": a.gpus or "all visible", "worker_lines": workers[:4],
                       "note": "includes process start-up (CUDA contexts, scratch allocation, page-locking)"}
         print(label, json.dumps({k: v for k, v in doc[label].items() if k != "worker_lines"}), flush=True)
