@@ -38,7 +38,6 @@ struct LenIdx {          // LENGTHINDEX, PLADE/util.h:347-350
   float length;
   int index;
 };
-inline bool cmp_less(const LenIdx &a, const LenIdx &b) { return a.length < b.length; }       // util.h:352
 inline bool cmp_greater(const LenIdx &a, const LenIdx &b) { return a.length > b.length; }    // util.h:360
 
 struct Side {            // MatchInformation, PLADE/util.h:80-102

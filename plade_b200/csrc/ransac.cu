@@ -306,13 +306,6 @@ score_points_kernel(const float4 *__restrict__ sub, int S, const float4 *__restr
   for (int c = tid; c < kStage2Cand; c += blockDim.x) if (cnt_s[c]) atomicAdd(&counts[c], cnt_s[c]);
 }
 
-// stage-1 keys: carried pool candidates are forced into stage 2; idx = iota
-__global__ void stage1_keys_kernel(unsigned int *__restrict__ counts1, int *__restrict__ idx, int n, int n_forced) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (i < n_forced) counts1[i] = kForcedKey;
-  idx[i] = i;
-}
 // Stage-1 selection: the kStage2Cand candidates a stable descending sort of the stage-1 counts would put first
 // (carried pool candidates forced to the front, ties by ascending candidate index), in that order, without
 // sorting all kCandPerRound of them: one block builds the histogram of the counts (<= kStage1Points), finds the
@@ -934,16 +927,6 @@ struct AcceptArgs {
   float band;
 };
 
-__device__ __forceinline__ double block_sum(double v, double *sh /* 32 */) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) sh[w] = v;
-  __syncthreads();
-  v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
-  if (w == 0) for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  return v;      // valid in thread 0
-}
 // N sums at once: two block barriers in total instead of two per value; results valid in thread 0
 template <int N>
 __device__ __forceinline__ void block_sum_n(double (&v)[N], double *sh /* N * 32 */) {
@@ -986,16 +969,6 @@ __device__ __forceinline__ void block_box4(float (&v)[4], float *sh /* 4 * 32 */
       v[k] = x;
     }
   }
-}
-__device__ __forceinline__ float block_minmax(float v, bool is_min, float *sh /* 32 */) {
-  for (int o = 16; o > 0; o >>= 1) { float t = __shfl_down_sync(0xffffffffu, v, o); v = is_min ? fminf(v, t) : fmaxf(v, t); }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) sh[w] = v;
-  __syncthreads();
-  v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : (is_min ? 3.4e38f : -3.4e38f);
-  if (w == 0) for (int o = 16; o > 0; o >>= 1) { float t = __shfl_down_sync(0xffffffffu, v, o); v = is_min ? fminf(v, t) : fmaxf(v, t); }
-  return v;      // valid in thread 0
 }
 __device__ __forceinline__ unsigned int cluster_rank() { unsigned int r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned int cluster_size() { unsigned int r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
@@ -1516,8 +1489,8 @@ void free_ransac_scratch(Registrar &r) {
   for (int lane = 0; lane < 2; ++lane) { delete static_cast<RansacScratch *>(r.ransac_scratch[lane]); r.ransac_scratch[lane] = nullptr; }
 }
 
-__global__ void remap_group_kernel(const int *__restrict__ assigned, int n, const int *__restrict__ remap, int n_remap,
-                                   int *__restrict__ group) {
+// (group may be the same array as assigned: the top-40 cut of extract() remaps in place)
+__global__ void remap_group_kernel(const int *assigned, int n, const int *__restrict__ remap, int n_remap, int *group) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int a = assigned[i];
