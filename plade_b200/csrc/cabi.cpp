@@ -125,6 +125,7 @@ int plade_set_param(plade_ctx *ctx, const char *name, double v) {
   else if (n == "max_trials") p.max_trials = (int) v;
   else if (n == "detect_margin") p.detect_margin = v;
   else if (n == "ransac_batch") p.ransac_batch = (int) v;
+  else if (n == "score_live") p.score_live = (int) v;
   else if (n == "detect_resume") p.detect_resume = (int) v;
   else if (n == "blocking_sync") set_blocking_sync((int) v);       // process-wide, see stream_sync
   else if (n == "kernel_clock") { ctx->reg->dev.clock.enabled = ctx->reg->dev2.clock.enabled = v != 0; }
