@@ -91,6 +91,14 @@ __device__ __forceinline__ bool compatible(const float4 &pl, const float4 &p, co
   return fabsf(dn) >= nthresh;
 }
 
+// compatible() without the early out (the same float operations, so the same answer): a short loop body with one candidate
+// per thread keeps several points in flight only if it has no branch
+__device__ __forceinline__ unsigned int compatible_bit(const float4 &pl, const float4 &p, const float4 &nr, float eps, float nthresh) {
+  const float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, p.x), __fmul_rn(pl.y, p.y)), __fmul_rn(pl.z, p.z));
+  const float dn = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, nr.x), __fmul_rn(pl.y, nr.y)), __fmul_rn(pl.z, nr.z));
+  return (unsigned int) (fabsf(__fsub_rn(pl.w, dp)) < eps) & (unsigned int) (fabsf(dn) >= nthresh);
+}
+
 // ---- Morton order -------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int expand10(unsigned int v) {
   v &= 0x3ff;
@@ -137,7 +145,8 @@ __global__ void bbox_kernel(const float4 *__restrict__ p, int n, int *__restrict
 // ---- candidate generation --------------------------------------------------------------------------------
 __global__ void gen_candidates_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm,
                                       const int *__restrict__ order, int m, int nlevels, float nthresh,
-                                      unsigned long long seed, float4 *__restrict__ cand, int *__restrict__ n_valid) {
+                                      unsigned long long seed, float4 *__restrict__ cand, int *__restrict__ n_valid,
+                                      unsigned int *__restrict__ valid_bits /* kCandPerRound / 32 words: bit c % 32 of word c / 32 = slot c holds a plane */) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   bool ok = false;
   float4 out = make_float4(0.f, 0.f, 0.f, 3.0e38f);
@@ -188,23 +197,26 @@ __global__ void gen_candidates_kernel(const float4 *__restrict__ pos, const floa
   }
   if (c < kCandPerRound) cand[c] = out;
   unsigned int mk = __ballot_sync(0xffffffffu, ok);
-  if ((threadIdx.x & 31) == 0 && mk) atomicAdd(n_valid, __popc(mk));
+  if ((threadIdx.x & 31) == 0) {
+    if (mk) atomicAdd(n_valid, __popc(mk));
+    if (c < kCandPerRound) valid_bits[c >> 5] = mk;      // (the grid is exactly kCandPerRound threads: every word is written)
+  }
 }
 
-// Slots of the round's candidate array that hold a plane (carried pool entries + the draws that passed Plane::Init and the
-// sample verification; measured: 12 % of the draws), in ascending slot order.  One block of 256 threads.
-__device__ void compact_live_slots(const float4 *__restrict__ cand, int *__restrict__ live, int *__restrict__ n_live) {
+// Slots of the round's candidate array that hold a plane -- the first n_forced (carried pool entries, copied over the draws
+// of those slots) and the draws that passed Plane::Init and the sample verification (gen_candidates_kernel's valid_bits;
+// measured: 12 % of the draws) -- in ascending slot order.  One block of 256 threads, two 32-slot words per thread.
+__device__ void compact_live_slots(const unsigned int *__restrict__ valid_bits, int n_forced, int *__restrict__ live, int *__restrict__ n_live) {
   static_assert(kCandPerRound == 256 * 64, "two 32-slot words per thread");
-  __shared__ unsigned int bits[kCandPerRound / 32];
   typedef cub::BlockScan<int, 256> Scan;
   __shared__ typename Scan::TempStorage scan_tmp;
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int base = (tid >> 5) * 32; base < kCandPerRound; base += 256) {
-    const unsigned int b = __ballot_sync(0xffffffffu, cand[base + lane].w < 3.0e38f);
-    if (lane == 0) bits[base >> 5] = b;
+  const int tid = threadIdx.x;
+  unsigned int w[2];
+  for (int h = 0; h < 2; ++h) {
+    const int first = 64 * tid + 32 * h;                   // slot of bit 0
+    const int f = min(max(n_forced - first, 0), 32);       // forced slots in this word
+    w[h] = valid_bits[2 * tid + h] | (f >= 32 ? 0xffffffffu : ((1u << f) - 1u));
   }
-  __syncthreads();
-  unsigned int w[2] = {bits[2 * tid], bits[2 * tid + 1]};
   int off, total;
   Scan(scan_tmp).ExclusiveSum(__popc(w[0]) + __popc(w[1]), off, total);
   for (int h = 0; h < 2; ++h)
@@ -218,8 +230,8 @@ __global__ void __launch_bounds__(256)
 gather_sub_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const int *__restrict__ order,
                   int m, int Sa, unsigned long long seed_a, float4 *__restrict__ sub_a, int Sb, unsigned long long seed_b,
                   float4 *__restrict__ sub_b /* [2*S]: pos | nrm interleaved per tile */,
-                  const float4 *__restrict__ cand, int *__restrict__ live, int *__restrict__ n_live) {
-  if (live != nullptr && blockIdx.x == gridDim.x - 1) { compact_live_slots(cand, live, n_live); return; }
+                  const unsigned int *__restrict__ valid_bits, int n_forced, int *__restrict__ live, int *__restrict__ n_live) {
+  if (live != nullptr && blockIdx.x == gridDim.x - 1) { compact_live_slots(valid_bits, n_forced, live, n_live); return; }
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Sa + Sb) return;
   const bool first = k < Sa;
@@ -289,11 +301,16 @@ score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__r
     phase[b] ^= 1;
     const int np = min(kScoreTile, S - t * kScoreTile);
     const float4 *P = buf[b], *N = buf[b] + kScoreTile;
+    if constexpr (C == 1) {
+#pragma unroll 8
+      for (int j = 0; j < np; ++j) cnt[0] += compatible_bit(pl[0], P[j], N[j], eps, nthresh);
+    } else {
 #pragma unroll 2
-    for (int j = 0; j < np; ++j) {
-      const float4 p = P[j], nr = N[j];
+      for (int j = 0; j < np; ++j) {
+        const float4 p = P[j], nr = N[j];
 #pragma unroll
-      for (int k = 0; k < C; ++k) cnt[k] += compatible(pl[k], p, nr, eps, nthresh) ? 1u : 0u;
+        for (int k = 0; k < C; ++k) cnt[k] += compatible(pl[k], p, nr, eps, nthresh) ? 1u : 0u;
+      }
     }
     __syncthreads();   // everyone done with buf[b] before it is refilled two iterations later
   }
@@ -1441,6 +1458,7 @@ struct RansacScratch {
   DevBuf<double> acc;
   DevBuf<double> refine_mem;      // RefineCtl at +0, RefineOut at +128 bytes
   DevBuf<int> cand_live;           // slots of `cand` that hold a plane this round (compact_live_slots)
+  DevBuf<unsigned int> cand_bits;  // one bit per slot: the draw passed (gen_candidates_kernel)
   DevBuf<unsigned int> round_buf;  // one scoring round: counts | counts2 | n_valid | selected planes (see kRound* offsets)
   PinBuf<unsigned int> round_host; // page-locked landing zone of the round's results and of the cluster kernel's verdict
   PinBuf<float4> pool_host;
@@ -1641,7 +1659,9 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     unsigned int *h_round = rs.round_host.ensure(kRoundEnd - kRoundCounts2 + 64);
     PLADE_CUDA(cudaMemsetAsync(rb, 0, sizeof(unsigned int) * kRoundTop, s));
     round_seed = mix64(round_seed + 1);
-    gen_candidates_kernel<<<div_up(kCandPerRound, 128), 128, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, nlevels, nthresh, round_seed, cand, d_nvalid);
+    static_assert(kCandPerRound % 128 == 0, "gen_candidates_kernel: one thread per slot, whole warps");
+    unsigned int *valid_bits = rs.cand_bits.ensure(kCandPerRound / 32);
+    gen_candidates_kernel<<<kCandPerRound / 128, 128, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, nlevels, nthresh, round_seed, cand, d_nvalid, valid_bits);
     if (!pool.empty()) {   // carried candidates occupy the first slots
       float4 *hp = rs.pool_host.ensure(kPoolSize);
       for (size_t q = 0; q < pool.size(); ++q) hp[q] = pool[q].pl;
@@ -1651,7 +1671,7 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     // all kCandPerRound slots, on an eighth of the blocks, one candidate per thread instead of two (score_live = 0: all slots)
     int *live = params.score_live ? rs.cand_live.ensure(kCandPerRound) : nullptr;
     gather_sub_kernel<<<div_up(S1 + S, 256) + (live ? 1 : 0), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S1, round_seed ^ 0x5bd1e995ull, sub1, S,
-                                                                          round_seed, sub, cand, live, d_nvalid + 1);
+                                                                          round_seed, sub, valid_bits, (int) pool.size(), live, d_nvalid + 1);
     {
       const int n_tiles = div_up(S1, kScoreTile);
       dev.clock.begin(KernelClock::kScoreCandidates, 28.0 * S1, s);     // 28 B per point per pass
