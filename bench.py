@@ -314,7 +314,7 @@ def run_ours(args):
     reg_ms_total = ms / args.steps
     lines = [kernel_line("accept_loop_kernel (K1b-d: per pool entry a band pass of the 16-CTA cluster over the cloud + the acceptance chain "
                          "(flags, raster, components, select, covariance) + accept; one launch per scoring round)", k1r, reg_ms_total),
-             kernel_line("score_candidates_kernel + score_points_kernel (K1a: 16384 candidates x 4096 points, then 256 x 65536, per round)", k1, reg_ms_total),
+             kernel_line("score_candidates_kernel x 2 (K1a: the live slots of 16384 candidate draws x 4096 points, then the best 256 x 65536, per round)", k1, reg_ms_total),
              kernel_line("band_compact_kernel (host-driven fallback path only)", k1b, reg_ms_total),
              kernel_line("verify_kernel (K5) inside the registration (H = %d surviving hypotheses)" % int(stage["verify_h"]), k5_in, reg_ms_total)]
     dom = max(lines[:2], key=lambda l: l["ms"])

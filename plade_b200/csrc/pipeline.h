@@ -43,7 +43,7 @@ struct Params {
   int detect_resume = 0;
   // RANSAC: pool entries one accept_loop_kernel launch may walk (1 = host-driven, one candidate per round trip; same planes)
   int ransac_batch = 64;
-  int score_live = 1;          // 1: stage 1 of a scoring round skips the candidate slots that hold no plane (same counts; 0: scores every slot)
+  int score_live = 2;          // scoring rounds: 1 = stage 1 skips the candidate slots that hold no plane, 2 = and stage 2 runs one candidate per thread (same counts; 0: every slot, one point per thread)
   // matching (PLADE/plade.cpp:46-56)
   // hypotheses taken to the penetration test and the verification, by matched planes then cluster size: the reference's budget
   // is 200 (PLADE/plade.cpp:54); on its own room pair the true transform often ranks between 200 and 1000 (seed sweep)

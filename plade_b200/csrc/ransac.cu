@@ -253,16 +253,18 @@ gather_sub_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm
 // K1a: every candidate of the round against the subsample.  grid = (tile groups, candidate groups).
 // C candidates per thread: the two shared-memory loads of a point (broadcast to the warp) are amortised over C
 // plane tests, and the C independent dependency chains keep the FP pipe busy with few warps per SM.
-// sel != null: only the slots sel[0 .. *n_sel) are scored (the live slots, compact_live_slots) and the counts land in
-// counts[sel[c]], i.e. where scoring every slot would have put them; blocks beyond *n_sel leave at once.
+// sel != null: only the slots sel[0 .. n_cand) are scored -- stage 1: the live slots (compact_live_slots; *n_sel of them,
+// blocks beyond that leave at once), counts in counts[sel[c]], i.e. where scoring every slot would have put them;
+// stage 2 (by_rank): the kStage2Cand slots select_top_kernel picked, counts in counts[c] (c = the rank).
 template <int C>
 __global__ void __launch_bounds__(kScoreThreads)
 score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__restrict__ cand, const int *__restrict__ sel,
-                        const int *__restrict__ n_sel, int n_cand, float eps, float nthresh, int tiles_per_block, unsigned int *__restrict__ counts) {
+                        const int *__restrict__ n_sel, int by_rank, int n_cand, float eps, float nthresh, int tiles_per_block,
+                        unsigned int *__restrict__ counts) {
   __shared__ __align__(128) float4 buf[2][2 * kScoreTile];
   __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x;
-  if (sel) n_cand = min(n_cand, *n_sel);
+  if (n_sel) n_cand = min(n_cand, *n_sel);
   if ((int) blockIdx.y * (kScoreThreads * C) >= n_cand) return;      // uniform over the block
   const int c0 = blockIdx.y * (kScoreThreads * C) + tid;          // this thread's candidates: c0 + k * kScoreThreads
   float4 pl[C];
@@ -317,7 +319,7 @@ score_candidates_kernel(const float4 *__restrict__ sub, int S, const float4 *__r
 #pragma unroll
   for (int k = 0; k < C; ++k) {
     const int c = c0 + k * kScoreThreads;
-    if (c < n_cand && cnt[k]) atomicAdd(&counts[sel ? sel[c] : c], cnt[k]);
+    if (c < n_cand && cnt[k]) atomicAdd(&counts[(sel && !by_rank) ? sel[c] : c], cnt[k]);
   }
 }
 
@@ -1669,6 +1671,8 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
     }
     // Stage 1 scores the live slots only (12 % of the draws hold a plane): the same counts in the same places as scoring
     // all kCandPerRound slots, on an eighth of the blocks, one candidate per thread instead of two (score_live = 0: all slots)
+    // Stage 2 (score_live = 2) is the same kernel, one of the 256 selected candidates per thread and one 512-point tile of
+    // the large subsample per block, instead of score_points_kernel (one point per thread, a ballot per candidate)
     int *live = params.score_live ? rs.cand_live.ensure(kCandPerRound) : nullptr;
     gather_sub_kernel<<<div_up(S1 + S, 256) + (live ? 1 : 0), 256, 0, s>>>(c.pos.p, c.nrm.p, cur_order, m, S1, round_seed ^ 0x5bd1e995ull, sub1, S,
                                                                           round_seed, sub, valid_bits, (int) pool.size(), live, d_nvalid + 1);
@@ -1676,16 +1680,20 @@ std::vector<PlaneParam> Registrar::detect_planes_dev(const CloudDev &c, int min_
       const int n_tiles = div_up(S1, kScoreTile);
       dev.clock.begin(KernelClock::kScoreCandidates, 28.0 * S1, s);     // 28 B per point per pass
       if (live)
-        score_candidates_kernel<1><<<dim3(n_tiles, kCandPerRound / kScoreThreads), kScoreThreads, 0, s>>>(sub1, S1, cand, live, d_nvalid + 1, kCandPerRound,
+        score_candidates_kernel<1><<<dim3(n_tiles, kCandPerRound / kScoreThreads), kScoreThreads, 0, s>>>(sub1, S1, cand, live, d_nvalid + 1, 0, kCandPerRound,
                                                                                                          eps, nthresh, 1, counts);
       else
-        score_candidates_kernel<kScoreC1><<<dim3(n_tiles, kCandPerRound / (kScoreThreads * kScoreC1)), kScoreThreads, 0, s>>>(sub1, S1, cand, nullptr, nullptr,
+        score_candidates_kernel<kScoreC1><<<dim3(n_tiles, kCandPerRound / (kScoreThreads * kScoreC1)), kScoreThreads, 0, s>>>(sub1, S1, cand, nullptr, nullptr, 0,
                                                                                                                              kCandPerRound, eps, nthresh, 1, counts);
       dev.clock.end(s);
     }
     select_top_kernel<<<1, kSelThreads, 0, s>>>(counts, kCandPerRound, (int) pool.size(), cidx_sorted, cand, cand_top);
     dev.clock.begin(KernelClock::kScoreCandidates, 28.0 * S, s);
-    score_points_kernel<<<div_up(S, 256), 256, 0, s>>>(sub, S, cand, cidx_sorted, eps, nthresh, counts2);
+    static_assert(kStage2Cand == kScoreThreads, "stage 2 by candidate: one block row");
+    if (params.score_live >= 2)
+      score_candidates_kernel<1><<<dim3(div_up(S, kScoreTile), 1), kScoreThreads, 0, s>>>(sub, S, cand, cidx_sorted, nullptr, 1, kStage2Cand, eps, nthresh, 1, counts2);
+    else
+      score_points_kernel<<<div_up(S, 256), 256, 0, s>>>(sub, S, cand, cidx_sorted, eps, nthresh, counts2);
     dev.clock.end(s);
     PLADE_LAUNCH_CHECK();
     dev.launches.add(5);

@@ -967,23 +967,26 @@ def test_accept_loop_on_the_device_extracts_the_same_planes(ctx, poly_pair):
         ctx.set_param("ransac_batch", 64)
 
 
-def test_stage1_scoring_on_the_live_slots_extracts_the_same_planes(ctx, poly_pair):
-    """Stage 1 of a scoring round scores only the candidate slots that hold a plane (score_live = 1: slot list from
-    gen_candidates_kernel's validity bits, one candidate per thread, predicate without the early out) -- the counts must land
-    where scoring every slot (score_live = 0) puts them, so the detection is the same plane by plane and point by point."""
+def test_scoring_on_the_live_slots_extracts_the_same_planes(ctx, poly_pair):
+    """A scoring round scores only the candidate slots that hold a plane (score_live >= 1: slot list from
+    gen_candidates_kernel's validity bits, one candidate per thread, predicate without the early out) and runs stage 2 with the
+    same candidate-per-thread kernel (score_live = 2, the default) -- the counts must land where scoring every slot with the
+    point-per-thread stage 2 (score_live = 0) puts them, so the detection is the same plane by plane and point by point."""
     clouds = [poly_pair["tgt"], poly_pair["src"], make_pair(n_points=200000, n_planes=20, seed=31)[0]]
     try:
         for cloud in clouds:
             for seed in (2, 11):
                 ctx.set_param("seed", seed)
-                ctx.set_param("score_live", 1)
-                a = ctx.detect_planes(cloud, 1250)
                 ctx.set_param("score_live", 0)
                 b = ctx.detect_planes(cloud, 1250)
-                assert len(a) == len(b) and len(a) >= 6
-                assert a.sizes().tolist() == b.sizes().tolist()
-                assert np.array_equal(a.params, b.params)
-                assert np.array_equal(a.indices, b.indices)
+                assert len(b) >= 6
+                for mode in (2, 1):
+                    ctx.set_param("score_live", mode)
+                    a = ctx.detect_planes(cloud, 1250)
+                    assert len(a) == len(b)
+                    assert a.sizes().tolist() == b.sizes().tolist()
+                    assert np.array_equal(a.params, b.params)
+                    assert np.array_equal(a.indices, b.indices)
     finally:
-        ctx.set_param("score_live", 1)
+        ctx.set_param("score_live", 2)
         ctx.set_param("seed", 2)
